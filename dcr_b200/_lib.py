@@ -1,0 +1,63 @@
+"""ctypes binding of libdcr_b200.so (include/dcr_b200.h).  The product path has no CPU fallback: if the library is
+missing or a call fails, a DcrError is raised."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from pathlib import Path
+
+PKG_DIR = Path(__file__).resolve().parent
+LIB_PATH = Path(os.environ.get("DCR_B200_LIB", PKG_DIR / "libdcr_b200.so"))
+
+
+class DcrError(RuntimeError):
+    pass
+
+
+# name -> (restype, argtypes); mirrors include/dcr_b200.h one to one (tests check the header against this table)
+SIGNATURES = {
+    "dcr_version": (C.c_int, []),
+    "dcr_last_error": (C.c_char_p, []),
+    "dcr_device_sm_count": (C.c_int, []),
+    "dcr_l2_normalize": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_void_p]),
+    "dcr_sim_topk_workspace_size": (C.c_size_t, [C.c_int, C.c_int, C.c_int, C.c_int]),
+    "dcr_sim_topk": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int64,
+                               C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "dcr_sim_topk_host": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p,
+                                    C.c_void_p]),
+    "dcr_sim_topk_last_stats": (C.c_int, [C.POINTER(C.c_int)]),
+    "dcr_topk_merge": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                 C.c_void_p]),
+}
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    """Load the shared library (once).  Raises DcrError with a build hint when it is absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists():
+        raise DcrError(
+            f"{LIB_PATH} not found: build it with `python -m dcr_b200.build` (needs nvcc). "
+            "dcr_b200 has no CPU fallback for its compute path.")
+    lib = C.CDLL(str(LIB_PATH))
+    for name, (res, args) in SIGNATURES.items():
+        try:
+            fn = getattr(lib, name)
+        except AttributeError as e:  # pragma: no cover
+            raise DcrError(f"{LIB_PATH} does not export {name}; rebuild (python -m dcr_b200.build --force)") from e
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def last_error() -> str:
+    return load().dcr_last_error().decode("utf-8", "replace")
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        raise DcrError(f"{what} failed (rc={rc}): {last_error()}")

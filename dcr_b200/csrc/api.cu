@@ -1,0 +1,107 @@
+// C-ABI entry points (include/dcr_b200.h).  Thin: argument checks + dispatch into the dcr:: functions.
+#include <cstring>
+
+#include "../../include/dcr_b200.h"
+#include "dcr_internal.cuh"
+#include "host_util.cuh"
+
+namespace {
+thread_local dcr::SimStats g_last_stats = {};
+inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+}  // namespace
+
+extern "C" {
+
+int dcr_version(void) { return DCR_B200_VERSION; }
+
+const char* dcr_last_error(void) { return dcr::last_error_storage().c_str(); }
+
+int dcr_device_sm_count(void) {
+  const dcr::DeviceInfo* di = dcr::device_info();
+  return di ? di->num_sms : -2;
+}
+
+int dcr_l2_normalize(float* x, int n, int d, float eps, void* stream) {
+  DCR_REQUIRE(x != nullptr || n == 0, "dcr_l2_normalize: null pointer");
+  return dcr::l2_normalize(x, n, d, eps, as_stream(stream));
+}
+
+size_t dcr_sim_topk_workspace_size(int nq, int ng, int d, int k) { return dcr::sim_topk_workspace_size(nq, ng, d, k); }
+
+int dcr_sim_topk(const float* q, int nq, const float* g, int ng, int d, int k, int64_t g_index_base,
+                 int64_t g_index_stride, float* out_scores, int64_t* out_idx, void* workspace, size_t workspace_bytes,
+                 void* stream) {
+  DCR_REQUIRE(q && g && out_scores && out_idx, "dcr_sim_topk: null pointer argument");
+  static_assert(sizeof(long long) == sizeof(int64_t), "int64 layout");
+  return dcr::sim_topk(q, nq, g, ng, d, k, g_index_base, g_index_stride, out_scores,
+                       reinterpret_cast<long long*>(out_idx), workspace, workspace_bytes, as_stream(stream),
+                       &g_last_stats);
+}
+
+int dcr_sim_topk_host(const float* q, int nq, const float* g, int ng, int d, int k, float* out_scores,
+                      int64_t* out_idx) {
+  DCR_REQUIRE(q && g && out_scores && out_idx, "dcr_sim_topk_host: null pointer argument");
+  const size_t ws_bytes = dcr::sim_topk_workspace_size(nq, ng, d, k);
+  if (ws_bytes == 0) return -1;
+  float *dq = nullptr, *dg = nullptr, *ds = nullptr;
+  long long* di = nullptr;
+  void* ws = nullptr;
+  cudaStream_t st = nullptr;
+  int rc = 0;
+  auto cleanup = [&]() {
+    if (dq) cudaFree(dq);
+    if (dg) cudaFree(dg);
+    if (ds) cudaFree(ds);
+    if (di) cudaFree(di);
+    if (ws) cudaFree(ws);
+    if (st) cudaStreamDestroy(st);
+  };
+#define DCR_TRY(expr)                                                                                    \
+  do {                                                                                                   \
+    cudaError_t _e = (expr);                                                                             \
+    if (_e != cudaSuccess) {                                                                             \
+      rc = dcr::set_error(-2, "%s failed: %s", #expr, cudaGetErrorString(_e));                           \
+      cleanup();                                                                                         \
+      return rc;                                                                                         \
+    }                                                                                                    \
+  } while (0)
+  DCR_TRY(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+  DCR_TRY(cudaMalloc(&dq, static_cast<size_t>(nq) * d * 4));
+  DCR_TRY(cudaMalloc(&dg, static_cast<size_t>(ng) * d * 4));
+  DCR_TRY(cudaMalloc(&ds, static_cast<size_t>(nq) * k * 4));
+  DCR_TRY(cudaMalloc(&di, static_cast<size_t>(nq) * k * 8));
+  DCR_TRY(cudaMalloc(&ws, ws_bytes));
+  DCR_TRY(cudaMemcpyAsync(dq, q, static_cast<size_t>(nq) * d * 4, cudaMemcpyHostToDevice, st));
+  DCR_TRY(cudaMemcpyAsync(dg, g, static_cast<size_t>(ng) * d * 4, cudaMemcpyHostToDevice, st));
+  rc = dcr::sim_topk(dq, nq, dg, ng, d, k, 0, 1, ds, di, ws, ws_bytes, st, &g_last_stats);
+  if (rc == 0) {
+    DCR_TRY(cudaMemcpyAsync(out_scores, ds, static_cast<size_t>(nq) * k * 4, cudaMemcpyDeviceToHost, st));
+    DCR_TRY(cudaMemcpyAsync(out_idx, di, static_cast<size_t>(nq) * k * 8, cudaMemcpyDeviceToHost, st));
+    DCR_TRY(cudaStreamSynchronize(st));
+  }
+#undef DCR_TRY
+  cleanup();
+  return rc;
+}
+
+int dcr_sim_topk_last_stats(int* out8) {
+  DCR_REQUIRE(out8 != nullptr, "dcr_sim_topk_last_stats: null pointer");
+  out8[0] = g_last_stats.cta_group;
+  out8[1] = g_last_stats.grid;
+  out8[2] = g_last_stats.smem_bytes;
+  out8[3] = g_last_stats.stages;
+  out8[4] = g_last_stats.kp;
+  out8[5] = g_last_stats.cap;
+  out8[6] = g_last_stats.n_flagged;
+  out8[7] = g_last_stats.d_pad;
+  return 0;
+}
+
+int dcr_topk_merge(const float* scores, const int64_t* idx, int nq, int nlists, int k_in, int k_out,
+                   float* out_scores, int64_t* out_idx, void* stream) {
+  DCR_REQUIRE(scores && idx && out_scores && out_idx, "dcr_topk_merge: null pointer argument");
+  return dcr::topk_merge(scores, reinterpret_cast<const long long*>(idx), nq, nlists, k_in, k_out, out_scores,
+                         reinterpret_cast<long long*>(out_idx), as_stream(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,48 @@
+// Host-side helpers shared by the .cu translation units: error capture for the C ABI, the driver entry point
+// for tensor-map encoding (no link-time dependency on libcuda), SM count cache.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <string>
+
+namespace dcr {
+
+// last error message, per host thread (returned by dcr_last_error()).
+std::string& last_error_storage();
+int set_error(int code, const char* fmt, ...);
+
+#define DCR_CUDA_CHECK(expr)                                                                           \
+  do {                                                                                                 \
+    cudaError_t _e = (expr);                                                                           \
+    if (_e != cudaSuccess)                                                                             \
+      return ::dcr::set_error(-2, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+  } while (0)
+
+#define DCR_REQUIRE(cond, ...)                        \
+  do {                                                \
+    if (!(cond)) return ::dcr::set_error(-1, __VA_ARGS__); \
+  } while (0)
+
+struct DeviceInfo {
+  int device = -1;
+  int num_sms = 0;
+  int cc_major = 0, cc_minor = 0;
+  size_t max_smem_optin = 0;
+};
+// cached per current device; returns nullptr and sets the error on failure
+const DeviceInfo* device_info();
+
+// 2-D row-major bf16 tensor [rows, cols] (cols contiguous), box = [box_rows, box_cols], 128-byte swizzle.
+// box_cols * 2 bytes must be 128.
+int make_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t row_stride_elems,
+                      uint32_t box_rows, uint32_t box_cols);
+
+// im2col tensor map over an NHWC bf16 activation tensor (see conv_gemm.cu)
+int make_tmap_im2col_bf16(CUtensorMap* out, const void* base, int n, int h, int w, int c, int pad_h, int pad_w,
+                          int kh, int kw, int stride, int channels_per_pixel, int pixels_per_column);
+
+}  // namespace dcr

@@ -1,0 +1,884 @@
+// Fused all-pairs similarity + per-query top-k for sm_100a.
+//
+// Replaces (reference, /root/reference):
+//   diff_retrieval.py:402      sim = torch.mm(values_features, query_features.T)          (fp32, [G,Q], CPU/MKL)
+//   diff_retrieval.py:417,613,621   simscores.topk(k, axis=1, largest=True)               k in {1,10}
+//   diff_retrieval.py:403,418-419   sim2 = mm(values, values.T); topk(2)[...,-1]           (same kernel, Q:=G, k=2)
+//   embedding_search/similarity_search.py:62-63   features @ batch.T ; max(dim=0)
+//
+// The [Q,G] score matrix is never written.  Three stages, all on the caller's stream:
+//   1. to_bf16_rows_kernel   fp32 descriptors -> zero-padded bf16 rows + per-row norms of the rounding residual
+//   2. sim_topk_kernel       tcgen05 bf16 GEMM (fp32 accumulate in TMEM) whose epilogue keeps, per query, the
+//                            kp (>= k) best approximate scores of its gallery segment (threshold filter on the
+//                            accumulator registers, warp-cooperative compaction in shared memory)
+//   3. rescore_select_kernel exact re-score (fp64 accumulate, fixed order) of the <= slots*kp candidates per query,
+//                            final order (score desc, gallery index asc), plus a per-query certificate that no
+//                            non-candidate can reach the k-th exact score.  Queries failing the certificate are
+//                            recomputed by brute force in fp64 (exact_scan_kernel / exact_select_kernel).
+// Result: indices identical to ranking all G exact dot products with ties broken by lowest index.
+#include <cuda_bf16.h>
+
+#include <algorithm>
+#include <cmath>
+
+#include "dcr_internal.cuh"
+#include "host_util.cuh"
+#include "ptx.cuh"
+
+namespace dcr {
+
+namespace {
+
+constexpr int kBlockM = 128;      // query rows per CTA (TMEM lanes)
+constexpr int kBlockN = 256;      // gallery rows per tile (TMEM columns per accumulator buffer)
+constexpr int kBlockK = 64;       // bf16 elements per 128-byte swizzled smem row
+constexpr int kMaxKB = 8;         // d_pad <= 512
+constexpr int kKPMax = 32;        // max candidates kept per (query, segment)
+constexpr int kWarmTiles = 4;     // tiles replayed at the start of every segment to seed the threshold
+constexpr int kThreads = 192;     // warp 0: TMA producer, warp 1: MMA issuer, warps 2..5: epilogue
+constexpr uint32_t kFull = 0xffffffffu;
+constexpr int kATileBytes = kBlockM * kBlockK * 2;  // 16 KB
+
+struct SimParams {
+  int nq, ng;
+  int num_kb;          // d_pad / 64
+  int n_qtiles;        // ceil(nq / (128*CG))
+  int n_gtiles;        // ceil(ng / 256)
+  int kp;              // candidates kept per (query, segment): 8, 16 or 32
+  int cap;             // shared-memory list capacity per query row (kp + 16 .. 64)
+  int stages;          // B pipeline depth
+  uint2* cand;         // [n_slots][rows_per_qtile][kKPMax]   (score bits, local gallery row)
+  int* cand_cnt;       // [n_slots][rows_per_qtile]
+  float* cand_thr;     // [n_slots][rows_per_qtile]
+};
+
+// ------------------------------------------------------------------------------------------------------------
+// stage 1: fp32 rows -> bf16 rows (zero padded to [n_pad, d_pad]) + norms needed by the error bound
+//   norms[0][r] = ||bf16(x_r)||, norms[1][r] = ||x_r - bf16(x_r)||, gmax[0] = max_r ||x_r||, gmax[1] = max_r residual
+__global__ void to_bf16_rows_kernel(const float* __restrict__ x, int n, int d, int n_pad, int d_pad,
+                                    __nv_bfloat16* __restrict__ out, float* __restrict__ norm_hat,
+                                    float* __restrict__ norm_res, unsigned int* __restrict__ gmax) {
+  const int warps_per_block = blockDim.x >> 5;
+  const int lane = threadIdx.x & 31;
+  for (int row = blockIdx.x * warps_per_block + (threadIdx.x >> 5); row < n_pad; row += gridDim.x * warps_per_block) {
+    float s_hat = 0.f, s_res = 0.f, s_x = 0.f;
+    __nv_bfloat16* o = out + static_cast<size_t>(row) * d_pad;
+    if (row < n) {
+      const float* xr = x + static_cast<size_t>(row) * d;
+      for (int c = lane * 2; c < d_pad; c += 64) {
+        float a = (c < d) ? xr[c] : 0.f;
+        float b = (c + 1 < d) ? xr[c + 1] : 0.f;
+        __nv_bfloat16 ha = __float2bfloat16_rn(a), hb = __float2bfloat16_rn(b);
+        float fa = __bfloat162float(ha), fb = __bfloat162float(hb);
+        s_hat += fa * fa + fb * fb;
+        s_res += (a - fa) * (a - fa) + (b - fb) * (b - fb);
+        s_x += a * a + b * b;
+        __nv_bfloat162 p;
+        p.x = ha;
+        p.y = hb;
+        *reinterpret_cast<__nv_bfloat162*>(o + c) = p;
+      }
+    } else {
+      for (int c = lane * 2; c < d_pad; c += 64) *reinterpret_cast<uint32_t*>(o + c) = 0u;
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      s_hat += __shfl_xor_sync(kFull, s_hat, off);
+      s_res += __shfl_xor_sync(kFull, s_res, off);
+      s_x += __shfl_xor_sync(kFull, s_x, off);
+    }
+    if (lane == 0 && row < n) {
+      // 1.0001: cover the fp32 rounding of the squared sums so the stored values are upper bounds
+      float nh = sqrtf(s_hat) * 1.0001f, nr = sqrtf(s_res) * 1.0001f, nx = sqrtf(s_x) * 1.0001f;
+      if (norm_hat) norm_hat[row] = nh;
+      if (norm_res) norm_res[row] = nr;
+      if (gmax) {
+        atomicMax(gmax + 0, __float_as_uint(nx));  // non-negative floats order like their bit patterns
+        atomicMax(gmax + 1, __float_as_uint(nr));
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// stage 2 helpers
+
+DCR_DEVICE float max8(const float* v) {
+  return fmaxf(fmaxf(fmaxf(v[0], v[1]), fmaxf(v[2], v[3])), fmaxf(fmaxf(v[4], v[5]), fmaxf(v[6], v[7])));
+}
+
+DCR_DEVICE void tmem_ld_wait_dep(uint32_t (&r)[32]) {
+  // the registers are tied to the wait so that no consumer of r[] can be scheduled above it
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                 "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]),
+                 "+r"(r[15]), "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]),
+                 "+r"(r[22]), "+r"(r[23]), "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]),
+                 "+r"(r[29]), "+r"(r[30]), "+r"(r[31])::"memory");
+}
+
+// Keep the kp best of lane L's n (kp < n <= 64) list entries, stored at list[j * 128] (j = 0..n-1); returns the
+// kp-th best score, which becomes that row's new threshold.  Whole warp cooperates; entries end up sorted.
+DCR_DEVICE float compact_one(uint2* list, int n, int kp, uint32_t lane) {
+  const uint2 none = make_uint2(0xff800000u, 0xffffffffu);  // -inf
+  uint2 e0 = (static_cast<int>(lane) < n) ? list[lane * 128] : none;
+  uint2 e1 = (static_cast<int>(lane) + 32 < n) ? list[(lane + 32) * 128] : none;
+  const float k0 = __uint_as_float(e0.x), k1 = __uint_as_float(e1.x);
+  int r0 = 0, r1 = 0;
+  for (int j = 0; j < n; ++j) {
+    float kj = (j < 32) ? __shfl_sync(kFull, k0, j) : __shfl_sync(kFull, k1, j - 32);
+    r0 += (kj > k0) || (kj == k0 && j < static_cast<int>(lane));
+    r1 += (kj > k1) || (kj == k1 && j < static_cast<int>(lane) + 32);
+  }
+  __syncwarp();
+  if (static_cast<int>(lane) < n && r0 < kp) list[r0 * 128] = e0;
+  if (static_cast<int>(lane) + 32 < n && r1 < kp) list[r1 * 128] = e1;
+  const unsigned b0 = __ballot_sync(kFull, static_cast<int>(lane) < n && r0 == kp - 1);
+  const unsigned b1 = __ballot_sync(kFull, static_cast<int>(lane) + 32 < n && r1 == kp - 1);
+  float t0 = __shfl_sync(kFull, k0, b0 ? (__ffs(b0) - 1) : 0);
+  float t1 = __shfl_sync(kFull, k1, b1 ? (__ffs(b1) - 1) : 0);
+  __syncwarp();
+  return b0 ? t0 : t1;
+}
+
+DCR_DEVICE void compact_warp(uint2* warp_list, unsigned need, int kp, float& thr, int& cnt, uint32_t lane) {
+  while (need) {
+    const int L = __ffs(need) - 1;
+    need &= need - 1;
+    const int n = __shfl_sync(kFull, cnt, L);
+    const float t = compact_one(warp_list + L, n, kp, lane);
+    if (static_cast<int>(lane) == L) {
+      thr = t;
+      cnt = kp;
+    }
+  }
+}
+
+// One 32-column chunk of the accumulator row held by this thread.
+template <bool kMaskTail>
+DCR_DEVICE void scan_chunk(const uint32_t (&r)[32], int gcol0, int ng, float& thr, int& cnt, uint2* my_list,
+                           uint2* warp_list, int kp, int cap, uint32_t lane) {
+  float v[32];
+#pragma unroll
+  for (int c = 0; c < 32; ++c) {
+    v[c] = __uint_as_float(r[c]);
+    if (kMaskTail && gcol0 + c >= ng) v[c] = -INFINITY;
+  }
+  float s[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) s[i] = max8(v + 8 * i);
+  const float m = fmaxf(fmaxf(s[0], s[1]), fmaxf(s[2], s[3]));
+  if (__any_sync(kFull, m > thr)) {
+#pragma unroll
+    for (int sub = 0; sub < 4; ++sub) {
+      if (__any_sync(kFull, s[sub] > thr)) {
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const float x = v[sub * 8 + c];
+          if (x > thr) {
+            my_list[cnt * 128] = make_uint2(__float_as_uint(x), static_cast<uint32_t>(gcol0 + sub * 8 + c));
+            ++cnt;
+          }
+        }
+        __syncwarp();
+        const unsigned need = __ballot_sync(kFull, cnt > cap - 8);
+        if (need) compact_warp(warp_list, need, kp, thr, cnt, lane);
+      }
+    }
+  }
+}
+
+// Warm-up chunk: running maxima of 32 column slots (slot = column mod 32); no candidates are recorded.
+template <bool kMaskTail>
+DCR_DEVICE void warm_chunk(const uint32_t (&r)[32], int gcol0, int ng, float (&slot)[32]) {
+#pragma unroll
+  for (int c = 0; c < 32; ++c) {
+    float x = __uint_as_float(r[c]);
+    if (kMaskTail && gcol0 + c >= ng) x = -INFINITY;
+    slot[c] = fmaxf(slot[c], x);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// stage 2: the fused kernel.  kCG = 1: one CTA per work unit (UMMA 128x256x16).  kCG = 2: a CTA pair per work
+// unit (UMMA 256x256x16, cta_group::2): each CTA keeps its own 128 queries resident and loads half of every
+// gallery tile, so L2->SMEM traffic per FLOP halves.
+//
+// Work decomposition: the (q-tile, g-tile) grid is linearised q-major into T = n_qtiles * n_gtiles tiles and cut
+// into gridDim/kCG equal contiguous ranges.  A unit's range is walked as "segments" (maximal runs inside one
+// q-tile); per segment the query tile is loaded once (A stays resident) and the thresholds are seeded by
+// replaying the first kWarmTiles tiles.  Segment (unit u, q-tile i) owns candidate slot u + i.
+template <int kCG>
+__global__ void __launch_bounds__(kThreads, 1)
+    sim_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_g,
+                    const SimParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // carve-up (all tile bases 1024-byte aligned for the 128B swizzle)
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  constexpr int kBRows = kBlockN / kCG;
+  constexpr int kBTileBytes = kBRows * kBlockK * 2;
+  uint8_t* smem_a = smem;                                   // num_kb x 16 KB
+  uint8_t* smem_b = smem_a + p.num_kb * kATileBytes;        // stages x kBTileBytes
+  uint2* cand = reinterpret_cast<uint2*>(smem_b + p.stages * kBTileBytes);  // [cap][128]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(cand) + p.cap * 128 * 8);
+  uint64_t* b_full = bars;              // [stages]
+  uint64_t* b_empty = bars + 8;         // [stages]
+  uint64_t* a_full = bars + 16;
+  uint64_t* a_empty = bars + 17;
+  uint64_t* t_full = bars + 18;         // [2]
+  uint64_t* t_empty = bars + 20;        // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 22);
+
+  const uint32_t warp = threadIdx.x >> 5;
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t cta_rank = (kCG == 2) ? cluster_ctarank() : 0;
+  const bool leader = (cta_rank == 0);
+
+  if (warp == 0 && elect_one()) {
+    tma_prefetch_desc(&tmap_q);
+    tma_prefetch_desc(&tmap_g);
+  }
+  if (warp == 1 && elect_one()) {
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(&b_full[s], kCG);
+      mbar_init(&b_empty[s], 1);
+    }
+    mbar_init(a_full, kCG);
+    mbar_init(a_empty, 1);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&t_full[b], 1);
+      mbar_init(&t_empty[b], 4 * kCG);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc<kCG>(tmem_slot, 512);
+    tmem_relinquish<kCG>();
+  }
+  tc_fence_before();
+  if constexpr (kCG == 2) cluster_sync(); else __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // this unit's tile range
+  const long long n_units = gridDim.x / kCG;
+  const long long unit = blockIdx.x / kCG;
+  const long long T = static_cast<long long>(p.n_qtiles) * p.n_gtiles;
+  const long long t_begin = unit * T / n_units;
+  const long long t_end = (unit + 1) * T / n_units;
+  const int rows_per_qtile = kBlockM * kCG;
+
+  if (warp == 0) {
+    // ===================================== TMA producer =====================================
+    if (lane == 0) {
+      uint32_t it = 0, seg = 0;
+      for (long long t = t_begin; t < t_end;) {
+        const int qi = static_cast<int>(t / p.n_gtiles);
+        const int g_begin = static_cast<int>(t % p.n_gtiles);
+        const long long seg_end = min(t_end, static_cast<long long>(qi + 1) * p.n_gtiles);
+        const int ntiles = static_cast<int>(seg_end - t);
+        const int warm = min(kWarmTiles, ntiles);
+        // resident query tile
+        mbar_wait(a_empty, (seg & 1) ^ 1);
+        if (leader) mbar_arrive_expect_tx(a_full, p.num_kb * kATileBytes * kCG);
+        else mbar_arrive_cluster(a_full, 0);
+        const int q_row = qi * rows_per_qtile + static_cast<int>(cta_rank) * kBlockM;
+        for (int kb = 0; kb < p.num_kb; ++kb)
+          tma_load_2d<kCG>(smem_a + kb * kATileBytes, &tmap_q, a_full, kb * kBlockK, q_row, kEvictNormal);
+        for (int j = 0; j < warm + ntiles; ++j) {
+          const int gi = g_begin + (j < warm ? j : j - warm);
+          const int g_row = gi * kBlockN + static_cast<int>(cta_rank) * kBRows;
+          for (int kb = 0; kb < p.num_kb; ++kb, ++it) {
+            const uint32_t s = it % p.stages, ph = (it / p.stages) & 1;
+            mbar_wait(&b_empty[s], ph ^ 1);
+            if (leader) mbar_arrive_expect_tx(&b_full[s], kBTileBytes * kCG);
+            else mbar_arrive_cluster(&b_full[s], 0);
+            tma_load_2d<kCG>(smem_b + s * kBTileBytes, &tmap_g, &b_full[s], kb * kBlockK, g_row, kEvictNormal);
+          }
+        }
+        t = seg_end;
+        ++seg;
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================== MMA issuer (leader CTA) =====================================
+    if (leader && lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(kBlockM * kCG, kBlockN);
+      uint32_t it = 0, seg = 0, tc = 0;
+      for (long long t = t_begin; t < t_end;) {
+        const int qi = static_cast<int>(t / p.n_gtiles);
+        const long long seg_end = min(t_end, static_cast<long long>(qi + 1) * p.n_gtiles);
+        const int ntiles = static_cast<int>(seg_end - t);
+        const int warm = min(kWarmTiles, ntiles);
+        mbar_wait(a_full, seg & 1);
+        tc_fence_after();
+        for (int j = 0; j < warm + ntiles; ++j, ++tc) {
+          const uint32_t buf = tc & 1;
+          mbar_wait(&t_empty[buf], ((tc >> 1) & 1) ^ 1);
+          tc_fence_after();
+          const uint32_t tmem_d = tmem_base + buf * kBlockN;
+          for (int kb = 0; kb < p.num_kb; ++kb, ++it) {
+            const uint32_t s = it % p.stages, ph = (it / p.stages) & 1;
+            mbar_wait(&b_full[s], ph);
+            tc_fence_after();
+            const uint64_t da = umma_desc_sw128(smem_u32(smem_a + kb * kATileBytes));
+            const uint64_t db = umma_desc_sw128(smem_u32(smem_b + s * kBTileBytes));
+#pragma unroll
+            for (int k = 0; k < kBlockK / 16; ++k)
+              umma_f16<kCG>(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);  // +32 B per K=16 step
+            umma_commit<kCG>(&b_empty[s]);   // frees this B stage (both CTAs) once the MMAs above retire
+            if (kb == p.num_kb - 1) {
+              umma_commit<kCG>(&t_full[buf]);
+              if (j == warm + ntiles - 1) umma_commit<kCG>(a_empty);
+            }
+          }
+        }
+        t = seg_end;
+        ++seg;
+      }
+    }
+  } else {
+    // ===================================== epilogue warps =====================================
+    const uint32_t quad = warp & 3;            // TMEM lane quadrant this warp may read
+    const uint32_t row = quad * 32 + lane;     // query row inside this CTA's tile
+    uint2* my_list = cand + row;
+    uint2* warp_list = cand + quad * 32;
+    const uint32_t tmem_row = tmem_base + ((quad * 32u) << 16);
+    const int kp = p.kp, cap = p.cap;
+    uint32_t tc = 0;
+    for (long long t = t_begin; t < t_end;) {
+      const int qi = static_cast<int>(t / p.n_gtiles);
+      const int g_begin = static_cast<int>(t % p.n_gtiles);
+      const long long seg_end = min(t_end, static_cast<long long>(qi + 1) * p.n_gtiles);
+      const int ntiles = static_cast<int>(seg_end - t);
+      const int warm = min(kWarmTiles, ntiles);
+      float thr = -INFINITY;
+      int cnt = 0;
+      float slot[32];
+#pragma unroll
+      for (int c = 0; c < 32; ++c) slot[c] = -INFINITY;
+
+      for (int j = 0; j < warm + ntiles; ++j, ++tc) {
+        const bool is_warm = j < warm;
+        const int gi = g_begin + (is_warm ? j : j - warm);
+        const int gcol_tile = gi * kBlockN;
+        const bool tail = gcol_tile + kBlockN > p.ng;
+        const uint32_t buf = tc & 1;
+        mbar_wait(&t_full[buf], (tc >> 1) & 1);
+        tc_fence_after();
+        const uint32_t taddr = tmem_row + buf * kBlockN;
+        uint32_t ra[32], rb[32];
+        tmem_ld_32x32(taddr, ra);
+#pragma unroll 1
+        for (int ch = 0; ch < kBlockN / 32; ch += 2) {
+          tmem_ld_wait_dep(ra);
+          tmem_ld_32x32(taddr + (ch + 1) * 32, rb);
+          if (is_warm) {
+            if (tail) warm_chunk<true>(ra, gcol_tile + ch * 32, p.ng, slot);
+            else warm_chunk<false>(ra, gcol_tile + ch * 32, p.ng, slot);
+          } else {
+            if (tail) scan_chunk<true>(ra, gcol_tile + ch * 32, p.ng, thr, cnt, my_list, warp_list, kp, cap, lane);
+            else scan_chunk<false>(ra, gcol_tile + ch * 32, p.ng, thr, cnt, my_list, warp_list, kp, cap, lane);
+          }
+          tmem_ld_wait_dep(rb);
+          if (ch + 2 < kBlockN / 32) {
+            tmem_ld_32x32(taddr + (ch + 2) * 32, ra);
+          } else {
+            // every column of this accumulator buffer is now in registers: hand it back to the MMA warp
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+              if constexpr (kCG == 2) mbar_arrive_cluster(&t_empty[buf], 0);
+              else mbar_arrive(&t_empty[buf]);
+            }
+          }
+          if (is_warm) {
+            if (tail) warm_chunk<true>(rb, gcol_tile + (ch + 1) * 32, p.ng, slot);
+            else warm_chunk<false>(rb, gcol_tile + (ch + 1) * 32, p.ng, slot);
+          } else {
+            if (tail) scan_chunk<true>(rb, gcol_tile + (ch + 1) * 32, p.ng, thr, cnt, my_list, warp_list, kp, cap, lane);
+            else scan_chunk<false>(rb, gcol_tile + (ch + 1) * 32, p.ng, thr, cnt, my_list, warp_list, kp, cap, lane);
+          }
+        }
+        if (is_warm && j == warm - 1) {
+          // seed: fold the 32 slot maxima into `groups` >= kp disjoint groups; the smallest group maximum is
+          // exceeded by at least groups-1 already-seen scores, so it is a safe (never too high for kp) start.
+          // Segments shorter than the warm-up still get a valid bound.
+          int groups = 32;
+          if (kp <= 16) {
+#pragma unroll
+            for (int c = 0; c < 16; ++c) slot[c] = fmaxf(slot[c], slot[c + 16]);
+            groups = 16;
+          }
+          if (kp <= 8) {
+#pragma unroll
+            for (int c = 0; c < 8; ++c) slot[c] = fmaxf(slot[c], slot[c + 8]);
+            groups = 8;
+          }
+          float lo = slot[0];
+#pragma unroll
+          for (int c = 1; c < 32; ++c)
+            if (c < groups) lo = fminf(lo, slot[c]);
+          // strictly below the smallest group maximum so that the maxima themselves are recorded
+          thr = (lo == -INFINITY) ? -INFINITY : __uint_as_float(__float_as_uint(lo) + (lo > 0.f ? -1 : (lo < 0.f ? 1 : 0)));
+          if (lo == 0.f) thr = -1e-30f;
+        }
+      }
+      // ---- flush this segment's lists: final compaction to kp, then coalesced copy to the slot ----
+      __syncwarp();
+      {
+        const unsigned need = __ballot_sync(kFull, cnt > kp);
+        if (need) compact_warp(warp_list, need, kp, thr, cnt, lane);
+      }
+      __syncwarp();
+      const size_t slot_row0 =
+          (static_cast<size_t>(unit + qi) * rows_per_qtile + cta_rank * kBlockM + quad * 32);
+      for (int L = 0; L < 32; ++L) {
+        const int n = __shfl_sync(kFull, cnt, L);
+        if (static_cast<int>(lane) < n) p.cand[(slot_row0 + L) * kKPMax + lane] = warp_list[L + lane * 128];
+      }
+      p.cand_cnt[slot_row0 + lane] = cnt;
+      p.cand_thr[slot_row0 + lane] = thr;
+      __syncwarp();
+      t = seg_end;
+    }
+  }
+
+  // teardown
+  tc_fence_before();
+  if constexpr (kCG == 2) cluster_sync(); else __syncthreads();
+  if (warp == 2) tmem_dealloc<kCG>(tmem_base, 512);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// exact dot product, fp64 accumulate, fixed association: lane l owns elements l*4 + 128*i (float4 granules),
+// accumulates them in order, then a fixed xor-butterfly.  Used by both the re-score and the brute-force path so
+// that the two produce bit-identical values.
+DCR_DEVICE double exact_dot_warp(const float* __restrict__ a_smem, const float* __restrict__ b, int d, uint32_t lane) {
+  double acc = 0.0;
+  for (int c = lane * 4; c < d; c += 128) {
+    if (c + 3 < d) {
+      const float4 bv = *reinterpret_cast<const float4*>(b + c);
+      acc = fma(static_cast<double>(a_smem[c]), static_cast<double>(bv.x), acc);
+      acc = fma(static_cast<double>(a_smem[c + 1]), static_cast<double>(bv.y), acc);
+      acc = fma(static_cast<double>(a_smem[c + 2]), static_cast<double>(bv.z), acc);
+      acc = fma(static_cast<double>(a_smem[c + 3]), static_cast<double>(bv.w), acc);
+    } else {
+      for (int e = c; e < d; ++e) acc = fma(static_cast<double>(a_smem[e]), static_cast<double>(b[e]), acc);
+    }
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(kFull, acc, off);
+  return acc;
+}
+
+// owner unit of linear tile t  (units own [u*T/U, (u+1)*T/U) )
+DCR_DEVICE long long owner_unit(long long t, long long T, long long U) { return ((t + 1) * U + T - 1) / T - 1; }
+
+// block-wide arg-best over (score desc, index asc); entries with taken[i] != 0 are skipped
+struct Best {
+  double s;
+  long long i;
+  int pos;
+};
+DCR_DEVICE bool better(double s, long long i, double bs, long long bi) { return (s > bs) || (s == bs && i < bi); }
+
+// stage 3: one block (128 threads) per query.
+__global__ void __launch_bounds__(128)
+    rescore_select_kernel(const float* __restrict__ q, const float* __restrict__ g, int nq, int ng, int d, int k,
+                          int n_qtiles, int n_gtiles, int n_units, int rows_per_qtile, int d_pad,
+                          const uint2* __restrict__ cand, const int* __restrict__ cand_cnt,
+                          const float* __restrict__ cand_thr, const float* __restrict__ q_norm_hat,
+                          const float* __restrict__ q_norm_res, const unsigned int* __restrict__ g_max,
+                          long long g_index_base, long long g_index_stride, float* __restrict__ out_scores,
+                          long long* __restrict__ out_idx, int* __restrict__ flagged, int* __restrict__ n_flagged,
+                          int max_cand) {
+  extern __shared__ __align__(16) uint8_t sm[];
+  float* qs = reinterpret_cast<float*>(sm);                         // [d]
+  double* sc = reinterpret_cast<double*>(sm + ((d * 4 + 15) & ~15)); // [max_cand]
+  int* ci = reinterpret_cast<int*>(sc + max_cand);                   // [max_cand]
+  __shared__ int s_n;
+  __shared__ float s_thr;
+  __shared__ double s_best[4];
+  __shared__ long long s_besti[4];
+  __shared__ int s_bestp[4];
+
+  const int qrow = blockIdx.x;
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int c = threadIdx.x; c < d; c += blockDim.x) qs[c] = q[static_cast<size_t>(qrow) * d + c];
+
+  const int qi = qrow / rows_per_qtile, r = qrow % rows_per_qtile;
+  const long long T = static_cast<long long>(n_qtiles) * n_gtiles;
+  const long long u_lo = owner_unit(static_cast<long long>(qi) * n_gtiles, T, n_units);
+  const long long u_hi = owner_unit(static_cast<long long>(qi + 1) * n_gtiles - 1, T, n_units);
+  if (threadIdx.x == 0) {
+    int n = 0;
+    float thr = -INFINITY;
+    for (long long u = u_lo; u <= u_hi; ++u) {
+      const size_t sr = static_cast<size_t>(u + qi) * rows_per_qtile + r;
+      const int c = cand_cnt[sr];
+      thr = fmaxf(thr, cand_thr[sr]);
+      for (int j = 0; j < c && n < max_cand; ++j) ci[n++] = static_cast<int>(cand[sr * kKPMax + j].y);
+    }
+    s_n = n;
+    s_thr = thr;
+  }
+  __syncthreads();
+  const int n = s_n;
+  for (int c = warp; c < n; c += 4) {
+    const double v = exact_dot_warp(qs, g + static_cast<size_t>(ci[c]) * d, d, lane);
+    if (lane == 0) sc[c] = v;
+  }
+  __syncthreads();
+
+  double kth = -INFINITY;
+  const int kk = min(k, n);
+  for (int round = 0; round < kk; ++round) {
+    double bs = -INFINITY;
+    long long bi = 0x7fffffffffffffffLL;
+    int bp = -1;
+    for (int c = threadIdx.x; c < n; c += blockDim.x) {
+      if (ci[c] >= 0 && (bp < 0 || better(sc[c], ci[c], bs, bi))) {
+        bs = sc[c];
+        bi = ci[c];
+        bp = c;
+      }
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      const double os = __shfl_xor_sync(kFull, bs, off);
+      const long long oi = __shfl_xor_sync(kFull, bi, off);
+      const int op = __shfl_xor_sync(kFull, bp, off);
+      if (op >= 0 && (bp < 0 || better(os, oi, bs, bi))) {
+        bs = os;
+        bi = oi;
+        bp = op;
+      }
+    }
+    if (lane == 0) {
+      s_best[warp] = bs;
+      s_besti[warp] = bi;
+      s_bestp[warp] = bp;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      for (int w = 1; w < 4; ++w)
+        if (s_bestp[w] >= 0 && (s_bestp[0] < 0 || better(s_best[w], s_besti[w], s_best[0], s_besti[0]))) {
+          s_best[0] = s_best[w];
+          s_besti[0] = s_besti[w];
+          s_bestp[0] = s_bestp[w];
+        }
+      out_scores[static_cast<size_t>(qrow) * k + round] = static_cast<float>(s_best[0]);
+      out_idx[static_cast<size_t>(qrow) * k + round] = g_index_base + g_index_stride * s_besti[0];
+      ci[s_bestp[0]] = -1 - ci[s_bestp[0]];  // mark taken
+    }
+    __syncthreads();
+    kth = s_best[0];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    // certificate: every gallery row that is not a candidate has approximate score <= s_thr, hence exact score
+    // <= s_thr + eps.  eps bounds |bf16 tensor-core score - exact score| for this query.
+    const float g_norm = __uint_as_float(g_max[0]), g_res = __uint_as_float(g_max[1]);
+    const float qh = q_norm_hat[qrow], qr = q_norm_res[qrow];
+    const float eps = 1.001f * (qh * g_res + qr * g_norm) + d_pad * 2.4e-7f * qh * (g_norm + g_res) + 1e-30f;
+    const bool closed = s_thr > -INFINITY;   // some segment dropped rows
+    const bool ok = (n >= k) && (!closed || kth > static_cast<double>(s_thr) + static_cast<double>(eps));
+    if (!ok) flagged[atomicAdd(n_flagged, 1)] = qrow;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// brute-force exact path for flagged queries (batch of <= kExactBatch): scores[f][g] in fp64, then select.
+constexpr int kExactBatch = 32;
+
+__global__ void __launch_bounds__(256)
+    exact_scan_kernel(const float* __restrict__ q, const float* __restrict__ g, int ng, int d,
+                      const int* __restrict__ flagged, int f_begin, const int* __restrict__ n_flagged,
+                      double* __restrict__ scores) {
+  extern __shared__ __align__(16) uint8_t sm[];
+  float* qs = reinterpret_cast<float*>(sm);  // [nb][d]
+  const int nb = min(kExactBatch, *n_flagged - f_begin);
+  if (nb <= 0) return;
+  for (int i = threadIdx.x; i < nb * d; i += blockDim.x) {
+    const int f = i / d, c = i % d;
+    qs[i] = q[static_cast<size_t>(flagged[f_begin + f]) * d + c];
+  }
+  __syncthreads();
+  const uint32_t lane = threadIdx.x & 31;
+  const int warps = (blockDim.x >> 5) * gridDim.x;
+  for (int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < ng; row += warps) {
+    const float* gr = g + static_cast<size_t>(row) * d;
+    for (int f = 0; f < nb; ++f) {
+      const double v = exact_dot_warp(qs + f * d, gr, d, lane);
+      if (lane == 0) scores[static_cast<size_t>(f) * ng + row] = v;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+    exact_select_kernel(double* __restrict__ scores, int ng, int k, const int* __restrict__ flagged, int f_begin,
+                        const int* __restrict__ n_flagged, long long g_index_base, long long g_index_stride,
+                        float* __restrict__ out_scores, long long* __restrict__ out_idx) {
+  const int f = blockIdx.x;
+  if (f_begin + f >= *n_flagged) return;
+  const int qrow = flagged[f_begin + f];
+  double* s = scores + static_cast<size_t>(f) * ng;
+  __shared__ double s_best[8];
+  __shared__ int s_besti[8];
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int round = 0; round < k; ++round) {
+    double bs = -INFINITY;
+    int bi = -1;
+    for (int c = threadIdx.x; c < ng; c += blockDim.x) {
+      const double v = s[c];
+      if (!(v != v) && (bi < 0 || v > bs)) {   // ascending c per thread => first (lowest index) max kept
+        bs = v;
+        bi = c;
+      }
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      const double os = __shfl_xor_sync(kFull, bs, off);
+      const int oi = __shfl_xor_sync(kFull, bi, off);
+      if (oi >= 0 && (bi < 0 || os > bs || (os == bs && oi < bi))) {
+        bs = os;
+        bi = oi;
+      }
+    }
+    if (lane == 0) {
+      s_best[warp] = bs;
+      s_besti[warp] = bi;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      for (int w = 1; w < 8; ++w)
+        if (s_besti[w] >= 0 && (s_besti[0] < 0 || s_best[w] > s_best[0] ||
+                                (s_best[w] == s_best[0] && s_besti[w] < s_besti[0]))) {
+          s_best[0] = s_best[w];
+          s_besti[0] = s_besti[w];
+        }
+      out_scores[static_cast<size_t>(qrow) * k + round] = static_cast<float>(s_best[0]);
+      out_idx[static_cast<size_t>(qrow) * k + round] = g_index_base + g_index_stride * s_besti[0];
+      s[s_besti[0]] = __longlong_as_double(0x7ff8000000000000LL);  // NaN marks "taken"
+    }
+    __syncthreads();
+  }
+}
+
+inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+struct SimPlan {
+  int cg;                 // 1 or 2
+  int d_pad, num_kb;
+  int nq_pad, ng_pad;
+  int n_qtiles, n_gtiles;
+  int n_units;            // CTAs / cg
+  int n_slots;
+  int rows_per_qtile;
+  int kp, cap, stages;
+  size_t smem_bytes;
+  int max_cand;           // per query, for stage 3
+  // workspace offsets
+  size_t off_qb, off_gb, off_qnh, off_qnr, off_gmax, off_cand, off_cnt, off_thr, off_flag, off_nflag, off_exact;
+  size_t total;
+};
+
+int make_plan(int nq, int ng, int d, int k, int cg, int num_sms, size_t max_smem, SimPlan* pl) {
+  DCR_REQUIRE(nq >= 1 && ng >= 1 && d >= 1, "sim_topk: empty problem (nq=%d ng=%d d=%d)", nq, ng, d);
+  DCR_REQUIRE(d <= kMaxKB * kBlockK, "sim_topk: descriptor dim %d > %d not supported by the resident-query kernel", d,
+              kMaxKB * kBlockK);
+  DCR_REQUIRE(k >= 1 && k <= 16, "sim_topk: k=%d outside [1,16]", k);
+  DCR_REQUIRE(k <= ng, "sim_topk: k=%d > gallery size %d", k, ng);
+  DCR_REQUIRE(cg == 1 || cg == 2, "sim_topk: cta group must be 1 or 2");
+  pl->cg = cg;
+  pl->d_pad = static_cast<int>(align_up(d, kBlockK));
+  pl->num_kb = pl->d_pad / kBlockK;
+  pl->rows_per_qtile = kBlockM * cg;
+  pl->n_qtiles = (nq + pl->rows_per_qtile - 1) / pl->rows_per_qtile;
+  pl->n_gtiles = (ng + kBlockN - 1) / kBlockN;
+  pl->nq_pad = pl->n_qtiles * pl->rows_per_qtile;
+  pl->ng_pad = pl->n_gtiles * kBlockN;
+  const long long T = static_cast<long long>(pl->n_qtiles) * pl->n_gtiles;
+  int units = num_sms / cg;
+  if (T < units) units = static_cast<int>(T);
+  pl->n_units = units;
+  pl->n_slots = units + pl->n_qtiles;
+  pl->kp = (k <= 2) ? 8 : (k <= 5 ? 16 : 32);
+  // shared memory: A + stages*B + cap KB of lists + barriers
+  const size_t a_bytes = static_cast<size_t>(pl->num_kb) * kATileBytes;
+  const size_t b_tile = static_cast<size_t>(kBlockN / cg) * kBlockK * 2;
+  const size_t fixed = 1024 /*align slack*/ + 256 /*barriers*/;
+  int cap = pl->kp + 16;
+  DCR_REQUIRE(max_smem >= a_bytes + 2 * b_tile + cap * 1024 + fixed, "sim_topk: not enough shared memory (%zu)", max_smem);
+  int stages = static_cast<int>((max_smem - fixed - a_bytes - static_cast<size_t>(cap) * 1024) / b_tile);
+  if (stages > 8) stages = 8;
+  // spend what is left on list capacity (fewer compactions), up to 64
+  size_t left = max_smem - fixed - a_bytes - stages * b_tile - static_cast<size_t>(cap) * 1024;
+  cap += static_cast<int>(left / 1024);
+  if (cap > 64) cap = 64;
+  pl->cap = cap;
+  pl->stages = stages;
+  pl->smem_bytes = fixed + a_bytes + stages * b_tile + static_cast<size_t>(cap) * 1024;
+  // a q-tile is covered by at most ceil(n_gtiles / (T/units)) + 1 units
+  const long long per_unit = std::max<long long>(1, T / units);
+  long long span = (pl->n_gtiles + per_unit - 1) / per_unit + 1;
+  if (span > units) span = units;
+  pl->max_cand = static_cast<int>(span) * pl->kp;
+
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    size_t o = off;
+    off = align_up(off + bytes, 256);
+    return o;
+  };
+  pl->off_qb = take(static_cast<size_t>(pl->nq_pad) * pl->d_pad * 2);
+  pl->off_gb = take(static_cast<size_t>(pl->ng_pad) * pl->d_pad * 2);
+  pl->off_qnh = take(static_cast<size_t>(pl->nq_pad) * 4);
+  pl->off_qnr = take(static_cast<size_t>(pl->nq_pad) * 4);
+  pl->off_gmax = take(16);
+  const size_t slot_rows = static_cast<size_t>(pl->n_slots) * pl->rows_per_qtile;
+  pl->off_cand = take(slot_rows * kKPMax * 8);
+  pl->off_cnt = take(slot_rows * 4);
+  pl->off_thr = take(slot_rows * 4);
+  pl->off_flag = take(static_cast<size_t>(nq) * 4);
+  pl->off_nflag = take(16);
+  pl->off_exact = take(static_cast<size_t>(kExactBatch) * ng * 8);
+  pl->total = off;
+  return 0;
+}
+
+int default_cg() {
+  const char* e = getenv("DCR_SIM_CTA_GROUP");
+  if (e && (e[0] == '1' || e[0] == '2')) return e[0] - '0';
+  return 2;
+}
+
+}  // namespace
+
+size_t sim_topk_workspace_size(int nq, int ng, int d, int k) {
+  const DeviceInfo* di = device_info();
+  SimPlan pl;
+  // size for the larger of the two variants so the same buffer works for either
+  size_t best = 0;
+  for (int cg = 1; cg <= 2; ++cg) {
+    if (make_plan(nq, ng, d, k, cg, di ? di->num_sms : 148, di ? di->max_smem_optin : 232448, &pl) != 0) return 0;
+    best = std::max(best, pl.total);
+  }
+  return best;
+}
+
+int sim_topk(const float* q, int nq, const float* g, int ng, int d, int k, long long g_index_base,
+             long long g_index_stride, float* out_scores, long long* out_idx, void* ws, size_t ws_bytes,
+             cudaStream_t stream, SimStats* stats) {
+  const DeviceInfo* di = device_info();
+  if (!di) return -2;
+  DCR_REQUIRE(di->cc_major == 10, "sim_topk: this build targets sm_100a; device reports sm_%d%d", di->cc_major, di->cc_minor);
+  const int cg = default_cg();
+  SimPlan pl;
+  if (int rc = make_plan(nq, ng, d, k, cg, di->num_sms, di->max_smem_optin, &pl)) return rc;
+  DCR_REQUIRE(ws != nullptr && ws_bytes >= pl.total, "sim_topk: workspace too small (%zu < %zu)", ws_bytes, pl.total);
+  DCR_REQUIRE((reinterpret_cast<uintptr_t>(ws) & 255) == 0, "sim_topk: workspace must be 256-byte aligned");
+  DCR_REQUIRE((reinterpret_cast<uintptr_t>(q) & 15) == 0 && (reinterpret_cast<uintptr_t>(g) & 15) == 0 && d % 4 == 0,
+              "sim_topk: q/g must be 16-byte aligned with d %% 4 == 0 (d=%d)", d);
+  uint8_t* w = static_cast<uint8_t*>(ws);
+  auto* qb = reinterpret_cast<__nv_bfloat16*>(w + pl.off_qb);
+  auto* gb = reinterpret_cast<__nv_bfloat16*>(w + pl.off_gb);
+  auto* qnh = reinterpret_cast<float*>(w + pl.off_qnh);
+  auto* qnr = reinterpret_cast<float*>(w + pl.off_qnr);
+  auto* gmax = reinterpret_cast<unsigned int*>(w + pl.off_gmax);
+  auto* cand = reinterpret_cast<uint2*>(w + pl.off_cand);
+  auto* ccnt = reinterpret_cast<int*>(w + pl.off_cnt);
+  auto* cthr = reinterpret_cast<float*>(w + pl.off_thr);
+  auto* flagged = reinterpret_cast<int*>(w + pl.off_flag);
+  auto* nflag = reinterpret_cast<int*>(w + pl.off_nflag);
+  auto* exact = reinterpret_cast<double*>(w + pl.off_exact);
+
+  DCR_CUDA_CHECK(cudaMemsetAsync(gmax, 0, 16, stream));
+  DCR_CUDA_CHECK(cudaMemsetAsync(nflag, 0, 16, stream));
+  const int conv_blocks = di->num_sms * 8;
+  to_bf16_rows_kernel<<<conv_blocks, 256, 0, stream>>>(q, nq, d, pl.nq_pad, pl.d_pad, qb, qnh, qnr, nullptr);
+  to_bf16_rows_kernel<<<conv_blocks, 256, 0, stream>>>(g, ng, d, pl.ng_pad, pl.d_pad, gb, nullptr, nullptr, gmax);
+  DCR_CUDA_CHECK(cudaGetLastError());
+
+  CUtensorMap tq, tg;
+  if (int rc = make_tmap_2d_bf16(&tq, qb, pl.nq_pad, pl.d_pad, pl.d_pad, kBlockM, kBlockK)) return rc;
+  if (int rc = make_tmap_2d_bf16(&tg, gb, pl.ng_pad, pl.d_pad, pl.d_pad, kBlockN / cg, kBlockK)) return rc;
+
+  SimParams p;
+  p.nq = nq;
+  p.ng = ng;
+  p.num_kb = pl.num_kb;
+  p.n_qtiles = pl.n_qtiles;
+  p.n_gtiles = pl.n_gtiles;
+  p.kp = pl.kp;
+  p.cap = pl.cap;
+  p.stages = pl.stages;
+  p.cand = cand;
+  p.cand_cnt = ccnt;
+  p.cand_thr = cthr;
+
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(pl.n_units * cg);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = pl.smem_bytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = cg;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  if (cg == 2) {
+    DCR_CUDA_CHECK(cudaFuncSetAttribute(sim_topk_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        static_cast<int>(pl.smem_bytes)));
+    DCR_CUDA_CHECK(cudaLaunchKernelEx(&cfg, sim_topk_kernel<2>, tq, tg, p));
+  } else {
+    DCR_CUDA_CHECK(cudaFuncSetAttribute(sim_topk_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        static_cast<int>(pl.smem_bytes)));
+    DCR_CUDA_CHECK(cudaLaunchKernelEx(&cfg, sim_topk_kernel<1>, tq, tg, p));
+  }
+
+  const size_t rs_smem = ((static_cast<size_t>(d) * 4 + 15) & ~size_t(15)) + static_cast<size_t>(pl.max_cand) * 12 + 16;
+  DCR_CUDA_CHECK(cudaFuncSetAttribute(rescore_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      static_cast<int>(rs_smem)));
+  rescore_select_kernel<<<nq, 128, rs_smem, stream>>>(q, g, nq, ng, d, k, pl.n_qtiles, pl.n_gtiles, pl.n_units,
+                                                      pl.rows_per_qtile, pl.d_pad, cand, ccnt, cthr, qnh, qnr, gmax,
+                                                      g_index_base, g_index_stride, out_scores, out_idx, flagged,
+                                                      nflag, pl.max_cand);
+  DCR_CUDA_CHECK(cudaGetLastError());
+
+  // exact path for queries whose certificate failed: first batch is launched blind (kernels exit when the
+  // device-side count is zero), further batches only if the count read back says so.
+  const size_t ex_smem = static_cast<size_t>(kExactBatch) * d * 4;
+  DCR_CUDA_CHECK(cudaFuncSetAttribute(exact_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      static_cast<int>(ex_smem)));
+  int h_nflag = 0;
+  int done = 0;
+  do {
+    exact_scan_kernel<<<di->num_sms * 2, 256, ex_smem, stream>>>(q, g, ng, d, flagged, done, nflag, exact);
+    exact_select_kernel<<<kExactBatch, 256, 0, stream>>>(exact, ng, k, flagged, done, nflag, g_index_base,
+                                                         g_index_stride, out_scores, out_idx);
+    DCR_CUDA_CHECK(cudaGetLastError());
+    if (done == 0) {
+      DCR_CUDA_CHECK(cudaMemcpyAsync(&h_nflag, nflag, sizeof(int), cudaMemcpyDeviceToHost, stream));
+      DCR_CUDA_CHECK(cudaStreamSynchronize(stream));
+    }
+    done += kExactBatch;
+  } while (done < h_nflag);
+
+  if (stats) {
+    stats->cta_group = cg;
+    stats->grid = pl.n_units * cg;
+    stats->smem_bytes = static_cast<int>(pl.smem_bytes);
+    stats->stages = pl.stages;
+    stats->kp = pl.kp;
+    stats->cap = pl.cap;
+    stats->n_flagged = h_nflag;
+    stats->d_pad = pl.d_pad;
+  }
+  return 0;
+}
+
+}  // namespace dcr

@@ -1,0 +1,113 @@
+"""Host mirror of the reference's similarity / top-k step.
+
+The reference has no function boundary here -- it is inline tensor code in `main_worker`:
+
+    values_features = nn.functional.normalize(values_features, dim=1, p=2)      diff_retrieval.py:388
+    query_features  = nn.functional.normalize(query_features,  dim=1, p=2)      diff_retrieval.py:389
+    sim = torch.mm(values_features, query_features.T)                            diff_retrieval.py:402
+    main_v, main_l = sim.T.topk(1, axis=1, largest=True)                         diff_retrieval.py:411,417
+    bg_v = (values @ values.T).T.topk(2, axis=1)[0][:, -1]                       diff_retrieval.py:403,418-419
+
+`sim_topk(query, gallery, k)` returns exactly what `torch.mm(gallery, query.T).T.topk(k, dim=1)` would (values,
+indices), with a defined tie rule (lowest gallery index first) and without materialising the [Q,G] matrix.
+All compute happens in libdcr_b200.so on the tensors' CUDA device.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+
+
+def _check_cuda_f32(name: str, t: torch.Tensor) -> torch.Tensor:
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise _lib.DcrError(f"{name} must be a CUDA tensor (dcr_b200 has no CPU compute path)")
+    if t.dtype != torch.float32:
+        raise _lib.DcrError(f"{name} must be float32, got {t.dtype}")
+    if t.dim() != 2:
+        raise _lib.DcrError(f"{name} must be 2-D [N, D], got shape {tuple(t.shape)}")
+    return t.contiguous()
+
+
+_ws_cache: dict = {}
+
+
+def _workspace(nbytes: int, device: torch.device) -> torch.Tensor:
+    key = (device.type, device.index)
+    ws = _ws_cache.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.empty(nbytes + 256, dtype=torch.uint8, device=device)
+        _ws_cache[key] = ws
+    return ws
+
+
+def _aligned_ptr(t: torch.Tensor, align: int = 256) -> int:
+    p = t.data_ptr()
+    return (p + align - 1) // align * align
+
+
+def l2_normalize_(x: torch.Tensor, eps: float = 1e-12) -> torch.Tensor:
+    """In-place `nn.functional.normalize(x, dim=1, p=2)` (diff_retrieval.py:388-389)."""
+    lib = _lib.load()
+    x = _check_cuda_f32("x", x)
+    with torch.cuda.device(x.device):
+        st = torch.cuda.current_stream().cuda_stream
+        _lib.check(lib.dcr_l2_normalize(x.data_ptr(), x.shape[0], x.shape[1], eps, st), "dcr_l2_normalize")
+    return x
+
+
+def sim_topk(query: torch.Tensor, gallery: torch.Tensor, k: int = 1, *, index_base: int = 0,
+             index_stride: int = 1) -> Tuple[torch.Tensor, torch.Tensor]:
+    """values f32[Q,k], indices i64[Q,k] of the k largest <query_i, gallery_j>, ties -> lowest j."""
+    lib = _lib.load()
+    q = _check_cuda_f32("query", query)
+    g = _check_cuda_f32("gallery", gallery)
+    if q.device != g.device:
+        raise _lib.DcrError("query and gallery must be on the same device")
+    if q.shape[1] != g.shape[1]:
+        raise _lib.DcrError(f"descriptor dims differ: {q.shape[1]} vs {g.shape[1]}")
+    nq, d = q.shape
+    ng = g.shape[0]
+    with torch.cuda.device(q.device):
+        nbytes = lib.dcr_sim_topk_workspace_size(nq, ng, d, k)
+        if nbytes == 0:
+            raise _lib.DcrError(f"dcr_sim_topk_workspace_size: {_lib.last_error()}")
+        ws = _workspace(nbytes, q.device)
+        out_s = torch.empty((nq, k), dtype=torch.float32, device=q.device)
+        out_i = torch.empty((nq, k), dtype=torch.int64, device=q.device)
+        st = torch.cuda.current_stream().cuda_stream
+        rc = lib.dcr_sim_topk(q.data_ptr(), nq, g.data_ptr(), ng, d, k, index_base, index_stride, out_s.data_ptr(),
+                              out_i.data_ptr(), _aligned_ptr(ws), nbytes, st)
+        _lib.check(rc, "dcr_sim_topk")
+    return out_s, out_i
+
+
+def sim_topk_stats() -> dict:
+    lib = _lib.load()
+    arr = (C.c_int * 8)()
+    lib.dcr_sim_topk_last_stats(arr)
+    keys = ["cta_group", "grid", "smem_bytes", "stages", "kp", "cap", "n_flagged", "d_pad"]
+    return dict(zip(keys, list(arr)))
+
+
+def topk_merge(scores: torch.Tensor, idx: torch.Tensor, k_out: Optional[int] = None
+               ) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Merge per-shard results: scores/idx [nlists, Q, k_in] -> [Q, k_out] by (score desc, idx asc)."""
+    lib = _lib.load()
+    if not (scores.is_cuda and idx.is_cuda):
+        raise _lib.DcrError("topk_merge needs CUDA tensors")
+    scores = scores.contiguous().float()
+    idx = idx.contiguous().long()
+    nl, nq, k_in = scores.shape
+    k_out = k_in if k_out is None else k_out
+    out_s = torch.empty((nq, k_out), dtype=torch.float32, device=scores.device)
+    out_i = torch.empty((nq, k_out), dtype=torch.int64, device=scores.device)
+    with torch.cuda.device(scores.device):
+        st = torch.cuda.current_stream().cuda_stream
+        rc = lib.dcr_topk_merge(scores.data_ptr(), idx.data_ptr(), nq, nl, k_in, k_out, out_s.data_ptr(),
+                                out_i.data_ptr(), st)
+        _lib.check(rc, "dcr_topk_merge")
+    return out_s, out_i

@@ -1,0 +1,80 @@
+/*
+ * dcr_b200.h -- C ABI of libdcr_b200.so: the B200 (sm_100a) replacement for DCR's embed -> match -> top-k (+FID)
+ * hot path.  Plain pointers and sizes only; no torch / CUDA types in any signature.
+ *
+ * The reference (somepago/DCR, /root/reference) is pure Python and has no FFI layer; each entry point below names
+ * the reference call site it replaces (file:line).  A Python maintainer binds these with ctypes.
+ *
+ * Conventions
+ *   - every function returning int: 0 = ok, < 0 = error; the message is available from dcr_last_error() (per host
+ *     thread).  Nothing throws, nothing aborts.
+ *   - "device pointer" arguments are raw CUDA device addresses on the CURRENT device; `stream` is a cudaStream_t
+ *     passed as void* (NULL = legacy default stream).  Work is enqueued on that stream; functions that must read a
+ *     result back (dcr_sim_topk: the count of queries that needed the exact fallback) synchronise that stream
+ *     before returning.
+ *   - workspaces are caller-owned device buffers, 256-byte aligned, sized by the matching *_workspace_size().
+ *   - the library never falls back to the CPU: on a machine without an sm_100 device every compute call fails with
+ *     a message.
+ */
+#ifndef DCR_B200_H_
+#define DCR_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DCR_B200_VERSION 100 /* 0.1.0 */
+
+/* ---- library ------------------------------------------------------------------------------------------------ */
+int dcr_version(void);
+const char* dcr_last_error(void);
+/* number of SMs of the current device, or < 0 when no usable device is visible */
+int dcr_device_sm_count(void);
+
+/* ---- descriptor post-processing ------------------------------------------------------------------------------- */
+/* x[n,d] (device, fp32, row-major) <- x / max(||x||_2, eps) per row.
+ * Replaces nn.functional.normalize(features, dim=1, p=2)          diff_retrieval.py:388-389 */
+int dcr_l2_normalize(float* x, int n, int d, float eps, void* stream);
+
+/* ---- similarity + top-k ------------------------------------------------------------------------------------- */
+/* Bytes of device workspace dcr_sim_topk needs for this problem size (0 on invalid arguments, see last error). */
+size_t dcr_sim_topk_workspace_size(int nq, int ng, int d, int k);
+
+/* For every query row q[i,:] the k gallery rows with the largest dot product, ordered by (score descending,
+ * gallery index ascending).  q[nq,d], g[ng,d]: device, fp32, row-major, 16-byte aligned, d % 4 == 0, d <= 512,
+ * 1 <= k <= 16, k <= ng.  out_scores[nq,k] fp32, out_idx[nq,k] int64 (device); reported index =
+ * g_index_base + g_index_stride * row (lets a rank that holds a contiguous or strided gallery shard report global
+ * indices).  Scores are the fp64-accumulated dot products of the fp32 inputs rounded to fp32; the [nq,ng] matrix
+ * is never materialised.
+ * Replaces   sim = torch.mm(values_features, query_features.T)         diff_retrieval.py:402
+ *            simscores.topk(k, axis=1, largest=True)                   diff_retrieval.py:417, 613, 621
+ *            sim2 = mm(values, values.T); bg.topk(2)                   diff_retrieval.py:403, 418-419 (q = g, k = 2)
+ *            features @ batch.T ; .max(dim=0)                          embedding_search/similarity_search.py:62-63 */
+int dcr_sim_topk(const float* q, int nq, const float* g, int ng, int d, int k, int64_t g_index_base,
+                 int64_t g_index_stride, float* out_scores, int64_t* out_idx, void* workspace,
+                 size_t workspace_bytes, void* stream);
+
+/* Same computation with HOST buffers (pageable or pinned): allocates device memory, copies in, runs, copies the
+ * results back, frees.  This is the call the end-to-end benchmark times. */
+int dcr_sim_topk_host(const float* q, int nq, const float* g, int ng, int d, int k, float* out_scores,
+                      int64_t* out_idx);
+
+/* Launch facts of the most recent dcr_sim_topk on this host thread:
+ * out[0]=cta_group out[1]=grid out[2]=dynamic smem bytes out[3]=pipeline stages out[4]=candidates kept per segment
+ * out[5]=list capacity out[6]=queries recomputed by the exact fallback out[7]=padded descriptor dim */
+int dcr_sim_topk_last_stats(int* out8);
+
+/* Merge nlists per-shard results.  scores/idx: device, layout [nlists][nq][k_in]; entries with idx < 0 are empty.
+ * Output [nq][k_out] ordered by (score desc, idx asc).  nlists*k_in <= 1024.
+ * Replaces the running cross-folder merge                        embedding_search/similarity_search.py:70-74
+ * and is the reduction after the per-shard top-k all-gather. */
+int dcr_topk_merge(const float* scores, const int64_t* idx, int nq, int nlists, int k_in, int k_out,
+                   float* out_scores, int64_t* out_idx, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DCR_B200_H_ */

@@ -1,0 +1,131 @@
+"""GPU parity: dcr_sim_topk (through the C ABI) vs the CPU oracle -- indices bit-exact, scores to fp32 rounding."""
+import numpy as np
+import pytest
+import torch
+
+from dcr_b200 import similarity, synthetic
+from oracle import similarity as osim
+
+pytestmark = pytest.mark.gpu
+
+
+def _run(q, g, k, **kw):
+    v, i = similarity.sim_topk(q.cuda(), g.cuda(), k, **kw)
+    torch.cuda.synchronize()
+    return v.cpu().numpy(), i.cpu().numpy()
+
+
+def _check(q, g, k, rows=None):
+    v, i = _run(q, g, k)
+    qn = q.numpy() if rows is None else q.numpy()[rows]
+    ov, oi = osim.sim_topk(qn, g.numpy(), k)
+    if rows is not None:
+        v, i = v[rows], i[rows]
+    bad = np.nonzero((i != oi).any(axis=1))[0]
+    assert bad.size == 0, f"{bad.size} query rows differ, first {bad[:5]}: got {i[bad[:3]]} want {oi[bad[:3]]}"
+    np.testing.assert_allclose(v, ov, rtol=0, atol=1.2e-7)   # fp64 dot rounded to fp32 on both sides
+    return similarity.sim_topk_stats()
+
+
+@pytest.mark.parametrize("nq,ng,d,k", [
+    (256, 1000, 512, 1),      # BASELINE config 1 (similarity part)
+    (256, 1000, 512, 10),
+    (1, 16, 64, 1),           # tiny
+    (7, 300, 100, 3),         # d not a multiple of 64, ragged everything
+    (130, 257, 384, 2),       # DINO dim, just over one tile in both directions
+    (513, 4097, 512, 5),
+    (300, 20000, 512, 10),    # several gallery tiles per unit
+    (2000, 3000, 256, 16),    # many q-tiles, max k
+])
+def test_parity_synthetic(nq, ng, d, k):
+    q, g = synthetic.descriptors(nq, ng, d, seed=nq + ng)
+    _check(q, g, k)
+
+
+def test_parity_unnormalised_negative():
+    gen = torch.Generator().manual_seed(5)
+    q = torch.randn(200, 128, generator=gen) * 3
+    g = -torch.rand(5000, 128, generator=gen) * q[:1].abs().mean()    # mostly negative scores for positive q
+    _check(q.abs(), g, 4)
+
+
+def test_duplicates_tie_rule():
+    q, g = synthetic.descriptors(128, 2048, 512, seed=9)
+    g[100:140] = g[7]                     # 41 identical gallery rows
+    g[1500] = q[3]
+    g[300] = q[3]                         # exact duplicate pair as best match of query 3
+    st = _check(q, g, 10)
+    v, i = _run(q, g, 10)
+    assert i[3, 0] == 300 and i[3, 1] == 1500
+
+
+def test_all_identical_gallery_forces_exact_fallback():
+    q, _ = synthetic.descriptors(64, 8, 64, seed=11)
+    g = q[:1].repeat(3000, 1).contiguous()
+    v, i = _run(q, g, 5)
+    assert (i == np.arange(5)[None, :]).all()
+    assert similarity.sim_topk_stats()["n_flagged"] == 64   # certificate cannot hold: everything ties
+
+
+def test_k_equals_gallery_size():
+    q, g = synthetic.descriptors(20, 16, 64, seed=12)
+    _check(q, g, 16)
+
+
+def test_index_base_and_stride():
+    q, g = synthetic.descriptors(50, 700, 128, seed=13)
+    v0, i0 = _run(q, g, 3)
+    v1, i1 = _run(q, g, 3, index_base=5, index_stride=4)
+    assert np.array_equal(i1, 5 + 4 * i0) and np.array_equal(v0, v1)
+
+
+def test_background_top2_is_self_then_neighbour():
+    _, g = synthetic.descriptors(8, 3000, 512, seed=14)
+    v, i = _run(g, g, 2)
+    assert (i[:, 0] == np.arange(3000)).all()
+    np.testing.assert_allclose(v[:, 1], osim.background_second_best(g.numpy()), atol=1.2e-7)
+
+
+def test_linearity_property_full_size():
+    """BASELINE config 2 shape (10k x 100k x 512): exact check on a query subsample + permutation invariance."""
+    q, g = synthetic.descriptors(10000, 100000, 512, seed=2)
+    rows = np.random.default_rng(0).choice(10000, 384, replace=False)
+    st = _check(q, g, 10, rows=np.sort(rows))
+    assert st["n_flagged"] < 100
+    # permuting the gallery permutes the indices and nothing else
+    perm = torch.randperm(100000, generator=torch.Generator().manual_seed(1))
+    v0, i0 = _run(q[:1024], g, 1)
+    v1, i1 = _run(q[:1024], g[perm].contiguous(), 1)
+    assert np.array_equal(perm.numpy()[i1[:, 0]], i0[:, 0]) and np.array_equal(v0, v1)
+
+
+def test_merge_matches_oracle():
+    q, g = synthetic.descriptors(300, 4000, 128, seed=15)
+    parts_v, parts_i = [], []
+    for s in range(4):
+        v, i = similarity.sim_topk(q.cuda(), g[s::4].contiguous().cuda(), 10, index_base=s, index_stride=4)
+        parts_v.append(v)
+        parts_i.append(i)
+    mv, mi = similarity.topk_merge(torch.stack(parts_v), torch.stack(parts_i), 10)
+    ov, oi = osim.sim_topk(q.numpy(), g.numpy(), 10)
+    assert np.array_equal(mi.cpu().numpy(), oi)
+    np.testing.assert_allclose(mv.cpu().numpy(), ov, atol=1.2e-7)
+
+
+def test_l2_normalize():
+    x = torch.randn(1000, 512, generator=torch.Generator().manual_seed(3))
+    x[5] = 0
+    ref = torch.nn.functional.normalize(x, dim=1, p=2)
+    got = similarity.l2_normalize_(x.clone().cuda()).cpu()
+    np.testing.assert_allclose(got.numpy(), ref.numpy(), rtol=5e-7, atol=1e-12)
+
+
+def test_rejects_bad_arguments():
+    from dcr_b200._lib import DcrError
+    q, g = synthetic.descriptors(4, 64, 64)
+    with pytest.raises(DcrError):
+        similarity.sim_topk(q, g.cuda(), 1)          # CPU tensor: no CPU path
+    with pytest.raises(DcrError):
+        similarity.sim_topk(q.cuda(), g.cuda(), 17)  # k > 16
+    with pytest.raises(DcrError):
+        similarity.sim_topk(q.cuda(), g[:3].cuda(), 5)  # k > G
