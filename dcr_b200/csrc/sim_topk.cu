@@ -118,30 +118,39 @@ DCR_DEVICE void tmem_ld_wait_dep(uint32_t (&r)[32]) {
 }
 
 // Keep the kp best of lane L's n (kp < n <= 64) list entries, stored at list[j * 128] (j = 0..n-1); returns the
-// kp-th best score, which becomes that row's new threshold.  Whole warp cooperates; entries end up sorted.
+// kp-th best score, which becomes that row's new threshold.  Whole warp cooperates: lane l ranks entries l and
+// l+32 against all n keys (broadcast shared-memory reads), winners are rewritten in rank order (sorted list).
 DCR_DEVICE float compact_one(uint2* list, int n, int kp, uint32_t lane) {
   const uint2 none = make_uint2(0xff800000u, 0xffffffffu);  // -inf
-  uint2 e0 = (static_cast<int>(lane) < n) ? list[lane * 128] : none;
-  uint2 e1 = (static_cast<int>(lane) + 32 < n) ? list[(lane + 32) * 128] : none;
+  const int l0 = static_cast<int>(lane), l1 = l0 + 32;
+  const uint2 e0 = (l0 < n) ? list[l0 * 128] : none;
+  const uint2 e1 = (l1 < n) ? list[l1 * 128] : none;
   const float k0 = __uint_as_float(e0.x), k1 = __uint_as_float(e1.x);
   int r0 = 0, r1 = 0;
-  for (int j = 0; j < n; ++j) {
-    float kj = (j < 32) ? __shfl_sync(kFull, k0, j) : __shfl_sync(kFull, k1, j - 32);
-    r0 += (kj > k0) || (kj == k0 && j < static_cast<int>(lane));
-    r1 += (kj > k1) || (kj == k1 && j < static_cast<int>(lane) + 32);
+  const float* keys = reinterpret_cast<const float*>(list);   // key j at keys[j * 256]
+  if (n <= 32) {
+#pragma unroll 4
+    for (int j = 0; j < n; ++j) {
+      const float kj = keys[j * 256];
+      r0 += (kj > k0) || (kj == k0 && j < l0);
+    }
+  } else {
+#pragma unroll 4
+    for (int j = 0; j < n; ++j) {
+      const float kj = keys[j * 256];
+      r0 += (kj > k0) || (kj == k0 && j < l0);
+      r1 += (kj > k1) || (kj == k1 && j < l1);
+    }
   }
   __syncwarp();
-  if (static_cast<int>(lane) < n && r0 < kp) list[r0 * 128] = e0;
-  if (static_cast<int>(lane) + 32 < n && r1 < kp) list[r1 * 128] = e1;
-  const unsigned b0 = __ballot_sync(kFull, static_cast<int>(lane) < n && r0 == kp - 1);
-  const unsigned b1 = __ballot_sync(kFull, static_cast<int>(lane) + 32 < n && r1 == kp - 1);
-  float t0 = __shfl_sync(kFull, k0, b0 ? (__ffs(b0) - 1) : 0);
-  float t1 = __shfl_sync(kFull, k1, b1 ? (__ffs(b1) - 1) : 0);
+  if (l0 < n && r0 < kp) list[r0 * 128] = e0;
+  if (l1 < n && r1 < kp) list[r1 * 128] = e1;
   __syncwarp();
-  return b0 ? t0 : t1;
+  return keys[(kp - 1) * 256];
 }
 
 DCR_DEVICE void compact_warp(uint2* warp_list, unsigned need, int kp, float& thr, int& cnt, uint32_t lane) {
+  __syncwarp();   // make every lane's list stores visible to the lanes that will rank them
   while (need) {
     const int L = __ffs(need) - 1;
     need &= need - 1;
@@ -154,9 +163,20 @@ DCR_DEVICE void compact_warp(uint2* warp_list, unsigned need, int kp, float& thr
   }
 }
 
-// One 32-column chunk of the accumulator row held by this thread.
+DCR_DEVICE void st_shared_v2_if(uint32_t saddr, uint32_t a, uint32_t b, bool p) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\t"
+      "setp.ne.b32 q, %3, 0;\n\t"
+      "@q st.shared.v2.b32 [%0], {%1, %2};\n\t}\n" ::"r"(saddr),
+      "r"(a), "r"(b), "r"(static_cast<uint32_t>(p))
+      : "memory");
+}
+
+// One 32-column chunk of the accumulator row held by this thread.  The common case (no lane of the warp has a
+// score above its threshold) costs a max-tree, one compare and one vote.  Otherwise the 8-column sub-chunks that
+// contain a hit are appended to the row lists with predicated stores (no per-lane branching).
 template <bool kMaskTail>
-DCR_DEVICE void scan_chunk(const uint32_t (&r)[32], int gcol0, int ng, float& thr, int& cnt, uint2* my_list,
+DCR_DEVICE void scan_chunk(const uint32_t (&r)[32], int gcol0, int ng, float& thr, int& cnt, uint32_t my_list_saddr,
                            uint2* warp_list, int kp, int cap, uint32_t lane) {
   float v[32];
 #pragma unroll
@@ -172,15 +192,15 @@ DCR_DEVICE void scan_chunk(const uint32_t (&r)[32], int gcol0, int ng, float& th
 #pragma unroll
     for (int sub = 0; sub < 4; ++sub) {
       if (__any_sync(kFull, s[sub] > thr)) {
+        uint32_t addr = my_list_saddr + static_cast<uint32_t>(cnt) * 1024u;
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
           const float x = v[sub * 8 + c];
-          if (x > thr) {
-            my_list[cnt * 128] = make_uint2(__float_as_uint(x), static_cast<uint32_t>(gcol0 + sub * 8 + c));
-            ++cnt;
-          }
+          const bool h = x > thr;
+          st_shared_v2_if(addr, __float_as_uint(x), static_cast<uint32_t>(gcol0 + sub * 8 + c), h);
+          addr += h ? 1024u : 0u;
         }
-        __syncwarp();
+        cnt = static_cast<int>((addr - my_list_saddr) >> 10);
         const unsigned need = __ballot_sync(kFull, cnt > cap - 8);
         if (need) compact_warp(warp_list, need, kp, thr, cnt, lane);
       }
@@ -341,7 +361,7 @@ __global__ void __launch_bounds__(kThreads, 1)
     // ===================================== epilogue warps =====================================
     const uint32_t quad = warp & 3;            // TMEM lane quadrant this warp may read
     const uint32_t row = quad * 32 + lane;     // query row inside this CTA's tile
-    uint2* my_list = cand + row;
+    const uint32_t my_list = smem_u32(cand + row);
     uint2* warp_list = cand + quad * 32;
     const uint32_t tmem_row = tmem_base + ((quad * 32u) << 16);
     const int kp = p.kp, cap = p.cap;
@@ -497,7 +517,7 @@ __global__ void __launch_bounds__(128)
   float* qs = reinterpret_cast<float*>(sm);                         // [d]
   double* sc = reinterpret_cast<double*>(sm + ((d * 4 + 15) & ~15)); // [max_cand]
   int* ci = reinterpret_cast<int*>(sc + max_cand);                   // [max_cand]
-  __shared__ int s_n;
+  __shared__ int s_n, s_overflow;
   __shared__ float s_thr;
   __shared__ double s_best[4];
   __shared__ long long s_besti[4];
@@ -512,16 +532,20 @@ __global__ void __launch_bounds__(128)
   const long long u_lo = owner_unit(static_cast<long long>(qi) * n_gtiles, T, n_units);
   const long long u_hi = owner_unit(static_cast<long long>(qi + 1) * n_gtiles - 1, T, n_units);
   if (threadIdx.x == 0) {
-    int n = 0;
+    int n = 0, overflow = 0;
     float thr = -INFINITY;
     for (long long u = u_lo; u <= u_hi; ++u) {
       const size_t sr = static_cast<size_t>(u + qi) * rows_per_qtile + r;
       const int c = cand_cnt[sr];
       thr = fmaxf(thr, cand_thr[sr]);
-      for (int j = 0; j < c && n < max_cand; ++j) ci[n++] = static_cast<int>(cand[sr * kKPMax + j].y);
+      for (int j = 0; j < c; ++j) {
+        if (n < max_cand) ci[n++] = static_cast<int>(cand[sr * kKPMax + j].y);
+        else overflow = 1;   // cannot happen with make_plan's bound; if it does, the exact path takes over
+      }
     }
     s_n = n;
     s_thr = thr;
+    s_overflow = overflow;
   }
   __syncthreads();
   const int n = s_n;
@@ -583,7 +607,7 @@ __global__ void __launch_bounds__(128)
     const float qh = q_norm_hat[qrow], qr = q_norm_res[qrow];
     const float eps = 1.001f * (qh * g_res + qr * g_norm) + d_pad * 2.4e-7f * qh * (g_norm + g_res) + 1e-30f;
     const bool closed = s_thr > -INFINITY;   // some segment dropped rows
-    const bool ok = (n >= k) && (!closed || kth > static_cast<double>(s_thr) + static_cast<double>(eps));
+    const bool ok = (n >= k) && !s_overflow && (!closed || kth > static_cast<double>(s_thr) + static_cast<double>(eps));
     if (!ok) flagged[atomicAdd(n_flagged, 1)] = qrow;
   }
 }
@@ -709,14 +733,15 @@ int make_plan(int nq, int ng, int d, int k, int cg, int num_sms, size_t max_smem
   const size_t a_bytes = static_cast<size_t>(pl->num_kb) * kATileBytes;
   const size_t b_tile = static_cast<size_t>(kBlockN / cg) * kBlockK * 2;
   const size_t fixed = 1024 /*align slack*/ + 256 /*barriers*/;
+  // priorities: 3 B stages, then list capacity up to 64 (fewer compactions), then more stages (up to 8)
   int cap = pl->kp + 16;
-  DCR_REQUIRE(max_smem >= a_bytes + 2 * b_tile + cap * 1024 + fixed, "sim_topk: not enough shared memory (%zu)", max_smem);
-  int stages = static_cast<int>((max_smem - fixed - a_bytes - static_cast<size_t>(cap) * 1024) / b_tile);
-  if (stages > 8) stages = 8;
-  // spend what is left on list capacity (fewer compactions), up to 64
-  size_t left = max_smem - fixed - a_bytes - stages * b_tile - static_cast<size_t>(cap) * 1024;
-  cap += static_cast<int>(left / 1024);
-  if (cap > 64) cap = 64;
+  int stages = 2;
+  DCR_REQUIRE(max_smem >= a_bytes + stages * b_tile + cap * 1024 + fixed,
+              "sim_topk: not enough shared memory (%zu B) for d=%d k=%d cta_group=%d", max_smem, d, k, cg);
+  auto fits = [&](int st, int cp) { return max_smem >= a_bytes + st * b_tile + static_cast<size_t>(cp) * 1024 + fixed; };
+  if (fits(3, cap)) stages = 3;
+  while (cap < 64 && fits(stages, cap + 1)) ++cap;
+  while (stages < 8 && fits(stages + 1, cap)) ++stages;
   pl->cap = cap;
   pl->stages = stages;
   pl->smem_bytes = fixed + a_bytes + stages * b_tile + static_cast<size_t>(cap) * 1024;
@@ -759,13 +784,9 @@ int default_cg() {
 size_t sim_topk_workspace_size(int nq, int ng, int d, int k) {
   const DeviceInfo* di = device_info();
   SimPlan pl;
-  // size for the larger of the two variants so the same buffer works for either
-  size_t best = 0;
-  for (int cg = 1; cg <= 2; ++cg) {
-    if (make_plan(nq, ng, d, k, cg, di ? di->num_sms : 148, di ? di->max_smem_optin : 232448, &pl) != 0) return 0;
-    best = std::max(best, pl.total);
-  }
-  return best;
+  if (make_plan(nq, ng, d, k, default_cg(), di ? di->num_sms : 148, di ? di->max_smem_optin : 232448, &pl) != 0)
+    return 0;
+  return pl.total;
 }
 
 int sim_topk(const float* q, int nq, const float* g, int ng, int d, int k, long long g_index_base,
