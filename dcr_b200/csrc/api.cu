@@ -104,4 +104,35 @@ int dcr_topk_merge(const float* scores, const int64_t* idx, int nq, int nlists, 
                          reinterpret_cast<long long*>(out_idx), as_stream(stream));
 }
 
+int dcr_conv2d_bf16(const void* x, int x_planes, int64_t x_plane_stride, int B, int H, int W, int C, const void* w,
+                    int w_planes, int64_t w_plane_stride, int N, int kh, int kw, int stride, int pad_h, int pad_w,
+                    int terms, const float* scale, const float* bias, const void* residual, int res_planes,
+                    int64_t res_plane_stride, int act, void* out, int out_planes, int64_t out_plane_stride, int ld_out,
+                    int out_col_off, float* out_f32, void* stream) {
+  DCR_REQUIRE(x && w, "dcr_conv2d_bf16: null input");
+  DCR_REQUIRE(out || out_f32, "dcr_conv2d_bf16: no output requested");
+  DCR_REQUIRE(terms == 1 || terms == 3 || terms == 6, "dcr_conv2d_bf16: terms must be 1, 3 or 6 (got %d)", terms);
+  const int need = terms == 1 ? 1 : (terms == 3 ? 2 : 3);
+  DCR_REQUIRE(x_planes >= need && w_planes >= need, "dcr_conv2d_bf16: terms=%d needs %d planes (x has %d, w has %d)",
+              terms, need, x_planes, w_planes);
+  dcr::ConvGemmDesc d;
+  d.in = static_cast<const __nv_bfloat16*>(x);
+  d.in_plane_stride = x_plane_stride;
+  d.B = B; d.H = H; d.W = W; d.C = C; d.ld_in = C;
+  d.weight = static_cast<const __nv_bfloat16*>(w);
+  d.w_plane_stride = w_plane_stride;
+  d.N = N; d.kh = kh; d.kw = kw; d.stride = stride; d.pad_h = pad_h; d.pad_w = pad_w;
+  static const int ta[6] = {0, 0, 1, 1, 0, 2}, tw[6] = {0, 1, 0, 1, 2, 0};
+  d.n_terms = terms;
+  for (int t = 0; t < terms; ++t) { d.term_a[t] = ta[t]; d.term_w[t] = tw[t]; }
+  d.scale = scale; d.bias = bias;
+  d.res = static_cast<const __nv_bfloat16*>(residual);
+  d.ld_res = N; d.res_planes = res_planes; d.res_plane_stride = res_plane_stride;
+  d.out = static_cast<__nv_bfloat16*>(out);
+  d.ld_out = ld_out; d.out_col_off = out_col_off; d.out_planes = out_planes; d.out_plane_stride = out_plane_stride;
+  d.out_f32 = out_f32; d.ld_out_f32 = N;
+  d.act = act;
+  return dcr::conv_gemm(d, as_stream(stream));
+}
+
 }  // extern "C"

@@ -1,0 +1,406 @@
+// tcgen05 GEMM / implicit-GEMM convolution with fused epilogue (sm_100a).
+//
+// One kernel family computes   Y[m, n] = act( scale[n] * sum_k A[m, k] * W[n, k] + bias[n] (+ R[m, n]) )
+// for every dense contraction of the descriptor networks:
+//   - 1x1 stride-1 convolutions and Linear layers: A is the NHWC activation matrix [M = B*H*W, K = C]   (TILED)
+//   - kxk / strided convolutions: A rows are gathered on the fly by TMA im2col loads from the NHWC tensor,
+//     one (filter tap, 64-channel block) per pipeline stage -- the im2col matrix never exists in HBM   (IM2COL)
+// Reference call sites this replaces (all reached through `model(samples)`, utils_ret.py:751):
+//   SSCD ResNet-50 trunk convs + BN + ReLU (+ residual)            (torchvision resnet50)
+//   DINO ViT-S qkv / proj / fc1(+GELU) / fc2 Linear layers          dino_vits.py:96-102,119,127
+//   FID Inception BasicConv2d (conv + BN eps=1e-3 + ReLU)           metrics/inception.py:197-341
+//
+// Precision: operands are bf16 "planes".  Fast mode uses one plane (plain bf16 x bf16 -> fp32).  Parity mode
+// stores every activation / weight as 2-3 bf16 planes (hi, mid, lo with x = hi + mid + lo to ~2^-24) and
+// accumulates the listed cross terms into the same TMEM accumulator, which reproduces fp32 arithmetic on the
+// tensor cores.
+//
+// Structure per CTA (192 threads, persistent over output tiles of 128 x BN):
+//   warp 0 : TMA producer (A tile 128x64, W tile BNx64 per stage, 128B swizzle)
+//   warp 1 : tcgen05.mma issuer (cta_group::1, UMMA 128 x BN x 16), accumulators double-buffered in TMEM
+//   warps 2-5 : epilogue (tcgen05.ld -> scale/bias/residual/activation -> bf16 planes / fp32 -> global)
+#include <cuda_bf16.h>
+
+#include <algorithm>
+#include <cstring>
+
+#include "dcr_internal.cuh"
+#include "host_util.cuh"
+#include "ptx.cuh"
+
+namespace dcr {
+
+namespace {
+
+constexpr int kBM = 128;
+constexpr int kBK = 64;
+constexpr int kThreads = 192;
+constexpr int kAStage = kBM * kBK * 2;   // 16 KB
+
+struct GemmMaps {
+  CUtensorMap a[3];
+  CUtensorMap w[3];
+};
+
+struct GemmParams {
+  int M, N;
+  int taps, kw, cblocks;      // filter taps (kh*kw), filter width, 64-channel blocks per tap
+  int n_terms;
+  int term_a[kMaxGemmTerms], term_w[kMaxGemmTerms];
+  int P, Q, stride, pad_h, pad_w;   // im2col geometry (output H, W)
+  int num_m_tiles, num_n_tiles, stages;
+  const float* scale;         // [N] or null (= 1)
+  const float* bias;          // [N] or null (= 0)
+  const __nv_bfloat16* res;   // residual planes [res_planes][M][ld_res] or null
+  int ld_res, res_planes;
+  long long res_plane_stride;
+  __nv_bfloat16* out;         // [out_planes][M][ld_out] (+ out_col_off) or null
+  int ld_out, out_col_off, out_planes;
+  long long out_plane_stride;
+  float* out_f32;             // [M][ld_out_f32] or null
+  int ld_out_f32;
+  int act;                    // 0 none, 1 relu, 2 gelu (erf)
+};
+
+DCR_DEVICE float apply_act(float y, int act) {
+  if (act == 1) return fmaxf(y, 0.f);
+  if (act == 2) return 0.5f * y * (1.f + erff(y * 0.70710678118654752440f));
+  return y;
+}
+
+DCR_DEVICE uint32_t pack_bf16(float a, float b) {
+  __nv_bfloat162 p = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&p);
+}
+
+DCR_DEVICE void tmem_ld_wait_dep32(uint32_t (&r)[32]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                 "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]),
+                 "+r"(r[15]), "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]),
+                 "+r"(r[22]), "+r"(r[23]), "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]),
+                 "+r"(r[29]), "+r"(r[30]), "+r"(r[31])::"memory");
+}
+
+template <int BN, bool kIm2col>
+__global__ void __launch_bounds__(kThreads, 1)
+    gemm_bf16_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  constexpr int kBStage = BN * kBK * 2;
+  constexpr int kStageBytes = kAStage + kBStage;
+  constexpr uint32_t kTmemCols = (2 * BN <= 128) ? 128 : (2 * BN <= 256 ? 256 : 512);
+  uint8_t* smem_ab = smem;
+  float* sb = reinterpret_cast<float*>(smem_ab + p.stages * kStageBytes);   // [2 bufs][2 (scale,bias)][BN]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sb + 4 * BN);
+  uint64_t* full = bars;          // [stages] (<= 12)
+  uint64_t* empty = bars + 12;    // [stages]
+  uint64_t* t_full = bars + 24;   // [2]
+  uint64_t* t_empty = bars + 26;  // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 28);
+
+  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    for (int i = 0; i < 3; ++i) {
+      tma_prefetch_desc(&maps.a[i]);
+      tma_prefetch_desc(&maps.w[i]);
+    }
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&t_full[b], 1);
+      mbar_init(&t_empty[b], 4);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc<1>(tmem_slot, kTmemCols);
+    tmem_relinquish<1>();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int num_tiles = p.num_m_tiles * p.num_n_tiles;
+  const int k_iters = p.n_terms * p.taps * p.cblocks;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m0 = (tile % p.num_m_tiles) * kBM;
+        const int n0 = (tile / p.num_m_tiles) * BN;
+        int img = 0, h0 = 0, w0 = 0;
+        if constexpr (kIm2col) {
+          const int pq = p.P * p.Q;
+          img = m0 / pq;
+          const int rem = m0 - img * pq;
+          const int p0 = rem / p.Q, q0 = rem - p0 * p.Q;
+          h0 = p0 * p.stride - p.pad_h;
+          w0 = q0 * p.stride - p.pad_w;
+        }
+        for (int t = 0; t < p.n_terms; ++t) {
+          const CUtensorMap* ma = &maps.a[p.term_a[t]];
+          const CUtensorMap* mw = &maps.w[p.term_w[t]];
+          for (int tap = 0; tap < p.taps; ++tap) {
+            const int r = tap / p.kw, sx = tap - r * p.kw;
+            for (int cb = 0; cb < p.cblocks; ++cb, ++it) {
+              const uint32_t s = it % p.stages, ph = (it / p.stages) & 1;
+              mbar_wait(&empty[s], ph ^ 1);
+              mbar_arrive_expect_tx(&full[s], kStageBytes);
+              uint8_t* sa = smem_ab + s * kStageBytes;
+              if constexpr (kIm2col)
+                tma_load_im2col_4d<1>(sa, ma, &full[s], cb * kBK, w0, h0, img, static_cast<uint16_t>(sx),
+                                      static_cast<uint16_t>(r));
+              else
+                tma_load_2d<1>(sa, ma, &full[s], cb * kBK, m0, kEvictNormal);
+              tma_load_2d<1>(sa + kAStage, mw, &full[s], (tap * p.cblocks + cb) * kBK, n0, kEvictNormal);
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(kBM, BN);
+      uint32_t it = 0, tc = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tc) {
+        const uint32_t buf = tc & 1;
+        mbar_wait(&t_empty[buf], ((tc >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + buf * BN;
+        for (int ki = 0; ki < k_iters; ++ki, ++it) {
+          const uint32_t s = it % p.stages, ph = (it / p.stages) & 1;
+          mbar_wait(&full[s], ph);
+          tc_fence_after();
+          const uint64_t da = umma_desc_sw128(smem_u32(smem_ab + s * kStageBytes));
+          const uint64_t db = umma_desc_sw128(smem_u32(smem_ab + s * kStageBytes + kAStage));
+#pragma unroll
+          for (int k = 0; k < kBK / 16; ++k) umma_f16<1>(tmem_d, da + 2 * k, db + 2 * k, idesc, (ki | k) != 0);
+          umma_commit<1>(&empty[s]);
+          if (ki == k_iters - 1) umma_commit<1>(&t_full[buf]);
+        }
+      }
+    }
+  } else {
+    const uint32_t quad = warp & 3;
+    const uint32_t row = quad * 32 + lane;
+    const uint32_t etid = (warp - 2) * 32 + lane;   // 0..127 among the epilogue threads
+    const uint32_t tmem_row = tmem_base + ((quad * 32u) << 16);
+    uint32_t tc = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tc) {
+      const int m0 = (tile % p.num_m_tiles) * kBM;
+      const int n0 = (tile / p.num_m_tiles) * BN;
+      const uint32_t buf = tc & 1;
+      float* s_scale = sb + buf * 2 * BN;
+      float* s_bias = s_scale + BN;
+      // stage the per-channel affine of this tile (safe: buffer `buf` was last read two tiles ago, and all four
+      // epilogue warps passed the named barrier of the previous tile since then)
+      for (int c = etid; c < BN; c += 128) {
+        const int n = n0 + c;
+        s_scale[c] = (p.scale && n < p.N) ? p.scale[n] : 1.f;
+        s_bias[c] = (p.bias && n < p.N) ? p.bias[n] : 0.f;
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      mbar_wait(&t_full[buf], (tc >> 1) & 1);
+      tc_fence_after();
+      const int m = m0 + static_cast<int>(row);
+      const bool row_ok = m < p.M;
+      const uint32_t taddr = tmem_row + buf * BN;
+#pragma unroll 1
+      for (int ch = 0; ch < BN / 32; ++ch) {
+        uint32_t r[32];
+        tmem_ld_32x32(taddr + ch * 32, r);
+        tmem_ld_wait_dep32(r);
+        if (ch == BN / 32 - 1) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&t_empty[buf]);
+        }
+        const int nc = n0 + ch * 32;
+        if (nc >= p.N || !row_ok) continue;
+        float y[32];
+#pragma unroll
+        for (int c = 0; c < 32; c += 4) {
+          const float4 sc = *reinterpret_cast<const float4*>(s_scale + ch * 32 + c);
+          const float4 bi = *reinterpret_cast<const float4*>(s_bias + ch * 32 + c);
+          y[c + 0] = fmaf(__uint_as_float(r[c + 0]), sc.x, bi.x);
+          y[c + 1] = fmaf(__uint_as_float(r[c + 1]), sc.y, bi.y);
+          y[c + 2] = fmaf(__uint_as_float(r[c + 2]), sc.z, bi.z);
+          y[c + 3] = fmaf(__uint_as_float(r[c + 3]), sc.w, bi.w);
+        }
+        const int nvalid = min(32, p.N - nc);   // multiple of 8 (N % 8 == 0 enforced on the host)
+        if (p.res) {
+          for (int pl = 0; pl < p.res_planes; ++pl) {
+            const __nv_bfloat16* rp = p.res + pl * p.res_plane_stride + static_cast<size_t>(m) * p.ld_res + nc;
+#pragma unroll
+            for (int c = 0; c < 32; c += 8) {
+              if (c < nvalid) {
+                const uint4 rv = *reinterpret_cast<const uint4*>(rp + c);
+                const uint32_t w[4] = {rv.x, rv.y, rv.z, rv.w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  y[c + 2 * j] += __uint_as_float(w[j] << 16);
+                  y[c + 2 * j + 1] += __uint_as_float(w[j] & 0xffff0000u);
+                }
+              }
+            }
+          }
+        }
+#pragma unroll
+        for (int c = 0; c < 32; ++c) y[c] = apply_act(y[c], p.act);
+        if (p.out_f32) {
+          float* op = p.out_f32 + static_cast<size_t>(m) * p.ld_out_f32 + nc;
+#pragma unroll
+          for (int c = 0; c < 32; c += 4)
+            if (c < nvalid) *reinterpret_cast<float4*>(op + c) = make_float4(y[c], y[c + 1], y[c + 2], y[c + 3]);
+        }
+        if (p.out) {
+          for (int pl = 0; pl < p.out_planes; ++pl) {
+            __nv_bfloat16* op = p.out + pl * p.out_plane_stride + static_cast<size_t>(m) * p.ld_out + p.out_col_off + nc;
+#pragma unroll
+            for (int c = 0; c < 32; c += 8) {
+              if (c < nvalid) {
+                uint4 v;
+                v.x = pack_bf16(y[c + 0], y[c + 1]);
+                v.y = pack_bf16(y[c + 2], y[c + 3]);
+                v.z = pack_bf16(y[c + 4], y[c + 5]);
+                v.w = pack_bf16(y[c + 6], y[c + 7]);
+                *reinterpret_cast<uint4*>(op + c) = v;
+              }
+            }
+            if (pl + 1 < p.out_planes) {
+              // next plane holds the rounding residual of this one
+#pragma unroll
+              for (int c = 0; c < 32; ++c) y[c] -= __bfloat162float(__float2bfloat16_rn(y[c]));
+            }
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc<1>(tmem_base, kTmemCols);
+}
+
+template <int BN, bool kIm2col>
+int launch(const GemmMaps& maps, GemmParams& p, int num_sms, size_t max_smem, cudaStream_t stream) {
+  constexpr int kStageBytes = kAStage + BN * kBK * 2;
+  const size_t fixed = 1024 + 4 * BN * 4 + 256;
+  int stages = static_cast<int>((max_smem - fixed) / kStageBytes);
+  stages = std::min(stages, 8);
+  DCR_REQUIRE(stages >= 2, "gemm: not enough shared memory");
+  p.stages = stages;
+  const size_t smem = fixed + static_cast<size_t>(stages) * kStageBytes;
+  auto kern = gemm_bf16_kernel<BN, kIm2col>;
+  static bool attr_set = false;   // per template instantiation
+  if (!attr_set) {
+    DCR_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(max_smem)));
+    attr_set = true;
+  }
+  const int tiles = p.num_m_tiles * p.num_n_tiles;
+  const int grid = std::min(tiles, num_sms);
+  kern<<<grid, kThreads, smem, stream>>>(maps, p);
+  DCR_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace
+
+int conv_gemm(const ConvGemmDesc& d, cudaStream_t stream) {
+  const DeviceInfo* di = device_info();
+  if (!di) return -2;
+  DCR_REQUIRE(di->cc_major == 10, "conv_gemm: this build targets sm_100a; device reports sm_%d%d", di->cc_major, di->cc_minor);
+  DCR_REQUIRE(d.n_terms >= 1 && d.n_terms <= kMaxGemmTerms, "conv_gemm: bad n_terms %d", d.n_terms);
+  DCR_REQUIRE(d.C % 8 == 0 && d.N % 8 == 0, "conv_gemm: C (%d) and N (%d) must be multiples of 8", d.C, d.N);
+  DCR_REQUIRE(d.kh >= 1 && d.kw >= 1 && d.stride >= 1, "conv_gemm: bad filter geometry");
+  const bool im2col = !(d.kh == 1 && d.kw == 1 && d.stride == 1 && d.pad_h == 0 && d.pad_w == 0);
+  const int P = (d.H + 2 * d.pad_h - d.kh) / d.stride + 1;
+  const int Q = (d.W + 2 * d.pad_w - d.kw) / d.stride + 1;
+  const long long M = static_cast<long long>(d.B) * P * Q;
+  DCR_REQUIRE(M > 0 && M < (1ll << 31), "conv_gemm: M out of range");
+  const int cblocks = (d.C + kBK - 1) / kBK;
+  const int ktot = d.kh * d.kw * cblocks * kBK;   // padded K of the prepared weights
+
+  GemmMaps maps;
+  memset(&maps, 0, sizeof(maps));
+  int a_planes = 0, w_planes = 0;
+  for (int t = 0; t < d.n_terms; ++t) {
+    a_planes = std::max(a_planes, d.term_a[t] + 1);
+    w_planes = std::max(w_planes, d.term_w[t] + 1);
+  }
+  DCR_REQUIRE(a_planes <= 3 && w_planes <= 3, "conv_gemm: at most 3 planes");
+  int BN = d.N <= 64 ? 64 : (d.N <= 128 ? 128 : 256);
+  if (d.force_bn) BN = d.force_bn;
+  for (int pl = 0; pl < 3; ++pl) {
+    const int pa = std::min(pl, a_planes - 1), pw = std::min(pl, w_planes - 1);
+    const __nv_bfloat16* abase = d.in + pa * d.in_plane_stride;
+    if (im2col) {
+      DCR_REQUIRE(d.ld_in == d.C, "conv_gemm: im2col input must be dense NHWC (ld_in == C)");
+      if (int rc = make_tmap_im2col_bf16(&maps.a[pl], abase, d.B, d.H, d.W, d.C, d.pad_h, d.pad_w, d.kh, d.kw, d.stride,
+                                         kBK, kBM))
+        return rc;
+    } else {
+      if (int rc = make_tmap_2d_bf16(&maps.a[pl], abase, M, d.C, d.ld_in, kBM, kBK)) return rc;
+    }
+    if (int rc = make_tmap_2d_bf16(&maps.w[pl], d.weight + pw * d.w_plane_stride, d.N, ktot, ktot, BN, kBK)) return rc;
+  }
+
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  p.M = static_cast<int>(M);
+  p.N = d.N;
+  p.taps = d.kh * d.kw;
+  p.kw = d.kw;
+  p.cblocks = cblocks;
+  p.n_terms = d.n_terms;
+  for (int t = 0; t < d.n_terms; ++t) {
+    p.term_a[t] = d.term_a[t];
+    p.term_w[t] = d.term_w[t];
+  }
+  p.P = P;
+  p.Q = Q;
+  p.stride = d.stride;
+  p.pad_h = d.pad_h;
+  p.pad_w = d.pad_w;
+  p.num_m_tiles = static_cast<int>((M + kBM - 1) / kBM);
+  p.num_n_tiles = (d.N + BN - 1) / BN;
+  p.scale = d.scale;
+  p.bias = d.bias;
+  p.res = d.res;
+  p.ld_res = d.ld_res;
+  p.res_planes = d.res ? std::max(1, d.res_planes) : 0;
+  p.res_plane_stride = d.res_plane_stride;
+  p.out = d.out;
+  p.ld_out = d.ld_out;
+  p.out_col_off = d.out_col_off;
+  p.out_planes = d.out ? std::max(1, d.out_planes) : 0;
+  p.out_plane_stride = d.out_plane_stride;
+  p.out_f32 = d.out_f32;
+  p.ld_out_f32 = d.ld_out_f32;
+  p.act = d.act;
+  DCR_REQUIRE(p.out == nullptr || (p.ld_out % 8 == 0 && p.out_col_off % 8 == 0), "conv_gemm: output leading dim / offset must be multiples of 8");
+  DCR_REQUIRE(p.res == nullptr || p.ld_res % 8 == 0, "conv_gemm: residual leading dim must be a multiple of 8");
+  DCR_REQUIRE(p.out_f32 == nullptr || p.ld_out_f32 % 4 == 0, "conv_gemm: fp32 output leading dim must be a multiple of 4");
+
+#define DCR_LAUNCH(BNv)                                                                          \
+  (im2col ? launch<BNv, true>(maps, p, di->num_sms, di->max_smem_optin, stream)                  \
+          : launch<BNv, false>(maps, p, di->num_sms, di->max_smem_optin, stream))
+  switch (BN) {
+    case 64: return DCR_LAUNCH(64);
+    case 128: return DCR_LAUNCH(128);
+    case 256: return DCR_LAUNCH(256);
+    default: return set_error(-1, "conv_gemm: unsupported BN %d", BN);
+  }
+#undef DCR_LAUNCH
+}
+
+}  // namespace dcr

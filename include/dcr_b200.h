@@ -74,6 +74,25 @@ int dcr_sim_topk_last_stats(int* out8);
 int dcr_topk_merge(const float* scores, const int64_t* idx, int nq, int nlists, int k_in, int k_out,
                    float* out_scores, int64_t* out_idx, void* stream);
 
+/* ---- dense contraction of the descriptor networks ------------------------------------------------------------- */
+/* y = act(scale[n] * conv2d(x, w)[.., n] + bias[n] (+ residual)) as a tcgen05 implicit GEMM.
+ *   x        NHWC bf16, `x_planes` planes of B*H*W*C elements each (plane p at x + p*x_plane_stride elements);
+ *            C % 8 == 0.  A Linear layer is the case H = W = kh = kw = 1, B = rows.
+ *   w        prepared weights: bf16 [w_planes][N][kh*kw*ceil64(C)], tap-major, channels zero-padded to 64
+ *            (dcr_b200.ops.prepare_conv_weight); N % 8 == 0.
+ *   terms    1 = bf16 x bf16 (fast); 3 or 6 = split-bf16 cross terms hi*hi, hi*mid, mid*hi[, mid*mid, hi*lo, lo*hi]
+ *            which need x_planes/w_planes >= 2 (3 terms) or 3 (6 terms) and reproduce fp32 accuracy.
+ *   scale/bias  fp32 [N] or NULL; residual: bf16 planes [res_planes][M][N] or NULL; act: 0 none, 1 ReLU, 2 GELU(erf)
+ *   out      bf16 planes [out_planes][M][ld_out] written at column offset out_col_off (concat by offset), or NULL;
+ *   out_f32  fp32 [M][N] or NULL.   M = B * Hout * Wout.
+ * Replaces the cuDNN / cuBLAS calls behind `model(samples)`        utils_ret.py:751 (nn.Conv2d+BatchNorm2d+ReLU of the
+ * SSCD trunk; nn.Linear of dino_vits.py:96-102,119,127; BasicConv2d of metrics/inception.py). */
+int dcr_conv2d_bf16(const void* x, int x_planes, int64_t x_plane_stride, int B, int H, int W, int C,
+                    const void* w, int w_planes, int64_t w_plane_stride, int N, int kh, int kw, int stride,
+                    int pad_h, int pad_w, int terms, const float* scale, const float* bias, const void* residual,
+                    int res_planes, int64_t res_plane_stride, int act, void* out, int out_planes,
+                    int64_t out_plane_stride, int ld_out, int out_col_off, float* out_f32, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

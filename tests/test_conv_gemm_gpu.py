@@ -1,0 +1,74 @@
+"""GPU numerics: the tcgen05 implicit-GEMM convolution vs torch.nn.functional.conv2d (fp32, TF32 off)."""
+import numpy as np
+import pytest
+import torch
+
+from dcr_b200 import ops
+
+pytestmark = pytest.mark.gpu
+
+# (B, H, W, C, N, kh, kw, stride, pad_h, pad_w)
+SHAPES = [
+    (2, 56, 56, 64, 64, 1, 1, 1, 0, 0),      # resnet layer1 conv1 (plain GEMM path)
+    (2, 56, 56, 64, 64, 3, 3, 1, 1, 1),      # resnet 3x3
+    (3, 56, 56, 128, 128, 3, 3, 2, 1, 1),    # resnet strided 3x3
+    (2, 56, 56, 256, 512, 1, 1, 2, 0, 0),    # strided 1x1 downsample
+    (5, 14, 14, 256, 256, 3, 3, 1, 1, 1),    # tile spans several images
+    (4, 7, 7, 512, 2048, 1, 1, 1, 0, 0),
+    (2, 17, 17, 128, 192, 1, 7, 1, 0, 3),    # inception 1x7
+    (2, 17, 17, 128, 192, 7, 1, 1, 3, 0),    # inception 7x1
+    (2, 35, 35, 48, 64, 5, 5, 1, 2, 2),      # inception 5x5, C not a multiple of 64
+    (2, 35, 35, 288, 384, 3, 3, 2, 0, 0),    # inception 3x3/2 no padding
+    (300, 1, 1, 384, 1152, 1, 1, 1, 0, 0),   # ViT qkv Linear
+    (1, 9, 9, 8, 8, 3, 3, 1, 1, 1),          # tiny
+]
+
+
+def _ref(x, w, scale, bias, res, act, stride, pad):
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    y = torch.nn.functional.conv2d(x.permute(0, 3, 1, 2).double(), w.double(), stride=stride, padding=pad)
+    y = y.permute(0, 2, 3, 1)
+    y = y * scale.double() + bias.double()
+    if res is not None:
+        y = y + res.double()
+    if act == 1:
+        y = torch.relu(y)
+    elif act == 2:
+        y = torch.nn.functional.gelu(y)
+    return y.float()
+
+
+@pytest.mark.parametrize("shape", SHAPES)
+@pytest.mark.parametrize("planes", [1, 3])
+def test_conv_matches_torch(shape, planes):
+    b, h, w_, c, n, kh, kw, stride, ph, pw = shape
+    gen = torch.Generator(device="cuda").manual_seed(b * 1000 + c + n + kh)
+    x = torch.randn(b, h, w_, c, device="cuda", generator=gen)
+    w = torch.randn(n, c, kh, kw, device="cuda", generator=gen) / (c * kh * kw) ** 0.5
+    scale = 0.5 + torch.rand(n, device="cuda", generator=gen)
+    bias = torch.randn(n, device="cuda", generator=gen) * 0.1
+    ho = (h + 2 * ph - kh) // stride + 1
+    wo = (w_ + 2 * pw - kw) // stride + 1
+    res = torch.randn(b, ho, wo, n, device="cuda", generator=gen)
+    act = 1 if kh == 3 else (2 if h == 1 else 0)
+
+    xp = ops.split_planes(x, planes)
+    wp = ops.prepare_conv_weight(w, planes)
+    rp = ops.split_planes(res, planes)
+    out, out32 = ops.conv2d(xp, wp, n, kh, kw, stride, ph, pw, scale=scale, bias=bias, residual=rp, act=act,
+                            want_f32=True)
+    torch.cuda.synchronize()
+    # reference on exactly the operands the kernel saw
+    ref = _ref(ops.merge_planes(xp), ops.merge_planes(wp).reshape(n, kh, kw, -1)[..., :c].permute(0, 3, 1, 2),
+               scale, bias, ops.merge_planes(rp), act, stride, (ph, pw))
+    # one plane: bf16 x bf16 products are exact in fp32, only the accumulation order differs from the reference;
+    # three planes (6 cross terms): fp32-level agreement, limited by the tensor core's fp32 accumulator rounding
+    mx = max(1.0, ref.abs().max().item())
+    tol = (1e-4 if planes == 1 else 2e-5) * mx
+    err32 = (out32 - ref).abs().max().item()
+    assert err32 < tol, f"fp32 out err {err32}"
+    got = ops.merge_planes(out)
+    errp = (got - ref).abs().max().item()
+    ptol = (2 ** -8 if planes == 1 else 2 ** -22) * mx + tol
+    assert errp < ptol, f"plane out err {errp}"
