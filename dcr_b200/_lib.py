@@ -30,6 +30,13 @@ SIGNATURES = {
                                   C.c_void_p, C.c_int, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                   C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_int,
                                   C.c_void_p, C.c_int, C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "dcr_net_create": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
+    "dcr_net_destroy": (None, [C.c_void_p]),
+    "dcr_net_add_tensor": (C.c_int, [C.c_void_p, C.c_int64, C.c_int]),
+    "dcr_net_add_param": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
+    "dcr_net_set_output": (C.c_int, [C.c_void_p, C.c_int]),
+    "dcr_net_add_op": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_int), C.c_int, C.POINTER(C.c_float), C.c_int]),
+    "dcr_net_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "dcr_topk_merge": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                  C.c_void_p]),
 }

@@ -135,4 +135,25 @@ int dcr_conv2d_bf16(const void* x, int x_planes, int64_t x_plane_stride, int B, 
   return dcr::conv_gemm(d, as_stream(stream));
 }
 
+struct dcr_net;   // opaque alias of dcr::Net
+
+int dcr_net_create(int max_batch, int planes, dcr_net** out) {
+  DCR_REQUIRE(out != nullptr, "dcr_net_create: null out pointer");
+  return dcr::net_create(max_batch, planes, reinterpret_cast<dcr::Net**>(out));
+}
+void dcr_net_destroy(dcr_net* net) { dcr::net_destroy(reinterpret_cast<dcr::Net*>(net)); }
+int dcr_net_add_tensor(dcr_net* net, int64_t rows_per_image, int channels) {
+  return dcr::net_add_tensor(reinterpret_cast<dcr::Net*>(net), rows_per_image, channels);
+}
+int dcr_net_add_param(dcr_net* net, const void* host_data, size_t bytes) {
+  return dcr::net_add_param(reinterpret_cast<dcr::Net*>(net), host_data, bytes);
+}
+int dcr_net_set_output(dcr_net* net, int dim) { return dcr::net_set_output(reinterpret_cast<dcr::Net*>(net), dim); }
+int dcr_net_add_op(dcr_net* net, int kind, const int* iargs, int n_iargs, const float* fargs, int n_fargs) {
+  return dcr::net_add_op(reinterpret_cast<dcr::Net*>(net), kind, iargs, n_iargs, fargs, n_fargs);
+}
+int dcr_net_forward(dcr_net* net, const uint8_t* images, int n, float* out, void* stream) {
+  return dcr::net_forward(reinterpret_cast<dcr::Net*>(net), images, n, out, as_stream(stream));
+}
+
 }  // extern "C"

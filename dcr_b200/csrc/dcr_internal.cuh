@@ -59,4 +59,46 @@ struct ConvGemmDesc {
 };
 int conv_gemm(const ConvGemmDesc& d, cudaStream_t stream);
 
+
+// ---- HBM-bound kernels (pool_norm.cu, attention.cu) ---------------------------------------------------------------
+int im2col_u8(const uint8_t* img, int B, int IH, int IW, int crop_y, int crop_x, int H, int W, int kh, int kw,
+              int stride, int pad, int k_pad, const float* mean3, const float* std3, float post_scale,
+              float post_shift, __nv_bfloat16* out, long long out_plane_stride, int planes, cudaStream_t stream);
+int pool2d(bool is_max, const __nv_bfloat16* in, long long in_plane_stride, __nv_bfloat16* out,
+           long long out_plane_stride, int planes, int B, int H, int W, int C, int k, int stride, int pad, int ld_out,
+           int out_col_off, cudaStream_t stream);
+int reduce_hw(bool gem, const __nv_bfloat16* in, long long in_plane_stride, int planes, int B, int HW, int C,
+              float p_exp, float eps, __nv_bfloat16* out, long long out_plane_stride, float* out_f32,
+              cudaStream_t stream);
+int layernorm(const __nv_bfloat16* in, long long in_plane_stride, int planes, int rows, int C, long long in_row_stride,
+              const float* gamma, const float* beta, float eps, __nv_bfloat16* out, long long out_plane_stride,
+              float* out_f32, cudaStream_t stream);
+int vit_tokens(const __nv_bfloat16* patch, long long patch_plane_stride, const float* cls, const float* pos,
+               __nv_bfloat16* out, long long out_plane_stride, int planes, int B, int NP, int C, cudaStream_t stream);
+int attention(const __nv_bfloat16* qkv, long long qkv_plane_stride, __nv_bfloat16* out, long long out_plane_stride,
+              int planes, int B, int T, int heads, int dh, float scale, cudaStream_t stream);
+
+// ---- network executor (net.cu) ------------------------------------------------------------------------------------
+enum NetOpKind {
+  NET_OP_IM2COL_U8 = 0,
+  NET_OP_CONV = 1,
+  NET_OP_MAXPOOL = 2,
+  NET_OP_AVGPOOL = 3,
+  NET_OP_GEM = 4,
+  NET_OP_GAP = 5,
+  NET_OP_LAYERNORM = 6,
+  NET_OP_VIT_TOKENS = 7,
+  NET_OP_ATTENTION = 8,
+  NET_OP_L2NORM_OUT = 9,
+  NET_OP_COUNT = 10
+};
+struct Net;
+int net_create(int max_batch, int planes, Net** out);
+void net_destroy(Net* n);
+int net_add_tensor(Net* n, long long rows_per_image, int C);
+int net_add_param(Net* n, const void* host, size_t bytes);
+int net_set_output(Net* n, int dim);
+int net_add_op(Net* n, int kind, const int* iargs, int ni, const float* fargs, int nf);
+int net_forward(Net* n, const uint8_t* images, int B, float* out, cudaStream_t stream);
+
 }  // namespace dcr

@@ -1,0 +1,392 @@
+// HBM-bound kernels between the tensor-core contractions of the descriptor networks.  Activations are NHWC bf16
+// "planes" (1 plane = fast bf16 mode, 3 planes = hi/mid/lo split that carries fp32 precision); every kernel reads the
+// sum of the planes, computes in fp32 and re-splits on store.  All channel counts are multiples of 8 so every access
+// is a 16-byte vector.
+//
+// Reference ops replaced:
+//   diff_retrieval.py:325-330  Resize(256)/CenterCrop(224)/ToTensor/Normalize            -> im2col_u8_kernel
+//   embedding_search/utils.py:35-50 (ImageNet mean/std variant)                           -> im2col_u8_kernel
+//   metrics/fid.py:104-110 + metrics/inception.py:152-153 (normalise twice)               -> im2col_u8_kernel (post affine)
+//   torchvision resnet maxpool(3,2,1); inception max_pool2d(3,2)                          -> maxpool_kernel
+//   metrics/inception.py:241,269,302 avg_pool2d(3,1,1,count_include_pad=False)            -> avgpool3_kernel
+//   SSCD GeM pooling (p=3, eps=1e-6) [upstream, unverified]                               -> gem_kernel
+//   metrics/inception.py adaptive_avg_pool2d((1,1))                                       -> global_avgpool_kernel
+//   dino_vits.py:144-150,252 nn.LayerNorm(eps=1e-6)                                       -> layernorm_kernel
+//   dino_vits.py:235-246 prepare_tokens (cls token + pos_embed)                           -> vit_tokens_kernel
+#include <cuda_bf16.h>
+
+#include <algorithm>
+
+#include "dcr_internal.cuh"
+#include "host_util.cuh"
+
+namespace dcr {
+namespace {
+
+constexpr uint32_t kFull = 0xffffffffu;
+
+__device__ __forceinline__ void load8(const __nv_bfloat16* base, long long plane_stride, int planes, size_t idx,
+                                      float (&v)[8]) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = 0.f;
+  for (int p = 0; p < planes; ++p) {
+    const uint4 u = *reinterpret_cast<const uint4*>(base + p * plane_stride + idx);
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      v[2 * j] += __uint_as_float(w[j] << 16);
+      v[2 * j + 1] += __uint_as_float(w[j] & 0xffff0000u);
+    }
+  }
+}
+
+__device__ __forceinline__ void store8(__nv_bfloat16* base, long long plane_stride, int planes, size_t idx,
+                                       float (&v)[8]) {
+  for (int p = 0; p < planes; ++p) {
+    uint32_t w[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const __nv_bfloat16 a = __float2bfloat16_rn(v[2 * j]), b = __float2bfloat16_rn(v[2 * j + 1]);
+      w[j] = static_cast<uint32_t>(__bfloat16_as_ushort(a)) | (static_cast<uint32_t>(__bfloat16_as_ushort(b)) << 16);
+      v[2 * j] -= __bfloat162float(a);
+      v[2 * j + 1] -= __bfloat162float(b);
+    }
+    *reinterpret_cast<uint4*>(base + p * plane_stride + idx) = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+}
+
+// ---- uint8 HWC image -> normalised im2col matrix for the (3-channel) first convolution ------------------------
+// out[m, k], m = (b, p, q) over the OHxOW output grid, k = (r*kw + s)*3 + c  (zero for k >= kh*kw*3 and for taps
+// that fall into the zero padding).  value = post_scale * ((u8/255 - mean[c]) / std[c]) + post_shift.
+struct Im2colU8Params {
+  const uint8_t* img;
+  int B, IH, IW, crop_y, crop_x, H, W;   // H, W: size after the centre crop
+  int kh, kw, stride, pad, OH, OW, k_pad;
+  float mean[3], std[3], post_scale, post_shift;
+  __nv_bfloat16* out;
+  long long out_plane_stride;
+  int planes;
+};
+
+__global__ void im2col_u8_kernel(const Im2colU8Params p) {
+  const int groups = p.k_pad / 8;
+  const long long total = static_cast<long long>(p.B) * p.OH * p.OW * groups;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int gk = static_cast<int>(i % groups);
+    const long long m = i / groups;
+    const int q = static_cast<int>(m % p.OW);
+    const int pp = static_cast<int>((m / p.OW) % p.OH);
+    const int b = static_cast<int>(m / (static_cast<long long>(p.OW) * p.OH));
+    float v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int k = gk * 8 + e;
+      float val = 0.f;
+      if (k < p.kh * p.kw * 3) {
+        const int c = k % 3, tap = k / 3;
+        const int r = tap / p.kw, s = tap % p.kw;
+        const int y = pp * p.stride - p.pad + r, x = q * p.stride - p.pad + s;
+        if (y >= 0 && y < p.H && x >= 0 && x < p.W) {
+          const uint8_t u = p.img[((static_cast<size_t>(b) * p.IH + (y + p.crop_y)) * p.IW + (x + p.crop_x)) * 3 + c];
+          val = (static_cast<float>(u) / 255.f - p.mean[c]) / p.std[c];   // ToTensor, then Normalize (fp32, IEEE div)
+          val = p.post_scale * val + p.post_shift;
+        }
+      }
+      v[e] = val;
+    }
+    store8(p.out, p.out_plane_stride, p.planes, static_cast<size_t>(m) * p.k_pad + gk * 8, v);
+  }
+}
+
+// ---- pooling -------------------------------------------------------------------------------------------------
+struct PoolParams {
+  const __nv_bfloat16* in;
+  long long in_plane_stride;
+  __nv_bfloat16* out;
+  long long out_plane_stride;
+  int planes;
+  int B, H, W, C, k, stride, pad, OH, OW, ld_out, out_col_off;
+};
+
+template <bool kMax>
+__global__ void pool_kernel(const PoolParams p) {
+  const int cg = p.C / 8;
+  const long long total = static_cast<long long>(p.B) * p.OH * p.OW * cg;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c8 = static_cast<int>(i % cg);
+    const long long m = i / cg;
+    const int q = static_cast<int>(m % p.OW);
+    const int pp = static_cast<int>((m / p.OW) % p.OH);
+    const int b = static_cast<int>(m / (static_cast<long long>(p.OW) * p.OH));
+    float acc[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] = kMax ? -INFINITY : 0.f;
+    int cnt = 0;
+    for (int r = 0; r < p.k; ++r) {
+      const int y = pp * p.stride - p.pad + r;
+      if (y < 0 || y >= p.H) continue;
+      for (int s = 0; s < p.k; ++s) {
+        const int x = q * p.stride - p.pad + s;
+        if (x < 0 || x >= p.W) continue;
+        float v[8];
+        load8(p.in, p.in_plane_stride, p.planes, ((static_cast<size_t>(b) * p.H + y) * p.W + x) * p.C + c8 * 8, v);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[e] = kMax ? fmaxf(acc[e], v[e]) : acc[e] + v[e];
+        ++cnt;
+      }
+    }
+    if (!kMax) {
+      // count_include_pad=False: divide by the number of in-bounds taps
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc[e] = acc[e] / static_cast<float>(cnt);
+    }
+    store8(p.out, p.out_plane_stride, p.planes, static_cast<size_t>(m) * p.ld_out + p.out_col_off + c8 * 8, acc);
+  }
+}
+
+// ---- GeM / global average over the spatial positions of one image --------------------------------------------
+// grid = (B, C/8 / 32 rounded up); each thread owns one 8-channel group of one image and walks HW positions.
+struct ReduceHWParams {
+  const __nv_bfloat16* in;
+  long long in_plane_stride;
+  int planes, B, HW, C;
+  float p_exp, eps;          // GeM only
+  __nv_bfloat16* out;        // planes [B, C] or null
+  long long out_plane_stride;
+  float* out_f32;            // [B, C] or null
+};
+
+template <bool kGem>
+__global__ void reduce_hw_kernel(const ReduceHWParams p) {
+  const int cg = p.C / 8;
+  const int b = blockIdx.x;
+  for (int c8 = blockIdx.y * blockDim.x + threadIdx.x; c8 < cg; c8 += gridDim.y * blockDim.x) {
+    float acc[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+    for (int i = 0; i < p.HW; ++i) {
+      float v[8];
+      load8(p.in, p.in_plane_stride, p.planes, (static_cast<size_t>(b) * p.HW + i) * p.C + c8 * 8, v);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        if (kGem) {
+          const float t = fmaxf(v[e], p.eps);
+          acc[e] += (p.p_exp == 3.f) ? t * t * t : powf(t, p.p_exp);
+        } else {
+          acc[e] += v[e];
+        }
+      }
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      acc[e] = acc[e] / static_cast<float>(p.HW);
+      if (kGem) acc[e] = (p.p_exp == 3.f) ? cbrtf(acc[e]) : powf(acc[e], 1.f / p.p_exp);
+    }
+    if (p.out_f32) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) p.out_f32[static_cast<size_t>(b) * p.C + c8 * 8 + e] = acc[e];
+    }
+    if (p.out) store8(p.out, p.out_plane_stride, p.planes, static_cast<size_t>(b) * p.C + c8 * 8, acc);
+  }
+}
+
+// ---- LayerNorm over the last dim, one warp per row -------------------------------------------------------------
+struct LayerNormParams {
+  const __nv_bfloat16* in;
+  long long in_plane_stride;
+  int planes, rows, C;
+  long long in_row_stride;    // elements between consecutive input rows (C for all rows, T*C for the CLS rows only)
+  const float* gamma;
+  const float* beta;
+  float eps;
+  __nv_bfloat16* out;         // planes [rows, C] or null
+  long long out_plane_stride;
+  float* out_f32;             // [rows, C] or null
+};
+
+__global__ void layernorm_kernel(const LayerNormParams p) {
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  constexpr int kMaxGroups = 4;   // C <= 32 lanes * 4 groups * 8 = 1024
+  for (int row = blockIdx.x * wpb + (threadIdx.x >> 5); row < p.rows; row += gridDim.x * wpb) {
+    const size_t base = static_cast<size_t>(row) * p.in_row_stride;
+    float v[kMaxGroups][8];
+    float s = 0.f;
+    const int cg = p.C / 8;
+#pragma unroll
+    for (int g = 0; g < kMaxGroups; ++g) {
+      const int c8 = lane + g * 32;
+      if (c8 < cg) {
+        load8(p.in, p.in_plane_stride, p.planes, base + c8 * 8, v[g]);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) s += v[g][e];
+      }
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(kFull, s, off);
+    const float mean = s / static_cast<float>(p.C);
+    float ss = 0.f;
+#pragma unroll
+    for (int g = 0; g < kMaxGroups; ++g) {
+      const int c8 = lane + g * 32;
+      if (c8 < cg) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const float d = v[g][e] - mean;
+          ss += d * d;
+        }
+      }
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) ss += __shfl_xor_sync(kFull, ss, off);
+    const float rstd = 1.f / sqrtf(ss / static_cast<float>(p.C) + p.eps);   // biased variance, as nn.LayerNorm
+#pragma unroll
+    for (int g = 0; g < kMaxGroups; ++g) {
+      const int c8 = lane + g * 32;
+      if (c8 < cg) {
+        float y[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) y[e] = (v[g][e] - mean) * rstd * p.gamma[c8 * 8 + e] + p.beta[c8 * 8 + e];
+        if (p.out_f32) {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) p.out_f32[static_cast<size_t>(row) * p.C + c8 * 8 + e] = y[e];
+        }
+        if (p.out) store8(p.out, p.out_plane_stride, p.planes, static_cast<size_t>(row) * p.C + c8 * 8, y);
+      }
+    }
+  }
+}
+
+// ---- ViT token assembly: tokens[b,0] = cls + pos[0]; tokens[b,1+i] = patch[b,i] + pos[1+i] ---------------------
+struct VitTokensParams {
+  const __nv_bfloat16* patch;   // planes [B*NP, C]
+  long long patch_plane_stride;
+  const float* cls;             // [C]
+  const float* pos;             // [(NP+1), C]
+  __nv_bfloat16* out;           // planes [B*(NP+1), C]
+  long long out_plane_stride;
+  int planes, B, NP, C;
+};
+
+__global__ void vit_tokens_kernel(const VitTokensParams p) {
+  const int cg = p.C / 8;
+  const long long total = static_cast<long long>(p.B) * (p.NP + 1) * cg;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c8 = static_cast<int>(i % cg);
+    const long long row = i / cg;
+    const int t = static_cast<int>(row % (p.NP + 1));
+    const int b = static_cast<int>(row / (p.NP + 1));
+    float v[8];
+    if (t == 0) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] = p.cls[c8 * 8 + e];
+    } else {
+      load8(p.patch, p.patch_plane_stride, p.planes, (static_cast<size_t>(b) * p.NP + (t - 1)) * p.C + c8 * 8, v);
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v[e] += p.pos[static_cast<size_t>(t) * p.C + c8 * 8 + e];
+    store8(p.out, p.out_plane_stride, p.planes, static_cast<size_t>(row) * p.C + c8 * 8, v);
+  }
+}
+
+int grid_for(long long work_items, int block, int num_sms) {
+  long long blocks = (work_items + block - 1) / block;
+  return static_cast<int>(std::min<long long>(blocks, static_cast<long long>(num_sms) * 16));
+}
+
+}  // namespace
+
+int im2col_u8(const uint8_t* img, int B, int IH, int IW, int crop_y, int crop_x, int H, int W, int kh, int kw,
+              int stride, int pad, int k_pad, const float* mean3, const float* std3, float post_scale,
+              float post_shift, __nv_bfloat16* out, long long out_plane_stride, int planes, cudaStream_t stream) {
+  const DeviceInfo* di = device_info();
+  if (!di) return -2;
+  DCR_REQUIRE(k_pad % 8 == 0 && k_pad >= kh * kw * 3, "im2col_u8: bad k_pad %d", k_pad);
+  DCR_REQUIRE(crop_y >= 0 && crop_x >= 0 && crop_y + H <= IH && crop_x + W <= IW, "im2col_u8: crop outside image");
+  Im2colU8Params p;
+  p.img = img; p.B = B; p.IH = IH; p.IW = IW; p.crop_y = crop_y; p.crop_x = crop_x; p.H = H; p.W = W;
+  p.kh = kh; p.kw = kw; p.stride = stride; p.pad = pad;
+  p.OH = (H + 2 * pad - kh) / stride + 1;
+  p.OW = (W + 2 * pad - kw) / stride + 1;
+  p.k_pad = k_pad;
+  for (int c = 0; c < 3; ++c) { p.mean[c] = mean3[c]; p.std[c] = std3[c]; }
+  p.post_scale = post_scale; p.post_shift = post_shift;
+  p.out = out; p.out_plane_stride = out_plane_stride; p.planes = planes;
+  if (B == 0) return 0;
+  const long long total = static_cast<long long>(B) * p.OH * p.OW * (k_pad / 8);
+  im2col_u8_kernel<<<grid_for(total, 256, di->num_sms), 256, 0, stream>>>(p);
+  DCR_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+int pool2d(bool is_max, const __nv_bfloat16* in, long long in_plane_stride, __nv_bfloat16* out,
+           long long out_plane_stride, int planes, int B, int H, int W, int C, int k, int stride, int pad, int ld_out,
+           int out_col_off, cudaStream_t stream) {
+  const DeviceInfo* di = device_info();
+  if (!di) return -2;
+  DCR_REQUIRE(C % 8 == 0 && ld_out % 8 == 0 && out_col_off % 8 == 0, "pool2d: channel counts must be multiples of 8");
+  PoolParams p;
+  p.in = in; p.in_plane_stride = in_plane_stride; p.out = out; p.out_plane_stride = out_plane_stride;
+  p.planes = planes; p.B = B; p.H = H; p.W = W; p.C = C; p.k = k; p.stride = stride; p.pad = pad;
+  p.OH = (H + 2 * pad - k) / stride + 1;
+  p.OW = (W + 2 * pad - k) / stride + 1;
+  p.ld_out = ld_out; p.out_col_off = out_col_off;
+  if (B == 0) return 0;
+  const long long total = static_cast<long long>(B) * p.OH * p.OW * (C / 8);
+  if (is_max) pool_kernel<true><<<grid_for(total, 256, di->num_sms), 256, 0, stream>>>(p);
+  else pool_kernel<false><<<grid_for(total, 256, di->num_sms), 256, 0, stream>>>(p);
+  DCR_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+int reduce_hw(bool gem, const __nv_bfloat16* in, long long in_plane_stride, int planes, int B, int HW, int C,
+              float p_exp, float eps, __nv_bfloat16* out, long long out_plane_stride, float* out_f32,
+              cudaStream_t stream) {
+  DCR_REQUIRE(C % 8 == 0, "reduce_hw: C must be a multiple of 8");
+  ReduceHWParams p;
+  p.in = in; p.in_plane_stride = in_plane_stride; p.planes = planes; p.B = B; p.HW = HW; p.C = C;
+  p.p_exp = p_exp; p.eps = eps; p.out = out; p.out_plane_stride = out_plane_stride; p.out_f32 = out_f32;
+  if (B == 0) return 0;
+  const int cg = C / 8;
+  dim3 grid(B, (cg + 63) / 64);
+  if (gem) reduce_hw_kernel<true><<<grid, 64, 0, stream>>>(p);
+  else reduce_hw_kernel<false><<<grid, 64, 0, stream>>>(p);
+  DCR_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+int layernorm(const __nv_bfloat16* in, long long in_plane_stride, int planes, int rows, int C, long long in_row_stride,
+              const float* gamma, const float* beta, float eps, __nv_bfloat16* out, long long out_plane_stride,
+              float* out_f32, cudaStream_t stream) {
+  const DeviceInfo* di = device_info();
+  if (!di) return -2;
+  DCR_REQUIRE(C % 8 == 0 && C <= 1024, "layernorm: C=%d must be a multiple of 8 and <= 1024", C);
+  LayerNormParams p;
+  p.in = in; p.in_plane_stride = in_plane_stride; p.planes = planes; p.rows = rows; p.C = C;
+  p.in_row_stride = in_row_stride; p.gamma = gamma; p.beta = beta; p.eps = eps;
+  p.out = out; p.out_plane_stride = out_plane_stride; p.out_f32 = out_f32;
+  if (rows == 0) return 0;
+  layernorm_kernel<<<std::min((rows + 7) / 8, di->num_sms * 16), 256, 0, stream>>>(p);
+  DCR_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+int vit_tokens(const __nv_bfloat16* patch, long long patch_plane_stride, const float* cls, const float* pos,
+               __nv_bfloat16* out, long long out_plane_stride, int planes, int B, int NP, int C, cudaStream_t stream) {
+  const DeviceInfo* di = device_info();
+  if (!di) return -2;
+  DCR_REQUIRE(C % 8 == 0, "vit_tokens: C must be a multiple of 8");
+  VitTokensParams p;
+  p.patch = patch; p.patch_plane_stride = patch_plane_stride; p.cls = cls; p.pos = pos; p.out = out;
+  p.out_plane_stride = out_plane_stride; p.planes = planes; p.B = B; p.NP = NP; p.C = C;
+  if (B == 0) return 0;
+  const long long total = static_cast<long long>(B) * (NP + 1) * (C / 8);
+  vit_tokens_kernel<<<grid_for(total, 256, di->num_sms), 256, 0, stream>>>(p);
+  DCR_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace dcr

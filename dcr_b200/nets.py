@@ -1,0 +1,276 @@
+"""Descriptor networks on the dcr_net executor (libdcr_b200.so).
+
+Host-side mirror of the reference's model zoo for the hot path:
+
+    --pt_style sscd  --arch resnet50 | resnet50_im | resnet50_disc     diff_retrieval.py:277-285
+        torch.jit.load(sscd_*.torchscript.pt): ResNet-50 trunk -> GeM(p=3) -> Linear(2048,512) -> L2
+        (architecture from facebookresearch/sscd-copy-detection; not vendored in the reference -- SURVEY.md 8c)
+    --pt_style dino  --arch vit_small  ->  dino_vits.dino_vits16           diff_retrieval.py:251-252, dino_vits.py:340
+        VisionTransformer(patch 16, dim 384, depth 12, heads 6)            dino_vits.py:171-289
+
+Each builder takes a state_dict (real weights when the user has them, seeded random weights in the tests), folds
+BatchNorm into a per-channel affine, lays the weights out for the tcgen05 GEMM kernel and records the op list.
+`forward` takes a uint8 NHWC image batch on the GPU and returns fp32 descriptors -- the resize/crop/ToTensor/
+Normalize of diff_retrieval.py:325-330 is fused into the first op.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Optional, Sequence
+
+import torch
+
+from . import _lib
+from .ops import prepare_conv_weight
+
+OP_IM2COL_U8, OP_CONV, OP_MAXPOOL, OP_AVGPOOL, OP_GEM, OP_GAP, OP_LAYERNORM, OP_VIT_TOKENS, OP_ATTENTION, \
+    OP_L2NORM_OUT = range(10)
+
+PRECISION_PLANES = {"fast": 1, "bf16": 1, "parity": 3, "fp32": 3, "bf16x3": 2}
+
+
+class DcrNet:
+    """Thin owner of a dcr_net handle."""
+
+    def __init__(self, max_batch: int, precision: str = "fast", device: Optional[torch.device] = None):
+        self.lib = _lib.load()
+        if not torch.cuda.is_available():
+            raise _lib.DcrError("dcr_b200 networks need a CUDA (sm_100a) device; there is no CPU path")
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.max_batch = int(max_batch)
+        self.planes = PRECISION_PLANES[precision]
+        self.precision = precision
+        self.out_dim = 0
+        self.in_shape = None          # (IH, IW) expected uint8 input
+        self.flops_per_image = 0.0
+        h = C.c_void_p()
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.dcr_net_create(self.max_batch, self.planes, C.byref(h)), "dcr_net_create")
+        self.handle = h
+
+    def __del__(self):
+        try:
+            if getattr(self, "handle", None):
+                self.lib.dcr_net_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+    # ---- graph construction -------------------------------------------------------------------------------------
+    def tensor(self, rows_per_image: int, channels: int) -> int:
+        with torch.cuda.device(self.device):
+            r = self.lib.dcr_net_add_tensor(self.handle, rows_per_image, channels)
+        if r < 0:
+            raise _lib.DcrError(f"dcr_net_add_tensor: {_lib.last_error()}")
+        return r
+
+    def param(self, t: torch.Tensor) -> int:
+        t = t.detach().contiguous().cpu()
+        with torch.cuda.device(self.device):
+            r = self.lib.dcr_net_add_param(self.handle, t.data_ptr(), t.numel() * t.element_size())
+        if r < 0:
+            raise _lib.DcrError(f"dcr_net_add_param: {_lib.last_error()}")
+        return r
+
+    def param_f32(self, t: torch.Tensor) -> int:
+        return self.param(t.detach().float())
+
+    def weight(self, w: torch.Tensor) -> int:
+        """conv / linear weight -> prepared bf16 planes."""
+        return self.param(prepare_conv_weight(w.detach().float().cpu(), self.planes))
+
+    def op(self, kind: int, iargs: Sequence[int], fargs: Sequence[float] = ()) -> int:
+        ia = (C.c_int * len(iargs))(*[int(v) for v in iargs])
+        fa = (C.c_float * max(1, len(fargs)))(*[float(v) for v in fargs])
+        r = self.lib.dcr_net_add_op(self.handle, kind, ia, len(iargs), fa, len(fargs))
+        if r < 0:
+            raise _lib.DcrError(f"dcr_net_add_op(kind={kind}): {_lib.last_error()}")
+        return r
+
+    def set_output(self, dim: int) -> None:
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.dcr_net_set_output(self.handle, dim), "dcr_net_set_output")
+        self.out_dim = dim
+
+    def conv(self, in_t: int, out_t: int, h: int, w: int, c: int, weight: torch.Tensor, *, stride: int = 1,
+             pad: Sequence[int] = (0, 0), scale: Optional[torch.Tensor] = None, bias: Optional[torch.Tensor] = None,
+             residual: int = -1, act: int = 0, out_col_off: int = 0, to_output: bool = False) -> None:
+        if weight.dim() == 2:
+            n, kh, kw = weight.shape[0], 1, 1
+        else:
+            n, _, kh, kw = weight.shape
+        ho = (h + 2 * pad[0] - kh) // stride + 1
+        wo = (w + 2 * pad[1] - kw) // stride + 1
+        self.flops_per_image += 2.0 * ho * wo * n * c * kh * kw
+        self.op(OP_CONV, [in_t, out_t, h, w, c, self.weight(weight), n, kh, kw, stride, pad[0], pad[1],
+                          self.param_f32(scale) if scale is not None else -1,
+                          self.param_f32(bias) if bias is not None else -1, residual, act, out_col_off,
+                          1 if to_output else 0])
+
+    # ---- execution ----------------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def forward(self, images_u8: torch.Tensor) -> torch.Tensor:
+        """images_u8: CUDA uint8 [n, IH, IW, 3] -> fp32 [n, out_dim] (same device)."""
+        if not (images_u8.is_cuda and images_u8.dtype == torch.uint8 and images_u8.dim() == 4
+                and images_u8.shape[3] == 3):
+            raise _lib.DcrError("forward expects a CUDA uint8 tensor [n, H, W, 3]")
+        if self.in_shape is not None and tuple(images_u8.shape[1:3]) != tuple(self.in_shape):
+            raise _lib.DcrError(f"network was built for {self.in_shape} inputs, got {tuple(images_u8.shape[1:3])}")
+        images_u8 = images_u8.contiguous()
+        n = images_u8.shape[0]
+        out = torch.empty((n, self.out_dim), dtype=torch.float32, device=images_u8.device)
+        with torch.cuda.device(images_u8.device):
+            st = torch.cuda.current_stream().cuda_stream
+            for s in range(0, n, self.max_batch):
+                b = min(self.max_batch, n - s)
+                rc = self.lib.dcr_net_forward(self.handle, images_u8[s:s + b].data_ptr(), b, out[s:s + b].data_ptr(), st)
+                _lib.check(rc, "dcr_net_forward")
+        return out
+
+    __call__ = forward
+
+
+def _fold_bn(sd: Dict[str, torch.Tensor], prefix: str, eps: float):
+    g, b = sd[prefix + ".weight"].double(), sd[prefix + ".bias"].double()
+    m, v = sd[prefix + ".running_mean"].double(), sd[prefix + ".running_var"].double()
+    scale = g / torch.sqrt(v + eps)
+    return scale.float(), (b - m * scale).float()
+
+
+def _strip(sd: Dict[str, torch.Tensor], prefixes: Sequence[str]) -> Dict[str, torch.Tensor]:
+    out = {}
+    for k, v in sd.items():
+        for p in prefixes:
+            if k.startswith(p):
+                k = k[len(p):]
+                break
+        out[k] = v
+    return out
+
+
+def _first_conv_weight(w: torch.Tensor, k_pad: int) -> torch.Tensor:
+    """[N,3,kh,kw] -> [N, k_pad] in (r, s, c) order (c fastest), zero padded: the layout im2col_u8 emits."""
+    n = w.shape[0]
+    flat = w.detach().float().permute(0, 2, 3, 1).reshape(n, -1)
+    out = torch.zeros((n, k_pad), dtype=torch.float32)
+    out[:, :flat.shape[1]] = flat
+    return out
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# SSCD: ResNet-50 trunk + GeM + Linear + L2
+def build_sscd_resnet50(state_dict: Dict[str, torch.Tensor], max_batch: int = 64, precision: str = "fast",
+                        mean: Sequence[float] = (0.5, 0.5, 0.5), std: Sequence[float] = (0.5, 0.5, 0.5),
+                        in_size: int = 256, crop: int = 224, gem_p: float = 3.0, gem_eps: float = 1e-6) -> DcrNet:
+    """state_dict keys: torchvision resnet50 names, optionally prefixed 'backbone.' / 'module.'; head Linear under
+    'embeddings.1' (SSCD), 'fc' or 'head'.  mean/std: (0.5, 0.5) for diff_retrieval.py:329, ImageNet statistics for
+    embedding_search/utils.py:37-39."""
+    sd = _strip({k: v.detach().cpu() for k, v in state_dict.items()}, ["module.", "model."])
+    sd = _strip(sd, ["backbone."])
+    head_w = head_b = None
+    for hp in ("embeddings.1", "embeddings.0", "fc", "head"):
+        if hp + ".weight" in sd and sd[hp + ".weight"].dim() == 2:
+            head_w, head_b = sd[hp + ".weight"], sd.get(hp + ".bias")
+            break
+    if head_w is None:
+        raise _lib.DcrError("SSCD state_dict has no head Linear (embeddings.1 / fc / head)")
+    net = DcrNet(max_batch, precision)
+    net.in_shape = (in_size, in_size)
+    off = (in_size - crop) // 2
+    eps = 1e-5
+    # stem: fused preprocess + im2col of the 7x7/2 conv, then a GEMM
+    s = (crop + 2 * 3 - 7) // 2 + 1   # 112
+    t_cols = net.tensor(s * s, 192)
+    net.op(OP_IM2COL_U8, [t_cols, in_size, in_size, off, off, crop, crop, 7, 7, 2, 3, 192],
+           list(mean) + list(std) + [1.0, 0.0])
+    sc, bi = _fold_bn(sd, "bn1", eps)
+    t_stem = net.tensor(s * s, 64)
+    net.conv(t_cols, t_stem, s * s, 1, 192, _first_conv_weight(sd["conv1.weight"], 192), scale=sc, bias=bi, act=1)
+    net.flops_per_image += 2.0 * s * s * 64 * (147 - 192)   # count the real 147-tap work, not the zero padding
+    hw = (s + 2 - 3) // 2 + 1         # 56
+    t = net.tensor(hw * hw, 64)
+    net.op(OP_MAXPOOL, [t_stem, t, s, s, 64, 3, 2, 1, 0])
+    c_in = 64
+    for li, (planes, blocks, stride) in enumerate([(64, 3, 1), (128, 4, 2), (256, 6, 2), (512, 3, 2)], start=1):
+        for bi_ in range(blocks):
+            pre = f"layer{li}.{bi_}"
+            st = stride if bi_ == 0 else 1
+            hw_out = (hw + 2 - 3) // st + 1
+            t1 = net.tensor(hw * hw, planes)
+            sc, bi = _fold_bn(sd, pre + ".bn1", eps)
+            net.conv(t, t1, hw, hw, c_in, sd[pre + ".conv1.weight"], scale=sc, bias=bi, act=1)
+            t2 = net.tensor(hw_out * hw_out, planes)
+            sc, bi = _fold_bn(sd, pre + ".bn2", eps)
+            net.conv(t1, t2, hw, hw, planes, sd[pre + ".conv2.weight"], stride=st, pad=(1, 1), scale=sc, bias=bi, act=1)
+            ident = t
+            if pre + ".downsample.0.weight" in sd:
+                ident = net.tensor(hw_out * hw_out, planes * 4)
+                sc, bi = _fold_bn(sd, pre + ".downsample.1", eps)
+                net.conv(t, ident, hw, hw, c_in, sd[pre + ".downsample.0.weight"], stride=st, scale=sc, bias=bi)
+            t3 = net.tensor(hw_out * hw_out, planes * 4)
+            sc, bi = _fold_bn(sd, pre + ".bn3", eps)
+            net.conv(t2, t3, hw_out, hw_out, planes, sd[pre + ".conv3.weight"], scale=sc, bias=bi, residual=ident, act=1)
+            t, c_in, hw = t3, planes * 4, hw_out
+    d = head_w.shape[0]
+    net.set_output(d)
+    t_pool = net.tensor(1, c_in)
+    net.op(OP_GEM, [t, t_pool, hw * hw, c_in, 0], [gem_p, gem_eps])
+    net.conv(t_pool, -1, 1, 1, c_in, head_w, bias=head_b, to_output=True)
+    net.op(OP_L2NORM_OUT, [], [1e-12])
+    return net
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# DINO ViT (dino_vits.py:171-289)
+def build_dino_vit(state_dict: Dict[str, torch.Tensor], max_batch: int = 64, precision: str = "fast",
+                   mean: Sequence[float] = (0.5, 0.5, 0.5), std: Sequence[float] = (0.5, 0.5, 0.5),
+                   in_size: int = 256, crop: int = 224, patch: int = 16, heads: int = 6) -> DcrNet:
+    sd = _strip({k: v.detach().cpu() for k, v in state_dict.items()}, ["module.", "backbone."])
+    dim = sd["cls_token"].shape[-1]
+    depth = 1 + max(int(k.split(".")[1]) for k in sd if k.startswith("blocks."))
+    grid = crop // patch
+    n_patch = grid * grid
+    tokens = n_patch + 1
+    if sd["pos_embed"].shape[1] != tokens:
+        raise _lib.DcrError(f"pos_embed has {sd['pos_embed'].shape[1]} positions, network input gives {tokens}; "
+                            "interpolate_pos_encoding (dino_vits.py:213-233) is not implemented")
+    net = DcrNet(max_batch, precision)
+    net.in_shape = (in_size, in_size)
+    off = (in_size - crop) // 2
+    k_pad = patch * patch * 3
+    t_cols = net.tensor(n_patch, k_pad)
+    net.op(OP_IM2COL_U8, [t_cols, in_size, in_size, off, off, crop, crop, patch, patch, patch, 0, k_pad],
+           list(mean) + list(std) + [1.0, 0.0])
+    t_patch = net.tensor(n_patch, dim)
+    net.conv(t_cols, t_patch, n_patch, 1, k_pad, _first_conv_weight(sd["patch_embed.proj.weight"], k_pad),
+             bias=sd["patch_embed.proj.bias"])
+    x = net.tensor(tokens, dim)
+    net.op(OP_VIT_TOKENS, [t_patch, x, n_patch, dim, net.param_f32(sd["cls_token"].reshape(-1)),
+                           net.param_f32(sd["pos_embed"].reshape(tokens, dim))])
+    dh = dim // heads
+    for i in range(depth):
+        pre = f"blocks.{i}"
+        t_ln = net.tensor(tokens, dim)
+        net.op(OP_LAYERNORM, [x, t_ln, tokens, dim, net.param_f32(sd[pre + ".norm1.weight"]),
+                              net.param_f32(sd[pre + ".norm1.bias"]), 1, 0], [1e-6])
+        t_qkv = net.tensor(tokens, 3 * dim)
+        net.conv(t_ln, t_qkv, tokens, 1, dim, sd[pre + ".attn.qkv.weight"], bias=sd.get(pre + ".attn.qkv.bias"))
+        t_att = net.tensor(tokens, dim)
+        net.op(OP_ATTENTION, [t_qkv, t_att, tokens, heads, dh], [dh ** -0.5])
+        net.flops_per_image += 4.0 * heads * tokens * tokens * dh
+        x2 = net.tensor(tokens, dim)
+        net.conv(t_att, x2, tokens, 1, dim, sd[pre + ".attn.proj.weight"], bias=sd[pre + ".attn.proj.bias"], residual=x)
+        t_ln2 = net.tensor(tokens, dim)
+        net.op(OP_LAYERNORM, [x2, t_ln2, tokens, dim, net.param_f32(sd[pre + ".norm2.weight"]),
+                              net.param_f32(sd[pre + ".norm2.bias"]), 1, 0], [1e-6])
+        hid = sd[pre + ".mlp.fc1.weight"].shape[0]
+        t_h = net.tensor(tokens, hid)
+        net.conv(t_ln2, t_h, tokens, 1, dim, sd[pre + ".mlp.fc1.weight"], bias=sd[pre + ".mlp.fc1.bias"], act=2)
+        x3 = net.tensor(tokens, dim)
+        net.conv(t_h, x3, tokens, 1, hid, sd[pre + ".mlp.fc2.weight"], bias=sd[pre + ".mlp.fc2.bias"], residual=x2)
+        x = x3
+    net.set_output(dim)
+    # final LayerNorm on the CLS rows only (dino_vits.py:252-254: norm, then x[:, 0])
+    net.op(OP_LAYERNORM, [x, -1, 1, dim, net.param_f32(sd["norm.weight"]), net.param_f32(sd["norm.bias"]), tokens, 1],
+           [1e-6])
+    return net

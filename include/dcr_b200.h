@@ -93,6 +93,37 @@ int dcr_conv2d_bf16(const void* x, int x_planes, int64_t x_plane_stride, int B, 
                     int res_planes, int64_t res_plane_stride, int act, void* out, int out_planes,
                     int64_t out_plane_stride, int ld_out, int out_col_off, float* out_f32, void* stream);
 
+/* ---- descriptor networks ---------------------------------------------------------------------------------------- */
+/* A dcr_net is an op list over numbered activation tensors, built once by the host from a model's weights
+ * (dcr_b200/nets.py mirrors torchvision ResNet-50 + SSCD head, dino_vits.VisionTransformer and
+ * metrics/inception.InceptionV3) and run per batch.  dcr_net_forward replaces `model(samples)`:
+ *   utils_ret.py:751 (extract_features), embedding_search/utils.py:101, metrics/fid.py:126.
+ *
+ * planes: 1 = bf16 activations/weights (fast); 3 = split-bf16 planes carrying fp32 precision (parity mode).
+ * Tensor ids / param ids / op ids are the non-negative return values; negative = error.
+ * Op kinds and their integer / float argument vectors (all sizes per image; the batch is given at forward time):
+ *   0 IM2COL_U8  i: out_t, IH, IW, crop_y, crop_x, H, W, kh, kw, stride, pad, k_pad     f: mean[3], std[3], post_scale, post_shift
+ *                uint8 HWC input -> normalised im2col rows of the first (3-channel) convolution / patch embedding
+ *   1 CONV       i: in_t, out_t|-1, H, W, C, w_param, N, kh, kw, stride, pad_h, pad_w, scale_param|-1, bias_param|-1,
+ *                   residual_t|-1, act(0 none,1 relu,2 gelu), out_col_off, to_output(0/1)
+ *   2 MAXPOOL / 3 AVGPOOL(count_include_pad=False)  i: in_t, out_t, H, W, C, k, stride, pad, out_col_off
+ *   4 GEM        i: in_t, out_t|-1, HW, C, to_output     f: p, eps
+ *   5 GAP        i: in_t, out_t|-1, HW, C, to_output     (global average pool)
+ *   6 LAYERNORM  i: in_t, out_t|-1, rows_out_per_image, C, gamma_param, beta_param, in_row_stride(rows), to_output   f: eps
+ *   7 VIT_TOKENS i: patch_t, out_t, n_patches, C, cls_param, pos_param
+ *   8 ATTENTION  i: qkv_t, out_t, T, heads, head_dim      f: scale
+ *   9 L2NORM_OUT f: eps        (row-normalise the fp32 output buffer in place) */
+typedef struct dcr_net dcr_net;
+int dcr_net_create(int max_batch, int planes, dcr_net** out);
+void dcr_net_destroy(dcr_net* net);
+int dcr_net_add_tensor(dcr_net* net, int64_t rows_per_image, int channels);
+/* copies `bytes` from HOST memory to a new device buffer */
+int dcr_net_add_param(dcr_net* net, const void* host_data, size_t bytes);
+int dcr_net_set_output(dcr_net* net, int dim);
+int dcr_net_add_op(dcr_net* net, int kind, const int* iargs, int n_iargs, const float* fargs, int n_fargs);
+/* images: DEVICE uint8 [n, IH, IW, 3]; out: DEVICE fp32 [n, dim]; n <= max_batch */
+int dcr_net_forward(dcr_net* net, const uint8_t* images, int n, float* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

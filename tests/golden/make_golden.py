@@ -1,0 +1,50 @@
+"""Generates the committed golden vectors by running the REFERENCE's own modules (importable parts only) in the
+build container:  python tests/golden/make_golden.py        (needs /root/reference; not run on the GPU box)
+
+  dino_vits16_seed{S}.npz : dino_vits.VisionTransformer (vit_small, patch 16) from /root/reference/dino_vits.py with
+                            the seeded state_dict of oracle.models.make_vit_state_dict(S) on seeded inputs.
+  fid_inception_seed{S}.npz: metrics.inception.InceptionV3 (FID variant) with seeded weights  (added with the FID row)
+"""
+import importlib.util
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+REF = "/root/reference"
+
+
+def _load(name, path):
+    spec = importlib.util.spec_from_file_location(name, path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def golden_inputs(seed, n=2, size=224):
+    return torch.randn(n, 3, size, size, generator=torch.Generator().manual_seed(7000 + seed))
+
+
+def make_dino(seed):
+    from oracle.models import make_vit_state_dict
+    dv = _load("ref_dino_vits", os.path.join(REF, "dino_vits.py"))
+    model = dv.vit_small(patch_size=16, num_classes=0)       # what dino_vits16 builds (dino_vits.py:346)
+    sd = make_vit_state_dict(seed)
+    missing, unexpected = model.load_state_dict(sd, strict=True)
+    model.eval()
+    x = golden_inputs(seed)
+    with torch.no_grad():
+        y = model(x)
+    np.savez_compressed(os.path.join(HERE, f"dino_vits16_seed{seed}.npz"), seed=seed, out=y.numpy(),
+                        in_checksum=float(x.double().sum()))
+    print("dino", seed, y.shape, float(y.abs().mean()))
+
+
+if __name__ == "__main__":
+    torch.manual_seed(0)
+    for s in (0, 1):
+        make_dino(s)

@@ -1,0 +1,81 @@
+"""GPU parity of the descriptor networks (through dcr_net_* C ABI) against the CPU oracle."""
+import numpy as np
+import pytest
+import torch
+
+from dcr_b200 import nets, synthetic
+from oracle import models as om
+
+pytestmark = pytest.mark.gpu
+
+
+def _imgs(n, seed):
+    return synthetic.images(n, seed=seed)
+
+
+def _report(name, got, ref):
+    err = (got - ref).abs().max().item()
+    cos = torch.nn.functional.cosine_similarity(got, ref, dim=1).min().item()
+    print(f"{name}: max_abs_err={err:.3e} min_cos={cos:.7f}")
+    return err, cos
+
+
+@pytest.mark.parametrize("mean,std", [((0.5, 0.5, 0.5), (0.5, 0.5, 0.5)),
+                                      ((0.485, 0.456, 0.406), (0.229, 0.224, 0.225))])
+def test_sscd_resnet50_parity_mode(mean, std):
+    sd = om.make_sscd_state_dict(0)
+    img = _imgs(5, 1)
+    ref = om.sscd_forward(sd, om.preprocess(img, mean, std))
+    net = nets.build_sscd_resnet50(sd, max_batch=4, precision="parity", mean=mean, std=std)   # 5 images: 4 + 1 tail
+    got = net(img.cuda()).cpu()
+    err, cos = _report("sscd parity", got, ref)
+    assert err < 1e-4, err
+    # scores (dot products of unit descriptors) within the 1e-4 tolerance of BASELINE.json north_star
+    assert (got @ got.T - ref @ ref.T).abs().max().item() < 1e-4
+
+
+def test_sscd_resnet50_fast_mode():
+    sd = om.make_sscd_state_dict(0)
+    img = _imgs(6, 2)
+    x = om.preprocess(img)
+    ref32 = om.sscd_forward(sd, x)
+    refq = om.sscd_forward(sd, x, bf16_points=True)
+    net = nets.build_sscd_resnet50(sd, max_batch=8, precision="fast")
+    got = net(img.cuda()).cpu()
+    err_q, _ = _report("sscd fast vs bf16-point oracle", got, refq)
+    err_32, cos = _report("sscd fast vs fp32 oracle", got, ref32)
+    assert err_q < 1.5e-2 and cos > 0.995
+
+
+def test_dino_vits16_parity_mode():
+    sd = om.make_vit_state_dict(0)
+    img = _imgs(3, 3)
+    ref = om.vit_forward(sd, om.preprocess(img))
+    net = nets.build_dino_vit(sd, max_batch=2, precision="parity")
+    got = net(img.cuda()).cpu()
+    err, cos = _report("vit parity", got, ref)
+    assert err < 2e-4 * max(1.0, ref.abs().max().item()), err
+    gn, rn = torch.nn.functional.normalize(got, dim=1), torch.nn.functional.normalize(ref, dim=1)
+    assert (gn @ gn.T - rn @ rn.T).abs().max().item() < 1e-4
+
+
+def test_dino_vits16_fast_mode():
+    sd = om.make_vit_state_dict(1)
+    img = _imgs(4, 4)
+    x = om.preprocess(img)
+    ref32 = om.vit_forward(sd, x)
+    refq = om.vit_forward(sd, x, bf16_points=True)
+    net = nets.build_dino_vit(sd, max_batch=4, precision="fast")
+    got = net(img.cuda()).cpu()
+    err_q, _ = _report("vit fast vs bf16-point oracle", got, refq)
+    err_32, cos = _report("vit fast vs fp32 oracle", got, ref32)
+    assert err_q < 6e-2 * max(1.0, refq.abs().max().item()) and cos > 0.99
+
+
+def test_forward_rejects_cpu_and_wrong_size():
+    from dcr_b200._lib import DcrError
+    net = nets.build_dino_vit(om.make_vit_state_dict(0, depth=1), max_batch=2)
+    with pytest.raises(DcrError):
+        net(_imgs(1, 0))                                  # CPU tensor
+    with pytest.raises(DcrError):
+        net(torch.zeros(1, 224, 224, 3, dtype=torch.uint8, device="cuda"))

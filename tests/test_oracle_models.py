@@ -1,0 +1,54 @@
+"""Oracle networks vs golden vectors produced by the reference's own modules / vs torchvision (CPU)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import models as om
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def _golden_inputs(seed, n=2, size=224):
+    return torch.randn(n, 3, size, size, generator=torch.Generator().manual_seed(7000 + seed))
+
+
+@pytest.mark.parametrize("seed", [0, 1])
+def test_vit_oracle_matches_reference_golden(seed):
+    g = np.load(os.path.join(GOLD, f"dino_vits16_seed{seed}.npz"))
+    x = _golden_inputs(seed)
+    assert abs(float(x.double().sum()) - float(g["in_checksum"])) < 1e-6
+    y = om.vit_forward(om.make_vit_state_dict(seed), x).numpy()
+    np.testing.assert_allclose(y, g["out"], rtol=0, atol=2e-5)
+
+
+def test_sscd_oracle_matches_torchvision_module():
+    """The functional restatement equals a torchvision ResNet-50 module with the same weights + GeM/Linear/L2 head."""
+    import torchvision
+    sd = om.make_sscd_state_dict(3)
+    m = torchvision.models.resnet50(weights=None)
+    tv = {k[len("backbone."):]: v for k, v in sd.items() if k.startswith("backbone.")}
+    tv["fc.weight"], tv["fc.bias"] = m.fc.weight.detach(), m.fc.bias.detach()
+    m.load_state_dict(tv)
+    m.eval()
+    x = torch.randn(2, 3, 224, 224, generator=torch.Generator().manual_seed(1))
+    with torch.no_grad():
+        f = m.layer4(m.layer3(m.layer2(m.layer1(m.maxpool(m.relu(m.bn1(m.conv1(x))))))))
+        f = f.clamp(min=1e-6).pow(3).mean(dim=(2, 3)).pow(1.0 / 3)
+        f = torch.nn.functional.linear(f, sd["embeddings.1.weight"], sd["embeddings.1.bias"])
+        ref = torch.nn.functional.normalize(f, dim=1)
+    got = om.sscd_forward(sd, x)
+    np.testing.assert_allclose(got.numpy(), ref.numpy(), atol=2e-5)
+    np.testing.assert_allclose(got.norm(dim=1).numpy(), 1.0, atol=1e-6)
+
+
+def test_preprocess_matches_torchvision_transform():
+    from torchvision import transforms
+    from PIL import Image
+    img = torch.randint(0, 256, (256, 256, 3), dtype=torch.uint8, generator=torch.Generator().manual_seed(2))
+    tf = transforms.Compose([transforms.Resize(256), transforms.CenterCrop(224), transforms.ToTensor(),
+                             transforms.Normalize([0.5, 0.5, 0.5], [0.5, 0.5, 0.5])])   # diff_retrieval.py:325-330
+    ref = tf(Image.fromarray(img.numpy()))
+    got = om.preprocess(img[None])[0]
+    assert torch.equal(got, ref)
