@@ -97,6 +97,10 @@ int dcr_sim_topk_last_stats(int* out8) {
   return 0;
 }
 
+float dcr_sim_topk_last_kernel_ms(void) { return g_last_stats.kernel_ms; }
+
+long long dcr_kernel_launch_count(void) { return dcr::launch_count(); }
+
 int dcr_topk_merge(const float* scores, const int64_t* idx, int nq, int nlists, int k_in, int k_out,
                    float* out_scores, int64_t* out_idx, void* stream) {
   DCR_REQUIRE(scores && idx && out_scores && out_idx, "dcr_topk_merge: null pointer argument");

@@ -112,6 +112,7 @@ int attention(const __nv_bfloat16* qkv, long long qkv_plane_stride, __nv_bfloat1
   DCR_CUDA_CHECK(cudaFuncSetAttribute(attention_fp32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       static_cast<int>(smem)));
   attention_fp32_kernel<<<B * heads, 256, smem, stream>>>(p);
+  count_launch();
   DCR_CUDA_CHECK(cudaGetLastError());
   return 0;
 }

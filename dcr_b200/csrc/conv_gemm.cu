@@ -309,6 +309,7 @@ int launch(const GemmMaps& maps, GemmParams& p, int num_sms, size_t max_smem, cu
   const int tiles = p.num_m_tiles * p.num_n_tiles;
   const int grid = std::min(tiles, num_sms);
   kern<<<grid, kThreads, smem, stream>>>(maps, p);
+  count_launch();
   DCR_CUDA_CHECK(cudaGetLastError());
   return 0;
 }

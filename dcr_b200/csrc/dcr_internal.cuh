@@ -17,6 +17,7 @@ struct SimStats {
   int cap;
   int n_flagged;
   int d_pad;
+  float kernel_ms;   // device time of the fused kernel alone (CUDA events)
 };
 
 size_t sim_topk_workspace_size(int nq, int ng, int d, int k);

@@ -1,6 +1,7 @@
 #include "host_util.cuh"
 
 #include <cstring>
+#include <atomic>
 #include <mutex>
 
 namespace dcr {
@@ -19,6 +20,10 @@ int set_error(int code, const char* fmt, ...) {
   last_error_storage() = buf;
   return code;
 }
+
+static std::atomic<long long> g_launches{0};
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+long long launch_count() { return g_launches.load(std::memory_order_relaxed); }
 
 const DeviceInfo* device_info() {
   static DeviceInfo cache[64];

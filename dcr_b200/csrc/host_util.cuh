@@ -33,6 +33,10 @@ struct DeviceInfo {
   int cc_major = 0, cc_minor = 0;
   size_t max_smem_optin = 0;
 };
+// cumulative number of kernels this library has launched (all threads)
+void count_launch(int n = 1);
+long long launch_count();
+
 // cached per current device; returns nullptr and sets the error on failure
 const DeviceInfo* device_info();
 

@@ -318,6 +318,7 @@ int im2col_u8(const uint8_t* img, int B, int IH, int IW, int crop_y, int crop_x,
   if (B == 0) return 0;
   const long long total = static_cast<long long>(B) * p.OH * p.OW * (k_pad / 8);
   im2col_u8_kernel<<<grid_for(total, 256, di->num_sms), 256, 0, stream>>>(p);
+  count_launch();
   DCR_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
@@ -338,6 +339,7 @@ int pool2d(bool is_max, const __nv_bfloat16* in, long long in_plane_stride, __nv
   const long long total = static_cast<long long>(B) * p.OH * p.OW * (C / 8);
   if (is_max) pool_kernel<true><<<grid_for(total, 256, di->num_sms), 256, 0, stream>>>(p);
   else pool_kernel<false><<<grid_for(total, 256, di->num_sms), 256, 0, stream>>>(p);
+  count_launch();
   DCR_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
@@ -354,6 +356,7 @@ int reduce_hw(bool gem, const __nv_bfloat16* in, long long in_plane_stride, int 
   dim3 grid(B, (cg + 63) / 64);
   if (gem) reduce_hw_kernel<true><<<grid, 64, 0, stream>>>(p);
   else reduce_hw_kernel<false><<<grid, 64, 0, stream>>>(p);
+  count_launch();
   DCR_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
@@ -370,6 +373,7 @@ int layernorm(const __nv_bfloat16* in, long long in_plane_stride, int planes, in
   p.out = out; p.out_plane_stride = out_plane_stride; p.out_f32 = out_f32;
   if (rows == 0) return 0;
   layernorm_kernel<<<std::min((rows + 7) / 8, di->num_sms * 16), 256, 0, stream>>>(p);
+  count_launch();
   DCR_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
@@ -385,6 +389,7 @@ int vit_tokens(const __nv_bfloat16* patch, long long patch_plane_stride, const f
   if (B == 0) return 0;
   const long long total = static_cast<long long>(B) * (NP + 1) * (C / 8);
   vit_tokens_kernel<<<grid_for(total, 256, di->num_sms), 256, 0, stream>>>(p);
+  count_launch();
   DCR_CUDA_CHECK(cudaGetLastError());
   return 0;
 }

@@ -90,6 +90,7 @@ int l2_normalize(float* x, int n, int d, float eps, cudaStream_t stream) {
   if (!di) return -2;
   const int blocks = std::min((n + 7) / 8, di->num_sms * 8);
   l2_normalize_kernel<<<blocks, 256, 0, stream>>>(x, n, d, eps);
+  count_launch();
   DCR_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
@@ -109,6 +110,7 @@ int topk_merge(const float* scores, const long long* idx, int nq, int nlists, in
                                       static_cast<int>(smem)));
   const int blocks = std::min((nq + wpb - 1) / wpb, di->num_sms * 8);
   topk_merge_kernel<<<blocks, wpb * 32, smem, stream>>>(scores, idx, nq, nlists, k_in, k_out, out_scores, out_idx);
+  count_launch();
   DCR_CUDA_CHECK(cudaGetLastError());
   return 0;
 }

@@ -819,7 +819,9 @@ int sim_topk(const float* q, int nq, const float* g, int ng, int d, int k, long 
   DCR_CUDA_CHECK(cudaMemsetAsync(nflag, 0, 16, stream));
   const int conv_blocks = di->num_sms * 8;
   to_bf16_rows_kernel<<<conv_blocks, 256, 0, stream>>>(q, nq, d, pl.nq_pad, pl.d_pad, qb, qnh, qnr, nullptr);
+  count_launch();
   to_bf16_rows_kernel<<<conv_blocks, 256, 0, stream>>>(g, ng, d, pl.ng_pad, pl.d_pad, gb, nullptr, nullptr, gmax);
+  count_launch();
   DCR_CUDA_CHECK(cudaGetLastError());
 
   CUtensorMap tq, tg;
@@ -839,6 +841,14 @@ int sim_topk(const float* q, int nq, const float* g, int ng, int d, int k, long 
   p.cand_cnt = ccnt;
   p.cand_thr = cthr;
 
+  // CUDA events around the fused kernel only (thread-local, created once): its duration is the roofline numerator's
+  // denominator in bench.py; read back after the stream sync below.
+  static thread_local cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  if (!ev0) {
+    DCR_CUDA_CHECK(cudaEventCreate(&ev0));
+    DCR_CUDA_CHECK(cudaEventCreate(&ev1));
+  }
+  DCR_CUDA_CHECK(cudaEventRecord(ev0, stream));
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(pl.n_units * cg);
   cfg.blockDim = dim3(kThreads);
@@ -855,11 +865,14 @@ int sim_topk(const float* q, int nq, const float* g, int ng, int d, int k, long 
     DCR_CUDA_CHECK(cudaFuncSetAttribute(sim_topk_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         static_cast<int>(pl.smem_bytes)));
     DCR_CUDA_CHECK(cudaLaunchKernelEx(&cfg, sim_topk_kernel<2>, tq, tg, p));
+    count_launch();
   } else {
     DCR_CUDA_CHECK(cudaFuncSetAttribute(sim_topk_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         static_cast<int>(pl.smem_bytes)));
     DCR_CUDA_CHECK(cudaLaunchKernelEx(&cfg, sim_topk_kernel<1>, tq, tg, p));
+    count_launch();
   }
+  DCR_CUDA_CHECK(cudaEventRecord(ev1, stream));
 
   const size_t rs_smem = ((static_cast<size_t>(d) * 4 + 15) & ~size_t(15)) + static_cast<size_t>(pl.max_cand) * 12 + 16;
   DCR_CUDA_CHECK(cudaFuncSetAttribute(rescore_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -868,6 +881,7 @@ int sim_topk(const float* q, int nq, const float* g, int ng, int d, int k, long 
                                                       pl.rows_per_qtile, pl.d_pad, cand, ccnt, cthr, qnh, qnr, gmax,
                                                       g_index_base, g_index_stride, out_scores, out_idx, flagged,
                                                       nflag, pl.max_cand);
+  count_launch();
   DCR_CUDA_CHECK(cudaGetLastError());
 
   // exact path for queries whose certificate failed: first batch is launched blind (kernels exit when the
@@ -879,8 +893,10 @@ int sim_topk(const float* q, int nq, const float* g, int ng, int d, int k, long 
   int done = 0;
   do {
     exact_scan_kernel<<<di->num_sms * 2, 256, ex_smem, stream>>>(q, g, ng, d, flagged, done, nflag, exact);
+    count_launch();
     exact_select_kernel<<<kExactBatch, 256, 0, stream>>>(exact, ng, k, flagged, done, nflag, g_index_base,
                                                          g_index_stride, out_scores, out_idx);
+    count_launch();
     DCR_CUDA_CHECK(cudaGetLastError());
     if (done == 0) {
       DCR_CUDA_CHECK(cudaMemcpyAsync(&h_nflag, nflag, sizeof(int), cudaMemcpyDeviceToHost, stream));
@@ -890,6 +906,9 @@ int sim_topk(const float* q, int nq, const float* g, int ng, int d, int k, long 
   } while (done < h_nflag);
 
   if (stats) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, ev0, ev1) != cudaSuccess) ms = 0.f;
+    stats->kernel_ms = ms;
     stats->cta_group = cg;
     stats->grid = pl.n_units * cg;
     stats->smem_bytes = static_cast<int>(pl.smem_bytes);

@@ -1,0 +1,82 @@
+"""Gallery-sharded retrieval over torch.distributed (one process per GPU, NCCL over NVLink/NVSwitch).
+
+The reference's multi-GPU path (diff_retrieval.py:237-246, 288-317, 345-348; utils_ret.py:762-786) shards only the
+gallery *loader* with a DistributedSampler, all_gathers (index, feats) after every batch and funnels everything to
+rank 0, which then does the similarity alone (and it dead-locks as committed -- SURVEY.md 3.2).  Here each rank keeps
+its 1/N of the gallery descriptors resident, every rank scores ALL queries against its shard with the fused kernel,
+and one all-gather of the [Q,k] (score, index) pairs + a merge gives every rank the global top-k:
+
+    rank r: embeds gallery rows [r*G/N, (r+1)*G/N) and queries [r*Q/N, (r+1)*Q/N)
+    all_gather(query descriptors)                       Q*D*4 bytes total            (one collective)
+    local fused sim+top-k with global index = base + local
+    all_gather(scores f32[Q,k], indices i64[Q,k])       N*Q*k*12 bytes               (one collective)
+    merge N lists -> top-k by (score desc, index asc)   == top-k over the concatenated gallery
+
+There is no data-path collective inside the kernels: the exchange is two small all-gathers per run (message sizes
+are KBs..MBs, latency bound), so NCCL is the right tool.  The functions take the local scorer / merger as arguments
+so the sharding logic is testable on CPU with the oracle under the gloo backend (tests/test_dist_cpu.py).
+"""
+from __future__ import annotations
+
+from typing import Callable, Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def shard_bounds(n: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous shard [lo, hi) of n items for `rank`; sizes differ by at most one."""
+    base, rem = divmod(n, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def all_gather_rows(x: torch.Tensor, sizes: Optional[list] = None) -> torch.Tensor:
+    """Concatenate row blocks of every rank (blocks may differ in length by one)."""
+    world = dist.get_world_size()
+    if world == 1:
+        return x
+    if sizes is None:
+        n = torch.tensor([x.shape[0]], device=x.device, dtype=torch.int64)
+        ns = [torch.zeros_like(n) for _ in range(world)]
+        dist.all_gather(ns, n)
+        sizes = [int(v.item()) for v in ns]
+    mx = max(sizes)
+    pad = torch.zeros((mx,) + tuple(x.shape[1:]), dtype=x.dtype, device=x.device)
+    pad[:x.shape[0]] = x
+    bufs = [torch.empty_like(pad) for _ in range(world)]
+    dist.all_gather(bufs, pad)
+    return torch.cat([b[:s] for b, s in zip(bufs, sizes)], dim=0)
+
+
+def sharded_topk(query_local: torch.Tensor, gallery_local: torch.Tensor, k: int, gallery_base: int,
+                 local_topk: Callable, merge: Callable, query_sizes: Optional[list] = None
+                 ) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Global top-k for ALL queries on every rank.  query_local: this rank's block of query descriptors;
+    gallery_local: this rank's gallery shard whose first row has global index `gallery_base`.
+    local_topk(q, g, k, index_base) -> (scores [Q,k], idx [Q,k]); merge(scores [N,Q,k], idx [N,Q,k], k) -> ([Q,k],[Q,k])."""
+    world = dist.get_world_size() if dist.is_initialized() else 1
+    q_all = all_gather_rows(query_local, query_sizes) if world > 1 else query_local
+    kk = min(k, gallery_local.shape[0])
+    s, i = local_topk(q_all, gallery_local, kk, gallery_base)
+    if kk < k:   # a shard smaller than k: pad with empty entries
+        pad_s = torch.full((s.shape[0], k - kk), float("-inf"), dtype=s.dtype, device=s.device)
+        pad_i = torch.full((i.shape[0], k - kk), -1, dtype=i.dtype, device=i.device)
+        s, i = torch.cat([s, pad_s], 1), torch.cat([i, pad_i], 1)
+    if world == 1:
+        return s, i
+    ss = [torch.empty_like(s) for _ in range(world)]
+    ii = [torch.empty_like(i) for _ in range(world)]
+    dist.all_gather(ss, s.contiguous())
+    dist.all_gather(ii, i.contiguous())
+    return merge(torch.stack(ss), torch.stack(ii), k)
+
+
+def cuda_local_topk(q, g, k, index_base):
+    from .similarity import sim_topk
+    return sim_topk(q, g, k, index_base=index_base)
+
+
+def cuda_merge(scores, idx, k):
+    from .similarity import topk_merge
+    return topk_merge(scores, idx, k)

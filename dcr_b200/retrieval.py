@@ -1,0 +1,110 @@
+"""Embed -> normalise -> similarity -> top-k: the host-side mirror of diff_retrieval.py's `main_worker` hot path.
+
+    extract_features(net, images)        utils_ret.py:704-787 (single process: H2D per batch, forward, rows kept on GPU)
+    retrieve(query, gallery, k)          diff_retrieval.py:388-389 (normalize) + :402,:411,:417 (mm, T, topk)
+    background_similarity(gallery)       diff_retrieval.py:403,:418-419
+    retrieval_stats(main_v, bg_v)        diff_retrieval.py:442-454 (same keys as the wandb/print dict :456-483)
+    run_retrieval(...)                   the `if args.rank == 0:` block :375-419 end to end
+
+Differences from the reference, all deliberate: features stay on the GPU (the reference moves
+every batch to the CPU, utils_ret.py:786, and runs mm/topk there); the full [Q,G] / [G,G] matrices are never
+built or saved; `torch.argsort(-sim)` (:405, result unused) is not computed; ties are ordered by lowest index.
+"""
+from __future__ import annotations
+
+from typing import Dict, Iterable, Optional, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib
+from .nets import DcrNet
+from .similarity import l2_normalize_, sim_topk
+
+
+@torch.no_grad()
+def extract_features(net: DcrNet, images: torch.Tensor, batch_size: Optional[int] = None) -> torch.Tensor:
+    """images: uint8 [N,H,W,3], either already on the GPU or on the host (pinned memory makes the copies async).
+    Returns fp32 [N, D] on the GPU.  Host batches are copied on a side stream and double buffered so the H2D
+    transfer of batch i+1 overlaps the forward pass of batch i (the reference copies synchronously per batch,
+    utils_ret.py:711-712)."""
+    if images.dtype != torch.uint8 or images.dim() != 4 or images.shape[-1] != 3:
+        raise _lib.DcrError("extract_features expects uint8 [N,H,W,3]")
+    bs = net.max_batch if batch_size is None else min(batch_size, net.max_batch)
+    n = images.shape[0]
+    dev = net.device
+    out = torch.empty((n, net.out_dim), dtype=torch.float32, device=dev)
+    if images.is_cuda:
+        for s in range(0, n, bs):
+            out[s:s + bs] = net(images[s:s + bs])
+        return out
+    compute = torch.cuda.current_stream(dev)
+    copy = torch.cuda.Stream(device=dev)
+    stage = [torch.empty((bs,) + tuple(images.shape[1:]), dtype=torch.uint8, device=dev) for _ in range(2)]
+    ready = [torch.cuda.Event() for _ in range(2)]
+    freed = [torch.cuda.Event() for _ in range(2)]
+    for i, s in enumerate(range(0, n, bs)):
+        b = min(bs, n - s)
+        slot = i & 1
+        with torch.cuda.stream(copy):
+            if i >= 2:
+                copy.wait_event(freed[slot])
+            stage[slot][:b].copy_(images[s:s + b], non_blocking=True)
+            ready[slot].record(copy)
+        compute.wait_event(ready[slot])
+        out[s:s + b] = net(stage[slot][:b])
+        freed[slot].record(compute)
+    return out
+
+
+def retrieve(query_features: torch.Tensor, gallery_features: torch.Tensor, k: int = 1, normalize: bool = True,
+             index_base: int = 0, index_stride: int = 1) -> Tuple[torch.Tensor, torch.Tensor]:
+    """(values [Q,k], indices [Q,k]) == torch.mm(normalize(G), normalize(Q).T).T.topk(k)  (diff_retrieval.py:388-417)."""
+    q = query_features.float().contiguous()
+    g = gallery_features.float().contiguous()
+    if normalize:                      # never modify the caller's tensors
+        q = l2_normalize_(q.clone())
+        g = l2_normalize_(g.clone())
+    return sim_topk(q, g, k, index_base=index_base, index_stride=index_stride)
+
+
+def background_similarity(gallery_features: torch.Tensor, normalize: bool = True) -> torch.Tensor:
+    """bg_v of diff_retrieval.py:403,418-419: per gallery row, the second largest similarity to the gallery (the largest
+    being the row itself)."""
+    g = gallery_features.float().contiguous()
+    if normalize:
+        g = l2_normalize_(g.clone())
+    v, _ = sim_topk(g, g, 2)
+    return v[:, -1]
+
+
+def retrieval_stats(main_v: torch.Tensor, bg_v: Optional[torch.Tensor] = None) -> Dict[str, float]:
+    """Same keys and numpy calls as diff_retrieval.py:442-454 (computed on the host on Q / G scalars)."""
+    x0 = main_v.detach().float().cpu().numpy().reshape(-1)
+    st = {"sim_mean": float(np.mean(x0)), "sim_std": float(np.std(x0)), "sim_75pc": float(np.percentile(x0, 75)),
+          "sim_90pc": float(np.percentile(x0, 90)), "sim_95pc": float(np.percentile(x0, 95)),
+          "sim_gt_05pc": float(np.sum(x0 > 0.5) / x0.shape[0])}
+    if bg_v is not None:
+        x1 = bg_v.detach().float().cpu().numpy().reshape(-1)
+        st.update({"bg_mean": float(np.mean(x1)), "bg_std": float(np.std(x1)), "bg_75pc": float(np.percentile(x1, 75)),
+                   "bg_90pc": float(np.percentile(x1, 90)), "bg_95pc": float(np.percentile(x1, 95))})
+    return st
+
+
+def run_retrieval(net: DcrNet, query_images: torch.Tensor, gallery_images: torch.Tensor, k: int = 1,
+                  with_background: bool = False, batch_size: Optional[int] = None) -> Dict[str, object]:
+    """Embed both image sets and match them (the rank-0 block of diff_retrieval.py:386-419)."""
+    values_features = extract_features(net, gallery_images, batch_size)       # :386
+    query_features = extract_features(net, query_images, batch_size)         # :387
+    l2_normalize_(values_features)                                           # :388
+    l2_normalize_(query_features)                                            # :389
+    main_v, main_l = sim_topk(query_features, values_features, k)             # :402, :411, :417
+    out = {"values": main_v, "indices": main_l, "query_features": query_features,
+           "gallery_features": values_features}
+    bg_v = None
+    if with_background:
+        bg, _ = sim_topk(values_features, values_features, 2)                 # :403, :418
+        bg_v = bg[:, -1]                                                      # :419
+        out["bg_values"] = bg_v
+    out["stats"] = retrieval_stats(main_v[:, 0], bg_v)
+    return out

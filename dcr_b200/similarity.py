@@ -90,7 +90,13 @@ def sim_topk_stats() -> dict:
     arr = (C.c_int * 8)()
     lib.dcr_sim_topk_last_stats(arr)
     keys = ["cta_group", "grid", "smem_bytes", "stages", "kp", "cap", "n_flagged", "d_pad"]
-    return dict(zip(keys, list(arr)))
+    st = dict(zip(keys, list(arr)))
+    st["kernel_ms"] = float(lib.dcr_sim_topk_last_kernel_ms())
+    return st
+
+
+def kernel_launch_count() -> int:
+    return int(_lib.load().dcr_kernel_launch_count())
 
 
 def topk_merge(scores: torch.Tensor, idx: torch.Tensor, k_out: Optional[int] = None

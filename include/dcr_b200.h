@@ -67,6 +67,13 @@ int dcr_sim_topk_host(const float* q, int nq, const float* g, int ng, int d, int
  * out[5]=list capacity out[6]=queries recomputed by the exact fallback out[7]=padded descriptor dim */
 int dcr_sim_topk_last_stats(int* out8);
 
+/* Device time (ms, CUDA events on the call's stream) of the fused similarity+top-k kernel alone in the most recent
+ * dcr_sim_topk on this host thread; the conversion / re-score kernels are excluded. */
+float dcr_sim_topk_last_kernel_ms(void);
+
+/* Cumulative number of CUDA kernels this library has launched in this process (all entry points). */
+long long dcr_kernel_launch_count(void);
+
 /* Merge nlists per-shard results.  scores/idx: device, layout [nlists][nq][k_in]; entries with idx < 0 are empty.
  * Output [nq][k_out] ordered by (score desc, idx asc).  nlists*k_in <= 1024.
  * Replaces the running cross-folder merge                        embedding_search/similarity_search.py:70-74
