@@ -110,8 +110,7 @@ def cpu_reference_sample(embed_imgs: int, sim_q: int, g_total: int, q_total: int
     from oracle import models as om
     from oracle import similarity as osim  # noqa: F401  (documented dependency; torch.mm/topk is the literal path)
     from dcr_b200 import synthetic
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
+    cores = torch.get_num_threads()   # torch's default: one thread per physical core of the host
     sd = om.make_sscd_state_dict(0)
     imgs = synthetic.images(embed_imgs, seed=seed)
     x = om.preprocess(imgs)

@@ -98,6 +98,7 @@ int dcr_sim_topk_last_stats(int* out8) {
 }
 
 float dcr_sim_topk_last_kernel_ms(void) { return g_last_stats.kernel_ms; }
+int dcr_sim_topk_last_second_pass(void) { return g_last_stats.n_second; }
 
 long long dcr_kernel_launch_count(void) { return dcr::launch_count(); }
 

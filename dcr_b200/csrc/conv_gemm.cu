@@ -40,6 +40,8 @@ constexpr int kAStage = kBM * kBK * 2;   // 16 KB
 struct GemmMaps {
   CUtensorMap a[3];
   CUtensorMap w[3];
+  CUtensorMap out;   // TMA-store epilogue (single-plane bf16 output)
+  CUtensorMap res;   // residual tile loads for that epilogue
 };
 
 struct GemmParams {
@@ -60,6 +62,7 @@ struct GemmParams {
   float* out_f32;             // [M][ld_out_f32] or null
   int ld_out_f32;
   int act;                    // 0 none, 1 relu, 2 gelu (erf)
+  int tma_epi;                // 1: stage the bf16 output tile in shared memory and write it with TMA stores
 };
 
 DCR_DEVICE float apply_act(float y, int act) {
@@ -82,6 +85,16 @@ DCR_DEVICE void tmem_ld_wait_dep32(uint32_t (&r)[32]) {
                  "+r"(r[29]), "+r"(r[30]), "+r"(r[31])::"memory");
 }
 
+DCR_DEVICE void tma_store_2d(const void* tmap, const void* src_smem, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(tmap)),
+               "r"(smem_u32(src_smem)), "r"(c0), "r"(c1)
+               : "memory");
+}
+DCR_DEVICE void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+DCR_DEVICE void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+DCR_DEVICE void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
 template <int BN, bool kIm2col>
 __global__ void __launch_bounds__(kThreads, 1)
     gemm_bf16_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
@@ -90,18 +103,23 @@ __global__ void __launch_bounds__(kThreads, 1)
   constexpr int kBStage = BN * kBK * 2;
   constexpr int kStageBytes = kAStage + kBStage;
   constexpr uint32_t kTmemCols = (2 * BN <= 128) ? 128 : (2 * BN <= 256 ? 256 : 512);
+  constexpr int kStagingBytes = (BN / 64) * kBM * 128;   // BN/64 slabs of [128 rows x 64 bf16], 128B swizzle
   uint8_t* smem_ab = smem;
-  float* sb = reinterpret_cast<float*>(smem_ab + p.stages * kStageBytes);   // [2 bufs][2 (scale,bias)][BN]
+  uint8_t* staging = smem_ab + p.stages * kStageBytes;                       // 1024-aligned (stages are)
+  float* sb = reinterpret_cast<float*>(staging + kStagingBytes);           // [2 bufs][2 (scale,bias)][BN]
   uint64_t* bars = reinterpret_cast<uint64_t*>(sb + 4 * BN);
   uint64_t* full = bars;          // [stages] (<= 12)
   uint64_t* empty = bars + 12;    // [stages]
   uint64_t* t_full = bars + 24;   // [2]
   uint64_t* t_empty = bars + 26;  // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 28);
+  uint64_t* res_full = bars + 28;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 29);
 
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&maps.out);
+    tma_prefetch_desc(&maps.res);
     for (int i = 0; i < 3; ++i) {
       tma_prefetch_desc(&maps.a[i]);
       tma_prefetch_desc(&maps.w[i]);
@@ -116,6 +134,7 @@ __global__ void __launch_bounds__(kThreads, 1)
       mbar_init(&t_full[b], 1);
       mbar_init(&t_empty[b], 4);
     }
+    mbar_init(res_full, 1);
     fence_mbar_init();
   }
   if (warp == 2) {
@@ -200,6 +219,20 @@ __global__ void __launch_bounds__(kThreads, 1)
       const uint32_t buf = tc & 1;
       float* s_scale = sb + buf * 2 * BN;
       float* s_bias = s_scale + BN;
+      if (p.tma_epi) {
+        // the staging tile is free once the previous tile's TMA stores have finished READING shared memory
+        if (etid == 0) tma_store_wait_read();
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (p.res && etid == 0) {
+          int slabs = 0;
+          for (int sl = 0; sl < BN / 64; ++sl)
+            if (n0 + sl * 64 < p.N) ++slabs;
+          mbar_arrive_expect_tx(res_full, slabs * kBM * 128);
+          for (int sl = 0; sl < BN / 64; ++sl)
+            if (n0 + sl * 64 < p.N)
+              tma_load_2d<1>(staging + sl * kBM * 128, &maps.res, res_full, n0 + sl * 64, m0, kEvictFirst);
+        }
+      }
       // stage the per-channel affine of this tile (safe: buffer `buf` was last read two tiles ago, and all four
       // epilogue warps passed the named barrier of the previous tile since then)
       for (int c = etid; c < BN; c += 128) {
@@ -210,9 +243,68 @@ __global__ void __launch_bounds__(kThreads, 1)
       asm volatile("bar.sync 1, 128;" ::: "memory");
       mbar_wait(&t_full[buf], (tc >> 1) & 1);
       tc_fence_after();
+      if (p.tma_epi && p.res) mbar_wait(res_full, tc & 1);
       const int m = m0 + static_cast<int>(row);
       const bool row_ok = m < p.M;
       const uint32_t taddr = tmem_row + buf * BN;
+      if (p.tma_epi) {
+#pragma unroll 1
+        for (int ch = 0; ch < BN / 32; ++ch) {
+          uint32_t r[32];
+          tmem_ld_32x32(taddr + ch * 32, r);
+          tmem_ld_wait_dep32(r);
+          if (ch == BN / 32 - 1) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&t_empty[buf]);
+          }
+          if (n0 + ch * 32 >= p.N) continue;
+          float y[32];
+#pragma unroll
+          for (int c = 0; c < 32; c += 4) {
+            const float4 sc = *reinterpret_cast<const float4*>(s_scale + ch * 32 + c);
+            const float4 bi = *reinterpret_cast<const float4*>(s_bias + ch * 32 + c);
+            y[c + 0] = fmaf(__uint_as_float(r[c + 0]), sc.x, bi.x);
+            y[c + 1] = fmaf(__uint_as_float(r[c + 1]), sc.y, bi.y);
+            y[c + 2] = fmaf(__uint_as_float(r[c + 2]), sc.z, bi.z);
+            y[c + 3] = fmaf(__uint_as_float(r[c + 3]), sc.w, bi.w);
+          }
+          // this thread's 32 columns live in slab ch/2 at 16-byte chunks (ch&1)*4 .. +3 of row `row` (128B swizzle)
+          uint8_t* srow = staging + (ch >> 1) * kBM * 128 + row * 128;
+          const uint32_t sw = row & 7;
+          if (p.res) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const uint4 rv = *reinterpret_cast<const uint4*>(srow + ((((ch & 1) * 4 + j) ^ sw) << 4));
+              const uint32_t w[4] = {rv.x, rv.y, rv.z, rv.w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                y[j * 8 + 2 * e] += __uint_as_float(w[e] << 16);
+                y[j * 8 + 2 * e + 1] += __uint_as_float(w[e] & 0xffff0000u);
+              }
+            }
+          }
+#pragma unroll
+          for (int c = 0; c < 32; ++c) y[c] = apply_act(y[c], p.act);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            uint4 v;
+            v.x = pack_bf16(y[j * 8 + 0], y[j * 8 + 1]);
+            v.y = pack_bf16(y[j * 8 + 2], y[j * 8 + 3]);
+            v.z = pack_bf16(y[j * 8 + 4], y[j * 8 + 5]);
+            v.w = pack_bf16(y[j * 8 + 6], y[j * 8 + 7]);
+            *reinterpret_cast<uint4*>(srow + ((((ch & 1) * 4 + j) ^ sw) << 4)) = v;
+          }
+        }
+        fence_proxy_async();   // generic-proxy writes -> visible to the TMA (async proxy)
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (etid == 0) {
+          for (int sl = 0; sl < BN / 64; ++sl)
+            if (n0 + sl * 64 < p.N) tma_store_2d(&maps.out, staging + sl * kBM * 128, p.out_col_off + n0 + sl * 64, m0);
+          tma_store_commit();
+        }
+        continue;
+      }
 #pragma unroll 1
       for (int ch = 0; ch < BN / 32; ++ch) {
         uint32_t r[32];
@@ -286,6 +378,7 @@ __global__ void __launch_bounds__(kThreads, 1)
     }
   }
 
+  if (p.tma_epi && warp == 2 && lane == 0) tma_store_wait_all();   // etid 0 issued the stores
   tc_fence_before();
   __syncthreads();
   if (warp == 2) tmem_dealloc<1>(tmem_base, kTmemCols);
@@ -294,7 +387,7 @@ __global__ void __launch_bounds__(kThreads, 1)
 template <int BN, bool kIm2col>
 int launch(const GemmMaps& maps, GemmParams& p, int num_sms, size_t max_smem, cudaStream_t stream) {
   constexpr int kStageBytes = kAStage + BN * kBK * 2;
-  const size_t fixed = 1024 + 4 * BN * 4 + 256;
+  const size_t fixed = 1024 + 4 * BN * 4 + 256 + static_cast<size_t>(BN / 64) * kBM * 128;
   int stages = static_cast<int>((max_smem - fixed) / kStageBytes);
   stages = std::min(stages, 8);
   DCR_REQUIRE(stages >= 2, "gemm: not enough shared memory");
@@ -388,6 +481,22 @@ int conv_gemm(const ConvGemmDesc& d, cudaStream_t stream) {
   p.out_f32 = d.out_f32;
   p.ld_out_f32 = d.ld_out_f32;
   p.act = d.act;
+  p.tma_epi = (p.out != nullptr && p.out_planes == 1 && p.out_f32 == nullptr && (p.res == nullptr || p.res_planes == 1) &&
+               getenv("DCR_GEMM_DIRECT_EPILOGUE") == nullptr)
+                  ? 1
+                  : 0;
+  if (p.tma_epi) {
+    // dim0 = col_off + N so that a partial last slab is clipped at this op's own columns (concat neighbours intact)
+    if (int rc = make_tmap_2d_bf16(&maps.out, p.out, M, p.out_col_off + d.N, p.ld_out, kBM, 64)) return rc;
+    if (p.res) {
+      if (int rc = make_tmap_2d_bf16(&maps.res, p.res, M, d.N, p.ld_res, kBM, 64)) return rc;
+    } else {
+      maps.res = maps.out;
+    }
+  } else {
+    maps.out = maps.w[0];
+    maps.res = maps.w[0];
+  }
   DCR_REQUIRE(p.out == nullptr || (p.ld_out % 8 == 0 && p.out_col_off % 8 == 0), "conv_gemm: output leading dim / offset must be multiples of 8");
   DCR_REQUIRE(p.res == nullptr || p.ld_res % 8 == 0, "conv_gemm: residual leading dim must be a multiple of 8");
   DCR_REQUIRE(p.out_f32 == nullptr || p.ld_out_f32 % 4 == 0, "conv_gemm: fp32 output leading dim must be a multiple of 4");

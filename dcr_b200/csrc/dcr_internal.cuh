@@ -15,7 +15,8 @@ struct SimStats {
   int stages;
   int kp;
   int cap;
-  int n_flagged;
+  int n_flagged;     // queries recomputed by the brute-force fp64 path
+  int n_second;      // queries that needed the second-chance pass (32 candidates)
   int d_pad;
   float kernel_ms;   // device time of the fused kernel alone (CUDA events)
 };

@@ -68,34 +68,50 @@ struct Im2colU8Params {
   int planes;
 };
 
-__global__ void im2col_u8_kernel(const Im2colU8Params p) {
-  const int groups = p.k_pad / 8;
-  const long long total = static_cast<long long>(p.B) * p.OH * p.OW * groups;
+// K layout: k = r * RP + s * 3 + c with RP = ceil8(3 * KW) (each filter row padded to a multiple of 8 elements so
+// that a thread owns whole 16-byte groups and every (s, c) index is a compile-time constant).  One thread per
+// (output pixel, filter row): 3*KW contiguous image bytes -> RP normalised bf16 values.
+template <int KW>
+__global__ void __launch_bounds__(256) im2col_u8_kernel(const Im2colU8Params p) {
+  constexpr int RP = (3 * KW + 7) / 8 * 8;
+  // per-channel lookup table u8 -> normalised value, computed once per block with the reference's exact arithmetic
+  // (ToTensor: u8/255, Normalize: (x-mean)/std, both fp32 with IEEE division), then the optional post affine
+  __shared__ float lut[3][256];
+  for (int i = threadIdx.x; i < 768; i += blockDim.x) {
+    const int c = i >> 8, u = i & 255;
+    const float val = (static_cast<float>(u) / 255.f - p.mean[c]) / p.std[c];
+    lut[c][u] = p.post_scale * val + p.post_shift;
+  }
+  __syncthreads();
+  const int rows_k = p.k_pad / RP;   // kh filter rows + zero rows up to k_pad
+  const long long total = static_cast<long long>(p.B) * p.OH * p.OW * rows_k;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int gk = static_cast<int>(i % groups);
-    const long long m = i / groups;
+    const int r = static_cast<int>(i % rows_k);
+    const long long m = i / rows_k;
     const int q = static_cast<int>(m % p.OW);
     const int pp = static_cast<int>((m / p.OW) % p.OH);
     const int b = static_cast<int>(m / (static_cast<long long>(p.OW) * p.OH));
-    float v[8];
+    const int y = pp * p.stride - p.pad + r;           // in crop coordinates
+    const int x0 = q * p.stride - p.pad;
+    const bool row_ok = r < p.kh && y >= 0 && y < p.H;
+    const uint8_t* src = p.img + ((static_cast<size_t>(b) * p.IH + (y + p.crop_y)) * p.IW + (x0 + p.crop_x)) * 3;
+    __nv_bfloat16* dst = p.out + static_cast<size_t>(m) * p.k_pad + r * RP;
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      const int k = gk * 8 + e;
-      float val = 0.f;
-      if (k < p.kh * p.kw * 3) {
-        const int c = k % 3, tap = k / 3;
-        const int r = tap / p.kw, s = tap % p.kw;
-        const int y = pp * p.stride - p.pad + r, x = q * p.stride - p.pad + s;
-        if (y >= 0 && y < p.H && x >= 0 && x < p.W) {
-          const uint8_t u = p.img[((static_cast<size_t>(b) * p.IH + (y + p.crop_y)) * p.IW + (x + p.crop_x)) * 3 + c];
-          val = (static_cast<float>(u) / 255.f - p.mean[c]) / p.std[c];   // ToTensor, then Normalize (fp32, IEEE div)
-          val = p.post_scale * val + p.post_shift;
-        }
+    for (int g = 0; g < RP / 8; ++g) {
+      float v[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        constexpr int dummy = 0;
+        (void)dummy;
+        const int j = g * 8 + e;          // compile-time after unrolling
+        const int s = j / 3, c = j % 3;
+        float val = 0.f;
+        if (j < 3 * KW && row_ok && x0 + s >= 0 && x0 + s < p.W) val = lut[c][src[j]];
+        v[e] = val;
       }
-      v[e] = val;
+      store8(dst, p.out_plane_stride, p.planes, g * 8, v);
     }
-    store8(p.out, p.out_plane_stride, p.planes, static_cast<size_t>(m) * p.k_pad + gk * 8, v);
   }
 }
 
@@ -304,7 +320,9 @@ int im2col_u8(const uint8_t* img, int B, int IH, int IW, int crop_y, int crop_x,
               float post_shift, __nv_bfloat16* out, long long out_plane_stride, int planes, cudaStream_t stream) {
   const DeviceInfo* di = device_info();
   if (!di) return -2;
-  DCR_REQUIRE(k_pad % 8 == 0 && k_pad >= kh * kw * 3, "im2col_u8: bad k_pad %d", k_pad);
+  const int rp = (3 * kw + 7) / 8 * 8;
+  DCR_REQUIRE(k_pad % rp == 0 && k_pad >= kh * rp, "im2col_u8: k_pad %d must be a multiple of %d and >= %d", k_pad, rp, kh * rp);
+  DCR_REQUIRE(kw == 3 || kw == 7 || kw == 16, "im2col_u8: filter width %d not instantiated (3, 7, 16)", kw);
   DCR_REQUIRE(crop_y >= 0 && crop_x >= 0 && crop_y + H <= IH && crop_x + W <= IW, "im2col_u8: crop outside image");
   Im2colU8Params p;
   p.img = img; p.B = B; p.IH = IH; p.IW = IW; p.crop_y = crop_y; p.crop_x = crop_x; p.H = H; p.W = W;
@@ -316,8 +334,11 @@ int im2col_u8(const uint8_t* img, int B, int IH, int IW, int crop_y, int crop_x,
   p.post_scale = post_scale; p.post_shift = post_shift;
   p.out = out; p.out_plane_stride = out_plane_stride; p.planes = planes;
   if (B == 0) return 0;
-  const long long total = static_cast<long long>(B) * p.OH * p.OW * (k_pad / 8);
-  im2col_u8_kernel<<<grid_for(total, 256, di->num_sms), 256, 0, stream>>>(p);
+  const long long total = static_cast<long long>(B) * p.OH * p.OW * (k_pad / rp);
+  const int grid = grid_for(total, 256, di->num_sms);
+  if (kw == 7) im2col_u8_kernel<7><<<grid, 256, 0, stream>>>(p);
+  else if (kw == 3) im2col_u8_kernel<3><<<grid, 256, 0, stream>>>(p);
+  else im2col_u8_kernel<16><<<grid, 256, 0, stream>>>(p);
   count_launch();
   DCR_CUDA_CHECK(cudaGetLastError());
   return 0;

@@ -148,12 +148,20 @@ def _strip(sd: Dict[str, torch.Tensor], prefixes: Sequence[str]) -> Dict[str, to
     return out
 
 
+def first_conv_k_pad(kh: int, kw: int) -> int:
+    """K of the im2col rows the IM2COL_U8 op emits: each filter row padded to ceil8(3*kw), total padded to 64."""
+    rp = (3 * kw + 7) // 8 * 8
+    return (kh * rp + 63) // 64 * 64
+
+
 def _first_conv_weight(w: torch.Tensor, k_pad: int) -> torch.Tensor:
-    """[N,3,kh,kw] -> [N, k_pad] in (r, s, c) order (c fastest), zero padded: the layout im2col_u8 emits."""
-    n = w.shape[0]
-    flat = w.detach().float().permute(0, 2, 3, 1).reshape(n, -1)
+    """[N,3,kh,kw] -> [N, k_pad] in the layout im2col_u8 emits: k = r*RP + s*3 + c, RP = ceil8(3*kw), zero padded."""
+    n, _, kh, kw = w.shape
+    rp = (3 * kw + 7) // 8 * 8
+    rows = torch.zeros((n, kh, rp), dtype=torch.float32)
+    rows[:, :, :3 * kw] = w.detach().float().permute(0, 2, 3, 1).reshape(n, kh, 3 * kw)
     out = torch.zeros((n, k_pad), dtype=torch.float32)
-    out[:, :flat.shape[1]] = flat
+    out[:, :kh * rp] = rows.reshape(n, kh * rp)
     return out
 
 
@@ -187,6 +195,7 @@ def build_sscd_resnet50(state_dict: Dict[str, torch.Tensor], max_batch: int = 64
     t_stem = net.tensor(s * s, 64)
     net.conv(t_cols, t_stem, s * s, 1, 192, _first_conv_weight(sd["conv1.weight"], 192), scale=sc, bias=bi, act=1)
     net.flops_per_image += 2.0 * s * s * 64 * (147 - 192)   # count the real 147-tap work, not the zero padding
+    assert first_conv_k_pad(7, 7) == 192
     hw = (s + 2 - 3) // 2 + 1         # 56
     t = net.tensor(hw * hw, 64)
     net.op(OP_MAXPOOL, [t_stem, t, s, s, 64, 3, 2, 1, 0])
@@ -237,7 +246,7 @@ def build_dino_vit(state_dict: Dict[str, torch.Tensor], max_batch: int = 64, pre
     net = DcrNet(max_batch, precision)
     net.in_shape = (in_size, in_size)
     off = (in_size - crop) // 2
-    k_pad = patch * patch * 3
+    k_pad = first_conv_k_pad(patch, patch)
     t_cols = net.tensor(n_patch, k_pad)
     net.op(OP_IM2COL_U8, [t_cols, in_size, in_size, off, off, crop, crop, patch, patch, patch, 0, k_pad],
            list(mean) + list(std) + [1.0, 0.0])

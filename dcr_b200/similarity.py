@@ -92,6 +92,7 @@ def sim_topk_stats() -> dict:
     keys = ["cta_group", "grid", "smem_bytes", "stages", "kp", "cap", "n_flagged", "d_pad"]
     st = dict(zip(keys, list(arr)))
     st["kernel_ms"] = float(lib.dcr_sim_topk_last_kernel_ms())
+    st["n_second"] = int(lib.dcr_sim_topk_last_second_pass())
     return st
 
 

@@ -70,6 +70,8 @@ int dcr_sim_topk_last_stats(int* out8);
 /* Device time (ms, CUDA events on the call's stream) of the fused similarity+top-k kernel alone in the most recent
  * dcr_sim_topk on this host thread; the conversion / re-score kernels are excluded. */
 float dcr_sim_topk_last_kernel_ms(void);
+/* number of queries that went through the second-chance pass (32 candidates) in that call */
+int dcr_sim_topk_last_second_pass(void);
 
 /* Cumulative number of CUDA kernels this library has launched in this process (all entry points). */
 long long dcr_kernel_launch_count(void);

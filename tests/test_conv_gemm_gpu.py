@@ -65,10 +65,20 @@ def test_conv_matches_torch(shape, planes):
     # one plane: bf16 x bf16 products are exact in fp32, only the accumulation order differs from the reference;
     # three planes (6 cross terms): fp32-level agreement, limited by the tensor core's fp32 accumulator rounding
     mx = max(1.0, ref.abs().max().item())
-    tol = (1e-4 if planes == 1 else 2e-5) * mx
+    tol = (3e-4 if planes == 1 else 5e-5) * mx   # the tensor core's fp32 accumulator truncates: ~1e-5 relative at K~2000
     err32 = (out32 - ref).abs().max().item()
     assert err32 < tol, f"fp32 out err {err32}"
     got = ops.merge_planes(out)
     errp = (got - ref).abs().max().item()
     ptol = (2 ** -8 if planes == 1 else 2 ** -22) * mx + tol
     assert errp < ptol, f"plane out err {errp}"
+    if planes == 1:
+        # without the fp32 side output the kernel takes the shared-memory staged TMA-store epilogue (residual tile
+        # fetched by TMA too); it must produce the same bf16 tensor bit for bit
+        out2, _ = ops.conv2d(xp, wp, n, kh, kw, stride, ph, pw, scale=scale, bias=bias, residual=rp, act=act)
+        torch.cuda.synchronize()
+        assert torch.equal(out2, out), f"TMA-store epilogue differs: {(out2.float() - out.float()).abs().max().item()}"
+        out3, _ = ops.conv2d(xp, wp, n, kh, kw, stride, ph, pw, scale=scale, bias=bias, act=act)
+        ref3 = _ref(ops.merge_planes(xp), ops.merge_planes(wp).reshape(n, kh, kw, -1)[..., :c].permute(0, 3, 1, 2),
+                    scale, bias, None, act, stride, (ph, pw))
+        assert (ops.merge_planes(out3) - ref3).abs().max().item() < ptol

@@ -67,6 +67,23 @@ def test_all_identical_gallery_forces_exact_fallback():
     assert similarity.sim_topk_stats()["n_flagged"] == 64   # certificate cannot hold: everything ties
 
 
+def test_concentrated_descriptors():
+    """Descriptors sharing a common component (un-whitened networks).  Gallery centring keeps the bf16 error bound
+    proportional to the spread of the gallery; results must stay exact either way, and for a moderate common
+    component almost no query may need the brute-force path."""
+    gen = torch.Generator().manual_seed(21)
+    common = torch.randn(1, 512, generator=gen)
+    q = torch.nn.functional.normalize(common + 1.0 * torch.randn(600, 512, generator=gen), dim=1)
+    g = torch.nn.functional.normalize(common + 1.0 * torch.randn(30000, 512, generator=gen), dim=1)
+    st = _check(q, g, 10)
+    assert st["n_flagged"] <= 6, st
+    # extreme case (all cosines > 0.99): the score spread is below bf16 resolution, the certificate must notice
+    # and the exact path must still return the oracle's answer
+    q2 = torch.nn.functional.normalize(common + 0.05 * torch.randn(64, 512, generator=gen), dim=1)
+    g2 = torch.nn.functional.normalize(common + 0.05 * torch.randn(5000, 512, generator=gen), dim=1)
+    _check(q2, g2, 5)
+
+
 def test_k_equals_gallery_size():
     q, g = synthetic.descriptors(20, 16, 64, seed=12)
     _check(q, g, 16)
