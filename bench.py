@@ -190,8 +190,16 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
 
-    net = nets.build_sscd_resnet50(om.make_sscd_state_dict(0), max_batch=args.batch, precision="fast")
     gal_u8 = gen_images_cuda(args.gallery, seed=100 + rank, device=dev)
+    # Seeded random weights (no network, no checkpoints).  A random trunk maps every image to almost the same
+    # direction; trained SSCD descriptors are spread over the sphere (that is what its training objective enforces).
+    # To get that property the synthetic head bias is set to minus the mean raw embedding of 512 synthetic images.
+    sd = om.make_sscd_state_dict(0)
+    cal = nets.build_sscd_resnet50(sd, max_batch=128, precision="fast", l2_normalize=False)
+    mean_raw = cal(gen_images_cuda(512, seed=999, device=dev)).mean(dim=0).cpu()
+    del cal
+    sd["embeddings.1.bias"] = sd["embeddings.1.bias"] - mean_raw
+    net = nets.build_sscd_resnet50(sd, max_batch=args.batch, precision="fast")
     qry_u8 = gen_images_cuda(args.queries, seed=200 + rank, device=dev, copies_of=gal_u8)
     g_base, _ = ddist.shard_bounds(g_total, rank, world) if world > 1 else (0, 0)
     g_base = rank * args.gallery

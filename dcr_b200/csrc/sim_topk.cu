@@ -1,6 +1,6 @@
 // Fused all-pairs similarity + per-query top-k for sm_100a.
 //
-// Replaces (reference, /root/reference):
+// Replaces (reference = somepago/DCR):
 //   diff_retrieval.py:402      sim = torch.mm(values_features, query_features.T)          (fp32, [G,Q], CPU/MKL)
 //   diff_retrieval.py:417,613,621   simscores.topk(k, axis=1, largest=True)               k in {1,10}
 //   diff_retrieval.py:403,418-419   sim2 = mm(values, values.T); topk(2)[...,-1]           (same kernel, Q:=G, k=2)

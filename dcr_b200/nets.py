@@ -169,7 +169,8 @@ def _first_conv_weight(w: torch.Tensor, k_pad: int) -> torch.Tensor:
 # SSCD: ResNet-50 trunk + GeM + Linear + L2
 def build_sscd_resnet50(state_dict: Dict[str, torch.Tensor], max_batch: int = 64, precision: str = "fast",
                         mean: Sequence[float] = (0.5, 0.5, 0.5), std: Sequence[float] = (0.5, 0.5, 0.5),
-                        in_size: int = 256, crop: int = 224, gem_p: float = 3.0, gem_eps: float = 1e-6) -> DcrNet:
+                        in_size: int = 256, crop: int = 224, gem_p: float = 3.0, gem_eps: float = 1e-6,
+                        l2_normalize: bool = True) -> DcrNet:
     """state_dict keys: torchvision resnet50 names, optionally prefixed 'backbone.' / 'module.'; head Linear under
     'embeddings.1' (SSCD), 'fc' or 'head'.  mean/std: (0.5, 0.5) for diff_retrieval.py:329, ImageNet statistics for
     embedding_search/utils.py:37-39."""
@@ -225,7 +226,8 @@ def build_sscd_resnet50(state_dict: Dict[str, torch.Tensor], max_batch: int = 64
     t_pool = net.tensor(1, c_in)
     net.op(OP_GEM, [t, t_pool, hw * hw, c_in, 0], [gem_p, gem_eps])
     net.conv(t_pool, -1, 1, 1, c_in, head_w, bias=head_b, to_output=True)
-    net.op(OP_L2NORM_OUT, [], [1e-12])
+    if l2_normalize:     # SSCD's final L2Norm; off only for calibration / inspection of the raw embedding
+        net.op(OP_L2NORM_OUT, [], [1e-12])
     return net
 
 
