@@ -88,9 +88,12 @@ def gen_images_cuda(n: int, seed: int, device, copies_of=None, copy_frac: float 
     g = torch.Generator(device=device).manual_seed(seed)
     for s in range(0, n, chunk):
         b = min(chunk, n - s)
-        low = torch.rand((b, 3, 8, 8), device=device, generator=g)
-        img = torch.nn.functional.interpolate(low, size=(IMG, IMG), mode="bilinear", align_corners=False)
-        img = img * 0.6 + 0.4 * torch.rand((b, 3, 1, 1), device=device, generator=g)
+        img = 0.4 * torch.rand((b, 3, 1, 1), device=device, generator=g)            # per-image colour offset
+        for res, amp in ((4, 0.35), (16, 0.3), (64, 0.25)):                          # three noise scales, random mixing
+            field = torch.rand((b, 3, res, res), device=device, generator=g)
+            gain = amp * torch.rand((b, 1, 1, 1), device=device, generator=g)
+            img = img + gain * torch.nn.functional.interpolate(field, size=(IMG, IMG), mode="bilinear",
+                                                              align_corners=False)
         img = img + 0.04 * torch.randn((b, 3, IMG, IMG), device=device, generator=g)
         out[s:s + b] = (img.clamp_(0, 1) * 255.0).round_().to(torch.uint8).permute(0, 2, 3, 1)
     if copies_of is not None and n > 0 and copy_frac > 0:
@@ -102,6 +105,41 @@ def gen_images_cuda(n: int, seed: int, device, copies_of=None, copy_frac: float 
         base = torch.roll(copies_of[src].float(), shifts=(sh, -sh), dims=(1, 2)) * gain
         out[dst] = base.clamp_(0, 255).round_().to(torch.uint8)
     return out
+
+
+def synthetic_sscd_weights(dev):
+    """Seeded random-init SSCD ResNet-50 weights (no network access, no checkpoints), made data-consistent the way
+    a freshly initialised PyTorch model becomes after its first training-mode batches: the BatchNorm running
+    statistics are set from 512 synthetic images (torch ops, set-up only -- nothing of this runs in a timed region),
+    and the head bias is shifted so that the mean raw embedding is zero.  Without this a random trunk maps every
+    image to nearly the same direction; trained SSCD descriptors are spread over the sphere by construction."""
+    import torchvision
+    from dcr_b200 import nets
+    from oracle import models as om
+    sd = om.make_sscd_state_dict(0)
+    cal_imgs = gen_images_cuda(512, seed=999, device=dev)
+    m = torchvision.models.resnet50(weights=None)
+    tv = {k[len("backbone."):]: v for k, v in sd.items() if k.startswith("backbone.")}
+    tv["fc.weight"], tv["fc.bias"] = m.fc.weight.detach(), m.fc.bias.detach()
+    m.load_state_dict(tv)
+    m = m.to(dev).train()
+    for mod in m.modules():
+        if isinstance(mod, torch.nn.BatchNorm2d):
+            mod.momentum = None            # cumulative average over the calibration batches
+            mod.reset_running_stats()
+    x = om.preprocess(cal_imgs.cpu()).to(dev)
+    with torch.no_grad():
+        for s in range(0, x.shape[0], 128):
+            m(x[s:s + 128])
+    for k, v in m.state_dict().items():
+        if "running_mean" in k or "running_var" in k:
+            sd["backbone." + k] = v.detach().float().cpu()
+    del m, x
+    cal = nets.build_sscd_resnet50(sd, max_batch=128, precision="fast", l2_normalize=False)
+    sd["embeddings.1.bias"] = sd["embeddings.1.bias"] - cal(cal_imgs).mean(dim=0).cpu()
+    del cal
+    torch.cuda.empty_cache()
+    return sd
 
 
 def cpu_reference_sample(embed_imgs: int, sim_q: int, g_total: int, q_total: int, seed: int = 0):
@@ -191,15 +229,7 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
 
     gal_u8 = gen_images_cuda(args.gallery, seed=100 + rank, device=dev)
-    # Seeded random weights (no network, no checkpoints).  A random trunk maps every image to almost the same
-    # direction; trained SSCD descriptors are spread over the sphere (that is what its training objective enforces).
-    # To get that property the synthetic head bias is set to minus the mean raw embedding of 512 synthetic images.
-    sd = om.make_sscd_state_dict(0)
-    cal = nets.build_sscd_resnet50(sd, max_batch=128, precision="fast", l2_normalize=False)
-    mean_raw = cal(gen_images_cuda(512, seed=999, device=dev)).mean(dim=0).cpu()
-    del cal
-    sd["embeddings.1.bias"] = sd["embeddings.1.bias"] - mean_raw
-    net = nets.build_sscd_resnet50(sd, max_batch=args.batch, precision="fast")
+    net = nets.build_sscd_resnet50(synthetic_sscd_weights(dev), max_batch=args.batch, precision="fast")
     qry_u8 = gen_images_cuda(args.queries, seed=200 + rank, device=dev, copies_of=gal_u8)
     g_base, _ = ddist.shard_bounds(g_total, rank, world) if world > 1 else (0, 0)
     g_base = rank * args.gallery

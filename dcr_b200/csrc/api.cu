@@ -161,4 +161,20 @@ int dcr_net_forward(dcr_net* net, const uint8_t* images, int n, float* out, void
   return dcr::net_forward(reinterpret_cast<dcr::Net*>(net), images, n, out, as_stream(stream));
 }
 
+struct dcr_fid;   // opaque alias of dcr::FidState
+int dcr_fid_create(int d, dcr_fid** out) {
+  DCR_REQUIRE(out != nullptr, "dcr_fid_create: null out pointer");
+  return dcr::fid_create(d, reinterpret_cast<dcr::FidState**>(out));
+}
+void dcr_fid_destroy(dcr_fid* st) { dcr::fid_destroy(reinterpret_cast<dcr::FidState*>(st)); }
+int dcr_fid_accumulate(dcr_fid* st, const float* act, int n, void* stream) {
+  return dcr::fid_accumulate(reinterpret_cast<dcr::FidState*>(st), act, n, as_stream(stream));
+}
+int dcr_fid_finalize(dcr_fid* st, double* mu, double* sigma, int64_t* n_out, void* stream) {
+  long long n = 0;
+  const int rc = dcr::fid_finalize(reinterpret_cast<dcr::FidState*>(st), mu, sigma, &n, as_stream(stream));
+  if (n_out) *n_out = n;
+  return rc;
+}
+
 }  // extern "C"

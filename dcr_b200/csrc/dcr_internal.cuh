@@ -103,4 +103,12 @@ int net_set_output(Net* n, int dim);
 int net_add_op(Net* n, int kind, const int* iargs, int ni, const float* fargs, int nf);
 int net_forward(Net* n, const uint8_t* images, int B, float* out, cudaStream_t stream);
 
+
+// ---- FID statistics (fid.cu) ----------------------------------------------------------------------------------------
+struct FidState;
+int fid_create(int d, FidState** out);
+void fid_destroy(FidState* s);
+int fid_accumulate(FidState* s, const float* act, int n, cudaStream_t stream);
+int fid_finalize(FidState* s, double* mu_host, double* sigma_host, long long* n_out, cudaStream_t stream);
+
 }  // namespace dcr

@@ -50,6 +50,8 @@ struct SimParams {
   uint2* cand;         // [n_slots][rows_per_qtile][kKPMax]   (score bits, local gallery row)
   int* cand_cnt;       // [n_slots][rows_per_qtile]
   float* cand_thr;     // [n_slots][rows_per_qtile]
+  const int* bias_flag;    // device flag: 0 = ignore col_bias (query centring switched off for this data)
+  const float* col_bias;   // [ng_pad] per-gallery-row score offset nu.(g-mu) added to every accumulator column; null = none
   const float* thr_init;   // per query row: start thresholds (second-chance pass); null = seed by warm-up replay
 };
 
@@ -62,11 +64,16 @@ struct SimParams {
 __global__ void to_bf16_rows_kernel(const float* __restrict__ x, int n, int d, int n_pad, int d_pad,
                                     const float* __restrict__ mu, __nv_bfloat16* __restrict__ out,
                                     float* __restrict__ norm_hat, float* __restrict__ norm_res,
-                                    float* __restrict__ norm_x, unsigned int* __restrict__ gmax) {
+                                    float* __restrict__ norm_x, unsigned int* __restrict__ gmax,
+                                    const float* __restrict__ nu, float* __restrict__ bias_out,
+                                    const int* __restrict__ mu_flag, const int* __restrict__ nu_flag) {
+  if (mu_flag && *mu_flag == 0) mu = nullptr;   // device-side decision (centre_decision_kernel)
+  if (nu_flag && *nu_flag == 0) nu = nullptr;
   const int warps_per_block = blockDim.x >> 5;
   const int lane = threadIdx.x & 31;
   for (int row = blockIdx.x * warps_per_block + (threadIdx.x >> 5); row < n_pad; row += gridDim.x * warps_per_block) {
     float s_hat = 0.f, s_res = 0.f, s_x = 0.f;
+    double s_bias = 0.0;   // nu . (x - mu) in fp64: the per-gallery-row score offset of query centring
     __nv_bfloat16* o = out + static_cast<size_t>(row) * d_pad;
     if (row < n) {
       const float* xr = x + static_cast<size_t>(row) * d;
@@ -77,6 +84,13 @@ __global__ void to_bf16_rows_kernel(const float* __restrict__ x, int n, int d, i
           if (mu) {
             const float4 m = *reinterpret_cast<const float4*>(mu + c);
             v.x -= m.x; v.y -= m.y; v.z -= m.z; v.w -= m.w;
+          }
+          if (nu) {
+            const float4 u = *reinterpret_cast<const float4*>(nu + c);
+            s_bias = fma(static_cast<double>(u.x), static_cast<double>(v.x), s_bias);
+            s_bias = fma(static_cast<double>(u.y), static_cast<double>(v.y), s_bias);
+            s_bias = fma(static_cast<double>(u.z), static_cast<double>(v.z), s_bias);
+            s_bias = fma(static_cast<double>(u.w), static_cast<double>(v.w), s_bias);
           }
         }
         const __nv_bfloat16 h0 = __float2bfloat16_rn(v.x), h1 = __float2bfloat16_rn(v.y);
@@ -98,7 +112,9 @@ __global__ void to_bf16_rows_kernel(const float* __restrict__ x, int n, int d, i
       s_hat += __shfl_xor_sync(kFull, s_hat, off);
       s_res += __shfl_xor_sync(kFull, s_res, off);
       s_x += __shfl_xor_sync(kFull, s_x, off);
+      s_bias += __shfl_xor_sync(kFull, s_bias, off);
     }
+    if (lane == 0 && bias_out) bias_out[row] = (row < n) ? static_cast<float>(s_bias) : 0.f;
     if (lane == 0 && row < n) {
       // 1.0001: cover the fp32 rounding of the squared sums so the stored values are upper bounds
       float nh = sqrtf(s_hat) * 1.0001f, nr = sqrtf(s_res) * 1.0001f, nx = sqrtf(s_x) * 1.0001f;
@@ -115,28 +131,49 @@ __global__ void to_bf16_rows_kernel(const float* __restrict__ x, int n, int d, i
 
 // column sums of x[n, d] accumulated in double (one atomicAdd per column per block); mean = sum / n afterwards
 // (rows r*row_stride, r < n: any fixed vector works as the centre, so a strided sample of the gallery is enough)
-__global__ void col_sum_kernel(const float* __restrict__ x, int n, int row_stride, int d, double* __restrict__ sums) {
+__global__ void col_sum_kernel(const float* __restrict__ x, int n, int row_stride, int d, double* __restrict__ sums,
+                               double* __restrict__ sq_sums) {
   const int rows_per_block = (n + gridDim.x - 1) / gridDim.x;
   const int r0 = blockIdx.x * rows_per_block, r1 = min(n, r0 + rows_per_block);
   for (int c = threadIdx.x; c < d; c += blockDim.x) {
-    float acc = 0.f;
-    double dacc = 0.0;
+    float acc = 0.f, acc2 = 0.f;
+    double dacc = 0.0, dacc2 = 0.0;
     int cnt = 0;
     for (int r = r0; r < r1; ++r) {
-      acc += x[static_cast<size_t>(r) * row_stride * d + c];
-      if (++cnt == 256) {   // flush the fp32 partial into the double accumulator every 256 rows
+      const float v = x[static_cast<size_t>(r) * row_stride * d + c];
+      acc += v;
+      acc2 += v * v;
+      if (++cnt == 256) {   // flush the fp32 partials into the double accumulators every 256 rows
         dacc += acc;
-        acc = 0.f;
+        dacc2 += acc2;
+        acc = acc2 = 0.f;
         cnt = 0;
       }
     }
     dacc += acc;
-    if (r1 > r0) atomicAdd(sums + c, dacc);
+    dacc2 += acc2;
+    if (r1 > r0) {
+      atomicAdd(sums + c, dacc);
+      if (sq_sums) atomicAdd(sq_sums + c, dacc2);
+    }
   }
 }
 __global__ void col_mean_finish_kernel(const double* __restrict__ sums, int n, int d, float* __restrict__ mu) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c < d) mu[c] = static_cast<float>(sums[c] / n);
+}
+// Query centring pays only when the centred queries are much shorter than the queries themselves (the bf16 error
+// bound shrinks by ||q-nu|| / ||q||) -- and costs a per-column offset in the fused epilogue.  flag = 1 when the
+// mean squared norm of the centred sample is below 1/16 of the uncentred one (a 4x tighter bound).
+__global__ void centre_decision_kernel(const double* __restrict__ sums, const double* __restrict__ sq_sums, int n, int d,
+                                       int* __restrict__ flag) {
+  double m2 = 0.0, nu2 = 0.0;
+  for (int c = 0; c < d; ++c) {
+    m2 += sq_sums[c] / n;
+    const double m = sums[c] / n;
+    nu2 += m * m;
+  }
+  *flag = (m2 - nu2 < m2 / 16.0) ? 1 : 0;
 }
 
 // second-chance pass: copy the bf16 rows of the flagged queries into a compact matrix (zero rows up to n_pad)
@@ -228,14 +265,21 @@ DCR_DEVICE void st_shared_v2_if(uint32_t saddr, uint32_t a, uint32_t b, bool p) 
 // score above its threshold) costs a max-tree, one compare and one vote.  Otherwise the 8-column sub-chunks that
 // contain a hit are appended to the row lists with predicated stores (no per-lane branching).
 template <bool kMaskTail>
-DCR_DEVICE void scan_chunk(const uint32_t (&r)[32], int gcol0, int ng, float& thr, int& cnt, uint32_t my_list_saddr,
-                           uint2* warp_list, int kp, int cap, uint32_t lane) {
+DCR_DEVICE void scan_chunk(const uint32_t (&r)[32], const float* sb, int gcol0, int ng, float& thr, int& cnt,
+                           uint32_t my_list_saddr, uint2* warp_list, int kp, int cap, uint32_t lane) {
   float v[32];
 #pragma unroll
-  for (int c = 0; c < 32; ++c) {
-    v[c] = __uint_as_float(r[c]);
-    if (kMaskTail && gcol0 + c >= ng) v[c] = -INFINITY;
+  for (int c = 0; c < 32; ++c) v[c] = __uint_as_float(r[c]);
+  if (sb) {   // warp-uniform
+#pragma unroll
+    for (int c = 0; c < 32; c += 4) {
+      const float4 b = *reinterpret_cast<const float4*>(sb + c);
+      v[c] += b.x; v[c + 1] += b.y; v[c + 2] += b.z; v[c + 3] += b.w;
+    }
   }
+#pragma unroll
+  for (int c = 0; c < 32; ++c)
+    if (kMaskTail && gcol0 + c >= ng) v[c] = -INFINITY;
   float s[4];
 #pragma unroll
   for (int i = 0; i < 4; ++i) s[i] = max8(v + 8 * i);
@@ -262,10 +306,11 @@ DCR_DEVICE void scan_chunk(const uint32_t (&r)[32], int gcol0, int ng, float& th
 
 // Warm-up chunk: running maxima of 32 column slots (slot = column mod 32); no candidates are recorded.
 template <bool kMaskTail>
-DCR_DEVICE void warm_chunk(const uint32_t (&r)[32], int gcol0, int ng, float (&slot)[32]) {
+DCR_DEVICE void warm_chunk(const uint32_t (&r)[32], const float* sb, int gcol0, int ng, float (&slot)[32]) {
 #pragma unroll
   for (int c = 0; c < 32; ++c) {
     float x = __uint_as_float(r[c]);
+    if (sb) x += sb[c];
     if (kMaskTail && gcol0 + c >= ng) x = -INFINITY;
     slot[c] = fmaxf(slot[c], x);
   }
@@ -300,6 +345,7 @@ __global__ void __launch_bounds__(kThreads, 1)
   uint64_t* t_full = bars + 18;         // [2]
   uint64_t* t_empty = bars + 20;        // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 22);
+  float* sbias = reinterpret_cast<float*>(bars + 32);   // [2][256] column offsets of the tile in each TMEM buffer
 
   const uint32_t warp = threadIdx.x >> 5;
   const uint32_t lane = threadIdx.x & 31;
@@ -417,6 +463,7 @@ __global__ void __launch_bounds__(kThreads, 1)
     uint2* warp_list = cand + quad * 32;
     const uint32_t tmem_row = tmem_base + ((quad * 32u) << 16);
     const int kp = p.kp, cap = p.cap;
+    const float* colbias = (p.col_bias && p.bias_flag && *p.bias_flag) ? p.col_bias : nullptr;
     uint32_t tc = 0;
     for (long long t = t_begin; t < t_end;) {
       const int qi = static_cast<int>(t / p.n_gtiles);
@@ -434,12 +481,26 @@ __global__ void __launch_bounds__(kThreads, 1)
 #pragma unroll
       for (int c = 0; c < 32; ++c) slot[c] = -INFINITY;
 
+      if (colbias) {   // offsets of this segment's first tile (later tiles are prefetched one tile ahead)
+        const int g0 = g_begin * kBlockN;
+        sbias[(tc & 1) * kBlockN + row * 2] = colbias[g0 + row * 2];
+        sbias[(tc & 1) * kBlockN + row * 2 + 1] = colbias[g0 + row * 2 + 1];
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+      }
       for (int j = 0; j < warm + ntiles; ++j, ++tc) {
         const bool is_warm = j < warm;
         const int gi = g_begin + (is_warm ? j : j - warm);
         const int gcol_tile = gi * kBlockN;
         const bool tail = gcol_tile + kBlockN > p.ng;
         const uint32_t buf = tc & 1;
+        const float* sb = colbias ? sbias + buf * kBlockN : nullptr;
+        float nb0 = 0.f, nb1 = 0.f;
+        const bool has_next = colbias && (j + 1 < warm + ntiles);
+        if (has_next) {
+          const int gn = (g_begin + ((j + 1) < warm ? (j + 1) : (j + 1) - warm)) * kBlockN;
+          nb0 = colbias[gn + row * 2];
+          nb1 = colbias[gn + row * 2 + 1];
+        }
         mbar_wait(&t_full[buf], (tc >> 1) & 1);
         tc_fence_after();
         const uint32_t taddr = tmem_row + buf * kBlockN;
@@ -450,11 +511,11 @@ __global__ void __launch_bounds__(kThreads, 1)
           tmem_ld_wait_dep(ra);
           tmem_ld_32x32(taddr + (ch + 1) * 32, rb);
           if (is_warm) {
-            if (tail) warm_chunk<true>(ra, gcol_tile + ch * 32, p.ng, slot);
-            else warm_chunk<false>(ra, gcol_tile + ch * 32, p.ng, slot);
+            if (tail) warm_chunk<true>(ra, sb ? sb + ch * 32 : nullptr, gcol_tile + ch * 32, p.ng, slot);
+            else warm_chunk<false>(ra, sb ? sb + ch * 32 : nullptr, gcol_tile + ch * 32, p.ng, slot);
           } else {
-            if (tail) scan_chunk<true>(ra, gcol_tile + ch * 32, p.ng, thr, cnt, my_list, warp_list, kp, cap, lane);
-            else scan_chunk<false>(ra, gcol_tile + ch * 32, p.ng, thr, cnt, my_list, warp_list, kp, cap, lane);
+            if (tail) scan_chunk<true>(ra, sb ? sb + ch * 32 : nullptr, gcol_tile + ch * 32, p.ng, thr, cnt, my_list, warp_list, kp, cap, lane);
+            else scan_chunk<false>(ra, sb ? sb + ch * 32 : nullptr, gcol_tile + ch * 32, p.ng, thr, cnt, my_list, warp_list, kp, cap, lane);
           }
           tmem_ld_wait_dep(rb);
           if (ch + 2 < kBlockN / 32) {
@@ -469,12 +530,19 @@ __global__ void __launch_bounds__(kThreads, 1)
             }
           }
           if (is_warm) {
-            if (tail) warm_chunk<true>(rb, gcol_tile + (ch + 1) * 32, p.ng, slot);
-            else warm_chunk<false>(rb, gcol_tile + (ch + 1) * 32, p.ng, slot);
+            if (tail) warm_chunk<true>(rb, sb ? sb + (ch + 1) * 32 : nullptr, gcol_tile + (ch + 1) * 32, p.ng, slot);
+            else warm_chunk<false>(rb, sb ? sb + (ch + 1) * 32 : nullptr, gcol_tile + (ch + 1) * 32, p.ng, slot);
           } else {
-            if (tail) scan_chunk<true>(rb, gcol_tile + (ch + 1) * 32, p.ng, thr, cnt, my_list, warp_list, kp, cap, lane);
-            else scan_chunk<false>(rb, gcol_tile + (ch + 1) * 32, p.ng, thr, cnt, my_list, warp_list, kp, cap, lane);
+            if (tail) scan_chunk<true>(rb, sb ? sb + (ch + 1) * 32 : nullptr, gcol_tile + (ch + 1) * 32, p.ng, thr, cnt, my_list, warp_list, kp, cap, lane);
+            else scan_chunk<false>(rb, sb ? sb + (ch + 1) * 32 : nullptr, gcol_tile + (ch + 1) * 32, p.ng, thr, cnt, my_list, warp_list, kp, cap, lane);
           }
+        }
+        if (colbias) {
+          if (has_next) {
+            sbias[(buf ^ 1) * kBlockN + row * 2] = nb0;
+            sbias[(buf ^ 1) * kBlockN + row * 2 + 1] = nb1;
+          }
+          asm volatile("bar.sync 1, 128;" ::: "memory");
         }
         if (is_warm && j == warm - 1) {
           // seed: fold the 32 slot maxima into `groups` >= kp disjoint groups; the smallest group maximum is
@@ -613,7 +681,8 @@ __global__ void __launch_bounds__(128)
                           int n_qtiles, int n_gtiles, int n_units, int rows_per_qtile, int d_pad,
                           const uint2* __restrict__ cand, const int* __restrict__ cand_cnt,
                           const float* __restrict__ cand_thr, const int* __restrict__ qmap,
-                          const float* __restrict__ mu, const float* __restrict__ q_norm_hat,
+                          const float* __restrict__ mu, const float* __restrict__ nu, const int* __restrict__ nu_flag,
+                          const float* __restrict__ q_norm_hat,
                           const float* __restrict__ q_norm_res, const float* __restrict__ q_norm_x,
                           const unsigned int* __restrict__ g_max,
                           long long g_index_base, long long g_index_stride, float* __restrict__ out_scores,
@@ -626,7 +695,7 @@ __global__ void __launch_bounds__(128)
   float* ap = reinterpret_cast<float*>(ci + max_cand);                  // [max_cand] approximate scores
   int* kc = reinterpret_cast<int*>(ap + max_cand);                      // [max_cand] gallery rows of the survivors
   __shared__ int s_n, s_overflow, s_kept, s_off[160], s_cnt[160];
-  __shared__ float s_thr, s_eps;
+  __shared__ float s_thr, s_eps, s_qx, s_gn;
   __shared__ double s_qmu;
   __shared__ BlockBest s_bb;
 
@@ -664,9 +733,19 @@ __global__ void __launch_bounds__(128)
     // (DESIGN.md section 4): bf16 rounding of both operands, fp32 accumulation, fp32 rounding of g - mu.
     const float g_norm = __uint_as_float(g_max[0]), g_res = __uint_as_float(g_max[1]);
     const float qh = q_norm_hat[qrow], qr = q_norm_res[qrow], qx = q_norm_x[qrow];
-    s_eps = 1.001f * (qh * g_res + qr * g_norm) + d_pad * 2.4e-7f * qh * (g_norm + g_res) + 1.2e-7f * qx * g_norm + 1e-30f;
+    s_eps = 1.001f * (qh * g_res + qr * g_norm) + d_pad * 2.4e-7f * qh * (g_norm + g_res) + 1e-30f;
+    s_qx = qx;
+    s_gn = g_norm;
   }
   __syncthreads();
+  if (warp == 1) {   // ||nu||: fp32 roundings of q - nu, g - mu, the offset nu.(g - mu) and its addition
+    float acc = 0.f;
+    if (nu && nu_flag && *nu_flag)
+      for (int c = lane; c < d; c += 32) acc += nu[c] * nu[c];
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(kFull, acc, off);
+    if (lane == 0) s_eps += 3e-7f * (s_qx + sqrtf(acc) * 1.001f) * s_gn;
+  }
   if (warp == 0) {   // q . mu in fp64: the constant the centred approximate scores are offset by
     double acc = 0.0;
     if (mu)
@@ -855,7 +934,7 @@ struct SimPlan {
   PassPlan p0, p1;        // p1 is sized for the worst case (every query flagged)
   // workspace offsets
   size_t off_qb, off_qb1, off_gb, off_qnh, off_qnr, off_qnx, off_gmax, off_colsum, off_mu, off_cand, off_cnt, off_thr,
-      off_flag0, off_flag1, off_thr1, off_counts, off_exact;
+      off_flag0, off_flag1, off_thr1, off_counts, off_exact, off_nu, off_bias;
   size_t total;
 };
 
@@ -872,7 +951,7 @@ int plan_pass(int nq, int kp, const SimPlan& sp, int num_sms, size_t max_smem, i
   // shared memory: resident A + stages*B + cap KB of lists + barriers
   const size_t a_bytes = static_cast<size_t>(sp.num_kb) * kATileBytes;
   const size_t b_tile = static_cast<size_t>(kBlockN / sp.cg) * kBlockK * 2;
-  const size_t fixed = 1024 /*align slack*/ + 256 /*barriers*/;
+  const size_t fixed = 1024 /*align slack*/ + 256 /*barriers*/ + 2048 /*column offsets*/;
   // priorities: 3 B stages, then list capacity up to 64 (fewer compactions), then more stages (up to 8)
   int cap = kp + 16;
   int stages = 2;
@@ -938,8 +1017,10 @@ int make_plan(int nq, int ng, int d, int k, int cg, int num_sms, size_t max_smem
   pl->off_qnr = take(static_cast<size_t>(big.nq_pad) * 4);
   pl->off_qnx = take(static_cast<size_t>(big.nq_pad) * 4);
   pl->off_gmax = take(16);
-  pl->off_colsum = take(static_cast<size_t>(d) * 8);
+  pl->off_colsum = take(static_cast<size_t>(d) * 16);   // column sums + column sums of squares
   pl->off_mu = take(static_cast<size_t>(d) * 4);
+  pl->off_nu = take(static_cast<size_t>(d) * 4);
+  pl->off_bias = take(static_cast<size_t>(pl->ng_pad) * 4);
   const size_t slot_rows = static_cast<size_t>(std::max(pl->p0.n_slots, pl->kp1 ? pl->p1.n_slots : 0)) * pl->rows_per_qtile;
   pl->off_cand = take(slot_rows * kKPMax * 8);
   pl->off_cnt = take(slot_rows * 4);
@@ -967,7 +1048,8 @@ struct PassBuffers {
 
 // one fused pass: qb (bf16, padded) x gb (bf16, centred, padded) -> candidate slots
 int launch_fused(const SimPlan& pl, const PassPlan& pp, const __nv_bfloat16* qb, const __nv_bfloat16* gb, int ng,
-                 const PassBuffers& pb, const float* thr_init, cudaStream_t stream) {
+                 const PassBuffers& pb, const float* col_bias, const int* bias_flag, const float* thr_init,
+                 cudaStream_t stream) {
   CUtensorMap tq, tg;
   if (int rc = make_tmap_2d_bf16(&tq, qb, pp.nq_pad, pl.d_pad, pl.d_pad, kBlockM, kBlockK)) return rc;
   if (int rc = make_tmap_2d_bf16(&tg, gb, pl.ng_pad, pl.d_pad, pl.d_pad, kBlockN / pl.cg, kBlockK)) return rc;
@@ -983,6 +1065,8 @@ int launch_fused(const SimPlan& pl, const PassPlan& pp, const __nv_bfloat16* qb,
   p.cand = pb.cand;
   p.cand_cnt = pb.ccnt;
   p.cand_thr = pb.cthr;
+  p.col_bias = col_bias;
+  p.bias_flag = bias_flag;
   p.thr_init = thr_init;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(pp.n_units * pl.cg);
@@ -1042,6 +1126,8 @@ int sim_topk(const float* q, int nq, const float* g, int ng, int d, int k, long 
   auto* gmax = reinterpret_cast<unsigned int*>(w + pl.off_gmax);
   auto* colsum = reinterpret_cast<double*>(w + pl.off_colsum);
   auto* mu = reinterpret_cast<float*>(w + pl.off_mu);
+  auto* nu = reinterpret_cast<float*>(w + pl.off_nu);
+  auto* bias = reinterpret_cast<float*>(w + pl.off_bias);
   PassBuffers pb;
   pb.cand = reinterpret_cast<uint2*>(w + pl.off_cand);
   pb.ccnt = reinterpret_cast<int*>(w + pl.off_cnt);
@@ -1054,23 +1140,40 @@ int sim_topk(const float* q, int nq, const float* g, int ng, int d, int k, long 
 
   const bool centre = env_int("DCR_SIM_CENTER", 1) != 0;
   DCR_CUDA_CHECK(cudaMemsetAsync(gmax, 0, 16, stream));
-  DCR_CUDA_CHECK(cudaMemsetAsync(counts, 0, 16, stream));
+  DCR_CUDA_CHECK(cudaMemsetAsync(counts, 0, 16, stream));   // [0],[1] flagged counts, [2] query-centring flag
   const int conv_blocks = di->num_sms * 8;
+  int* qflag = counts + 2;   // device flag: query centring on/off
+  auto sampled_mean = [&](const float* x, int n, float* out, bool decide) -> int {
+    // any fixed vector works as a centre, so a strided sample of <= 8192 rows is enough
+    DCR_CUDA_CHECK(cudaMemsetAsync(colsum, 0, static_cast<size_t>(d) * 16, stream));
+    const int row_stride = std::max(1, n / 8192);
+    const int n_sample = (n + row_stride - 1) / row_stride;
+    col_sum_kernel<<<std::min(n_sample, di->num_sms * 4), 256, 0, stream>>>(x, n_sample, row_stride, d, colsum,
+                                                                            decide ? colsum + d : nullptr);
+    count_launch();
+    col_mean_finish_kernel<<<(d + 255) / 256, 256, 0, stream>>>(colsum, n_sample, d, out);
+    count_launch();
+    if (decide) {
+      centre_decision_kernel<<<1, 1, 0, stream>>>(colsum, colsum + d, n_sample, d, qflag);
+      count_launch();
+    }
+    return 0;
+  };
   if (centre) {
-    DCR_CUDA_CHECK(cudaMemsetAsync(colsum, 0, static_cast<size_t>(d) * 8, stream));
-    const int row_stride = std::max(1, ng / 8192);
-    const int n_sample = (ng + row_stride - 1) / row_stride;
-    col_sum_kernel<<<std::min(n_sample, di->num_sms * 4), 256, 0, stream>>>(g, n_sample, row_stride, d, colsum);
-    count_launch();
-    col_mean_finish_kernel<<<(d + 255) / 256, 256, 0, stream>>>(colsum, n_sample, d, mu);
-    count_launch();
+    if (int rc = sampled_mean(g, ng, mu, false)) return rc;    // gallery centre mu (always used)
+    if (int rc = sampled_mean(q, nq, nu, true)) return rc;     // query centre nu + the decision whether to use it
   }
-  to_bf16_rows_kernel<<<conv_blocks, 256, 0, stream>>>(q, nq, d, pl.p0.nq_pad, pl.d_pad, nullptr, qb, qnh, qnr, qnx, nullptr);
+  // q' = q - nu, g' = g - mu:  q.g = q'.g' + nu.g' + q.mu  -- the tensor cores see only the centred parts, nu.g' is a
+  // per-gallery-row offset added to the accumulator columns, q.mu a per-query constant that cannot change the ranking
+  to_bf16_rows_kernel<<<conv_blocks, 256, 0, stream>>>(q, nq, d, pl.p0.nq_pad, pl.d_pad, centre ? nu : nullptr, qb, qnh,
+                                                      qnr, qnx, nullptr, nullptr, nullptr, qflag, nullptr);
   count_launch();
   to_bf16_rows_kernel<<<conv_blocks, 256, 0, stream>>>(g, ng, d, pl.ng_pad, pl.d_pad, centre ? mu : nullptr, gb, nullptr,
-                                                      nullptr, nullptr, gmax);
+                                                      nullptr, nullptr, gmax, centre ? nu : nullptr,
+                                                      centre ? bias : nullptr, nullptr, qflag);
   count_launch();
   DCR_CUDA_CHECK(cudaGetLastError());
+  const float* col_bias = centre ? bias : nullptr;
 
   // CUDA events around the first fused pass only (thread-local, created once): bench.py's roofline numerator
   static thread_local cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -1079,7 +1182,7 @@ int sim_topk(const float* q, int nq, const float* g, int ng, int d, int k, long 
     DCR_CUDA_CHECK(cudaEventCreate(&ev1));
   }
   DCR_CUDA_CHECK(cudaEventRecord(ev0, stream));
-  if (int rc = launch_fused(pl, pl.p0, qb, gb, ng, pb, nullptr, stream)) return rc;
+  if (int rc = launch_fused(pl, pl.p0, qb, gb, ng, pb, col_bias, qflag, nullptr, stream)) return rc;
   DCR_CUDA_CHECK(cudaEventRecord(ev1, stream));
 
   auto rescore = [&](const PassPlan& pp, const int* qmap, int* flagged, int* n_flagged, float* thr_next) -> int {
@@ -1088,7 +1191,7 @@ int sim_topk(const float* q, int nq, const float* g, int ng, int d, int k, long 
                                         static_cast<int>(rs_smem)));
     rescore_select_kernel<<<pp.nq, 128, rs_smem, stream>>>(
         q, g, nq, ng, d, k, pp.n_qtiles, pl.n_gtiles, pp.n_units, pl.rows_per_qtile, pl.d_pad, pb.cand, pb.ccnt,
-        pb.cthr, qmap, centre ? mu : nullptr, qnh, qnr, qnx, gmax, g_index_base, g_index_stride, out_scores, out_idx,
+        pb.cthr, qmap, centre ? mu : nullptr, centre ? nu : nullptr, qflag, qnh, qnr, qnx, gmax, g_index_base, g_index_stride, out_scores, out_idx,
         flagged, n_flagged, thr_next, pp.max_cand);
     count_launch();
     DCR_CUDA_CHECK(cudaGetLastError());
@@ -1110,7 +1213,7 @@ int sim_topk(const float* q, int nq, const float* g, int ng, int d, int k, long 
     gather_rows_kernel<<<std::min(di->num_sms * 8, (p1.nq_pad * (pl.d_pad / 8) + 255) / 256), 256, 0, stream>>>(
         qb, flag0, n_second, p1.nq_pad, pl.d_pad, qb1);
     count_launch();
-    if (int rc = launch_fused(pl, p1, qb1, gb, ng, pb, thr1, stream)) return rc;
+    if (int rc = launch_fused(pl, p1, qb1, gb, ng, pb, col_bias, qflag, thr1, stream)) return rc;
     if (int rc = rescore(p1, flag0, flag1, counts + 1, nullptr)) return rc;
     DCR_CUDA_CHECK(cudaMemcpyAsync(h_counts, counts, 8, cudaMemcpyDeviceToHost, stream));
     DCR_CUDA_CHECK(cudaStreamSynchronize(stream));

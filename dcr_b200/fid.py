@@ -1,0 +1,131 @@
+"""FID on the B200 path: the host mirror of metrics/fid.py.
+
+    get_activations / calculate_activation_statistics   metrics/fid.py:76-139, 199-221
+        -> ActivationStatistics: Inception pool3 features computed by the dcr_net executor are folded, batch by batch,
+           into a float64 (sum, X^T X) pair on the device (dcr_fid_*); the [N, 2048] float64 host array of the
+           reference (:118) never exists.
+    calculate_frechet_distance                          metrics/fid.py:142-196
+        -> frechet_distance: same formula; Tr sqrtm(S1 S2) is evaluated as sum(sqrt(eig(S1^1/2 S2 S1^1/2))) with two
+           symmetric eigendecompositions in float64 (torch.linalg.eigh on the GPU -- an O(d^3) library call outside the
+           hot loop) instead of scipy's Schur-based sqrtm of the non-symmetric product; agrees to ~1e-9 relative.
+    calculate_fid_given_paths                           metrics/fid.py:239-255
+        -> fid_from_images(net, real_u8, gen_u8)  (the images are resized to 299 on the host with PIL exactly like
+           metrics/fid.py:104-106; `load_resized` below does it for a directory)
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib
+from .nets import DcrNet
+from .retrieval import extract_features
+
+
+class ActivationStatistics:
+    def __init__(self, dim: int = 2048, device: Optional[torch.device] = None):
+        self.lib = _lib.load()
+        if not torch.cuda.is_available():
+            raise _lib.DcrError("ActivationStatistics needs a CUDA device")
+        self.dim = dim
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        h = C.c_void_p()
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.dcr_fid_create(dim, C.byref(h)), "dcr_fid_create")
+        self.handle = h
+        self.count = 0
+
+    def __del__(self):
+        try:
+            if getattr(self, "handle", None):
+                self.lib.dcr_fid_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+    def update(self, act: torch.Tensor) -> None:
+        """act: CUDA float32 [n, dim]."""
+        if not (act.is_cuda and act.dtype == torch.float32 and act.dim() == 2 and act.shape[1] == self.dim):
+            raise _lib.DcrError(f"update expects CUDA float32 [n, {self.dim}]")
+        act = act.contiguous()
+        with torch.cuda.device(act.device):
+            st = torch.cuda.current_stream().cuda_stream
+            _lib.check(self.lib.dcr_fid_accumulate(self.handle, act.data_ptr(), act.shape[0], st), "dcr_fid_accumulate")
+        self.count += act.shape[0]
+
+    def finalize(self) -> Tuple[np.ndarray, np.ndarray]:
+        mu = np.empty(self.dim, dtype=np.float64)
+        sigma = np.empty((self.dim, self.dim), dtype=np.float64)
+        n = C.c_int64(0)
+        with torch.cuda.device(self.device):
+            st = torch.cuda.current_stream().cuda_stream
+            _lib.check(self.lib.dcr_fid_finalize(self.handle, mu.ctypes.data, sigma.ctypes.data, C.byref(n), st),
+                       "dcr_fid_finalize")
+        return mu, sigma
+
+
+def frechet_distance(mu1, sigma1, mu2, sigma2, eps: float = 1e-6, device: Optional[torch.device] = None) -> float:
+    """d^2 = ||mu1-mu2||^2 + Tr(s1) + Tr(s2) - 2 Tr(sqrt(s1 s2))   (metrics/fid.py:142-196)."""
+    dev = torch.device("cuda") if (device is None and torch.cuda.is_available()) else (device or torch.device("cpu"))
+    m1 = torch.as_tensor(np.atleast_1d(mu1), dtype=torch.float64, device=dev)
+    m2 = torch.as_tensor(np.atleast_1d(mu2), dtype=torch.float64, device=dev)
+    s1 = torch.as_tensor(np.atleast_2d(sigma1), dtype=torch.float64, device=dev)
+    s2 = torch.as_tensor(np.atleast_2d(sigma2), dtype=torch.float64, device=dev)
+    if m1.shape != m2.shape:
+        raise ValueError("Training and test mean vectors have different lengths")          # fid.py:170-171
+    if s1.shape != s2.shape:
+        raise ValueError("Training and test covariances have different dimensions")        # fid.py:172-173
+
+    def tr_sqrt_product(a, b):
+        w, v = torch.linalg.eigh((a + a.T) * 0.5)
+        ra = (v * torch.sqrt(w.clamp_min(0))) @ v.T            # a^(1/2)
+        m = ra @ b @ ra
+        ev = torch.linalg.eigvalsh((m + m.T) * 0.5)
+        return torch.sqrt(ev.clamp_min(0)).sum()
+
+    tr = tr_sqrt_product(s1, s2)
+    if not torch.isfinite(tr):                                                              # fid.py:179-184
+        off = torch.eye(s1.shape[0], dtype=torch.float64, device=dev) * eps
+        tr = tr_sqrt_product(s1 + off, s2 + off)
+    diff = m1 - m2
+    return float(diff.dot(diff) + torch.trace(s1) + torch.trace(s2) - 2 * tr)
+
+
+def statistics_of_images(net: DcrNet, images_u8: torch.Tensor, batch_size: int = 50) -> Tuple[np.ndarray, np.ndarray]:
+    """calculate_activation_statistics (metrics/fid.py:199-221) for uint8 [N,299,299,3] images (host or device)."""
+    stats = ActivationStatistics(net.out_dim, net.device)
+    n = images_u8.shape[0]
+    chunk = max(batch_size, net.max_batch) * 8
+    for s in range(0, n, chunk):
+        stats.update(extract_features(net, images_u8[s:s + chunk], batch_size))
+    return stats.finalize()
+
+
+def fid_from_images(net: DcrNet, real_u8: torch.Tensor, gen_u8: torch.Tensor, batch_size: int = 50) -> float:
+    """calculate_fid_given_paths (metrics/fid.py:239-255) on already decoded + resized images."""
+    m1, s1 = statistics_of_images(net, real_u8, batch_size)
+    m2, s2 = statistics_of_images(net, gen_u8, batch_size)
+    return frechet_distance(m1, s1, m2, s2)
+
+
+def load_resized(path: str, size: int = 299) -> torch.Tensor:
+    """All **/*.JPEG|png|jpg under `path` (glob order of metrics/fid.py:231), PIL RGB, Resize(299) bilinear +
+    CenterCrop(299) as metrics/fid.py:104-107 -> uint8 [N,299,299,3]."""
+    import glob
+    import os
+
+    from PIL import Image
+    from torchvision import transforms
+    if not os.path.exists(path):
+        raise RuntimeError("Invalid path: %s" % path)                                       # fid.py:243
+    files = (list(glob.glob(os.path.join(path, "**/*.JPEG"), recursive=True)) +
+             list(glob.glob(os.path.join(path, "**/*.png"), recursive=True)) +
+             list(glob.glob(os.path.join(path, "**/*.jpg"), recursive=True)))
+    tf = transforms.Compose([transforms.Resize(size), transforms.CenterCrop(size)])
+    out = torch.empty((len(files), size, size, 3), dtype=torch.uint8)
+    for i, f in enumerate(files):
+        out[i] = torch.from_numpy(np.asarray(tf(Image.open(f).convert("RGB"))))
+    return out

@@ -285,3 +285,168 @@ def build_dino_vit(state_dict: Dict[str, torch.Tensor], max_batch: int = 64, pre
     net.op(OP_LAYERNORM, [x, -1, 1, dim, net.param_f32(sd["norm.weight"]), net.param_f32(sd["norm.bias"]), tokens, 1],
            [1e-6])
     return net
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# FID Inception-v3 (metrics/inception.py:16-341): pool3 features [N, 2048]
+def build_fid_inception(state_dict: Dict[str, torch.Tensor], max_batch: int = 50, precision: str = "fast",
+                        stop_after: Optional[str] = None) -> DcrNet:
+    """Input: uint8 [n,299,299,3] -- the caller resizes with PIL exactly as metrics/fid.py:104-106 does
+    (Resize(299) bilinear on uint8, CenterCrop(299)).  ToTensor, Normalize(0.5,0.5) (fid.py:108-109) and the SECOND
+    `2*x-1` of InceptionV3.forward (inception.py:152-153) are fused into the first op."""
+    sd = _strip({k: v.detach().cpu() for k, v in state_dict.items()}, ["module."])
+    net = DcrNet(max_batch, precision)
+    net.in_shape = (299, 299)
+    eps = 1e-3
+
+    def bconv(in_t, h, w, c, name, *, stride=1, pad=(0, 0), out_t=None, out_c=None, col_off=0):
+        wt = sd[name + ".conv.weight"]
+        n, _, kh, kw = wt.shape
+        ho = (h + 2 * pad[0] - kh) // stride + 1
+        wo = (w + 2 * pad[1] - kw) // stride + 1
+        if out_t is None:
+            out_t = net.tensor(ho * wo, n)
+        sc, bi = _fold_bn(sd, name + ".bn", eps)
+        net.conv(in_t, out_t, h, w, c, wt, stride=stride, pad=pad, scale=sc, bias=bi, act=1, out_col_off=col_off)
+        return out_t, ho, wo, n
+
+    def finish(t, hw, c):
+        net.set_output(c)
+        net.op(OP_GAP, [t, -1, hw, c, 1])
+        return net
+
+    # block 0
+    k_pad = first_conv_k_pad(3, 3)
+    s = (299 - 3) // 2 + 1   # 149
+    t_cols = net.tensor(s * s, k_pad)
+    net.op(OP_IM2COL_U8, [t_cols, 299, 299, 0, 0, 299, 299, 3, 3, 2, 0, k_pad], [0.5] * 3 + [0.5] * 3 + [2.0, -1.0])
+    w1 = sd["Conv2d_1a_3x3.conv.weight"]
+    sc, bi = _fold_bn(sd, "Conv2d_1a_3x3.bn", eps)
+    t = net.tensor(s * s, 32)
+    net.conv(t_cols, t, s * s, 1, k_pad, _first_conv_weight(w1, k_pad), scale=sc, bias=bi, act=1)
+    net.flops_per_image += 2.0 * s * s * 32 * (27 - k_pad)
+    h = w = s
+    if stop_after == "Conv2d_1a_3x3":
+        return finish(t, h * w, 32)
+    t, h, w, c = bconv(t, h, w, 32, "Conv2d_2a_3x3")
+    if stop_after == "Conv2d_2a_3x3":
+        return finish(t, h * w, c)
+    t, h, w, c = bconv(t, h, w, c, "Conv2d_2b_3x3", pad=(1, 1))
+    if stop_after == "Conv2d_2b_3x3":
+        return finish(t, h * w, c)
+
+    def maxpool(in_t, h, w, c, k, stride, pad, out_t=None, out_c=None, col_off=0):
+        ho = (h + 2 * pad - k) // stride + 1
+        if out_t is None:
+            out_t = net.tensor(ho * ho, c)
+        net.op(OP_MAXPOOL, [in_t, out_t, h, w, c, k, stride, pad, col_off])
+        return out_t, ho, ho
+
+    t, h, w = maxpool(t, h, w, c, 3, 2, 0)
+    if stop_after == "pool1":
+        return finish(t, h * w, c)
+    # block 1
+    t, h, w, c = bconv(t, h, w, c, "Conv2d_3b_1x1")
+    if stop_after == "Conv2d_3b_1x1":
+        return finish(t, h * w, c)
+    t, h, w, c = bconv(t, h, w, c, "Conv2d_4a_3x3")
+    if stop_after == "Conv2d_4a_3x3":
+        return finish(t, h * w, c)
+    t, h, w = maxpool(t, h, w, c, 3, 2, 0)
+    if stop_after == "pool2":
+        return finish(t, h * w, c)
+
+    def avgpool3(in_t, h, w, c):
+        o = net.tensor(h * w, c)
+        net.op(OP_AVGPOOL, [in_t, o, h, w, c, 3, 1, 1, 0])
+        return o
+
+    def inception_a(x, h, w, c, p):
+        pool_c = sd[p + ".branch_pool.conv.weight"].shape[0]
+        out_c = 64 + 64 + 96 + pool_c
+        o = net.tensor(h * w, out_c)
+        bconv(x, h, w, c, p + ".branch1x1", out_t=o, col_off=0)
+        b, _, _, bc = bconv(x, h, w, c, p + ".branch5x5_1")
+        bconv(b, h, w, bc, p + ".branch5x5_2", pad=(2, 2), out_t=o, col_off=64)
+        b, _, _, bc = bconv(x, h, w, c, p + ".branch3x3dbl_1")
+        b, _, _, bc = bconv(b, h, w, bc, p + ".branch3x3dbl_2", pad=(1, 1))
+        bconv(b, h, w, bc, p + ".branch3x3dbl_3", pad=(1, 1), out_t=o, col_off=128)
+        bconv(avgpool3(x, h, w, c), h, w, c, p + ".branch_pool", out_t=o, col_off=224)
+        return o, out_c
+
+    def inception_b(x, h, w, c, p):
+        ho = (h - 3) // 2 + 1
+        out_c = 384 + 96 + c
+        o = net.tensor(ho * ho, out_c)
+        bconv(x, h, w, c, p + ".branch3x3", stride=2, out_t=o, col_off=0)
+        b, _, _, bc = bconv(x, h, w, c, p + ".branch3x3dbl_1")
+        b, _, _, bc = bconv(b, h, w, bc, p + ".branch3x3dbl_2", pad=(1, 1))
+        bconv(b, h, w, bc, p + ".branch3x3dbl_3", stride=2, out_t=o, col_off=384)
+        net.op(OP_MAXPOOL, [x, o, h, w, c, 3, 2, 0, 480])
+        return o, out_c, ho
+
+    def inception_c(x, h, w, c, p):
+        o = net.tensor(h * w, 768)
+        bconv(x, h, w, c, p + ".branch1x1", out_t=o, col_off=0)
+        b, _, _, bc = bconv(x, h, w, c, p + ".branch7x7_1")
+        b, _, _, bc = bconv(b, h, w, bc, p + ".branch7x7_2", pad=(0, 3))
+        bconv(b, h, w, bc, p + ".branch7x7_3", pad=(3, 0), out_t=o, col_off=192)
+        b, _, _, bc = bconv(x, h, w, c, p + ".branch7x7dbl_1")
+        b, _, _, bc = bconv(b, h, w, bc, p + ".branch7x7dbl_2", pad=(3, 0))
+        b, _, _, bc = bconv(b, h, w, bc, p + ".branch7x7dbl_3", pad=(0, 3))
+        b, _, _, bc = bconv(b, h, w, bc, p + ".branch7x7dbl_4", pad=(3, 0))
+        bconv(b, h, w, bc, p + ".branch7x7dbl_5", pad=(0, 3), out_t=o, col_off=384)
+        bconv(avgpool3(x, h, w, c), h, w, c, p + ".branch_pool", out_t=o, col_off=576)
+        return o, 768
+
+    def inception_d(x, h, w, c, p):
+        ho = (h - 3) // 2 + 1
+        out_c = 320 + 192 + c
+        o = net.tensor(ho * ho, out_c)
+        b, _, _, bc = bconv(x, h, w, c, p + ".branch3x3_1")
+        bconv(b, h, w, bc, p + ".branch3x3_2", stride=2, out_t=o, col_off=0)
+        b, _, _, bc = bconv(x, h, w, c, p + ".branch7x7x3_1")
+        b, _, _, bc = bconv(b, h, w, bc, p + ".branch7x7x3_2", pad=(0, 3))
+        b, _, _, bc = bconv(b, h, w, bc, p + ".branch7x7x3_3", pad=(3, 0))
+        bconv(b, h, w, bc, p + ".branch7x7x3_4", stride=2, out_t=o, col_off=320)
+        net.op(OP_MAXPOOL, [x, o, h, w, c, 3, 2, 0, 512])
+        return o, out_c, ho
+
+    def inception_e(x, h, w, c, p, max_pool):
+        o = net.tensor(h * w, 2048)
+        bconv(x, h, w, c, p + ".branch1x1", out_t=o, col_off=0)
+        b, _, _, bc = bconv(x, h, w, c, p + ".branch3x3_1")
+        bconv(b, h, w, bc, p + ".branch3x3_2a", pad=(0, 1), out_t=o, col_off=320)
+        bconv(b, h, w, bc, p + ".branch3x3_2b", pad=(1, 0), out_t=o, col_off=704)
+        b, _, _, bc = bconv(x, h, w, c, p + ".branch3x3dbl_1")
+        b, _, _, bc = bconv(b, h, w, bc, p + ".branch3x3dbl_2", pad=(1, 1))
+        bconv(b, h, w, bc, p + ".branch3x3dbl_3a", pad=(0, 1), out_t=o, col_off=1088)
+        bconv(b, h, w, bc, p + ".branch3x3dbl_3b", pad=(1, 0), out_t=o, col_off=1472)
+        pooled = net.tensor(h * w, c)
+        net.op(OP_MAXPOOL if max_pool else OP_AVGPOOL, [x, pooled, h, w, c, 3, 1, 1, 0])   # E_2 uses MAX (:337)
+        bconv(pooled, h, w, c, p + ".branch_pool", out_t=o, col_off=1856)
+        return o, 2048
+
+    for name in ("Mixed_5b", "Mixed_5c", "Mixed_5d"):
+        t, c = inception_a(t, h, w, c, name)
+        if stop_after == name:
+            return finish(t, h * w, c)
+    t, c, h = inception_b(t, h, w, c, "Mixed_6a")
+    w = h
+    if stop_after == "Mixed_6a":
+        return finish(t, h * w, c)
+    for name in ("Mixed_6b", "Mixed_6c", "Mixed_6d", "Mixed_6e"):
+        t, c = inception_c(t, h, w, c, name)
+        if stop_after == name:
+            return finish(t, h * w, c)
+    t, c, h = inception_d(t, h, w, c, "Mixed_7a")
+    w = h
+    if stop_after == "Mixed_7a":
+        return finish(t, h * w, c)
+    t, c = inception_e(t, h, w, c, "Mixed_7b", False)
+    if stop_after == "Mixed_7b":
+        return finish(t, h * w, c)
+    t, c = inception_e(t, h, w, c, "Mixed_7c", True)
+    net.set_output(2048)
+    net.op(OP_GAP, [t, -1, h * w, c, 1])
+    return net

@@ -133,6 +133,16 @@ int dcr_net_add_op(dcr_net* net, int kind, const int* iargs, int n_iargs, const 
 /* images: DEVICE uint8 [n, IH, IW, 3]; out: DEVICE fp32 [n, dim]; n <= max_batch */
 int dcr_net_forward(dcr_net* net, const uint8_t* images, int n, float* out, void* stream);
 
+/* ---- FID statistics ---------------------------------------------------------------------------------------------- */
+/* Streaming mean / unbiased covariance (float64) of activation rows, accumulated on the device batch by batch.
+ * Replaces  pred_arr (float64 [N,2048] host buffer, metrics/fid.py:118,135) + np.mean / np.cov   (metrics/fid.py:219-220).
+ * act: DEVICE fp32 [n, d].  finalize writes HOST buffers mu[d], sigma[d*d] (row-major) and the sample count. */
+typedef struct dcr_fid dcr_fid;
+int dcr_fid_create(int d, dcr_fid** out);
+void dcr_fid_destroy(dcr_fid* st);
+int dcr_fid_accumulate(dcr_fid* st, const float* act, int n, void* stream);
+int dcr_fid_finalize(dcr_fid* st, double* mu, double* sigma, int64_t* n_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -44,7 +44,34 @@ def make_dino(seed):
     print("dino", seed, y.shape, float(y.abs().mean()))
 
 
+def make_fid_inception(seed):
+    """metrics/inception.InceptionV3([3]) exactly as metrics/fid.py:245-247 builds it, with the URL weight load
+    (inception.py:219) replaced by the seeded state_dict of oracle.models.make_inception_state_dict(seed)."""
+    from oracle.models import make_inception_state_dict, fid_preprocess
+    sys.path.insert(0, REF)
+    inc = _load("ref_inception", os.path.join(REF, "metrics", "inception.py"))
+    sd = make_inception_state_dict(seed)
+    full = dict(sd)
+
+    def fake_loader(url, progress=True):
+        import torchvision
+        m = torchvision.models.inception_v3(weights=None, aux_logits=False, init_weights=False, num_classes=1008)
+        base = m.state_dict()
+        base.update(full)
+        return base
+
+    inc.load_state_dict_from_url = fake_loader
+    model = inc.InceptionV3([3], resize_input=True, normalize_input=True)
+    model.eval()
+    img = torch.randint(0, 256, (2, 299, 299, 3), dtype=torch.uint8, generator=torch.Generator().manual_seed(8000 + seed))
+    with torch.no_grad():
+        y = model(fid_preprocess(img))[0].squeeze(-1).squeeze(-1)
+    np.savez_compressed(os.path.join(HERE, f"fid_inception_seed{seed}.npz"), seed=seed, out=y.numpy())
+    print("inception", seed, y.shape, float(y.abs().mean()))
+
+
 if __name__ == "__main__":
     torch.manual_seed(0)
     for s in (0, 1):
         make_dino(s)
+    make_fid_inception(0)

@@ -1,0 +1,52 @@
+"""Host-side logic that needs no GPU: dataset ordering, CLI surface."""
+import os
+
+import numpy as np
+import pytest
+
+from dcr_b200 import cli, data
+
+
+def test_natural_order_matches_natsort_semantics(tmp_path):
+    names = ["10.png", "2.png", "1.png", "img12.jpg", "img3.jpg", "a/5.png", "a/40.png", "b/1.JPEG", "skip.txt"]
+    for n in names:
+        p = tmp_path / "gen" / n
+        p.parent.mkdir(parents=True, exist_ok=True)
+        p.write_bytes(b"x")
+    got = [os.path.relpath(f, tmp_path / "gen") for f in data.list_images(str(tmp_path / "gen"))]
+    # only leaf folders contribute (diff_retrieval.py:75-77): the files next to sub-folders a/, b/ are skipped
+    assert got == ["a/5.png", "a/40.png", "b/1.JPEG"]
+    leaf = tmp_path / "leaf"
+    leaf.mkdir()
+    for n in ["10.png", "2.png", "1.png", "img12.jpg", "img3.jpg"]:
+        (leaf / n).write_bytes(b"x")
+    assert [os.path.basename(f) for f in data.list_images(str(leaf))] == ["1.png", "2.png", "10.png", "img3.jpg", "img12.jpg"]
+
+
+def test_load_image_matches_reference_transform(tmp_path):
+    import torch
+    from PIL import Image
+    from torchvision import transforms
+    arr = np.random.default_rng(0).integers(0, 256, (300, 420, 3), dtype=np.uint8)
+    f = tmp_path / "x.png"
+    Image.fromarray(arr).save(f)
+    u8 = data.load_image_u8(str(f))
+    assert u8.shape == (256, 256, 3)
+    ref = transforms.Compose([transforms.Resize(256), transforms.CenterCrop(224), transforms.ToTensor(),
+                              transforms.Normalize([0.5] * 3, [0.5] * 3)])(Image.open(f).convert("RGB"))
+    from oracle import models as om
+    assert torch.equal(om.preprocess(u8[None])[0], ref)      # centre 224 of our 256 crop == reference crop
+
+
+def test_cli_flag_surface_matches_reference():
+    p = cli.build_parser()
+    opts = {a for act in p._actions for a in act.option_strings}
+    for flag in ["--query_dir", "--val_dir", "--pt_style", "-a", "--arch", "-j", "--workers", "-b", "--batch-size",
+                 "--world-size", "--rank", "--dist-url", "--dist-backend", "--seed", "--gpu",
+                 "--multiprocessing-distributed", "--multiscale", "--pretrained", "--similarity_metric",
+                 "--num_loss_chunks", "--numpatches", "--isvit", "--layer", "--stype", "--keephead", "--keeppredictor",
+                 "-ssp", "--sim_save_path", "--einsum_chunks", "--dontsave", "--num_matches", "--imsize", "--noeval"]:
+        assert flag in opts, flag
+    d = p.parse_args(["--query_dir", "q", "--val_dir", "v"])
+    assert (d.pt_style, d.arch, d.similarity_metric, d.workers, d.batch_size, d.dist_backend, d.layer,
+            d.einsum_chunks, d.num_matches, d.imsize) == ("sscd", "resnet50", "dotproduct", 4, 128, "nccl", 1, 30, 4, 224)

@@ -77,11 +77,12 @@ def test_concentrated_descriptors():
     g = torch.nn.functional.normalize(common + 1.0 * torch.randn(30000, 512, generator=gen), dim=1)
     st = _check(q, g, 10)
     assert st["n_flagged"] <= 6, st
-    # extreme case (all cosines > 0.99): the score spread is below bf16 resolution, the certificate must notice
-    # and the exact path must still return the oracle's answer
-    q2 = torch.nn.functional.normalize(common + 0.05 * torch.randn(64, 512, generator=gen), dim=1)
-    g2 = torch.nn.functional.normalize(common + 0.05 * torch.randn(5000, 512, generator=gen), dim=1)
-    _check(q2, g2, 5)
+    # extreme case (all cosines > 0.99): with query AND gallery centring the tensor cores only see the small
+    # centred parts, so even this stays on the fast path
+    q2 = torch.nn.functional.normalize(common + 0.05 * torch.randn(600, 512, generator=gen), dim=1)
+    g2 = torch.nn.functional.normalize(common + 0.05 * torch.randn(30000, 512, generator=gen), dim=1)
+    st = _check(q2, g2, 10)
+    assert st["n_flagged"] <= 6, st
 
 
 def test_k_equals_gallery_size():
