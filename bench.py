@@ -111,8 +111,8 @@ def synthetic_sscd_weights(dev):
     """Seeded random-init SSCD ResNet-50 weights (no network access, no checkpoints), made data-consistent the way
     a freshly initialised PyTorch model becomes after its first training-mode batches: the BatchNorm running
     statistics are set from 512 synthetic images (torch ops, set-up only -- nothing of this runs in a timed region),
-    and the head bias is shifted so that the mean raw embedding is zero.  Without this a random trunk maps every
-    image to nearly the same direction; trained SSCD descriptors are spread over the sphere by construction."""
+    and the head Linear is PCA-whitened on 2048 synthetic images.  Without this a random trunk maps every image
+    to nearly the same direction; trained SSCD descriptors are spread over the sphere by construction."""
     import torchvision
     from dcr_b200 import nets
     from oracle import models as om
@@ -135,9 +135,19 @@ def synthetic_sscd_weights(dev):
         if "running_mean" in k or "running_var" in k:
             sd["backbone." + k] = v.detach().float().cpu()
     del m, x
+    # PCA-whiten the head on 2048 synthetic images: SSCD is trained (entropy regulariser) to spread its descriptors
+    # uniformly over the sphere; a random head on a random trunk concentrates them in a few directions instead.
     cal = nets.build_sscd_resnet50(sd, max_batch=128, precision="fast", l2_normalize=False)
-    sd["embeddings.1.bias"] = sd["embeddings.1.bias"] - cal(cal_imgs).mean(dim=0).cpu()
+    emb = torch.cat([cal(cal_imgs), cal(gen_images_cuda(1536, seed=998, device=dev))]).double().cpu()
     del cal
+    mean = emb.mean(dim=0)
+    cov = torch.cov((emb - mean).T)
+    lam, u = torch.linalg.eigh(cov)
+    lam = lam.clamp_min(lam.max() * 1e-6)
+    wh = (u / lam.sqrt()).T                                    # Lambda^-1/2 U^T
+    w, bias = sd["embeddings.1.weight"].double(), sd["embeddings.1.bias"].double()
+    sd["embeddings.1.weight"] = (wh @ w).float()
+    sd["embeddings.1.bias"] = (wh @ (bias - mean)).float()
     torch.cuda.empty_cache()
     return sd
 

@@ -38,12 +38,15 @@ constexpr int kWarmTiles = 4;     // tiles replayed at the start of every segmen
 constexpr int kThreads = 192;     // warp 0: TMA producer, warp 1: MMA issuer, warps 2..5: epilogue
 constexpr uint32_t kFull = 0xffffffffu;
 constexpr int kATileBytes = kBlockM * kBlockK * 2;  // 16 KB
+constexpr int kMaxSlotsPerQuery = 512;  // (chunk, unit) segments that may cover one q-tile
 
 struct SimParams {
   int nq, ng;
   int num_kb;          // d_pad / 64
   int n_qtiles;        // ceil(nq / (128*CG))
   int n_gtiles;        // ceil(ng / 256)
+  int gchunk;          // gallery tiles per L2-sized chunk (all units sweep chunk c before chunk c+1)
+  int n_chunks;
   int kp;              // candidates kept per (query, segment): 8, 16 or 32
   int cap;             // shared-memory list capacity per query row (kp + 16 .. 64)
   int stages;          // B pipeline depth
@@ -52,6 +55,7 @@ struct SimParams {
   float* cand_thr;     // [n_slots][rows_per_qtile]
   const int* bias_flag;    // device flag: 0 = ignore col_bias (query centring switched off for this data)
   const float* col_bias;   // [ng_pad] per-gallery-row score offset nu.(g-mu) added to every accumulator column; null = none
+  int debug_mode;          // timing experiments only: 1 = epilogue loads TMEM but does not scan, 2 = does not even load
   const float* thr_init;   // per query row: start thresholds (second-chance pass); null = seed by warm-up replay
 };
 
@@ -304,6 +308,13 @@ DCR_DEVICE void scan_chunk(const uint32_t (&r)[32], const float* sb, int gcol0, 
   }
 }
 
+// last gallery tile only: columns past the end of the gallery never win (-inf survives the offset add)
+DCR_DEVICE void mask_tail(uint32_t (&r)[32], int gcol0, int ng) {
+#pragma unroll
+  for (int c = 0; c < 32; ++c)
+    if (gcol0 + c >= ng) r[c] = 0xff800000u;
+}
+
 // Warm-up chunk: running maxima of 32 column slots (slot = column mod 32); no candidates are recorded.
 template <bool kMaskTail>
 DCR_DEVICE void warm_chunk(const uint32_t (&r)[32], const float* sb, int gcol0, int ng, float (&slot)[32]) {
@@ -316,6 +327,53 @@ DCR_DEVICE void warm_chunk(const uint32_t (&r)[32], const float* sb, int gcol0, 
   }
 }
 
+// Work decomposition shared by the three warp roles (and mirrored by rescore_select_kernel): for every gallery chunk
+// c (chunks are L2-sized so that the units, which all sweep chunk c at about the same time, share its tiles in L2)
+// the (q-tile, g-tile-in-chunk) grid is linearised q-major and cut into n_units equal contiguous ranges; a unit's range
+// is walked as segments = maximal runs inside one q-tile.  Thresholds carry over from chunk to chunk: `carried` says
+// that this unit finished a segment of the same q-tile before (its final per-row thresholds are valid lower bounds, so
+// no warm-up replay is needed).
+struct SegWalker {
+  int n_qtiles, n_gtiles, gchunk, n_chunks;
+  long long unit, n_units;
+  // current segment
+  int chunk, qi, g_begin, ntiles, slot;
+  bool carried;
+  // state
+  long long t, t_end;
+  int ncg, g_lo;
+  int tag[4];
+  __device__ SegWalker(int nq_t, int ng_t, int gc, int nc, long long u, long long nu)
+      : n_qtiles(nq_t), n_gtiles(ng_t), gchunk(gc), n_chunks(nc), unit(u), n_units(nu), chunk(-1), t(0), t_end(0) {
+    tag[0] = tag[1] = tag[2] = tag[3] = -1;
+  }
+  __device__ bool next() {
+    if (chunk >= 0) {   // close the previous segment
+      const int s4 = qi & 3;
+      if (s4 == 0) tag[0] = qi; else if (s4 == 1) tag[1] = qi; else if (s4 == 2) tag[2] = qi; else tag[3] = qi;
+    }
+    while (t >= t_end) {
+      ++chunk;
+      if (chunk >= n_chunks) return false;
+      g_lo = chunk * gchunk;
+      ncg = min(gchunk, n_gtiles - g_lo);
+      const long long T = static_cast<long long>(n_qtiles) * ncg;
+      t = unit * T / n_units;
+      t_end = (unit + 1) * T / n_units;
+    }
+    qi = static_cast<int>(t / ncg);
+    g_begin = g_lo + static_cast<int>(t % ncg);
+    const long long seg_end = min(t_end, static_cast<long long>(qi + 1) * ncg);
+    ntiles = static_cast<int>(seg_end - t);
+    slot = chunk * (static_cast<int>(n_units) + n_qtiles) + static_cast<int>(unit) + qi;
+    const int s4 = qi & 3;
+    const int tg = s4 == 0 ? tag[0] : (s4 == 1 ? tag[1] : (s4 == 2 ? tag[2] : tag[3]));
+    carried = (tg == qi);
+    t = seg_end;
+    return true;
+  }
+};
+
 // ------------------------------------------------------------------------------------------------------------
 // stage 2: the fused kernel.  kCG = 1: one CTA per work unit (UMMA 128x256x16).  kCG = 2: a CTA pair per work
 // unit (UMMA 256x256x16, cta_group::2): each CTA keeps its own 128 queries resident and loads half of every
@@ -325,10 +383,13 @@ DCR_DEVICE void warm_chunk(const uint32_t (&r)[32], const float* sb, int gcol0, 
 // into gridDim/kCG equal contiguous ranges.  A unit's range is walked as "segments" (maximal runs inside one
 // q-tile); per segment the query tile is loaded once (A stays resident) and the thresholds are seeded by
 // replaying the first kWarmTiles tiles.  Segment (unit u, q-tile i) owns candidate slot u + i.
-template <int kCG>
+// kBias: compiled with / without the per-column offset path of query centring.  Both variants are launched; the one
+// that does not match the device-side decision (p.bias_flag) exits at once -- no host synchronisation needed.
+template <int kCG, bool kBias>
 __global__ void __launch_bounds__(kThreads, 1)
     sim_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_g,
                     const SimParams p) {
+  if (((p.col_bias != nullptr) && (p.bias_flag != nullptr) && (*p.bias_flag != 0)) != kBias) return;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // carve-up (all tile bases 1024-byte aligned for the 128B swizzle)
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -346,6 +407,7 @@ __global__ void __launch_bounds__(kThreads, 1)
   uint64_t* t_empty = bars + 20;        // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 22);
   float* sbias = reinterpret_cast<float*>(bars + 32);   // [2][256] column offsets of the tile in each TMEM buffer
+  float* carry = sbias + 2 * kBlockN;                   // [4][128] thresholds carried to the next chunk, by q-tile & 3
 
   const uint32_t warp = threadIdx.x >> 5;
   const uint32_t lane = threadIdx.x & 31;
@@ -381,21 +443,16 @@ __global__ void __launch_bounds__(kThreads, 1)
   // this unit's tile range
   const long long n_units = gridDim.x / kCG;
   const long long unit = blockIdx.x / kCG;
-  const long long T = static_cast<long long>(p.n_qtiles) * p.n_gtiles;
-  const long long t_begin = unit * T / n_units;
-  const long long t_end = (unit + 1) * T / n_units;
   const int rows_per_qtile = kBlockM * kCG;
 
   if (warp == 0) {
     // ===================================== TMA producer =====================================
     if (lane == 0) {
       uint32_t it = 0, seg = 0;
-      for (long long t = t_begin; t < t_end;) {
-        const int qi = static_cast<int>(t / p.n_gtiles);
-        const int g_begin = static_cast<int>(t % p.n_gtiles);
-        const long long seg_end = min(t_end, static_cast<long long>(qi + 1) * p.n_gtiles);
-        const int ntiles = static_cast<int>(seg_end - t);
-        const int warm = p.thr_init ? 0 : min(kWarmTiles, ntiles);
+      SegWalker w(p.n_qtiles, p.n_gtiles, p.gchunk, p.n_chunks, unit, n_units);
+      while (w.next()) {
+        const int qi = w.qi, g_begin = w.g_begin, ntiles = w.ntiles;
+        const int warm = (p.thr_init || w.carried) ? 0 : min(kWarmTiles, ntiles);
         // resident query tile
         mbar_wait(a_empty, (seg & 1) ^ 1);
         if (leader) mbar_arrive_expect_tx(a_full, p.num_kb * kATileBytes * kCG);
@@ -414,7 +471,6 @@ __global__ void __launch_bounds__(kThreads, 1)
             tma_load_2d<kCG>(smem_b + s * kBTileBytes, &tmap_g, &b_full[s], kb * kBlockK, g_row, kEvictNormal);
           }
         }
-        t = seg_end;
         ++seg;
       }
     }
@@ -423,11 +479,10 @@ __global__ void __launch_bounds__(kThreads, 1)
     if (leader && lane == 0) {
       constexpr uint32_t idesc = umma_idesc_bf16(kBlockM * kCG, kBlockN);
       uint32_t it = 0, seg = 0, tc = 0;
-      for (long long t = t_begin; t < t_end;) {
-        const int qi = static_cast<int>(t / p.n_gtiles);
-        const long long seg_end = min(t_end, static_cast<long long>(qi + 1) * p.n_gtiles);
-        const int ntiles = static_cast<int>(seg_end - t);
-        const int warm = p.thr_init ? 0 : min(kWarmTiles, ntiles);
+      SegWalker w(p.n_qtiles, p.n_gtiles, p.gchunk, p.n_chunks, unit, n_units);
+      while (w.next()) {
+        const int ntiles = w.ntiles;
+        const int warm = (p.thr_init || w.carried) ? 0 : min(kWarmTiles, ntiles);
         mbar_wait(a_full, seg & 1);
         tc_fence_after();
         for (int j = 0; j < warm + ntiles; ++j, ++tc) {
@@ -451,7 +506,6 @@ __global__ void __launch_bounds__(kThreads, 1)
             }
           }
         }
-        t = seg_end;
         ++seg;
       }
     }
@@ -463,19 +517,19 @@ __global__ void __launch_bounds__(kThreads, 1)
     uint2* warp_list = cand + quad * 32;
     const uint32_t tmem_row = tmem_base + ((quad * 32u) << 16);
     const int kp = p.kp, cap = p.cap;
-    const float* colbias = (p.col_bias && p.bias_flag && *p.bias_flag) ? p.col_bias : nullptr;
-    uint32_t tc = 0;
-    for (long long t = t_begin; t < t_end;) {
-      const int qi = static_cast<int>(t / p.n_gtiles);
-      const int g_begin = static_cast<int>(t % p.n_gtiles);
-      const long long seg_end = min(t_end, static_cast<long long>(qi + 1) * p.n_gtiles);
-      const int ntiles = static_cast<int>(seg_end - t);
-      const int warm = p.thr_init ? 0 : min(kWarmTiles, ntiles);
+    const float* colbias = kBias ? p.col_bias : nullptr;
+    uint32_t tc = 0, dbg = 0;
+    SegWalker w(p.n_qtiles, p.n_gtiles, p.gchunk, p.n_chunks, unit, n_units);
+    while (w.next()) {
+      const int qi = w.qi, g_begin = w.g_begin, ntiles = w.ntiles;
+      const int warm = (p.thr_init || w.carried) ? 0 : min(kWarmTiles, ntiles);
       float thr = -INFINITY;
       if (p.thr_init) {
         const int qrow_g = qi * rows_per_qtile + static_cast<int>(cta_rank) * kBlockM + static_cast<int>(row);
         thr = qrow_g < p.nq ? p.thr_init[qrow_g] : INFINITY;   // padding rows collect nothing
       }
+      // a threshold this row reached on an earlier gallery chunk is a valid (and usually tight) start here
+      if (w.carried) thr = fmaxf(thr, carry[(qi & 3) * kBlockM + row]);
       int cnt = 0;
       float slot[32];
 #pragma unroll
@@ -493,7 +547,7 @@ __global__ void __launch_bounds__(kThreads, 1)
         const int gcol_tile = gi * kBlockN;
         const bool tail = gcol_tile + kBlockN > p.ng;
         const uint32_t buf = tc & 1;
-        const float* sb = colbias ? sbias + buf * kBlockN : nullptr;
+        const float* sb = kBias ? sbias + buf * kBlockN : nullptr;
         float nb0 = 0.f, nb1 = 0.f;
         const bool has_next = colbias && (j + 1 < warm + ntiles);
         if (has_next) {
@@ -505,17 +559,27 @@ __global__ void __launch_bounds__(kThreads, 1)
         tc_fence_after();
         const uint32_t taddr = tmem_row + buf * kBlockN;
         uint32_t ra[32], rb[32];
+        if (p.debug_mode == 2) {   // timing experiment: do not even read the accumulator (results are meaningless)
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            if constexpr (kCG == 2) mbar_arrive_cluster(&t_empty[buf], 0);
+            else mbar_arrive(&t_empty[buf]);
+          }
+          continue;
+        }
+        // TMEM read pipeline: chunk i+1 is in flight while chunk i is scanned
         tmem_ld_32x32(taddr, ra);
 #pragma unroll 1
         for (int ch = 0; ch < kBlockN / 32; ch += 2) {
           tmem_ld_wait_dep(ra);
           tmem_ld_32x32(taddr + (ch + 1) * 32, rb);
-          if (is_warm) {
-            if (tail) warm_chunk<true>(ra, sb ? sb + ch * 32 : nullptr, gcol_tile + ch * 32, p.ng, slot);
-            else warm_chunk<false>(ra, sb ? sb + ch * 32 : nullptr, gcol_tile + ch * 32, p.ng, slot);
-          } else {
-            if (tail) scan_chunk<true>(ra, sb ? sb + ch * 32 : nullptr, gcol_tile + ch * 32, p.ng, thr, cnt, my_list, warp_list, kp, cap, lane);
+          if (tail) mask_tail(ra, gcol_tile + ch * 32, p.ng);
+          if (p.debug_mode == 0) {
+            if (is_warm) warm_chunk<false>(ra, sb ? sb + ch * 32 : nullptr, gcol_tile + ch * 32, p.ng, slot);
             else scan_chunk<false>(ra, sb ? sb + ch * 32 : nullptr, gcol_tile + ch * 32, p.ng, thr, cnt, my_list, warp_list, kp, cap, lane);
+          } else {
+            dbg ^= ra[0] ^ ra[31];
           }
           tmem_ld_wait_dep(rb);
           if (ch + 2 < kBlockN / 32) {
@@ -529,12 +593,12 @@ __global__ void __launch_bounds__(kThreads, 1)
               else mbar_arrive(&t_empty[buf]);
             }
           }
-          if (is_warm) {
-            if (tail) warm_chunk<true>(rb, sb ? sb + (ch + 1) * 32 : nullptr, gcol_tile + (ch + 1) * 32, p.ng, slot);
-            else warm_chunk<false>(rb, sb ? sb + (ch + 1) * 32 : nullptr, gcol_tile + (ch + 1) * 32, p.ng, slot);
-          } else {
-            if (tail) scan_chunk<true>(rb, sb ? sb + (ch + 1) * 32 : nullptr, gcol_tile + (ch + 1) * 32, p.ng, thr, cnt, my_list, warp_list, kp, cap, lane);
+          if (tail) mask_tail(rb, gcol_tile + (ch + 1) * 32, p.ng);
+          if (p.debug_mode == 0) {
+            if (is_warm) warm_chunk<false>(rb, sb ? sb + (ch + 1) * 32 : nullptr, gcol_tile + (ch + 1) * 32, p.ng, slot);
             else scan_chunk<false>(rb, sb ? sb + (ch + 1) * 32 : nullptr, gcol_tile + (ch + 1) * 32, p.ng, thr, cnt, my_list, warp_list, kp, cap, lane);
+          } else {
+            dbg ^= rb[0] ^ rb[31];
           }
         }
         if (colbias) {
@@ -580,16 +644,15 @@ __global__ void __launch_bounds__(kThreads, 1)
         if (need) compact_warp(warp_list, need, kp, thr, cnt, lane);
       }
       __syncwarp();
-      const size_t slot_row0 =
-          (static_cast<size_t>(unit + qi) * rows_per_qtile + cta_rank * kBlockM + quad * 32);
+      carry[(qi & 3) * kBlockM + row] = thr;
+      const size_t slot_row0 = (static_cast<size_t>(w.slot) * rows_per_qtile + cta_rank * kBlockM + quad * 32);
       for (int L = 0; L < 32; ++L) {
         const int n = __shfl_sync(kFull, cnt, L);
         if (static_cast<int>(lane) < n) p.cand[(slot_row0 + L) * kKPMax + lane] = warp_list[L + lane * 128];
       }
       p.cand_cnt[slot_row0 + lane] = cnt;
-      p.cand_thr[slot_row0 + lane] = thr;
+      p.cand_thr[slot_row0 + lane] = (p.debug_mode && dbg == 0x12345678u) ? 0.f : thr;   // keeps `dbg` live in the timing modes
       __syncwarp();
-      t = seg_end;
     }
   }
 
@@ -678,8 +741,8 @@ DCR_DEVICE void block_argbest(double& bs, long long& bi, int& bp, BlockBest* sb,
 //      a threshold for the second-chance pass (thr_next).
 __global__ void __launch_bounds__(128)
     rescore_select_kernel(const float* __restrict__ q, const float* __restrict__ g, int nq, int ng, int d, int k,
-                          int n_qtiles, int n_gtiles, int n_units, int rows_per_qtile, int d_pad,
-                          const uint2* __restrict__ cand, const int* __restrict__ cand_cnt,
+                          int n_qtiles, int n_gtiles, int gchunk, int n_chunks, int n_units, int rows_per_qtile,
+                          int d_pad, const uint2* __restrict__ cand, const int* __restrict__ cand_cnt,
                           const float* __restrict__ cand_thr, const int* __restrict__ qmap,
                           const float* __restrict__ mu, const float* __restrict__ nu, const int* __restrict__ nu_flag,
                           const float* __restrict__ q_norm_hat,
@@ -694,7 +757,7 @@ __global__ void __launch_bounds__(128)
   int* ci = reinterpret_cast<int*>(sc + max_cand);                      // [max_cand] gallery rows of all candidates
   float* ap = reinterpret_cast<float*>(ci + max_cand);                  // [max_cand] approximate scores
   int* kc = reinterpret_cast<int*>(ap + max_cand);                      // [max_cand] gallery rows of the survivors
-  __shared__ int s_n, s_overflow, s_kept, s_off[160], s_cnt[160];
+  __shared__ int s_n, s_overflow, s_kept, s_nslots, s_off[kMaxSlotsPerQuery], s_cnt[kMaxSlotsPerQuery], s_slot[kMaxSlotsPerQuery];
   __shared__ float s_thr, s_eps, s_qx, s_gn;
   __shared__ double s_qmu;
   __shared__ BlockBest s_bb;
@@ -706,25 +769,34 @@ __global__ void __launch_bounds__(128)
   for (int c = threadIdx.x; c < d; c += blockDim.x) qs[c] = q[static_cast<size_t>(qrow) * d + c];
 
   const int qi = crow / rows_per_qtile, r = crow % rows_per_qtile;
-  const long long T = static_cast<long long>(n_qtiles) * n_gtiles;
-  const long long u_lo = owner_unit(static_cast<long long>(qi) * n_gtiles, T, n_units);
-  const long long u_hi = owner_unit(static_cast<long long>(qi + 1) * n_gtiles - 1, T, n_units);
-  const int nslots = static_cast<int>(u_hi - u_lo + 1);   // <= number of units <= 148
   if (threadIdx.x == 0) {
-    int n = 0, overflow = 0;
+    int n = 0, overflow = 0, ns = 0;
     float thr = -INFINITY;
-    for (int s = 0; s < nslots; ++s) {
-      const size_t sr = static_cast<size_t>(u_lo + s + qi) * rows_per_qtile + r;
-      int c = cand_cnt[sr];
-      thr = fmaxf(thr, cand_thr[sr]);
-      if (n + c > max_cand) {   // cannot happen with make_plan's bound; if it does, the exact path takes over
-        c = max_cand - n;
-        overflow = 1;
+    for (int c = 0; c < n_chunks; ++c) {      // mirror of SegWalker: which (chunk, unit) segments cover this q-tile
+      const int g_lo = c * gchunk;
+      const int ncg = min(gchunk, n_gtiles - g_lo);
+      const long long T = static_cast<long long>(n_qtiles) * ncg;
+      const long long u_lo = owner_unit(static_cast<long long>(qi) * ncg, T, n_units);
+      const long long u_hi = owner_unit(static_cast<long long>(qi + 1) * ncg - 1, T, n_units);
+      for (long long u = u_lo; u <= u_hi; ++u) {
+        const int slot = c * (n_units + n_qtiles) + static_cast<int>(u) + qi;
+        const size_t sr = static_cast<size_t>(slot) * rows_per_qtile + r;
+        int cc = cand_cnt[sr];
+        thr = fmaxf(thr, cand_thr[sr]);
+        if (n + cc > max_cand || ns >= kMaxSlotsPerQuery) {   // cannot happen with make_plan's bounds
+          cc = 0;
+          overflow = 1;
+        }
+        if (ns < kMaxSlotsPerQuery) {
+          s_off[ns] = n;
+          s_cnt[ns] = cc;
+          s_slot[ns] = slot;
+          ++ns;
+        }
+        n += cc;
       }
-      s_off[s] = n;
-      s_cnt[s] = c;
-      n += c;
     }
+    s_nslots = ns;
     s_n = n;
     s_thr = thr;
     s_overflow = overflow;
@@ -754,10 +826,11 @@ __global__ void __launch_bounds__(128)
     for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(kFull, acc, off);
     if (lane == 0) s_qmu = acc;
   }
+  const int nslots = s_nslots;
   for (int t = threadIdx.x; t < nslots * kKPMax; t += blockDim.x) {
     const int s = t / kKPMax, j = t % kKPMax;
     if (j < s_cnt[s]) {
-      const size_t sr = static_cast<size_t>(u_lo + s + qi) * rows_per_qtile + r;
+      const size_t sr = static_cast<size_t>(s_slot[s]) * rows_per_qtile + r;
       const uint2 e = cand[sr * kKPMax + j];
       ci[s_off[s] + j] = static_cast<int>(e.y);
       ap[s_off[s] + j] = __uint_as_float(e.x);
@@ -921,15 +994,18 @@ __global__ void __launch_bounds__(256)
 }
 
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+int env_int(const char* name, int dflt);
 
 // launch geometry of one fused pass over nq queries
 struct PassPlan {
   int nq, nq_pad, n_qtiles, n_units, n_slots, kp, cap, stages, max_cand;
+  int gchunk, n_chunks;   // gallery tiles per L2-sized chunk for this pass
   size_t smem_bytes;
 };
 
 struct SimPlan {
   int cg, d_pad, num_kb, ng_pad, n_gtiles, rows_per_qtile;
+  int gchunk, n_chunks;   // preferred gallery chunking (a pass may use fewer chunks)
   int kp0, kp1;           // candidates kept by the first pass / by the second-chance pass (0 = no second pass)
   PassPlan p0, p1;        // p1 is sized for the worst case (every query flagged)
   // workspace offsets
@@ -942,34 +1018,54 @@ int plan_pass(int nq, int kp, const SimPlan& sp, int num_sms, size_t max_smem, i
   pp->nq = nq;
   pp->n_qtiles = (nq + sp.rows_per_qtile - 1) / sp.rows_per_qtile;
   pp->nq_pad = pp->n_qtiles * sp.rows_per_qtile;
-  const long long T = static_cast<long long>(pp->n_qtiles) * sp.n_gtiles;
-  int units = num_sms / sp.cg;
-  if (T < units) units = static_cast<int>(T);
+  pp->gchunk = sp.gchunk;
+  pp->n_chunks = sp.n_chunks;
+  int units = 1;
+  long long span_total = 0;
+  for (;;) {
+    const long long T = static_cast<long long>(pp->n_qtiles) * pp->gchunk;   // tiles of one (full) gallery chunk
+    units = num_sms / sp.cg;
+    if (T < units) units = static_cast<int>(std::max<long long>(1, T));
+    // per chunk a q-tile is covered by at most ceil(tiles_in_chunk / (T_c / units)) + 1 units
+    span_total = 0;
+    for (int c = 0; c < pp->n_chunks; ++c) {
+      const int ncg = std::min(pp->gchunk, sp.n_gtiles - c * pp->gchunk);
+      const long long Tc = static_cast<long long>(pp->n_qtiles) * ncg;
+      const long long per_unit = std::max<long long>(1, Tc / units);
+      long long span = (ncg + per_unit - 1) / per_unit + 1;
+      if (span > units) span = units;
+      span_total += span;
+    }
+    // the re-score kernel keeps every candidate of a query in shared memory (20 B each): few queries spread over all
+    // units and many chunks would not fit -> use fewer chunks for such a pass
+    if (pp->n_chunks == 1 || (span_total <= kMaxSlotsPerQuery && span_total * kp * 20 <= 150 * 1024)) break;
+    pp->n_chunks = (pp->n_chunks + 1) / 2;
+    pp->gchunk = (sp.n_gtiles + pp->n_chunks - 1) / pp->n_chunks;
+    pp->n_chunks = (sp.n_gtiles + pp->gchunk - 1) / pp->gchunk;
+  }
   pp->n_units = units;
-  pp->n_slots = units + pp->n_qtiles;
+  pp->n_slots = pp->n_chunks * (units + pp->n_qtiles);
   pp->kp = kp;
   // shared memory: resident A + stages*B + cap KB of lists + barriers
   const size_t a_bytes = static_cast<size_t>(sp.num_kb) * kATileBytes;
   const size_t b_tile = static_cast<size_t>(kBlockN / sp.cg) * kBlockK * 2;
-  const size_t fixed = 1024 /*align slack*/ + 256 /*barriers*/ + 2048 /*column offsets*/;
+  const size_t fixed = 1024 /*align slack*/ + 256 /*barriers*/ + 2048 /*column offsets*/ + 2048 /*carried thresholds*/;
   // priorities: 3 B stages, then list capacity up to 64 (fewer compactions), then more stages (up to 8)
   int cap = kp + 16;
+  const int cap_max = std::max(cap, std::min(64, env_int("DCR_SIM_CAP", 64)));
   int stages = 2;
   DCR_REQUIRE(max_smem >= a_bytes + stages * b_tile + cap * 1024 + fixed,
               "sim_topk: not enough shared memory (%zu B) for d=%d k=%d cta_group=%d", max_smem, d, k, sp.cg);
   auto fits = [&](int st, int cp) { return max_smem >= a_bytes + st * b_tile + static_cast<size_t>(cp) * 1024 + fixed; };
   if (fits(3, cap)) stages = 3;
-  while (cap < 64 && fits(stages, cap + 1)) ++cap;
+  if (env_int("DCR_SIM_STAGES", 0) > 3 && fits(env_int("DCR_SIM_STAGES", 0), cap)) stages = env_int("DCR_SIM_STAGES", 0);
+  while (cap < cap_max && fits(stages, cap + 1)) ++cap;
   while (stages < 8 && fits(stages + 1, cap)) ++stages;
   pp->cap = cap;
   pp->stages = stages;
   pp->smem_bytes = fixed + a_bytes + stages * b_tile + static_cast<size_t>(cap) * 1024;
-  // a q-tile is covered by at most ceil(n_gtiles / (T/units)) + 1 units
-  const long long per_unit = std::max<long long>(1, T / units);
-  long long span = (sp.n_gtiles + per_unit - 1) / per_unit + 1;
-  if (span > units) span = units;
-  pp->max_cand = static_cast<int>(span) * kp;
-  DCR_REQUIRE(span <= 160, "sim_topk: more than 160 segments per query tile");
+  DCR_REQUIRE(span_total <= kMaxSlotsPerQuery, "sim_topk: %lld segments per query tile (max %d)", span_total, kMaxSlotsPerQuery);
+  pp->max_cand = static_cast<int>(span_total) * kp;
   return 0;
 }
 
@@ -991,6 +1087,15 @@ int make_plan(int nq, int ng, int d, int k, int cg, int num_sms, size_t max_smem
   pl->rows_per_qtile = kBlockM * cg;
   pl->n_gtiles = (ng + kBlockN - 1) / kBlockN;
   pl->ng_pad = pl->n_gtiles * kBlockN;
+  // gallery chunks of ~DCR_SIM_CHUNK_MB of bf16 rows: the units sweep one chunk at a time so that it stays L2 resident
+  const long long chunk_bytes = static_cast<long long>(env_int("DCR_SIM_CHUNK_MB", 40)) << 20;
+  int gchunk = static_cast<int>(std::max<long long>(16, chunk_bytes / (static_cast<long long>(kBlockN) * pl->d_pad * 2)));
+  int n_chunks = (pl->n_gtiles + gchunk - 1) / gchunk;
+  if (n_chunks > 64) n_chunks = 64;
+  gchunk = (pl->n_gtiles + n_chunks - 1) / n_chunks;   // equal chunks
+  n_chunks = (pl->n_gtiles + gchunk - 1) / gchunk;
+  pl->gchunk = gchunk;
+  pl->n_chunks = n_chunks;
   // first pass keeps few candidates per (query, segment) -- enough unless many gallery rows sit within the error
   // bound of the k-th score; such queries get a second chance with 32 candidates before the brute-force path
   int kp0 = (k <= 2) ? 4 : (k <= 5 ? 8 : (k <= 10 ? 16 : 32));
@@ -1059,12 +1164,15 @@ int launch_fused(const SimPlan& pl, const PassPlan& pp, const __nv_bfloat16* qb,
   p.num_kb = pl.num_kb;
   p.n_qtiles = pp.n_qtiles;
   p.n_gtiles = pl.n_gtiles;
+  p.gchunk = pp.gchunk;
+  p.n_chunks = pp.n_chunks;
   p.kp = pp.kp;
   p.cap = pp.cap;
   p.stages = pp.stages;
   p.cand = pb.cand;
   p.cand_cnt = pb.ccnt;
   p.cand_thr = pb.cthr;
+  p.debug_mode = env_int("DCR_SIM_DEBUG_EPILOGUE", 0);
   p.col_bias = col_bias;
   p.bias_flag = bias_flag;
   p.thr_init = thr_init;
@@ -1080,16 +1188,21 @@ int launch_fused(const SimPlan& pl, const PassPlan& pp, const __nv_bfloat16* qb,
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
+  auto launch = [&](auto kern) -> int {
+    DCR_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(pp.smem_bytes)));
+    DCR_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, tq, tg, p));
+    count_launch();
+    return 0;
+  };
+  // the variant without the offset path always runs unless the device flag says otherwise; the offset variant is only
+  // launched when query centring is possible at all (it returns immediately when the flag is 0)
   if (pl.cg == 2) {
-    DCR_CUDA_CHECK(cudaFuncSetAttribute(sim_topk_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        static_cast<int>(pp.smem_bytes)));
-    DCR_CUDA_CHECK(cudaLaunchKernelEx(&cfg, sim_topk_kernel<2>, tq, tg, p));
+    if (int rc = launch(sim_topk_kernel<2, false>)) return rc;
+    if (col_bias) return launch(sim_topk_kernel<2, true>);
   } else {
-    DCR_CUDA_CHECK(cudaFuncSetAttribute(sim_topk_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        static_cast<int>(pp.smem_bytes)));
-    DCR_CUDA_CHECK(cudaLaunchKernelEx(&cfg, sim_topk_kernel<1>, tq, tg, p));
+    if (int rc = launch(sim_topk_kernel<1, false>)) return rc;
+    if (col_bias) return launch(sim_topk_kernel<1, true>);
   }
-  count_launch();
   return 0;
 }
 
@@ -1190,7 +1303,8 @@ int sim_topk(const float* q, int nq, const float* g, int ng, int d, int k, long 
     DCR_CUDA_CHECK(cudaFuncSetAttribute(rescore_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         static_cast<int>(rs_smem)));
     rescore_select_kernel<<<pp.nq, 128, rs_smem, stream>>>(
-        q, g, nq, ng, d, k, pp.n_qtiles, pl.n_gtiles, pp.n_units, pl.rows_per_qtile, pl.d_pad, pb.cand, pb.ccnt,
+        q, g, nq, ng, d, k, pp.n_qtiles, pl.n_gtiles, pp.gchunk, pp.n_chunks, pp.n_units, pl.rows_per_qtile, pl.d_pad,
+        pb.cand, pb.ccnt,
         pb.cthr, qmap, centre ? mu : nullptr, centre ? nu : nullptr, qflag, qnh, qnr, qnx, gmax, g_index_base, g_index_stride, out_scores, out_idx,
         flagged, n_flagged, thr_next, pp.max_cand);
     count_launch();

@@ -70,6 +70,7 @@ def test_fid_pipeline_small():
     m1, s1 = dfid.statistics_of_images(net, real, batch_size=8)
     act = om.fid_inception_forward(sd, om.fid_preprocess(real)).numpy()
     rm, rs = ofid.activation_statistics(act)
-    assert np.abs(m1 - rm).max() < 5e-3 and np.abs(s1 - rs).max() < 5e-3   # activations reach ~25 (see parity test)
+    tol = 1e-3 * np.abs(act).max()      # parity mode is ~3e-4 relative on Inception (see test_inception_parity_mode)
+    assert np.abs(m1 - rm).max() < tol and np.abs(s1 - rs).max() < tol * np.abs(act).max()
     v = dfid.fid_from_images(net, real, gen, batch_size=8)
     assert np.isfinite(v) and v >= -1e-6
