@@ -34,7 +34,7 @@ namespace {
 
 constexpr int kBM = 128;
 constexpr int kBK = 64;
-constexpr int kThreads = 192;
+constexpr int kThreads = 320;   // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue
 constexpr int kAStage = kBM * kBK * 2;   // 16 KB
 
 struct GemmMaps {
@@ -63,6 +63,8 @@ struct GemmParams {
   int ld_out_f32;
   int act;                    // 0 none, 1 relu, 2 gelu (erf)
   int tma_epi;                // 1: stage the bf16 output tile in shared memory and write it with TMA stores
+  int n_out_bufs;             // 1 or 2 output staging tiles (2: the TMA store of tile i drains during tile i+1)
+  int n_res_bufs;             // 0 or 2 residual staging tiles (the residual of tile i+1 is prefetched during tile i)
 };
 
 DCR_DEVICE float apply_act(float y, int act) {
@@ -93,29 +95,43 @@ DCR_DEVICE void tma_store_2d(const void* tmap, const void* src_smem, int c0, int
 }
 DCR_DEVICE void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 DCR_DEVICE void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+DCR_DEVICE void tma_store_wait_read_1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 DCR_DEVICE void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
-template <int BN, bool kIm2col>
+// kEpi: 0 = direct epilogue (any number of planes, optional fp32 output, runtime activation; parity mode and final
+//           layers), 1/2/3 = TMA-store epilogue with compile-time activation none / ReLU / GELU (fast mode hot path).
+// Eight epilogue warps: warps w and w+4 share a TMEM lane quadrant and split the tile's columns, so every SM
+// sub-partition has two epilogue warps to switch between (the epilogue is latency bound, not issue bound).
+template <int BN, bool kIm2col, int kEpi>
 __global__ void __launch_bounds__(kThreads, 1)
     gemm_bf16_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  constexpr bool kTma = kEpi != 0;
   constexpr int kBStage = BN * kBK * 2;
   constexpr int kStageBytes = kAStage + kBStage;
   constexpr uint32_t kTmemCols = (2 * BN <= 128) ? 128 : (2 * BN <= 256 ? 256 : 512);
   constexpr int kStagingBytes = (BN / 64) * kBM * 128;   // BN/64 slabs of [128 rows x 64 bf16], 128B swizzle
+  constexpr int kChunksPerWarp = BN / 64;                // 32-column chunks each epilogue warp handles per tile
+  const int stages = p.stages;
   uint8_t* smem_ab = smem;
-  uint8_t* staging = smem_ab + p.stages * kStageBytes;                       // 1024-aligned (stages are)
-  float* sb = reinterpret_cast<float*>(staging + kStagingBytes);           // [2 bufs][2 (scale,bias)][BN]
+  uint8_t* out_stage = smem_ab + stages * kStageBytes;                      // n_out_bufs tiles, 1024-aligned
+  uint8_t* res_stage = out_stage + p.n_out_bufs * kStagingBytes;            // n_res_bufs tiles
+  float* sb = reinterpret_cast<float*>(res_stage + p.n_res_bufs * kStagingBytes);   // [2 bufs][2 (scale,bias)][BN]
   uint64_t* bars = reinterpret_cast<uint64_t*>(sb + 4 * BN);
   uint64_t* full = bars;          // [stages] (<= 12)
   uint64_t* empty = bars + 12;    // [stages]
   uint64_t* t_full = bars + 24;   // [2]
   uint64_t* t_empty = bars + 26;  // [2]
-  uint64_t* res_full = bars + 28;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 29);
+  uint64_t* res_full = bars + 28;   // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 30);
 
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // hoist everything the tile loops need out of the constant bank once
+  const int M = p.M, N = p.N, num_m_tiles = p.num_m_tiles;
+  const int num_tiles = p.num_m_tiles * p.num_n_tiles;
+  const int k_iters = p.n_terms * p.taps * p.cblocks;
+  const bool has_res = p.res != nullptr;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&maps.out);
@@ -126,15 +142,15 @@ __global__ void __launch_bounds__(kThreads, 1)
     }
   }
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < p.stages; ++s) {
+    for (int s = 0; s < stages; ++s) {
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], 1);
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&t_full[b], 1);
-      mbar_init(&t_empty[b], 4);
+      mbar_init(&t_empty[b], 8);
+      mbar_init(&res_full[b], 1);
     }
-    mbar_init(res_full, 1);
     fence_mbar_init();
   }
   if (warp == 2) {
@@ -146,15 +162,13 @@ __global__ void __launch_bounds__(kThreads, 1)
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int num_tiles = p.num_m_tiles * p.num_n_tiles;
-  const int k_iters = p.n_terms * p.taps * p.cblocks;
-
   if (warp == 0) {
     if (lane == 0) {
+      const int n_terms = p.n_terms, taps = p.taps, kw = p.kw, cblocks = p.cblocks;
       uint32_t it = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m0 = (tile % p.num_m_tiles) * kBM;
-        const int n0 = (tile / p.num_m_tiles) * BN;
+        const int m0 = (tile % num_m_tiles) * kBM;
+        const int n0 = (tile / num_m_tiles) * BN;
         int img = 0, h0 = 0, w0 = 0;
         if constexpr (kIm2col) {
           const int pq = p.P * p.Q;
@@ -164,13 +178,13 @@ __global__ void __launch_bounds__(kThreads, 1)
           h0 = p0 * p.stride - p.pad_h;
           w0 = q0 * p.stride - p.pad_w;
         }
-        for (int t = 0; t < p.n_terms; ++t) {
+        for (int t = 0; t < n_terms; ++t) {
           const CUtensorMap* ma = &maps.a[p.term_a[t]];
           const CUtensorMap* mw = &maps.w[p.term_w[t]];
-          for (int tap = 0; tap < p.taps; ++tap) {
-            const int r = tap / p.kw, sx = tap - r * p.kw;
-            for (int cb = 0; cb < p.cblocks; ++cb, ++it) {
-              const uint32_t s = it % p.stages, ph = (it / p.stages) & 1;
+          for (int tap = 0; tap < taps; ++tap) {
+            const int r = tap / kw, sx = tap - r * kw;
+            for (int cb = 0; cb < cblocks; ++cb, ++it) {
+              const uint32_t s = it % stages, ph = (it / stages) & 1;
               mbar_wait(&empty[s], ph ^ 1);
               mbar_arrive_expect_tx(&full[s], kStageBytes);
               uint8_t* sa = smem_ab + s * kStageBytes;
@@ -179,7 +193,7 @@ __global__ void __launch_bounds__(kThreads, 1)
                                       static_cast<uint16_t>(r));
               else
                 tma_load_2d<1>(sa, ma, &full[s], cb * kBK, m0, kEvictNormal);
-              tma_load_2d<1>(sa + kAStage, mw, &full[s], (tap * p.cblocks + cb) * kBK, n0, kEvictNormal);
+              tma_load_2d<1>(sa + kAStage, mw, &full[s], (tap * cblocks + cb) * kBK, n0, kEvictNormal);
             }
           }
         }
@@ -195,7 +209,7 @@ __global__ void __launch_bounds__(kThreads, 1)
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + buf * BN;
         for (int ki = 0; ki < k_iters; ++ki, ++it) {
-          const uint32_t s = it % p.stages, ph = (it / p.stages) & 1;
+          const uint32_t s = it % stages, ph = (it / stages) & 1;
           mbar_wait(&full[s], ph);
           tc_fence_after();
           const uint64_t da = umma_desc_sw128(smem_u32(smem_ab + s * kStageBytes));
@@ -208,115 +222,71 @@ __global__ void __launch_bounds__(kThreads, 1)
       }
     }
   } else {
-    const uint32_t quad = warp & 3;
+    const uint32_t ewarp = warp - 2;               // 0..7
+    const uint32_t quad = warp & 3;                // TMEM lane quadrant
+    const uint32_t half = ewarp >> 2;              // which half of the tile's columns
     const uint32_t row = quad * 32 + lane;
-    const uint32_t etid = (warp - 2) * 32 + lane;   // 0..127 among the epilogue threads
+    const uint32_t etid = ewarp * 32 + lane;       // 0..255 among the epilogue threads
     const uint32_t tmem_row = tmem_base + ((quad * 32u) << 16);
+    const int act = p.act;
     uint32_t tc = 0;
+    auto load_residual = [&](int tile_idx, uint32_t rbuf) {   // one thread: residual tile -> res_stage[rbuf]
+      const int rm0 = (tile_idx % num_m_tiles) * kBM;
+      const int rn0 = (tile_idx / num_m_tiles) * BN;
+      int slabs = 0;
+      for (int sl = 0; sl < BN / 64; ++sl)
+        if (rn0 + sl * 64 < N) ++slabs;
+      mbar_arrive_expect_tx(&res_full[rbuf], slabs * kBM * 128);
+      for (int sl = 0; sl < BN / 64; ++sl)
+        if (rn0 + sl * 64 < N)
+          tma_load_2d<1>(res_stage + rbuf * kStagingBytes + sl * kBM * 128, &maps.res, &res_full[rbuf], rn0 + sl * 64, rm0,
+                         kEvictFirst);
+    };
+    if (kTma && has_res && etid == 0 && static_cast<int>(blockIdx.x) < num_tiles) load_residual(blockIdx.x, 0);
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tc) {
-      const int m0 = (tile % p.num_m_tiles) * kBM;
-      const int n0 = (tile / p.num_m_tiles) * BN;
+      const int m0 = (tile % num_m_tiles) * kBM;
+      const int n0 = (tile / num_m_tiles) * BN;
       const uint32_t buf = tc & 1;
       float* s_scale = sb + buf * 2 * BN;
       float* s_bias = s_scale + BN;
-      if (p.tma_epi) {
-        // the staging tile is free once the previous tile's TMA stores have finished READING shared memory
-        if (etid == 0) tma_store_wait_read();
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        if (p.res && etid == 0) {
-          int slabs = 0;
-          for (int sl = 0; sl < BN / 64; ++sl)
-            if (n0 + sl * 64 < p.N) ++slabs;
-          mbar_arrive_expect_tx(res_full, slabs * kBM * 128);
-          for (int sl = 0; sl < BN / 64; ++sl)
-            if (n0 + sl * 64 < p.N)
-              tma_load_2d<1>(staging + sl * kBM * 128, &maps.res, res_full, n0 + sl * 64, m0, kEvictFirst);
+      uint8_t* ostage = out_stage + ((p.n_out_bufs == 2) ? (tc & 1) : 0) * kStagingBytes;
+      const uint8_t* rstage = res_stage + (tc & 1) * kStagingBytes;
+      if constexpr (kTma) {
+        if (etid == 0) {
+          // this tile's output staging buffer is free once the store that last used it has finished READING it:
+          // with two buffers that is the store of tile tc-2 (at most the newest group may still be pending)
+          if (p.n_out_bufs == 2) tma_store_wait_read_1(); else tma_store_wait_read();
+          // prefetch the NEXT tile's residual; its buffer was last read in tile tc-1 (all warps passed that barrier)
+          if (has_res && tile + static_cast<int>(gridDim.x) < num_tiles) load_residual(tile + gridDim.x, (tc & 1) ^ 1);
         }
       }
-      // stage the per-channel affine of this tile (safe: buffer `buf` was last read two tiles ago, and all four
-      // epilogue warps passed the named barrier of the previous tile since then)
-      for (int c = etid; c < BN; c += 128) {
+      // stage the per-channel affine of this tile (buffer `buf` was last read two tiles ago; every epilogue warp has
+      // passed the barrier of the previous tile since then)
+      for (int c = etid; c < BN; c += 256) {
         const int n = n0 + c;
-        s_scale[c] = (p.scale && n < p.N) ? p.scale[n] : 1.f;
-        s_bias[c] = (p.bias && n < p.N) ? p.bias[n] : 0.f;
+        s_scale[c] = (p.scale && n < N) ? p.scale[n] : 1.f;
+        s_bias[c] = (p.bias && n < N) ? p.bias[n] : 0.f;
       }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      asm volatile("bar.sync 1, 256;" ::: "memory");
       mbar_wait(&t_full[buf], (tc >> 1) & 1);
       tc_fence_after();
-      if (p.tma_epi && p.res) mbar_wait(res_full, tc & 1);
+      if (kTma && has_res) mbar_wait(&res_full[tc & 1], (tc >> 1) & 1);
       const int m = m0 + static_cast<int>(row);
-      const bool row_ok = m < p.M;
+      const bool row_ok = m < M;
       const uint32_t taddr = tmem_row + buf * BN;
-      if (p.tma_epi) {
 #pragma unroll 1
-        for (int ch = 0; ch < BN / 32; ++ch) {
-          uint32_t r[32];
-          tmem_ld_32x32(taddr + ch * 32, r);
-          tmem_ld_wait_dep32(r);
-          if (ch == BN / 32 - 1) {
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&t_empty[buf]);
-          }
-          if (n0 + ch * 32 >= p.N) continue;
-          float y[32];
-#pragma unroll
-          for (int c = 0; c < 32; c += 4) {
-            const float4 sc = *reinterpret_cast<const float4*>(s_scale + ch * 32 + c);
-            const float4 bi = *reinterpret_cast<const float4*>(s_bias + ch * 32 + c);
-            y[c + 0] = fmaf(__uint_as_float(r[c + 0]), sc.x, bi.x);
-            y[c + 1] = fmaf(__uint_as_float(r[c + 1]), sc.y, bi.y);
-            y[c + 2] = fmaf(__uint_as_float(r[c + 2]), sc.z, bi.z);
-            y[c + 3] = fmaf(__uint_as_float(r[c + 3]), sc.w, bi.w);
-          }
-          // this thread's 32 columns live in slab ch/2 at 16-byte chunks (ch&1)*4 .. +3 of row `row` (128B swizzle)
-          uint8_t* srow = staging + (ch >> 1) * kBM * 128 + row * 128;
-          const uint32_t sw = row & 7;
-          if (p.res) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const uint4 rv = *reinterpret_cast<const uint4*>(srow + ((((ch & 1) * 4 + j) ^ sw) << 4));
-              const uint32_t w[4] = {rv.x, rv.y, rv.z, rv.w};
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                y[j * 8 + 2 * e] += __uint_as_float(w[e] << 16);
-                y[j * 8 + 2 * e + 1] += __uint_as_float(w[e] & 0xffff0000u);
-              }
-            }
-          }
-#pragma unroll
-          for (int c = 0; c < 32; ++c) y[c] = apply_act(y[c], p.act);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            uint4 v;
-            v.x = pack_bf16(y[j * 8 + 0], y[j * 8 + 1]);
-            v.y = pack_bf16(y[j * 8 + 2], y[j * 8 + 3]);
-            v.z = pack_bf16(y[j * 8 + 4], y[j * 8 + 5]);
-            v.w = pack_bf16(y[j * 8 + 6], y[j * 8 + 7]);
-            *reinterpret_cast<uint4*>(srow + ((((ch & 1) * 4 + j) ^ sw) << 4)) = v;
-          }
-        }
-        fence_proxy_async();   // generic-proxy writes -> visible to the TMA (async proxy)
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        if (etid == 0) {
-          for (int sl = 0; sl < BN / 64; ++sl)
-            if (n0 + sl * 64 < p.N) tma_store_2d(&maps.out, staging + sl * kBM * 128, p.out_col_off + n0 + sl * 64, m0);
-          tma_store_commit();
-        }
-        continue;
-      }
-#pragma unroll 1
-      for (int ch = 0; ch < BN / 32; ++ch) {
+      for (int ci = 0; ci < kChunksPerWarp; ++ci) {
+        const int ch = half * kChunksPerWarp + ci;
         uint32_t r[32];
         tmem_ld_32x32(taddr + ch * 32, r);
-        tmem_ld_wait_dep32(r);
-        if (ch == BN / 32 - 1) {
+        tmem_ld_wait_regs(r);
+        if (ci == kChunksPerWarp - 1) {
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&t_empty[buf]);
         }
         const int nc = n0 + ch * 32;
-        if (nc >= p.N || !row_ok) continue;
+        if (nc >= N) continue;
         float y[32];
 #pragma unroll
         for (int c = 0; c < 32; c += 4) {
@@ -327,73 +297,120 @@ __global__ void __launch_bounds__(kThreads, 1)
           y[c + 2] = fmaf(__uint_as_float(r[c + 2]), sc.z, bi.z);
           y[c + 3] = fmaf(__uint_as_float(r[c + 3]), sc.w, bi.w);
         }
-        const int nvalid = min(32, p.N - nc);   // multiple of 8 (N % 8 == 0 enforced on the host)
-        if (p.res) {
-          for (int pl = 0; pl < p.res_planes; ++pl) {
-            const __nv_bfloat16* rp = p.res + pl * p.res_plane_stride + static_cast<size_t>(m) * p.ld_res + nc;
+        if constexpr (kTma) {
+          // this thread's 32 columns live in slab ch/2 at 16-byte chunks (ch&1)*4 .. +3 of row `row` (128B swizzle)
+          uint8_t* srow = ostage + (ch >> 1) * kBM * 128 + row * 128;
+          const uint8_t* rrow = rstage + (ch >> 1) * kBM * 128 + row * 128;
+          const uint32_t sw = row & 7;
+          if (has_res) {
 #pragma unroll
-            for (int c = 0; c < 32; c += 8) {
-              if (c < nvalid) {
-                const uint4 rv = *reinterpret_cast<const uint4*>(rp + c);
-                const uint32_t w[4] = {rv.x, rv.y, rv.z, rv.w};
+            for (int j = 0; j < 4; ++j) {
+              const uint4 rv = *reinterpret_cast<const uint4*>(rrow + ((((ch & 1) * 4 + j) ^ sw) << 4));
+              const uint32_t w[4] = {rv.x, rv.y, rv.z, rv.w};
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                  y[c + 2 * j] += __uint_as_float(w[j] << 16);
-                  y[c + 2 * j + 1] += __uint_as_float(w[j] & 0xffff0000u);
+              for (int e = 0; e < 4; ++e) {
+                y[j * 8 + 2 * e] += __uint_as_float(w[e] << 16);
+                y[j * 8 + 2 * e + 1] += __uint_as_float(w[e] & 0xffff0000u);
+              }
+            }
+          }
+#pragma unroll
+          for (int c = 0; c < 32; ++c) y[c] = apply_act(y[c], kEpi - 1);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            uint4 v;
+            v.x = pack_bf16(y[j * 8 + 0], y[j * 8 + 1]);
+            v.y = pack_bf16(y[j * 8 + 2], y[j * 8 + 3]);
+            v.z = pack_bf16(y[j * 8 + 4], y[j * 8 + 5]);
+            v.w = pack_bf16(y[j * 8 + 6], y[j * 8 + 7]);
+            *reinterpret_cast<uint4*>(srow + ((((ch & 1) * 4 + j) ^ sw) << 4)) = v;
+          }
+        } else {
+          if (!row_ok) continue;
+          const int nvalid = min(32, N - nc);   // multiple of 8 (N % 8 == 0 enforced on the host)
+          if (has_res) {
+            for (int pl = 0; pl < p.res_planes; ++pl) {
+              const __nv_bfloat16* rp = p.res + pl * p.res_plane_stride + static_cast<size_t>(m) * p.ld_res + nc;
+#pragma unroll
+              for (int c = 0; c < 32; c += 8) {
+                if (c < nvalid) {
+                  const uint4 rv = *reinterpret_cast<const uint4*>(rp + c);
+                  const uint32_t w[4] = {rv.x, rv.y, rv.z, rv.w};
+#pragma unroll
+                  for (int j = 0; j < 4; ++j) {
+                    y[c + 2 * j] += __uint_as_float(w[j] << 16);
+                    y[c + 2 * j + 1] += __uint_as_float(w[j] & 0xffff0000u);
+                  }
                 }
               }
             }
           }
-        }
 #pragma unroll
-        for (int c = 0; c < 32; ++c) y[c] = apply_act(y[c], p.act);
-        if (p.out_f32) {
-          float* op = p.out_f32 + static_cast<size_t>(m) * p.ld_out_f32 + nc;
+          for (int c = 0; c < 32; ++c) y[c] = apply_act(y[c], act);
+          if (p.out_f32) {
+            float* op = p.out_f32 + static_cast<size_t>(m) * p.ld_out_f32 + nc;
 #pragma unroll
-          for (int c = 0; c < 32; c += 4)
-            if (c < nvalid) *reinterpret_cast<float4*>(op + c) = make_float4(y[c], y[c + 1], y[c + 2], y[c + 3]);
-        }
-        if (p.out) {
-          for (int pl = 0; pl < p.out_planes; ++pl) {
-            __nv_bfloat16* op = p.out + pl * p.out_plane_stride + static_cast<size_t>(m) * p.ld_out + p.out_col_off + nc;
+            for (int c = 0; c < 32; c += 4)
+              if (c < nvalid) *reinterpret_cast<float4*>(op + c) = make_float4(y[c], y[c + 1], y[c + 2], y[c + 3]);
+          }
+          if (p.out) {
+            for (int pl = 0; pl < p.out_planes; ++pl) {
+              __nv_bfloat16* op = p.out + pl * p.out_plane_stride + static_cast<size_t>(m) * p.ld_out + p.out_col_off + nc;
 #pragma unroll
-            for (int c = 0; c < 32; c += 8) {
-              if (c < nvalid) {
-                uint4 v;
-                v.x = pack_bf16(y[c + 0], y[c + 1]);
-                v.y = pack_bf16(y[c + 2], y[c + 3]);
-                v.z = pack_bf16(y[c + 4], y[c + 5]);
-                v.w = pack_bf16(y[c + 6], y[c + 7]);
-                *reinterpret_cast<uint4*>(op + c) = v;
+              for (int c = 0; c < 32; c += 8) {
+                if (c < nvalid) {
+                  uint4 v;
+                  v.x = pack_bf16(y[c + 0], y[c + 1]);
+                  v.y = pack_bf16(y[c + 2], y[c + 3]);
+                  v.z = pack_bf16(y[c + 4], y[c + 5]);
+                  v.w = pack_bf16(y[c + 6], y[c + 7]);
+                  *reinterpret_cast<uint4*>(op + c) = v;
+                }
+              }
+              if (pl + 1 < p.out_planes) {
+                // next plane holds the rounding residual of this one
+#pragma unroll
+                for (int c = 0; c < 32; ++c) y[c] -= __bfloat162float(__float2bfloat16_rn(y[c]));
               }
             }
-            if (pl + 1 < p.out_planes) {
-              // next plane holds the rounding residual of this one
-#pragma unroll
-              for (int c = 0; c < 32; ++c) y[c] -= __bfloat162float(__float2bfloat16_rn(y[c]));
-            }
           }
+        }
+      }
+      if constexpr (kTma) {
+        fence_proxy_async();   // generic-proxy writes -> visible to the TMA (async proxy)
+        asm volatile("bar.sync 2, 256;" ::: "memory");
+        if (etid == 0) {
+          for (int sl = 0; sl < BN / 64; ++sl)
+            if (n0 + sl * 64 < N) tma_store_2d(&maps.out, ostage + sl * kBM * 128, p.out_col_off + n0 + sl * 64, m0);
+          tma_store_commit();
         }
       }
     }
   }
 
-  if (p.tma_epi && warp == 2 && lane == 0) tma_store_wait_all();   // etid 0 issued the stores
+  if (kTma && warp == 2 && lane == 0) tma_store_wait_all();   // etid 0 issued the stores
   tc_fence_before();
   __syncthreads();
   if (warp == 2) tmem_dealloc<1>(tmem_base, kTmemCols);
 }
 
-template <int BN, bool kIm2col>
+template <int BN, bool kIm2col, int kEpi>
 int launch(const GemmMaps& maps, GemmParams& p, int num_sms, size_t max_smem, cudaStream_t stream) {
   constexpr int kStageBytes = kAStage + BN * kBK * 2;
-  const size_t fixed = 1024 + 4 * BN * 4 + 256 + static_cast<size_t>(BN / 64) * kBM * 128;
+  constexpr size_t kStagingBytes = static_cast<size_t>(BN / 64) * kBM * 128;
+  // staging tiles: residual layers get 2 residual + 2 output tiles (prefetch / drain a full tile ahead) when they still
+  // leave >= 3 pipeline stages, otherwise one output tile (plus two residual tiles if needed)
+  p.n_res_bufs = (p.tma_epi && p.res) ? 2 : 0;
+  p.n_out_bufs = p.tma_epi ? 2 : 0;
+  auto fixed_for = [&](int nout, int nres) { return 1024 + 4 * BN * 4 + 256 + static_cast<size_t>(nout + nres) * kStagingBytes; };
+  if (p.tma_epi && (max_smem - fixed_for(p.n_out_bufs, p.n_res_bufs)) / kStageBytes < 3) p.n_out_bufs = 1;
+  const size_t fixed = fixed_for(p.n_out_bufs, p.n_res_bufs);
+  DCR_REQUIRE(max_smem > fixed + 2 * kStageBytes, "gemm: not enough shared memory");
   int stages = static_cast<int>((max_smem - fixed) / kStageBytes);
   stages = std::min(stages, 8);
-  DCR_REQUIRE(stages >= 2, "gemm: not enough shared memory");
   p.stages = stages;
   const size_t smem = fixed + static_cast<size_t>(stages) * kStageBytes;
-  auto kern = gemm_bf16_kernel<BN, kIm2col>;
+  auto kern = gemm_bf16_kernel<BN, kIm2col, kEpi>;
   static bool attr_set = false;   // per template instantiation
   if (!attr_set) {
     DCR_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(max_smem)));
@@ -433,6 +450,10 @@ int conv_gemm(const ConvGemmDesc& d, cudaStream_t stream) {
   }
   DCR_REQUIRE(a_planes <= 3 && w_planes <= 3, "conv_gemm: at most 3 planes");
   int BN = d.N <= 64 ? 64 : (d.N <= 128 ? 128 : 256);
+  // memory-bound shapes (residual epilogue, or little K per output) favour 128-wide tiles: their staging tiles can be
+  // double buffered; compute-bound shapes keep 256 (fewer re-reads of A)
+  const bool single_plane = d.out && d.out_planes <= 1 && !d.out_f32 && (!d.res || d.res_planes <= 1);
+  if (BN == 256 && single_plane && (d.res != nullptr || static_cast<long long>(d.kh) * d.kw * d.C <= 256)) BN = 128;
   if (d.force_bn) BN = d.force_bn;
   for (int pl = 0; pl < 3; ++pl) {
     const int pa = std::min(pl, a_planes - 1), pw = std::min(pl, w_planes - 1);
@@ -501,15 +522,19 @@ int conv_gemm(const ConvGemmDesc& d, cudaStream_t stream) {
   DCR_REQUIRE(p.res == nullptr || p.ld_res % 8 == 0, "conv_gemm: residual leading dim must be a multiple of 8");
   DCR_REQUIRE(p.out_f32 == nullptr || p.ld_out_f32 % 4 == 0, "conv_gemm: fp32 output leading dim must be a multiple of 4");
 
+#define DCR_LAUNCH_E(BNv, E)                                                                      \
+  (im2col ? launch<BNv, true, E>(maps, p, di->num_sms, di->max_smem_optin, stream)              \
+          : launch<BNv, false, E>(maps, p, di->num_sms, di->max_smem_optin, stream))
 #define DCR_LAUNCH(BNv)                                                                          \
-  (im2col ? launch<BNv, true>(maps, p, di->num_sms, di->max_smem_optin, stream)                  \
-          : launch<BNv, false>(maps, p, di->num_sms, di->max_smem_optin, stream))
+  (epi == 0 ? DCR_LAUNCH_E(BNv, 0) : (epi == 1 ? DCR_LAUNCH_E(BNv, 1) : (epi == 2 ? DCR_LAUNCH_E(BNv, 2) : DCR_LAUNCH_E(BNv, 3))))
+  const int epi = p.tma_epi ? 1 + p.act : 0;   // compile-time activation on the TMA-store path
   switch (BN) {
     case 64: return DCR_LAUNCH(64);
     case 128: return DCR_LAUNCH(128);
     case 256: return DCR_LAUNCH(256);
     default: return set_error(-1, "conv_gemm: unsupported BN %d", BN);
   }
+#undef DCR_LAUNCH_E
 #undef DCR_LAUNCH
 }
 

@@ -43,6 +43,7 @@ class DcrNet:
         self.out_dim = 0
         self.in_shape = None          # (IH, IW) expected uint8 input
         self.flops_per_image = 0.0
+        self.meta = []                # one entry per op, in launch order (tools/layer_profile.py)
         h = C.c_void_p()
         with torch.cuda.device(self.device):
             _lib.check(self.lib.dcr_net_create(self.max_batch, self.planes, C.byref(h)), "dcr_net_create")
@@ -83,6 +84,7 @@ class DcrNet:
         ia = (C.c_int * len(iargs))(*[int(v) for v in iargs])
         fa = (C.c_float * max(1, len(fargs)))(*[float(v) for v in fargs])
         r = self.lib.dcr_net_add_op(self.handle, kind, ia, len(iargs), fa, len(fargs))
+        self.meta.append((kind, [int(v) for v in iargs]))
         if r < 0:
             raise _lib.DcrError(f"dcr_net_add_op(kind={kind}): {_lib.last_error()}")
         return r
