@@ -107,7 +107,7 @@ __global__ void __launch_bounds__(256) attention_fp32_kernel(const AttnParams p)
 
 // ---------------------------------------------------------------------------------------------------------------
 // tcgen05 attention
-constexpr int kAttnThreads = 160;   // warps 0-3: softmax / epilogue (TMEM lane quadrants 0-3), warp 4: TMA + MMA issue
+constexpr int kAttnThreads = 288;   // warps 0-3 / 4-7: softmax + epilogue of query tile 0 / 1, warp 8: TMA + MMA issue
 
 DCR_DEVICE uint64_t umma_desc_sw128_mn(uint32_t smem_addr) {
   // MN-major operand, 128B swizzle: 64 contiguous elements along MN per row, rows = K, 8-row groups 1024 B apart
@@ -133,8 +133,8 @@ __global__ void __launch_bounds__(kAttnThreads, 1)
   uint8_t* s_q = smem;                 // 2 x [128 x 64] bf16
   uint8_t* s_k = s_q + 2 * 16384;      // [256 x 64]
   uint8_t* s_v = s_k + 32768;          // [256 x 64]
-  uint8_t* s_p = s_v + 32768;          // 4 k-blocks x [128 x 64]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_p + 65536);
+  uint8_t* s_p = s_v + 32768;          // per query tile: 4 k-blocks x [128 x 64]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_p + 2 * 65536);
   uint64_t* bar_load = bars;           // TMA landed
   uint64_t* s_full = bars + 1;         // [2] S tile ready in TMEM
   uint64_t* p_ready = bars + 3;        // [2] P written + S consumed (128 arrivals)
@@ -146,7 +146,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1)
   const int row0 = b * p.T;
   const int n_mtiles = (p.T + 127) / 128;
 
-  if (warp == 4 && lane == 0) {
+  if (warp == 8 && lane == 0) {
     tma_prefetch_desc(&tmap_qkv);
     mbar_init(bar_load, 1);
     for (int i = 0; i < 2; ++i) {
@@ -165,7 +165,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1)
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 4) {
+  if (warp == 8) {
     if (lane == 0) {
       const int cq = h * 64, ck = p.heads * 64 + h * 64, cv = 2 * p.heads * 64 + h * 64;
       mbar_arrive_expect_tx(bar_load, 6 * 16384);
@@ -191,7 +191,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1)
         tc_fence_after();
 #pragma unroll 1
         for (int kb = 0; kb < 4; ++kb) {
-          const uint64_t da = umma_desc_sw128(smem_u32(s_p + kb * 16384));
+          const uint64_t da = umma_desc_sw128(smem_u32(s_p + mt * 65536 + kb * 16384));
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
             // A: +32 B per 16 keys inside the 64-key block; B (V, MN-major): +16 rows * 128 B per 16 keys
@@ -203,10 +203,12 @@ __global__ void __launch_bounds__(kAttnThreads, 1)
       }
     }
   } else {
-    const uint32_t row = warp * 32 + lane;
-    const uint32_t tmem_row = tmem_base + ((warp * 32u) << 16);
+    const int mt = static_cast<int>(warp >> 2);          // the query tile this warp group owns
+    const uint32_t quad = warp & 3;
+    const uint32_t row = quad * 32 + lane;
+    const uint32_t tmem_row = tmem_base + ((quad * 32u) << 16);
     const uint32_t sw = row & 7;
-    for (int mt = 0; mt < n_mtiles; ++mt) {
+    if (mt < n_mtiles) {
       mbar_wait(&s_full[mt], 0);
       tc_fence_after();
       const uint32_t taddr = tmem_row + mt * 256;
@@ -223,9 +225,6 @@ __global__ void __launch_bounds__(kAttnThreads, 1)
           if (ch * 32 + c < p.T) mx = fmaxf(mx, __uint_as_float(r[c]));
       }
       const float mxs = mx * p.scale_log2e;
-      if (mt == 1) {            // P is single buffered: tile 0's P.V must have finished reading it
-        mbar_wait(&o_full[0], 0);
-      }
       // pass 2: exp, row sum, P -> shared memory (bf16, K-major, 128B swizzle)
       float sum = 0.f;
 #pragma unroll 1
@@ -247,7 +246,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1)
 #pragma unroll
           for (int c = 0; c < 32; ++c) pv[c] = 0.f;
         }
-        uint8_t* prow = s_p + (ch >> 1) * 16384 + row * 128;
+        uint8_t* prow = s_p + mt * 65536 + (ch >> 1) * 16384 + row * 128;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           uint4 v;
@@ -314,7 +313,7 @@ int attention(const __nv_bfloat16* qkv, long long qkv_plane_stride, __nv_bfloat1
     AttnTcParams tp;
     tp.out = out; tp.B = B; tp.T = T; tp.heads = heads;
     tp.scale_log2e = scale * 1.4426950408889634f;
-    const size_t smem = 1024 + 2 * 16384 + 32768 + 32768 + 65536 + 256;
+    const size_t smem = 1024 + 2 * 16384 + 32768 + 32768 + 2 * 65536 + 256;
     DCR_CUDA_CHECK(cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         static_cast<int>(smem)));
     attention_tc_kernel<<<B * heads, kAttnThreads, smem, stream>>>(tm, tp);

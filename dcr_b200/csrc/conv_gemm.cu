@@ -433,7 +433,8 @@ int conv_gemm(const ConvGemmDesc& d, cudaStream_t stream) {
   DCR_REQUIRE(d.n_terms >= 1 && d.n_terms <= kMaxGemmTerms, "conv_gemm: bad n_terms %d", d.n_terms);
   DCR_REQUIRE(d.C % 8 == 0 && d.N % 8 == 0, "conv_gemm: C (%d) and N (%d) must be multiples of 8", d.C, d.N);
   DCR_REQUIRE(d.kh >= 1 && d.kw >= 1 && d.stride >= 1, "conv_gemm: bad filter geometry");
-  const bool im2col = !(d.kh == 1 && d.kw == 1 && d.stride == 1 && d.pad_h == 0 && d.pad_w == 0);
+  const bool windowed = d.in_stride_w != 0;
+  const bool im2col = windowed || !(d.kh == 1 && d.kw == 1 && d.stride == 1 && d.pad_h == 0 && d.pad_w == 0);
   const int P = (d.H + 2 * d.pad_h - d.kh) / d.stride + 1;
   const int Q = (d.W + 2 * d.pad_w - d.kw) / d.stride + 1;
   const long long M = static_cast<long long>(d.B) * P * Q;
@@ -459,9 +460,9 @@ int conv_gemm(const ConvGemmDesc& d, cudaStream_t stream) {
     const int pa = std::min(pl, a_planes - 1), pw = std::min(pl, w_planes - 1);
     const __nv_bfloat16* abase = d.in + pa * d.in_plane_stride;
     if (im2col) {
-      DCR_REQUIRE(d.ld_in == d.C, "conv_gemm: im2col input must be dense NHWC (ld_in == C)");
+      DCR_REQUIRE(windowed || d.ld_in == d.C, "conv_gemm: im2col input must be dense NHWC (ld_in == C)");
       if (int rc = make_tmap_im2col_bf16(&maps.a[pl], abase, d.B, d.H, d.W, d.C, d.pad_h, d.pad_w, d.kh, d.kw, d.stride,
-                                         kBK, kBM))
+                                         kBK, kBM, d.in_stride_w, d.in_stride_h, d.in_stride_n))
         return rc;
     } else {
       if (int rc = make_tmap_2d_bf16(&maps.a[pl], abase, M, d.C, d.ld_in, kBM, kBK)) return rc;

@@ -40,6 +40,9 @@ struct ConvGemmDesc {
   const __nv_bfloat16* in = nullptr;
   long long in_plane_stride = 0;
   int B = 0, H = 1, W = 1, C = 0, ld_in = 0;
+  // optional element strides of an overlapping-window NHWC view (0 = dense): used by the space-to-depth stem, where
+  // 4 horizontally adjacent 16-channel pixels are read as one 64-channel pixel
+  long long in_stride_w = 0, in_stride_h = 0, in_stride_n = 0;
   const __nv_bfloat16* weight = nullptr;
   long long w_plane_stride = 0;
   int N = 0, kh = 1, kw = 1, stride = 1, pad_h = 0, pad_w = 0;
@@ -66,6 +69,9 @@ int conv_gemm(const ConvGemmDesc& d, cudaStream_t stream);
 int im2col_u8(const uint8_t* img, int B, int IH, int IW, int crop_y, int crop_x, int H, int W, int kh, int kw,
               int stride, int pad, int k_pad, const float* mean3, const float* std3, float post_scale,
               float post_shift, __nv_bfloat16* out, long long out_plane_stride, int planes, cudaStream_t stream);
+int stem_s2d_u8(const uint8_t* img, int B, int IH, int IW, int crop_y, int crop_x, int H, int W, const float* mean3,
+                const float* std3, float post_scale, float post_shift, __nv_bfloat16* out, long long out_plane_stride,
+                int planes, cudaStream_t stream);
 int pool2d(bool is_max, const __nv_bfloat16* in, long long in_plane_stride, __nv_bfloat16* out,
            long long out_plane_stride, int planes, int B, int H, int W, int C, int k, int stride, int pad, int ld_out,
            int out_col_off, cudaStream_t stream);
@@ -92,7 +98,8 @@ enum NetOpKind {
   NET_OP_VIT_TOKENS = 7,
   NET_OP_ATTENTION = 8,
   NET_OP_L2NORM_OUT = 9,
-  NET_OP_COUNT = 10
+  NET_OP_STEM_S2D = 10,
+  NET_OP_COUNT = 11
 };
 struct Net;
 int net_create(int max_batch, int planes, Net** out);

@@ -88,13 +88,19 @@ int make_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t rows, uint64_
 }
 
 int make_tmap_im2col_bf16(CUtensorMap* out, const void* base, int n, int h, int w, int c, int pad_h, int pad_w,
-                          int kh, int kw, int stride, int channels_per_pixel, int pixels_per_column) {
+                          int kh, int kw, int stride, int channels_per_pixel, int pixels_per_column,
+                          long long stride_w, long long stride_h, long long stride_n) {
   static PFN_encodeIm2col fn = reinterpret_cast<PFN_encodeIm2col>(driver_fn("cuTensorMapEncodeIm2col"));
   DCR_REQUIRE(fn != nullptr, "cuTensorMapEncodeIm2col driver entry point not available");
   DCR_REQUIRE(channels_per_pixel * 2 == 128, "im2col box inner extent must be 128 bytes");
   DCR_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, "tensor-map base must be 16-byte aligned");
   cuuint64_t gdim[4] = {(cuuint64_t)c, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)n};
-  cuuint64_t gstride[3] = {(cuuint64_t)c * 2, (cuuint64_t)w * c * 2, (cuuint64_t)h * w * c * 2};
+  if (stride_w == 0) stride_w = c;
+  if (stride_h == 0) stride_h = static_cast<long long>(w) * c;
+  if (stride_n == 0) stride_n = static_cast<long long>(h) * w * c;
+  DCR_REQUIRE((stride_w * 2) % 16 == 0 && (stride_h * 2) % 16 == 0 && (stride_n * 2) % 16 == 0,
+              "im2col tensor map: strides must be multiples of 16 bytes");
+  cuuint64_t gstride[3] = {(cuuint64_t)stride_w * 2, (cuuint64_t)stride_h * 2, (cuuint64_t)stride_n * 2};
   // base-pixel bounding box: lower corner = -pad, upper corner = pad - (filter - 1)   {W, H} order
   int lower[2] = {-pad_w, -pad_h};
   int upper[2] = {pad_w - (kw - 1), pad_h - (kh - 1)};

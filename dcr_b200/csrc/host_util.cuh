@@ -46,7 +46,9 @@ int make_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t rows, uint64_
                       uint32_t box_rows, uint32_t box_cols);
 
 // im2col tensor map over an NHWC bf16 activation tensor (see conv_gemm.cu)
+// stride_w/h/n: element strides of the (possibly overlapping-window) NHWC view; 0 = dense
 int make_tmap_im2col_bf16(CUtensorMap* out, const void* base, int n, int h, int w, int c, int pad_h, int pad_w,
-                          int kh, int kw, int stride, int channels_per_pixel, int pixels_per_column);
+                          int kh, int kw, int stride, int channels_per_pixel, int pixels_per_column,
+                          long long stride_w = 0, long long stride_h = 0, long long stride_n = 0);
 
 }  // namespace dcr

@@ -110,8 +110,9 @@ int net_add_op(Net* n, int kind, const int* iargs, int ni, const float* fargs, i
   auto param_ok = [&](int id, bool optional) { return (optional && id < 0) || (id >= 0 && id < (int)n->params.size()); };
   switch (kind) {
     case NET_OP_IM2COL_U8: DCR_REQUIRE(ni == 12 && nf == 8 && tensor_ok(op.i[0], false), "im2col_u8 op: bad args"); break;
+    case NET_OP_STEM_S2D: DCR_REQUIRE(ni == 7 && nf == 8 && tensor_ok(op.i[0], false), "stem_s2d op: bad args"); break;
     case NET_OP_CONV:
-      DCR_REQUIRE(ni == 18 && tensor_ok(op.i[0], false) && tensor_ok(op.i[1], true) && param_ok(op.i[5], false) &&
+      DCR_REQUIRE((ni == 18 || ni == 20) && tensor_ok(op.i[0], false) && tensor_ok(op.i[1], true) && param_ok(op.i[5], false) &&
                       param_ok(op.i[12], true) && param_ok(op.i[13], true) && tensor_ok(op.i[14], true),
                   "conv op: bad args");
       break;
@@ -153,6 +154,12 @@ int net_forward(Net* n, const uint8_t* images, int B, float* out, cudaStream_t s
                        &op.f[3], op.f[6], op.f[7], t.ptr, t.plane_stride, P, stream);
         break;
       }
+      case NET_OP_STEM_S2D: {
+        NetTensor& t = n->tensors[a[0]];
+        rc = stem_s2d_u8(images, B, a[1], a[2], a[3], a[4], a[5], a[6], &op.f[0], &op.f[3], op.f[6], op.f[7], t.ptr,
+                         t.plane_stride, P, stream);
+        break;
+      }
       case NET_OP_CONV: {
         const NetTensor& in = n->tensors[a[0]];
         ConvGemmDesc d;
@@ -161,6 +168,11 @@ int net_forward(Net* n, const uint8_t* images, int B, float* out, cudaStream_t s
         d.B = B; d.H = a[2]; d.W = a[3]; d.C = a[4]; d.ld_in = in.C;
         d.weight = static_cast<const __nv_bfloat16*>(n->params[a[5]]);
         d.N = a[6]; d.kh = a[7]; d.kw = a[8]; d.stride = a[9]; d.pad_h = a[10]; d.pad_w = a[11];
+        if (a[18] > 0) {   // overlapping-window view: a[18] = elements per stored pixel, a[19] = stored pixels per row
+          d.in_stride_w = a[18];
+          d.in_stride_h = static_cast<long long>(a[18]) * a[19];
+          d.in_stride_n = in.rows_per_image * in.C;
+        }
         const int cpad = (d.C + 63) / 64 * 64;
         d.w_plane_stride = static_cast<long long>(d.N) * d.kh * d.kw * cpad;
         d.n_terms = n->terms;

@@ -115,6 +115,61 @@ __global__ void __launch_bounds__(256) im2col_u8_kernel(const Im2colU8Params p) 
   }
 }
 
+// ---- space-to-depth stem input (7x7 / stride 2 / pad 3 first convolution of the ResNet trunk) ----------------------
+// Z[b, u, v, (i*2+j)*3 + c] = xn[2u + i - 3, 2v + j - 3, c]  (zero outside the image), channels 12..15 = 0, with
+// xn the normalised crop.  A 7x7/2 convolution of xn equals a 4x4/1 convolution of Z (weights regrouped on the host),
+// which the GEMM kernel reads through an overlapping-window tensor map -- no im2col matrix in HBM.
+struct StemS2dParams {
+  const uint8_t* img;
+  int B, IH, IW, crop_y, crop_x, H, W, U, V;
+  float mean[3], std[3], post_scale, post_shift;
+  __nv_bfloat16* out;
+  long long out_plane_stride;
+  int planes;
+};
+
+__global__ void __launch_bounds__(256) stem_s2d_u8_kernel(const StemS2dParams p) {
+  __shared__ float lut[3][256];
+  for (int i = threadIdx.x; i < 768; i += blockDim.x) {
+    const int c = i >> 8, u = i & 255;
+    const float val = (static_cast<float>(u) / 255.f - p.mean[c]) / p.std[c];   // ToTensor + Normalize, IEEE fp32
+    lut[c][u] = p.post_scale * val + p.post_shift;
+  }
+  __syncthreads();
+  const long long total = static_cast<long long>(p.B) * p.U * p.V;
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int v = static_cast<int>(idx % p.V);
+    const int u = static_cast<int>((idx / p.V) % p.U);
+    const int b = static_cast<int>(idx / (static_cast<long long>(p.V) * p.U));
+    const uint8_t* img = p.img + static_cast<size_t>(b) * p.IH * p.IW * 3;
+    float z[16];
+#pragma unroll
+    for (int e = 0; e < 16; ++e) z[e] = 0.f;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int y = 2 * u + i - 3;
+      if (y < 0 || y >= p.H) continue;
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const int x = 2 * v + j - 3;
+        if (x < 0 || x >= p.W) continue;
+        const uint8_t* px = img + (static_cast<size_t>(y + p.crop_y) * p.IW + (x + p.crop_x)) * 3;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) z[(i * 2 + j) * 3 + c] = lut[c][px[c]];
+      }
+    }
+    float lo[8], hi[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      lo[e] = z[e];
+      hi[e] = z[8 + e];
+    }
+    store8(p.out, p.out_plane_stride, p.planes, static_cast<size_t>(idx) * 16, lo);
+    store8(p.out, p.out_plane_stride, p.planes, static_cast<size_t>(idx) * 16 + 8, hi);
+  }
+}
+
 // ---- pooling -------------------------------------------------------------------------------------------------
 struct PoolParams {
   const __nv_bfloat16* in;
@@ -262,12 +317,19 @@ __global__ void layernorm_kernel(const LayerNormParams p) {
     for (int g = 0; g < kMaxGroups; ++g) {
       const int c8 = lane + g * 32;
       if (c8 < cg) {
+        const float4 g0 = *reinterpret_cast<const float4*>(p.gamma + c8 * 8);
+        const float4 g1 = *reinterpret_cast<const float4*>(p.gamma + c8 * 8 + 4);
+        const float4 b0 = *reinterpret_cast<const float4*>(p.beta + c8 * 8);
+        const float4 b1 = *reinterpret_cast<const float4*>(p.beta + c8 * 8 + 4);
+        const float gm[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+        const float bt[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
         float y[8];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) y[e] = (v[g][e] - mean) * rstd * p.gamma[c8 * 8 + e] + p.beta[c8 * 8 + e];
+        for (int e = 0; e < 8; ++e) y[e] = (v[g][e] - mean) * rstd * gm[e] + bt[e];
         if (p.out_f32) {
-#pragma unroll
-          for (int e = 0; e < 8; ++e) p.out_f32[static_cast<size_t>(row) * p.C + c8 * 8 + e] = y[e];
+          float* o = p.out_f32 + static_cast<size_t>(row) * p.C + c8 * 8;
+          *reinterpret_cast<float4*>(o) = make_float4(y[0], y[1], y[2], y[3]);
+          *reinterpret_cast<float4*>(o + 4) = make_float4(y[4], y[5], y[6], y[7]);
         }
         if (p.out) store8(p.out, p.out_plane_stride, p.planes, static_cast<size_t>(row) * p.C + c8 * 8, y);
       }
@@ -344,6 +406,27 @@ int im2col_u8(const uint8_t* img, int B, int IH, int IW, int crop_y, int crop_x,
   return 0;
 }
 
+int stem_s2d_u8(const uint8_t* img, int B, int IH, int IW, int crop_y, int crop_x, int H, int W, const float* mean3,
+                const float* std3, float post_scale, float post_shift, __nv_bfloat16* out, long long out_plane_stride,
+                int planes, cudaStream_t stream) {
+  const DeviceInfo* di = device_info();
+  if (!di) return -2;
+  DCR_REQUIRE(crop_y >= 0 && crop_x >= 0 && crop_y + H <= IH && crop_x + W <= IW, "stem_s2d_u8: crop outside image");
+  DCR_REQUIRE(H % 2 == 0 && W % 2 == 0, "stem_s2d_u8: crop size must be even");
+  StemS2dParams p;
+  p.img = img; p.B = B; p.IH = IH; p.IW = IW; p.crop_y = crop_y; p.crop_x = crop_x; p.H = H; p.W = W;
+  p.U = (H + 6) / 2; p.V = (W + 6) / 2;
+  for (int c = 0; c < 3; ++c) { p.mean[c] = mean3[c]; p.std[c] = std3[c]; }
+  p.post_scale = post_scale; p.post_shift = post_shift;
+  p.out = out; p.out_plane_stride = out_plane_stride; p.planes = planes;
+  if (B == 0) return 0;
+  const long long total = static_cast<long long>(B) * p.U * p.V;
+  stem_s2d_u8_kernel<<<grid_for(total, 256, di->num_sms), 256, 0, stream>>>(p);
+  count_launch();
+  DCR_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
 int pool2d(bool is_max, const __nv_bfloat16* in, long long in_plane_stride, __nv_bfloat16* out,
            long long out_plane_stride, int planes, int B, int H, int W, int C, int k, int stride, int pad, int ld_out,
            int out_col_off, cudaStream_t stream) {
@@ -393,7 +476,7 @@ int layernorm(const __nv_bfloat16* in, long long in_plane_stride, int planes, in
   p.in_row_stride = in_row_stride; p.gamma = gamma; p.beta = beta; p.eps = eps;
   p.out = out; p.out_plane_stride = out_plane_stride; p.out_f32 = out_f32;
   if (rows == 0) return 0;
-  layernorm_kernel<<<std::min((rows + 7) / 8, di->num_sms * 16), 256, 0, stream>>>(p);
+  layernorm_kernel<<<std::min((rows + 3) / 4, di->num_sms * 32), 128, 0, stream>>>(p);
   count_launch();
   DCR_CUDA_CHECK(cudaGetLastError());
   return 0;

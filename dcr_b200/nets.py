@@ -24,7 +24,7 @@ from . import _lib
 from .ops import prepare_conv_weight
 
 OP_IM2COL_U8, OP_CONV, OP_MAXPOOL, OP_AVGPOOL, OP_GEM, OP_GAP, OP_LAYERNORM, OP_VIT_TOKENS, OP_ATTENTION, \
-    OP_L2NORM_OUT = range(10)
+    OP_L2NORM_OUT, OP_STEM_S2D = range(11)
 
 PRECISION_PLANES = {"fast": 1, "bf16": 1, "parity": 3, "fp32": 3, "bf16x3": 2}
 
@@ -96,7 +96,8 @@ class DcrNet:
 
     def conv(self, in_t: int, out_t: int, h: int, w: int, c: int, weight: torch.Tensor, *, stride: int = 1,
              pad: Sequence[int] = (0, 0), scale: Optional[torch.Tensor] = None, bias: Optional[torch.Tensor] = None,
-             residual: int = -1, act: int = 0, out_col_off: int = 0, to_output: bool = False) -> None:
+             residual: int = -1, act: int = 0, out_col_off: int = 0, to_output: bool = False,
+             window: Optional[Sequence[int]] = None) -> None:
         if weight.dim() == 2:
             n, kh, kw = weight.shape[0], 1, 1
         else:
@@ -107,7 +108,7 @@ class DcrNet:
         self.op(OP_CONV, [in_t, out_t, h, w, c, self.weight(weight), n, kh, kw, stride, pad[0], pad[1],
                           self.param_f32(scale) if scale is not None else -1,
                           self.param_f32(bias) if bias is not None else -1, residual, act, out_col_off,
-                          1 if to_output else 0])
+                          1 if to_output else 0] + (list(window) if window else []))
 
     # ---- execution ----------------------------------------------------------------------------------------------
     @torch.no_grad()
@@ -150,6 +151,23 @@ def _strip(sd: Dict[str, torch.Tensor], prefixes: Sequence[str]) -> Dict[str, to
     return out
 
 
+def _stem_s2d_weight(w: torch.Tensor) -> torch.Tensor:
+    """[N,3,7,7] -> [N, 64, 4, 1]: tap a = filter row pair, channel c' = b*16 + (i*2+j)*3 + c holds w[n, c, 2a+i, 2b+j]
+    (zero where 2a+i or 2b+j exceeds 6, and for the 4 padding channels of every stored pixel)."""
+    n = w.shape[0]
+    out = torch.zeros((n, 64, 4, 1), dtype=torch.float32)
+    wf = w.detach().float()
+    for a in range(4):
+        for b in range(4):
+            for i in range(2):
+                for j in range(2):
+                    r, s = 2 * a + i, 2 * b + j
+                    if r < 7 and s < 7:
+                        base = b * 16 + (i * 2 + j) * 3
+                        out[:, base:base + 3, a, 0] = wf[:, :, r, s]
+    return out
+
+
 def first_conv_k_pad(kh: int, kw: int) -> int:
     """K of the im2col rows the IM2COL_U8 op emits: each filter row padded to ceil8(3*kw), total padded to 64."""
     rp = (3 * kw + 7) // 8 * 8
@@ -189,16 +207,17 @@ def build_sscd_resnet50(state_dict: Dict[str, torch.Tensor], max_batch: int = 64
     net.in_shape = (in_size, in_size)
     off = (in_size - crop) // 2
     eps = 1e-5
-    # stem: fused preprocess + im2col of the 7x7/2 conv, then a GEMM
+    # stem: 7x7/2/pad-3 conv == 4x4/1 conv over the zero-padded 2x2 space-to-depth input (12 -> 16 channels); the
+    # preprocessing (crop, ToTensor, Normalize) is fused into the space-to-depth kernel, and the GEMM kernel reads 4
+    # horizontally adjacent 16-channel pixels as one 64-channel pixel through an overlapping-window tensor map
     s = (crop + 2 * 3 - 7) // 2 + 1   # 112
-    t_cols = net.tensor(s * s, 192)
-    net.op(OP_IM2COL_U8, [t_cols, in_size, in_size, off, off, crop, crop, 7, 7, 2, 3, 192],
-           list(mean) + list(std) + [1.0, 0.0])
+    u = (crop + 6) // 2               # 115 stored rows / pixels per row
+    t_z = net.tensor(u * u, 16)
+    net.op(OP_STEM_S2D, [t_z, in_size, in_size, off, off, crop, crop], list(mean) + list(std) + [1.0, 0.0])
     sc, bi = _fold_bn(sd, "bn1", eps)
     t_stem = net.tensor(s * s, 64)
-    net.conv(t_cols, t_stem, s * s, 1, 192, _first_conv_weight(sd["conv1.weight"], 192), scale=sc, bias=bi, act=1)
-    net.flops_per_image += 2.0 * s * s * 64 * (147 - 192)   # count the real 147-tap work, not the zero padding
-    assert first_conv_k_pad(7, 7) == 192
+    net.conv(t_z, t_stem, u, u - 3, 64, _stem_s2d_weight(sd["conv1.weight"]), scale=sc, bias=bi, act=1, window=(16, u))
+    net.flops_per_image += 2.0 * s * s * 64 * (147 - 256)   # count the real 147-tap work, not the zero padding
     hw = (s + 2 - 3) // 2 + 1         # 56
     t = net.tensor(hw * hw, 64)
     net.op(OP_MAXPOOL, [t_stem, t, s, s, 64, 3, 2, 1, 0])
