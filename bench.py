@@ -201,7 +201,8 @@ def main():
                           f"synthetic 256x256 images ({args.queries} q + {args.gallery} g per GPU)",
               "queries": q_total, "gallery": g_total, "descriptor_dim": D_DESC, "k": K_TOP,
               "images_embedded_per_step": q_total + g_total, "parallelism": f"gallery-shard x{world}",
-              "l2": "inputs (21.6 GB of images per GPU) are larger than L2; no explicit flush"}
+              "l2": f"inputs ({(args.queries + args.gallery) * IMG * IMG * 3 / 1e9:.1f} GB of images per GPU) are larger than "
+                    "the 126 MB L2; no explicit flush"}
 
     if args.impl == "reference":
         # the reference's own CPU path, restated (the reference scripts cannot be imported/installed: torch._six,

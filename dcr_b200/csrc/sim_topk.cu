@@ -169,15 +169,34 @@ __global__ void col_mean_finish_kernel(const double* __restrict__ sums, int n, i
 // Query centring pays only when the centred queries are much shorter than the queries themselves (the bf16 error
 // bound shrinks by ||q-nu|| / ||q||) -- and costs a per-column offset in the fused epilogue.  flag = 1 when the
 // mean squared norm of the centred sample is below 1/16 of the uncentred one (a 4x tighter bound).
-__global__ void centre_decision_kernel(const double* __restrict__ sums, const double* __restrict__ sq_sums, int n, int d,
-                                       int* __restrict__ flag) {
+__global__ void __launch_bounds__(256)
+    centre_decision_kernel(const double* __restrict__ sums, const double* __restrict__ sq_sums, int n, int d,
+                           int* __restrict__ flag) {
+  __shared__ double s_m2[8], s_nu2[8];
   double m2 = 0.0, nu2 = 0.0;
-  for (int c = 0; c < d; ++c) {
+  for (int c = threadIdx.x; c < d; c += blockDim.x) {
     m2 += sq_sums[c] / n;
     const double m = sums[c] / n;
     nu2 += m * m;
   }
-  *flag = (m2 - nu2 < m2 / 16.0) ? 1 : 0;
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    m2 += __shfl_xor_sync(kFull, m2, off);
+    nu2 += __shfl_xor_sync(kFull, nu2, off);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    s_m2[threadIdx.x >> 5] = m2;
+    s_nu2[threadIdx.x >> 5] = nu2;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    m2 = nu2 = 0.0;
+    for (int w = 0; w < 8; ++w) {
+      m2 += s_m2[w];
+      nu2 += s_nu2[w];
+    }
+    *flag = (m2 - nu2 < m2 / 16.0) ? 1 : 0;
+  }
 }
 
 // second-chance pass: copy the bf16 rows of the flagged queries into a compact matrix (zero rows up to n_pad)
@@ -1267,7 +1286,7 @@ int sim_topk(const float* q, int nq, const float* g, int ng, int d, int k, long 
     col_mean_finish_kernel<<<(d + 255) / 256, 256, 0, stream>>>(colsum, n_sample, d, out);
     count_launch();
     if (decide) {
-      centre_decision_kernel<<<1, 1, 0, stream>>>(colsum, colsum + d, n_sample, d, qflag);
+      centre_decision_kernel<<<1, 256, 0, stream>>>(colsum, colsum + d, n_sample, d, qflag);
       count_launch();
     }
     return 0;

@@ -9,9 +9,14 @@ kind, batch, precision = sys.argv[1], int(sys.argv[2]), sys.argv[3]
 iters = int(sys.argv[4]) if len(sys.argv) > 4 else 5
 if kind == "sscd":
     net = nets.build_sscd_resnet50(om.make_sscd_state_dict(0), max_batch=batch, precision=precision)
-else:
+elif kind == "vit":
     net = nets.build_dino_vit(om.make_vit_state_dict(0), max_batch=batch, precision=precision)
-img = synthetic.images(min(batch, 64), seed=0).cuda()
+else:
+    net = nets.build_fid_inception(om.make_inception_state_dict(0), max_batch=batch, precision=precision)
+if kind == "inception":
+    img = torch.randint(0, 256, (min(batch, 64), 299, 299, 3), dtype=torch.uint8).cuda()
+else:
+    img = synthetic.images(min(batch, 64), seed=0).cuda()
 img = img.repeat((batch + img.shape[0] - 1) // img.shape[0], 1, 1, 1)[:batch].contiguous()
 for _ in range(2):
     net(img)
