@@ -1119,7 +1119,7 @@ int make_plan(int nq, int ng, int d, int k, int cg, int num_sms, size_t max_smem
   // bound of the k-th score; such queries get a second chance with 32 candidates before the brute-force path
   int kp0 = (k <= 2) ? 4 : (k <= 5 ? 8 : (k <= 10 ? 16 : 32));
   kp0 = env_int("DCR_SIM_KP0", kp0);
-  DCR_REQUIRE(kp0 == 4 || kp0 == 8 || kp0 == 16 || kp0 == 32, "sim_topk: DCR_SIM_KP0 must be 4, 8, 16 or 32");
+  DCR_REQUIRE(kp0 >= 1 && kp0 <= kKPMax, "sim_topk: DCR_SIM_KP0 must be in [1, 32]");
   DCR_REQUIRE(kp0 >= k, "sim_topk: first-pass candidate count %d < k=%d", kp0, k);
   pl->kp0 = kp0;
   pl->kp1 = (kp0 < kKPMax) ? kKPMax : 0;
