@@ -27,6 +27,8 @@ SIGNATURES = {
                                     C.c_void_p]),
     "dcr_sim_topk_last_stats": (C.c_int, [C.POINTER(C.c_int)]),
     "dcr_sim_topk_last_kernel_ms": (C.c_float, []),
+    "dcr_sim_topk_last_sm_mhz": (C.c_float, []),
+    "dcr_sim_topk_last_epilogue_sets": (C.c_int, []),
     "dcr_sim_topk_last_second_pass": (C.c_int, []),
     "dcr_kernel_launch_count": (C.c_longlong, []),
     "dcr_conv2d_bf16": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int,

@@ -98,6 +98,8 @@ int dcr_sim_topk_last_stats(int* out8) {
 }
 
 float dcr_sim_topk_last_kernel_ms(void) { return g_last_stats.kernel_ms; }
+float dcr_sim_topk_last_sm_mhz(void) { return g_last_stats.sm_mhz; }
+int dcr_sim_topk_last_epilogue_sets(void) { return g_last_stats.n_sets; }
 int dcr_sim_topk_last_second_pass(void) { return g_last_stats.n_second; }
 
 long long dcr_kernel_launch_count(void) { return dcr::launch_count(); }

@@ -19,6 +19,8 @@ struct SimStats {
   int n_second;      // queries that needed the second-chance pass (32 candidates)
   int d_pad;
   float kernel_ms;   // device time of the fused kernel alone (CUDA events)
+  float sm_mhz;      // SM clock while the fused kernel ran (clock64 / globaltimer of CTA 0; with both bias variants launched: the last one)
+  int n_sets;        // epilogue warp sets of the first pass
 };
 
 size_t sim_topk_workspace_size(int nq, int ng, int d, int k);

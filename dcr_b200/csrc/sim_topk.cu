@@ -20,6 +20,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <type_traits>
 
 #include "dcr_internal.cuh"
 #include "host_util.cuh"
@@ -35,7 +36,6 @@ constexpr int kBlockK = 64;       // bf16 elements per 128-byte swizzled smem ro
 constexpr int kMaxKB = 8;         // d_pad <= 512
 constexpr int kKPMax = 32;        // max candidates kept per (query, segment)
 constexpr int kWarmTiles = 4;     // tiles replayed at the start of every segment to seed the threshold
-constexpr int kThreads = 192;     // warp 0: TMA producer, warp 1: MMA issuer, warps 2..5: epilogue
 constexpr uint32_t kFull = 0xffffffffu;
 constexpr int kATileBytes = kBlockM * kBlockK * 2;  // 16 KB
 constexpr int kMaxSlotsPerQuery = 512;  // (chunk, unit) segments that may cover one q-tile
@@ -57,6 +57,7 @@ struct SimParams {
   const float* col_bias;   // [ng_pad] per-gallery-row score offset nu.(g-mu) added to every accumulator column; null = none
   int debug_mode;          // timing experiments only: 1 = epilogue loads TMEM but does not scan, 2 = does not even load
   const float* thr_init;   // per query row: start thresholds (second-chance pass); null = seed by warm-up replay
+  unsigned long long* clk; // [4] clock64 / globaltimer at the start and end of CTA 0 (SM clock under this kernel); null = off
 };
 
 // ------------------------------------------------------------------------------------------------------------
@@ -215,6 +216,12 @@ __global__ void gather_rows_kernel(const __nv_bfloat16* __restrict__ src, const 
 // ------------------------------------------------------------------------------------------------------------
 // stage 2 helpers
 
+DCR_DEVICE unsigned long long global_timer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+
 DCR_DEVICE float max8(const float* v) {
   return fmaxf(fmaxf(fmaxf(v[0], v[1]), fmaxf(v[2], v[3])), fmaxf(fmaxf(v[4], v[5]), fmaxf(v[6], v[7])));
 }
@@ -346,6 +353,36 @@ DCR_DEVICE void warm_chunk(const uint32_t (&r)[32], const float* sb, int gcol0, 
   }
 }
 
+// Seed of a segment's threshold from the warm-up maxima: fold the 32 slot maxima into `groups` >= kp disjoint groups;
+// the smallest group maximum is exceeded by at least groups-1 already-seen scores, so it is a safe (never too high
+// for kp) start.  Segments shorter than the warm-up still get a valid bound.
+DCR_DEVICE float seed_threshold(float (&slot)[32], int kp) {
+  int groups = 32;
+  if (kp <= 16) {
+#pragma unroll
+    for (int c = 0; c < 16; ++c) slot[c] = fmaxf(slot[c], slot[c + 16]);
+    groups = 16;
+  }
+  if (kp <= 8) {
+#pragma unroll
+    for (int c = 0; c < 8; ++c) slot[c] = fmaxf(slot[c], slot[c + 8]);
+    groups = 8;
+  }
+  if (kp <= 4) {
+#pragma unroll
+    for (int c = 0; c < 4; ++c) slot[c] = fmaxf(slot[c], slot[c + 4]);
+    groups = 4;
+  }
+  float lo = slot[0];
+#pragma unroll
+  for (int c = 1; c < 32; ++c)
+    if (c < groups) lo = fminf(lo, slot[c]);
+  // strictly below the smallest group maximum so that the maxima themselves are recorded
+  float thr = (lo == -INFINITY) ? -INFINITY : __uint_as_float(__float_as_uint(lo) + (lo > 0.f ? -1 : (lo < 0.f ? 1 : 0)));
+  if (lo == 0.f) thr = -1e-30f;
+  return thr;
+}
+
 // Work decomposition shared by the three warp roles (and mirrored by rescore_select_kernel): for every gallery chunk
 // c (chunks are L2-sized so that the units, which all sweep chunk c at about the same time, share its tiles in L2)
 // the (q-tile, g-tile-in-chunk) grid is linearised q-major and cut into n_units equal contiguous ranges; a unit's range
@@ -404,8 +441,8 @@ struct SegWalker {
 // replaying the first kWarmTiles tiles.  Segment (unit u, q-tile i) owns candidate slot u + i.
 // kBias: compiled with / without the per-column offset path of query centring.  Both variants are launched; the one
 // that does not match the device-side decision (p.bias_flag) exits at once -- no host synchronisation needed.
-template <int kCG, bool kBias>
-__global__ void __launch_bounds__(kThreads, 1)
+template <int kCG, bool kBias, int kSets>
+__global__ void __launch_bounds__(64 + 128 * kSets, 1)
     sim_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_g,
                     const SimParams p) {
   if (((p.col_bias != nullptr) && (p.bias_flag != nullptr) && (*p.bias_flag != 0)) != kBias) return;
@@ -416,8 +453,8 @@ __global__ void __launch_bounds__(kThreads, 1)
   constexpr int kBTileBytes = kBRows * kBlockK * 2;
   uint8_t* smem_a = smem;                                   // num_kb x 16 KB
   uint8_t* smem_b = smem_a + p.num_kb * kATileBytes;        // stages x kBTileBytes
-  uint2* cand = reinterpret_cast<uint2*>(smem_b + p.stages * kBTileBytes);  // [cap][128]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(cand) + p.cap * 128 * 8);
+  uint2* cand = reinterpret_cast<uint2*>(smem_b + p.stages * kBTileBytes);  // [kSets][cap][128]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(cand) + kSets * p.cap * 128 * 8);
   uint64_t* b_full = bars;              // [stages]
   uint64_t* b_empty = bars + 8;         // [stages]
   uint64_t* a_full = bars + 16;
@@ -425,8 +462,7 @@ __global__ void __launch_bounds__(kThreads, 1)
   uint64_t* t_full = bars + 18;         // [2]
   uint64_t* t_empty = bars + 20;        // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 22);
-  float* sbias = reinterpret_cast<float*>(bars + 32);   // [2][256] column offsets of the tile in each TMEM buffer
-  float* carry = sbias + 2 * kBlockN;                   // [4][128] thresholds carried to the next chunk, by q-tile & 3
+  float* carry = reinterpret_cast<float*>(bars + 32);   // [kSets][4][128] thresholds carried to the next chunk, by q-tile & 3
 
   const uint32_t warp = threadIdx.x >> 5;
   const uint32_t lane = threadIdx.x & 31;
@@ -446,7 +482,7 @@ __global__ void __launch_bounds__(kThreads, 1)
     mbar_init(a_empty, 1);
     for (int b = 0; b < 2; ++b) {
       mbar_init(&t_full[b], 1);
-      mbar_init(&t_empty[b], 4 * kCG);
+      mbar_init(&t_empty[b], 4 * kSets * kCG);
     }
     fence_mbar_init();
   }
@@ -458,6 +494,10 @@ __global__ void __launch_bounds__(kThreads, 1)
   if constexpr (kCG == 2) cluster_sync(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (p.clk && blockIdx.x == 0 && threadIdx.x == 0) {
+    p.clk[0] = clock64();
+    p.clk[1] = global_timer_ns();
+  }
 
   // this unit's tile range
   const long long n_units = gridDim.x / kCG;
@@ -482,6 +522,7 @@ __global__ void __launch_bounds__(kThreads, 1)
         for (int j = 0; j < warm + ntiles; ++j) {
           const int gi = g_begin + (j < warm ? j : j - warm);
           const int g_row = gi * kBlockN + static_cast<int>(cta_rank) * kBRows;
+          if (p.debug_mode == 3) continue;   // timing experiment: no gallery loads at all
           for (int kb = 0; kb < p.num_kb; ++kb, ++it) {
             const uint32_t s = it % p.stages, ph = (it / p.stages) & 1;
             mbar_wait(&b_empty[s], ph ^ 1);
@@ -511,14 +552,14 @@ __global__ void __launch_bounds__(kThreads, 1)
           const uint32_t tmem_d = tmem_base + buf * kBlockN;
           for (int kb = 0; kb < p.num_kb; ++kb, ++it) {
             const uint32_t s = it % p.stages, ph = (it / p.stages) & 1;
-            mbar_wait(&b_full[s], ph);
+            if (p.debug_mode != 3) mbar_wait(&b_full[s], ph);
             tc_fence_after();
             const uint64_t da = umma_desc_sw128(smem_u32(smem_a + kb * kATileBytes));
             const uint64_t db = umma_desc_sw128(smem_u32(smem_b + s * kBTileBytes));
 #pragma unroll
             for (int k = 0; k < kBlockK / 16; ++k)
               umma_f16<kCG>(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);  // +32 B per K=16 step
-            umma_commit<kCG>(&b_empty[s]);   // frees this B stage (both CTAs) once the MMAs above retire
+            if (p.debug_mode != 3) umma_commit<kCG>(&b_empty[s]);   // frees this B stage (both CTAs) once the MMAs above retire
             if (kb == p.num_kb - 1) {
               umma_commit<kCG>(&t_full[buf]);
               if (j == warm + ntiles - 1) umma_commit<kCG>(a_empty);
@@ -530,11 +571,17 @@ __global__ void __launch_bounds__(kThreads, 1)
     }
   } else {
     // ===================================== epilogue warps =====================================
-    const uint32_t quad = warp & 3;            // TMEM lane quadrant this warp may read
-    const uint32_t row = quad * 32 + lane;     // query row inside this CTA's tile
-    const uint32_t my_list = smem_u32(cand + row);
-    uint2* warp_list = cand + quad * 32;
+    // kSets = 2: two warps per TMEM lane quadrant, each owning one column half ("set") of every accumulator tile and
+    // its own candidate lists / slot -- the filter is issue- and latency-bound with a single warp per sub-partition.
+    const uint32_t quad = warp & 3;             // TMEM lane quadrant this warp may read
+    const uint32_t set = (warp - 2) >> 2;       // column range [set * kSetCols, (set + 1) * kSetCols) of every tile
+    const uint32_t row = quad * 32 + lane;      // query row inside this CTA's tile
+    constexpr int kSetCols = kBlockN / kSets;
+    uint2* set_list = cand + set * p.cap * 128;
+    const uint32_t my_list = smem_u32(set_list + row);
+    uint2* warp_list = set_list + quad * 32;
     const uint32_t tmem_row = tmem_base + ((quad * 32u) << 16);
+    float* my_carry = carry + set * 4 * kBlockM;
     const int kp = p.kp, cap = p.cap;
     const float* colbias = kBias ? p.col_bias : nullptr;
     uint32_t tc = 0, dbg = 0;
@@ -548,113 +595,70 @@ __global__ void __launch_bounds__(kThreads, 1)
         thr = qrow_g < p.nq ? p.thr_init[qrow_g] : INFINITY;   // padding rows collect nothing
       }
       // a threshold this row reached on an earlier gallery chunk is a valid (and usually tight) start here
-      if (w.carried) thr = fmaxf(thr, carry[(qi & 3) * kBlockM + row]);
+      if (w.carried) thr = fmaxf(thr, my_carry[(qi & 3) * kBlockM + row]);
       int cnt = 0;
-      float slot[32];
-#pragma unroll
-      for (int c = 0; c < 32; ++c) slot[c] = -INFINITY;
 
-      if (colbias) {   // offsets of this segment's first tile (later tiles are prefetched one tile ahead)
-        const int g0 = g_begin * kBlockN;
-        sbias[(tc & 1) * kBlockN + row * 2] = colbias[g0 + row * 2];
-        sbias[(tc & 1) * kBlockN + row * 2 + 1] = colbias[g0 + row * 2 + 1];
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-      }
-      for (int j = 0; j < warm + ntiles; ++j, ++tc) {
-        const bool is_warm = j < warm;
-        const int gi = g_begin + (is_warm ? j : j - warm);
-        const int gcol_tile = gi * kBlockN;
-        const bool tail = gcol_tile + kBlockN > p.ng;
+      // one accumulator tile: warm-up tiles only track column-slot maxima, the others feed the candidate lists.  Two
+      // separate loops so that the 32 slot registers are dead while the lists are live.
+      auto tile = [&](auto warm_tag, int gi, float (&slot)[32]) {
+        constexpr bool kWarm = decltype(warm_tag)::value;
+        const int gcol0 = gi * kBlockN + static_cast<int>(set) * kSetCols;
+        const bool tail = gcol0 + kSetCols > p.ng;
         const uint32_t buf = tc & 1;
-        const float* sb = kBias ? sbias + buf * kBlockN : nullptr;
-        float nb0 = 0.f, nb1 = 0.f;
-        const bool has_next = colbias && (j + 1 < warm + ntiles);
-        if (has_next) {
-          const int gn = (g_begin + ((j + 1) < warm ? (j + 1) : (j + 1) - warm)) * kBlockN;
-          nb0 = colbias[gn + row * 2];
-          nb1 = colbias[gn + row * 2 + 1];
-        }
+        const float* sb = kBias ? colbias + gcol0 : nullptr;   // per-column offsets: warp-uniform (broadcast) loads
         mbar_wait(&t_full[buf], (tc >> 1) & 1);
         tc_fence_after();
-        const uint32_t taddr = tmem_row + buf * kBlockN;
+        const uint32_t taddr = tmem_row + buf * kBlockN + set * kSetCols;
         uint32_t ra[32], rb[32];
-        if (p.debug_mode == 2) {   // timing experiment: do not even read the accumulator (results are meaningless)
+        auto release = [&]() {   // this warp's columns of the accumulator buffer are in registers
           tc_fence_before();
           __syncwarp();
           if (lane == 0) {
             if constexpr (kCG == 2) mbar_arrive_cluster(&t_empty[buf], 0);
             else mbar_arrive(&t_empty[buf]);
           }
-          continue;
+        };
+        if (p.debug_mode >= 2) {   // timing experiment: do not even read the accumulator (results are meaningless)
+          release();
+          return;
         }
         // TMEM read pipeline: chunk i+1 is in flight while chunk i is scanned
         tmem_ld_32x32(taddr, ra);
 #pragma unroll 1
-        for (int ch = 0; ch < kBlockN / 32; ch += 2) {
+        for (int ch = 0; ch < kSetCols / 32; ch += 2) {
           tmem_ld_wait_dep(ra);
           tmem_ld_32x32(taddr + (ch + 1) * 32, rb);
-          if (tail) mask_tail(ra, gcol_tile + ch * 32, p.ng);
+          if (tail) mask_tail(ra, gcol0 + ch * 32, p.ng);
           if (p.debug_mode == 0) {
-            if (is_warm) warm_chunk<false>(ra, sb ? sb + ch * 32 : nullptr, gcol_tile + ch * 32, p.ng, slot);
-            else scan_chunk<false>(ra, sb ? sb + ch * 32 : nullptr, gcol_tile + ch * 32, p.ng, thr, cnt, my_list, warp_list, kp, cap, lane);
+            if constexpr (kWarm) warm_chunk<false>(ra, sb ? sb + ch * 32 : nullptr, gcol0 + ch * 32, p.ng, slot);
+            else scan_chunk<false>(ra, sb ? sb + ch * 32 : nullptr, gcol0 + ch * 32, p.ng, thr, cnt, my_list, warp_list, kp, cap, lane);
           } else {
             dbg ^= ra[0] ^ ra[31];
           }
           tmem_ld_wait_dep(rb);
-          if (ch + 2 < kBlockN / 32) {
-            tmem_ld_32x32(taddr + (ch + 2) * 32, ra);
-          } else {
-            // every column of this accumulator buffer is now in registers: hand it back to the MMA warp
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) {
-              if constexpr (kCG == 2) mbar_arrive_cluster(&t_empty[buf], 0);
-              else mbar_arrive(&t_empty[buf]);
-            }
-          }
-          if (tail) mask_tail(rb, gcol_tile + (ch + 1) * 32, p.ng);
+          if (ch + 2 < kSetCols / 32) tmem_ld_32x32(taddr + (ch + 2) * 32, ra);
+          else release();
+          if (tail) mask_tail(rb, gcol0 + (ch + 1) * 32, p.ng);
           if (p.debug_mode == 0) {
-            if (is_warm) warm_chunk<false>(rb, sb ? sb + (ch + 1) * 32 : nullptr, gcol_tile + (ch + 1) * 32, p.ng, slot);
-            else scan_chunk<false>(rb, sb ? sb + (ch + 1) * 32 : nullptr, gcol_tile + (ch + 1) * 32, p.ng, thr, cnt, my_list, warp_list, kp, cap, lane);
+            if constexpr (kWarm) warm_chunk<false>(rb, sb ? sb + (ch + 1) * 32 : nullptr, gcol0 + (ch + 1) * 32, p.ng, slot);
+            else scan_chunk<false>(rb, sb ? sb + (ch + 1) * 32 : nullptr, gcol0 + (ch + 1) * 32, p.ng, thr, cnt, my_list, warp_list, kp, cap, lane);
           } else {
             dbg ^= rb[0] ^ rb[31];
           }
         }
-        if (colbias) {
-          if (has_next) {
-            sbias[(buf ^ 1) * kBlockN + row * 2] = nb0;
-            sbias[(buf ^ 1) * kBlockN + row * 2 + 1] = nb1;
-          }
-          asm volatile("bar.sync 1, 128;" ::: "memory");
-        }
-        if (is_warm && j == warm - 1) {
-          // seed: fold the 32 slot maxima into `groups` >= kp disjoint groups; the smallest group maximum is
-          // exceeded by at least groups-1 already-seen scores, so it is a safe (never too high for kp) start.
-          // Segments shorter than the warm-up still get a valid bound.
-          int groups = 32;
-          if (kp <= 16) {
+      };
+      if (warm > 0) {
+        float slot[32];
 #pragma unroll
-            for (int c = 0; c < 16; ++c) slot[c] = fmaxf(slot[c], slot[c + 16]);
-            groups = 16;
-          }
-          if (kp <= 8) {
-#pragma unroll
-            for (int c = 0; c < 8; ++c) slot[c] = fmaxf(slot[c], slot[c + 8]);
-            groups = 8;
-          }
-          if (kp <= 4) {
-#pragma unroll
-            for (int c = 0; c < 4; ++c) slot[c] = fmaxf(slot[c], slot[c + 4]);
-            groups = 4;
-          }
-          float lo = slot[0];
-#pragma unroll
-          for (int c = 1; c < 32; ++c)
-            if (c < groups) lo = fminf(lo, slot[c]);
-          // strictly below the smallest group maximum so that the maxima themselves are recorded
-          thr = (lo == -INFINITY) ? -INFINITY : __uint_as_float(__float_as_uint(lo) + (lo > 0.f ? -1 : (lo < 0.f ? 1 : 0)));
-          if (lo == 0.f) thr = -1e-30f;
-        }
+        for (int c = 0; c < 32; ++c) slot[c] = -INFINITY;
+#pragma unroll 1
+        for (int j = 0; j < warm; ++j, ++tc) tile(std::true_type{}, g_begin + j, slot);
+        thr = seed_threshold(slot, kp);
+      }
+      {
+        float unused[32];
+#pragma unroll 1
+        for (int j = 0; j < ntiles; ++j, ++tc) tile(std::false_type{}, g_begin + j, unused);
       }
       // ---- flush this segment's lists: final compaction to kp, then coalesced copy to the slot ----
       __syncwarp();
@@ -663,8 +667,8 @@ __global__ void __launch_bounds__(kThreads, 1)
         if (need) compact_warp(warp_list, need, kp, thr, cnt, lane);
       }
       __syncwarp();
-      carry[(qi & 3) * kBlockM + row] = thr;
-      const size_t slot_row0 = (static_cast<size_t>(w.slot) * rows_per_qtile + cta_rank * kBlockM + quad * 32);
+      my_carry[(qi & 3) * kBlockM + row] = thr;
+      const size_t slot_row0 = (static_cast<size_t>(w.slot) * kSets + set) * rows_per_qtile + cta_rank * kBlockM + quad * 32;
       for (int L = 0; L < 32; ++L) {
         const int n = __shfl_sync(kFull, cnt, L);
         if (static_cast<int>(lane) < n) p.cand[(slot_row0 + L) * kKPMax + lane] = warp_list[L + lane * 128];
@@ -679,6 +683,10 @@ __global__ void __launch_bounds__(kThreads, 1)
   tc_fence_before();
   if constexpr (kCG == 2) cluster_sync(); else __syncthreads();
   if (warp == 2) tmem_dealloc<kCG>(tmem_base, 512);
+  if (p.clk && blockIdx.x == 0 && threadIdx.x == 0) {
+    p.clk[2] = clock64();
+    p.clk[3] = global_timer_ns();
+  }
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -761,7 +769,7 @@ DCR_DEVICE void block_argbest(double& bs, long long& bi, int& bp, BlockBest* sb,
 __global__ void __launch_bounds__(128)
     rescore_select_kernel(const float* __restrict__ q, const float* __restrict__ g, int nq, int ng, int d, int k,
                           int n_qtiles, int n_gtiles, int gchunk, int n_chunks, int n_units, int rows_per_qtile,
-                          int d_pad, const uint2* __restrict__ cand, const int* __restrict__ cand_cnt,
+                          int n_sets, int d_pad, const uint2* __restrict__ cand, const int* __restrict__ cand_cnt,
                           const float* __restrict__ cand_thr, const int* __restrict__ qmap,
                           const float* __restrict__ mu, const float* __restrict__ nu, const int* __restrict__ nu_flag,
                           const float* __restrict__ q_norm_hat,
@@ -797,8 +805,8 @@ __global__ void __launch_bounds__(128)
       const long long T = static_cast<long long>(n_qtiles) * ncg;
       const long long u_lo = owner_unit(static_cast<long long>(qi) * ncg, T, n_units);
       const long long u_hi = owner_unit(static_cast<long long>(qi + 1) * ncg - 1, T, n_units);
-      for (long long u = u_lo; u <= u_hi; ++u) {
-        const int slot = c * (n_units + n_qtiles) + static_cast<int>(u) + qi;
+      for (long long us = u_lo * n_sets; us < (u_hi + 1) * n_sets; ++us) {   // n_sets candidate slots per segment
+        const int slot = (c * (n_units + n_qtiles) + static_cast<int>(us / n_sets) + qi) * n_sets + static_cast<int>(us % n_sets);
         const size_t sr = static_cast<size_t>(slot) * rows_per_qtile + r;
         int cc = cand_cnt[sr];
         thr = fmaxf(thr, cand_thr[sr]);
@@ -1018,18 +1026,20 @@ int env_int(const char* name, int dflt);
 // launch geometry of one fused pass over nq queries
 struct PassPlan {
   int nq, nq_pad, n_qtiles, n_units, n_slots, kp, cap, stages, max_cand;
+  int n_sets;             // epilogue warp sets = candidate slots per segment (column halves with their own lists)
   int gchunk, n_chunks;   // gallery tiles per L2-sized chunk for this pass
   size_t smem_bytes;
 };
 
 struct SimPlan {
   int cg, d_pad, num_kb, ng_pad, n_gtiles, rows_per_qtile;
+  int max_sets;  // upper bound for PassPlan::n_sets (1 or 2)
   int gchunk, n_chunks;   // preferred gallery chunking (a pass may use fewer chunks)
   int kp0, kp1;           // candidates kept by the first pass / by the second-chance pass (0 = no second pass)
   PassPlan p0, p1;        // p1 is sized for the worst case (every query flagged)
   // workspace offsets
   size_t off_qb, off_qb1, off_gb, off_qnh, off_qnr, off_qnx, off_gmax, off_colsum, off_mu, off_cand, off_cnt, off_thr,
-      off_flag0, off_flag1, off_thr1, off_counts, off_exact, off_nu, off_bias;
+      off_flag0, off_flag1, off_thr1, off_counts, off_exact, off_nu, off_bias, off_clk;
   size_t total;
 };
 
@@ -1037,6 +1047,33 @@ int plan_pass(int nq, int kp, const SimPlan& sp, int num_sms, size_t max_smem, i
   pp->nq = nq;
   pp->n_qtiles = (nq + sp.rows_per_qtile - 1) / sp.rows_per_qtile;
   pp->nq_pad = pp->n_qtiles * sp.rows_per_qtile;
+  pp->kp = kp;
+  // ---- shared memory: resident A + stages*B + n_sets * cap KB of lists + barriers + carried thresholds ----
+  const size_t a_bytes = static_cast<size_t>(sp.num_kb) * kATileBytes;
+  const size_t b_tile = static_cast<size_t>(kBlockN / sp.cg) * kBlockK * 2;
+  const size_t fixed = 1024 /*align slack*/ + 256 /*barriers*/ + 4096 /*carried thresholds*/;
+  auto fits = [&](int st, int cp, int sets) {
+    return max_smem >= a_bytes + st * b_tile + static_cast<size_t>(cp) * 1024 * sets + fixed;
+  };
+  // two epilogue warp sets whenever their lists (at least kp + 8 entries per row and set) fit next to 3 B stages
+  int sets = (sp.max_sets >= 2 && fits(3, kp + 8, 2)) ? 2 : 1;
+  int cap = kp + (sets == 2 ? 8 : 16);
+  const int cap_max = std::max(cap, std::min(64, env_int("DCR_SIM_CAP", 64)));
+  int stages = 2;
+  DCR_REQUIRE(fits(stages, cap, sets), "sim_topk: not enough shared memory (%zu B) for d=%d k=%d cta_group=%d", max_smem,
+              d, k, sp.cg);
+  // priorities: 3 B stages, then list capacity up to 64 (fewer compactions), then more stages (up to 8)
+  if (fits(3, cap, sets)) stages = 3;
+  const int want_stages = env_int("DCR_SIM_STAGES", 0);
+  if (want_stages > 3 && fits(want_stages, cap, sets)) stages = want_stages;
+  while (cap < cap_max && fits(stages, cap + 1, sets)) ++cap;
+  while (stages < 8 && fits(stages + 1, cap, sets)) ++stages;
+  pp->cap = cap;
+  pp->stages = stages;
+  pp->n_sets = sets;
+  pp->smem_bytes = fixed + a_bytes + stages * b_tile + static_cast<size_t>(cap) * 1024 * sets;
+
+  // ---- gallery chunking and work units ----
   pp->gchunk = sp.gchunk;
   pp->n_chunks = sp.n_chunks;
   int units = 1;
@@ -1053,7 +1090,7 @@ int plan_pass(int nq, int kp, const SimPlan& sp, int num_sms, size_t max_smem, i
       const long long per_unit = std::max<long long>(1, Tc / units);
       long long span = (ncg + per_unit - 1) / per_unit + 1;
       if (span > units) span = units;
-      span_total += span;
+      span_total += span * sets;
     }
     // the re-score kernel keeps every candidate of a query in shared memory (20 B each): few queries spread over all
     // units and many chunks would not fit -> use fewer chunks for such a pass
@@ -1063,27 +1100,9 @@ int plan_pass(int nq, int kp, const SimPlan& sp, int num_sms, size_t max_smem, i
     pp->n_chunks = (sp.n_gtiles + pp->gchunk - 1) / pp->gchunk;
   }
   pp->n_units = units;
-  pp->n_slots = pp->n_chunks * (units + pp->n_qtiles);
-  pp->kp = kp;
-  // shared memory: resident A + stages*B + cap KB of lists + barriers
-  const size_t a_bytes = static_cast<size_t>(sp.num_kb) * kATileBytes;
-  const size_t b_tile = static_cast<size_t>(kBlockN / sp.cg) * kBlockK * 2;
-  const size_t fixed = 1024 /*align slack*/ + 256 /*barriers*/ + 2048 /*column offsets*/ + 2048 /*carried thresholds*/;
-  // priorities: 3 B stages, then list capacity up to 64 (fewer compactions), then more stages (up to 8)
-  int cap = kp + 16;
-  const int cap_max = std::max(cap, std::min(64, env_int("DCR_SIM_CAP", 64)));
-  int stages = 2;
-  DCR_REQUIRE(max_smem >= a_bytes + stages * b_tile + cap * 1024 + fixed,
-              "sim_topk: not enough shared memory (%zu B) for d=%d k=%d cta_group=%d", max_smem, d, k, sp.cg);
-  auto fits = [&](int st, int cp) { return max_smem >= a_bytes + st * b_tile + static_cast<size_t>(cp) * 1024 + fixed; };
-  if (fits(3, cap)) stages = 3;
-  if (env_int("DCR_SIM_STAGES", 0) > 3 && fits(env_int("DCR_SIM_STAGES", 0), cap)) stages = env_int("DCR_SIM_STAGES", 0);
-  while (cap < cap_max && fits(stages, cap + 1)) ++cap;
-  while (stages < 8 && fits(stages + 1, cap)) ++stages;
-  pp->cap = cap;
-  pp->stages = stages;
-  pp->smem_bytes = fixed + a_bytes + stages * b_tile + static_cast<size_t>(cap) * 1024;
-  DCR_REQUIRE(span_total <= kMaxSlotsPerQuery, "sim_topk: %lld segments per query tile (max %d)", span_total, kMaxSlotsPerQuery);
+  pp->n_slots = pp->n_chunks * (units + pp->n_qtiles) * sets;
+  DCR_REQUIRE(span_total <= kMaxSlotsPerQuery, "sim_topk: %lld candidate slots per query tile (max %d)", span_total,
+              kMaxSlotsPerQuery);
   pp->max_cand = static_cast<int>(span_total) * kp;
   return 0;
 }
@@ -1104,6 +1123,11 @@ int make_plan(int nq, int ng, int d, int k, int cg, int num_sms, size_t max_smem
   pl->d_pad = static_cast<int>(align_up(d, kBlockK));
   pl->num_kb = pl->d_pad / kBlockK;
   pl->rows_per_qtile = kBlockM * cg;
+  // DCR_SIM_SETS=2 gives every TMEM lane quadrant two epilogue warps (column halves with their own lists).  Measured
+  // on B200 (10k x 100k x 512): no faster for k=1 (0.97 ms both ways) and slower for k=10 (the lists of two sets only
+  // fit with a small capacity) -- the filter's cost is the rare-hit slow path, which does not split by columns.  Off
+  // by default; kept for experiments.
+  pl->max_sets = (cg == 2) ? std::max(1, std::min(2, env_int("DCR_SIM_SETS", 1))) : 1;
   pl->n_gtiles = (ng + kBlockN - 1) / kBlockN;
   pl->ng_pad = pl->n_gtiles * kBlockN;
   // gallery chunks of ~DCR_SIM_CHUNK_MB of bf16 rows: the units sweep one chunk at a time so that it stays L2 resident
@@ -1117,7 +1141,8 @@ int make_plan(int nq, int ng, int d, int k, int cg, int num_sms, size_t max_smem
   pl->n_chunks = n_chunks;
   // first pass keeps few candidates per (query, segment) -- enough unless many gallery rows sit within the error
   // bound of the k-th score; such queries get a second chance with 32 candidates before the brute-force path
-  int kp0 = (k <= 2) ? 4 : (k <= 5 ? 8 : (k <= 10 ? 16 : 32));
+  // (with two epilogue warp sets every (segment, column half) keeps its own kp0 candidates, so fewer are enough)
+  int kp0 = (k <= 2) ? 4 : (k <= 5 ? 8 : (k <= 10 ? (pl->max_sets == 2 ? 12 : 16) : 32));
   kp0 = env_int("DCR_SIM_KP0", kp0);
   DCR_REQUIRE(kp0 >= 1 && kp0 <= kKPMax, "sim_topk: DCR_SIM_KP0 must be in [1, 32]");
   DCR_REQUIRE(kp0 >= k, "sim_topk: first-pass candidate count %d < k=%d", kp0, k);
@@ -1145,7 +1170,7 @@ int make_plan(int nq, int ng, int d, int k, int cg, int num_sms, size_t max_smem
   pl->off_mu = take(static_cast<size_t>(d) * 4);
   pl->off_nu = take(static_cast<size_t>(d) * 4);
   pl->off_bias = take(static_cast<size_t>(pl->ng_pad) * 4);
-  const size_t slot_rows = static_cast<size_t>(std::max(pl->p0.n_slots, pl->kp1 ? pl->p1.n_slots : 0)) * pl->rows_per_qtile;
+  const size_t slot_rows = static_cast<size_t>(std::max(pl->p0.n_slots, pl->kp1 ? pl->p1.n_slots : 0)) * pl->rows_per_qtile;   // n_slots counts sets
   pl->off_cand = take(slot_rows * kKPMax * 8);
   pl->off_cnt = take(slot_rows * 4);
   pl->off_thr = take(slot_rows * 4);
@@ -1153,6 +1178,7 @@ int make_plan(int nq, int ng, int d, int k, int cg, int num_sms, size_t max_smem
   pl->off_flag1 = take(static_cast<size_t>(nq) * 4);
   pl->off_thr1 = take(static_cast<size_t>(nq) * 4);
   pl->off_counts = take(16);
+  pl->off_clk = take(32);
   pl->off_exact = take(static_cast<size_t>(kExactBatch) * ng * 8);
   pl->total = off;
   return 0;
@@ -1173,7 +1199,7 @@ struct PassBuffers {
 // one fused pass: qb (bf16, padded) x gb (bf16, centred, padded) -> candidate slots
 int launch_fused(const SimPlan& pl, const PassPlan& pp, const __nv_bfloat16* qb, const __nv_bfloat16* gb, int ng,
                  const PassBuffers& pb, const float* col_bias, const int* bias_flag, const float* thr_init,
-                 cudaStream_t stream) {
+                 unsigned long long* clk, cudaStream_t stream) {
   CUtensorMap tq, tg;
   if (int rc = make_tmap_2d_bf16(&tq, qb, pp.nq_pad, pl.d_pad, pl.d_pad, kBlockM, kBlockK)) return rc;
   if (int rc = make_tmap_2d_bf16(&tg, gb, pl.ng_pad, pl.d_pad, pl.d_pad, kBlockN / pl.cg, kBlockK)) return rc;
@@ -1195,9 +1221,10 @@ int launch_fused(const SimPlan& pl, const PassPlan& pp, const __nv_bfloat16* qb,
   p.col_bias = col_bias;
   p.bias_flag = bias_flag;
   p.thr_init = thr_init;
+  p.clk = clk;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(pp.n_units * pl.cg);
-  cfg.blockDim = dim3(kThreads);
+  cfg.blockDim = dim3(64 + 128 * pp.n_sets);
   cfg.dynamicSmemBytes = pp.smem_bytes;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
@@ -1215,12 +1242,15 @@ int launch_fused(const SimPlan& pl, const PassPlan& pp, const __nv_bfloat16* qb,
   };
   // the variant without the offset path always runs unless the device flag says otherwise; the offset variant is only
   // launched when query centring is possible at all (it returns immediately when the flag is 0)
-  if (pl.cg == 2) {
-    if (int rc = launch(sim_topk_kernel<2, false>)) return rc;
-    if (col_bias) return launch(sim_topk_kernel<2, true>);
+  if (pl.cg == 2 && pp.n_sets == 2) {
+    if (int rc = launch(sim_topk_kernel<2, false, 2>)) return rc;
+    if (col_bias) return launch(sim_topk_kernel<2, true, 2>);
+  } else if (pl.cg == 2) {
+    if (int rc = launch(sim_topk_kernel<2, false, 1>)) return rc;
+    if (col_bias) return launch(sim_topk_kernel<2, true, 1>);
   } else {
-    if (int rc = launch(sim_topk_kernel<1, false>)) return rc;
-    if (col_bias) return launch(sim_topk_kernel<1, true>);
+    if (int rc = launch(sim_topk_kernel<1, false, 1>)) return rc;
+    if (col_bias) return launch(sim_topk_kernel<1, true, 1>);
   }
   return 0;
 }
@@ -1269,6 +1299,7 @@ int sim_topk(const float* q, int nq, const float* g, int ng, int d, int k, long 
   auto* thr1 = reinterpret_cast<float*>(w + pl.off_thr1);
   auto* counts = reinterpret_cast<int*>(w + pl.off_counts);   // [0] flagged by pass 0, [1] flagged by pass 1
   auto* exact = reinterpret_cast<double*>(w + pl.off_exact);
+  auto* clk = reinterpret_cast<unsigned long long*>(w + pl.off_clk);
 
   const bool centre = env_int("DCR_SIM_CENTER", 1) != 0;
   DCR_CUDA_CHECK(cudaMemsetAsync(gmax, 0, 16, stream));
@@ -1314,7 +1345,7 @@ int sim_topk(const float* q, int nq, const float* g, int ng, int d, int k, long 
     DCR_CUDA_CHECK(cudaEventCreate(&ev1));
   }
   DCR_CUDA_CHECK(cudaEventRecord(ev0, stream));
-  if (int rc = launch_fused(pl, pl.p0, qb, gb, ng, pb, col_bias, qflag, nullptr, stream)) return rc;
+  if (int rc = launch_fused(pl, pl.p0, qb, gb, ng, pb, col_bias, qflag, nullptr, clk, stream)) return rc;
   DCR_CUDA_CHECK(cudaEventRecord(ev1, stream));
 
   auto rescore = [&](const PassPlan& pp, const int* qmap, int* flagged, int* n_flagged, float* thr_next) -> int {
@@ -1322,7 +1353,7 @@ int sim_topk(const float* q, int nq, const float* g, int ng, int d, int k, long 
     DCR_CUDA_CHECK(cudaFuncSetAttribute(rescore_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         static_cast<int>(rs_smem)));
     rescore_select_kernel<<<pp.nq, 128, rs_smem, stream>>>(
-        q, g, nq, ng, d, k, pp.n_qtiles, pl.n_gtiles, pp.gchunk, pp.n_chunks, pp.n_units, pl.rows_per_qtile, pl.d_pad,
+        q, g, nq, ng, d, k, pp.n_qtiles, pl.n_gtiles, pp.gchunk, pp.n_chunks, pp.n_units, pl.rows_per_qtile, pp.n_sets, pl.d_pad,
         pb.cand, pb.ccnt,
         pb.cthr, qmap, centre ? mu : nullptr, centre ? nu : nullptr, qflag, qnh, qnr, qnx, gmax, g_index_base, g_index_stride, out_scores, out_idx,
         flagged, n_flagged, thr_next, pp.max_cand);
@@ -1333,7 +1364,9 @@ int sim_topk(const float* q, int nq, const float* g, int ng, int d, int k, long 
   if (int rc = rescore(pl.p0, nullptr, flag0, counts + 0, thr1)) return rc;
 
   int h_counts[2] = {0, 0};
+  unsigned long long h_clk[4] = {0, 0, 0, 0};
   DCR_CUDA_CHECK(cudaMemcpyAsync(h_counts, counts, 8, cudaMemcpyDeviceToHost, stream));
+  DCR_CUDA_CHECK(cudaMemcpyAsync(h_clk, clk, 32, cudaMemcpyDeviceToHost, stream));
   DCR_CUDA_CHECK(cudaStreamSynchronize(stream));
   int n_second = 0;
   const int* exact_list = flag0;
@@ -1346,7 +1379,7 @@ int sim_topk(const float* q, int nq, const float* g, int ng, int d, int k, long 
     gather_rows_kernel<<<std::min(di->num_sms * 8, (p1.nq_pad * (pl.d_pad / 8) + 255) / 256), 256, 0, stream>>>(
         qb, flag0, n_second, p1.nq_pad, pl.d_pad, qb1);
     count_launch();
-    if (int rc = launch_fused(pl, p1, qb1, gb, ng, pb, col_bias, qflag, thr1, stream)) return rc;
+    if (int rc = launch_fused(pl, p1, qb1, gb, ng, pb, col_bias, qflag, thr1, nullptr, stream)) return rc;
     if (int rc = rescore(p1, flag0, flag1, counts + 1, nullptr)) return rc;
     DCR_CUDA_CHECK(cudaMemcpyAsync(h_counts, counts, 8, cudaMemcpyDeviceToHost, stream));
     DCR_CUDA_CHECK(cudaStreamSynchronize(stream));
@@ -1375,6 +1408,10 @@ int sim_topk(const float* q, int nq, const float* g, int ng, int d, int k, long 
     float ms = 0.f;
     if (cudaEventElapsedTime(&ms, ev0, ev1) != cudaSuccess) ms = 0.f;
     stats->kernel_ms = ms;
+    stats->sm_mhz = (h_clk[3] > h_clk[1]) ? static_cast<float>(static_cast<double>(h_clk[2] - h_clk[0]) * 1e3 /
+                                                               static_cast<double>(h_clk[3] - h_clk[1]))
+                                          : 0.f;
+    stats->n_sets = pl.p0.n_sets;
     stats->cta_group = cg;
     stats->grid = pl.p0.n_units * cg;
     stats->smem_bytes = static_cast<int>(pl.p0.smem_bytes);

@@ -93,6 +93,8 @@ def sim_topk_stats() -> dict:
     st = dict(zip(keys, list(arr)))
     st["kernel_ms"] = float(lib.dcr_sim_topk_last_kernel_ms())
     st["n_second"] = int(lib.dcr_sim_topk_last_second_pass())
+    st["sm_mhz"] = float(lib.dcr_sim_topk_last_sm_mhz())
+    st["epilogue_sets"] = int(lib.dcr_sim_topk_last_epilogue_sets())
     return st
 
 

@@ -70,6 +70,10 @@ int dcr_sim_topk_last_stats(int* out8);
 /* Device time (ms, CUDA events on the call's stream) of the fused similarity+top-k kernel alone in the most recent
  * dcr_sim_topk on this host thread; the conversion / re-score kernels are excluded. */
 float dcr_sim_topk_last_kernel_ms(void);
+/* SM clock (MHz) while that kernel ran, from clock64 / %globaltimer read by its first CTA (0 if not measured), and
+ * the number of epilogue warp sets (4 warps each) it ran with. */
+float dcr_sim_topk_last_sm_mhz(void);
+int dcr_sim_topk_last_epilogue_sets(void);
 /* number of queries that went through the second-chance pass (32 candidates) in that call */
 int dcr_sim_topk_last_second_pass(void);
 
