@@ -62,7 +62,8 @@ def build_parser() -> argparse.ArgumentParser:
     # additions of this implementation (all optional)
     p.add_argument("--weights", default="", type=str, help="state_dict / TorchScript file of the descriptor model "
                    "(default: the reference's hard-coded ./pretrainedmodels/ paths)")
-    p.add_argument("--precision", default="fast", choices=["fast", "parity"])
+    p.add_argument("--precision", default="fast", choices=["fast", "parity", "exact"],
+                   help="fast: bf16 tensor cores; parity: split-bf16 tensor cores (fp32-level); exact: float64 accumulation")
     p.add_argument("--topk", default=10, type=int, help="matches kept per query (reference: 1 for the statistics, 10 for the galleries)")
     p.add_argument("--fid_weights", default="", type=str, help="pt_inception-2015-12-05 state_dict; enables FID")
     return p

@@ -148,6 +148,7 @@ int dcr_net_create(int max_batch, int planes, dcr_net** out) {
   DCR_REQUIRE(out != nullptr, "dcr_net_create: null out pointer");
   return dcr::net_create(max_batch, planes, reinterpret_cast<dcr::Net**>(out));
 }
+int dcr_net_set_exact(dcr_net* net, int on) { return dcr::net_set_exact(reinterpret_cast<dcr::Net*>(net), on); }
 void dcr_net_destroy(dcr_net* net) { dcr::net_destroy(reinterpret_cast<dcr::Net*>(net)); }
 int dcr_net_add_tensor(dcr_net* net, int64_t rows_per_image, int channels) {
   return dcr::net_add_tensor(reinterpret_cast<dcr::Net*>(net), rows_per_image, channels);

@@ -433,6 +433,7 @@ int conv_gemm(const ConvGemmDesc& d, cudaStream_t stream) {
   DCR_REQUIRE(d.n_terms >= 1 && d.n_terms <= kMaxGemmTerms, "conv_gemm: bad n_terms %d", d.n_terms);
   DCR_REQUIRE(d.C % 8 == 0 && d.N % 8 == 0, "conv_gemm: C (%d) and N (%d) must be multiples of 8", d.C, d.N);
   DCR_REQUIRE(d.kh >= 1 && d.kw >= 1 && d.stride >= 1, "conv_gemm: bad filter geometry");
+  if (d.exact) return conv_exact(d, stream);
   const bool windowed = d.in_stride_w != 0;
   const bool im2col = windowed || !(d.kh == 1 && d.kw == 1 && d.stride == 1 && d.pad_h == 0 && d.pad_w == 0);
   const int P = (d.H + 2 * d.pad_h - d.kh) / d.stride + 1;

@@ -63,8 +63,10 @@ struct ConvGemmDesc {
   int ld_out_f32 = 0;
   int act = 0;        // 0 none, 1 relu, 2 gelu(erf)
   int force_bn = 0;   // 0 = auto tile width
+  int exact = 0;      // 1 = float64 accumulation on the CUDA cores (conv_exact.cu) instead of the tensor cores
 };
 int conv_gemm(const ConvGemmDesc& d, cudaStream_t stream);
+int conv_exact(const ConvGemmDesc& d, cudaStream_t stream);
 
 
 // ---- HBM-bound kernels (pool_norm.cu, attention.cu) ---------------------------------------------------------------
@@ -105,6 +107,7 @@ enum NetOpKind {
 };
 struct Net;
 int net_create(int max_batch, int planes, Net** out);
+int net_set_exact(Net* n, int on);
 void net_destroy(Net* n);
 int net_add_tensor(Net* n, long long rows_per_image, int C);
 int net_add_param(Net* n, const void* host, size_t bytes);

@@ -31,6 +31,7 @@ struct Net {
   int max_batch = 0;
   int planes = 1;
   int terms = 1;
+  int exact = 0;   // convolutions / linear layers accumulate in float64 (needs planes == 3)
   int out_dim = 0;
   float* out_f32 = nullptr;   // [max_batch, out_dim]
   std::vector<NetTensor> tensors;
@@ -53,6 +54,13 @@ int net_create(int max_batch, int planes, Net** out) {
   n->planes = planes;
   n->terms = planes == 1 ? 1 : (planes == 2 ? 3 : 6);
   *out = n;
+  return 0;
+}
+
+int net_set_exact(Net* n, int on) {
+  DCR_REQUIRE(n != nullptr, "net_set_exact: null handle");
+  DCR_REQUIRE(!on || n->planes == 3, "net_set_exact: exact arithmetic needs the 3-plane (fp32) tensor format");
+  n->exact = on ? 1 : 0;
   return 0;
 }
 
@@ -184,6 +192,7 @@ int net_forward(Net* n, const uint8_t* images, int B, float* out, cudaStream_t s
           d.res = r.ptr; d.ld_res = r.C; d.res_planes = P; d.res_plane_stride = r.plane_stride;
         }
         d.act = a[15];
+        d.exact = n->exact;
         if (a[1] >= 0) {
           NetTensor& o = n->tensors[a[1]];
           d.out = o.ptr; d.ld_out = o.C; d.out_col_off = a[16]; d.out_planes = P; d.out_plane_stride = o.plane_stride;

@@ -26,7 +26,9 @@ from .ops import prepare_conv_weight
 OP_IM2COL_U8, OP_CONV, OP_MAXPOOL, OP_AVGPOOL, OP_GEM, OP_GAP, OP_LAYERNORM, OP_VIT_TOKENS, OP_ATTENTION, \
     OP_L2NORM_OUT, OP_STEM_S2D = range(11)
 
-PRECISION_PLANES = {"fast": 1, "bf16": 1, "parity": 3, "fp32": 3, "bf16x3": 2}
+# fast/bf16: one bf16 plane, tensor cores.  parity/fp32: three planes (exact fp32 values), 6 tensor-core cross terms.
+# exact: three planes, products accumulated in float64 on the CUDA cores (correctly rounded fp32 layer outputs).
+PRECISION_PLANES = {"fast": 1, "bf16": 1, "parity": 3, "fp32": 3, "bf16x3": 2, "exact": 3}
 
 
 class DcrNet:
@@ -47,6 +49,8 @@ class DcrNet:
         h = C.c_void_p()
         with torch.cuda.device(self.device):
             _lib.check(self.lib.dcr_net_create(self.max_batch, self.planes, C.byref(h)), "dcr_net_create")
+            if precision == "exact":
+                _lib.check(self.lib.dcr_net_set_exact(h, 1), "dcr_net_set_exact")
         self.handle = h
 
     def __del__(self):

@@ -132,6 +132,9 @@ int dcr_conv2d_bf16(const void* x, int x_planes, int64_t x_plane_stride, int B, 
  *                per row) to read 4 adjacent stored pixels as one 64-channel pixel (kh = 4, kw = 1). */
 typedef struct dcr_net dcr_net;
 int dcr_net_create(int max_batch, int planes, dcr_net** out);
+/* on != 0: every CONV op accumulates its products in float64 on the CUDA cores (correctly rounded fp32 layer outputs,
+ * the mode the parity tests use against the fp32 oracle); needs planes == 3.  Default 0: tcgen05 tensor cores. */
+int dcr_net_set_exact(dcr_net* net, int on);
 void dcr_net_destroy(dcr_net* net);
 int dcr_net_add_tensor(dcr_net* net, int64_t rows_per_image, int channels);
 /* copies `bytes` from HOST memory to a new device buffer */

@@ -27,6 +27,38 @@ def test_inception_parity_mode():
     assert err < 5e-4 * max(1.0, ref.abs().max().item())
 
 
+def test_inception_exact_mode_matches_reference_golden():
+    """Exact mode (float64 accumulation) against the activations the REFERENCE's own metrics/inception.py produced for
+    the same seeded weights and images (tests/golden/make_golden.py) -- and against the oracle."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "fid_inception_seed0.npz"))
+    sd = om.make_inception_state_dict(0)
+    img = torch.randint(0, 256, (2, 299, 299, 3), dtype=torch.uint8, generator=torch.Generator().manual_seed(8000))
+    net = nets.build_fid_inception(sd, max_batch=2, precision="exact")
+    got = net(img.cuda()).cpu().numpy()
+    gold = g["out"]
+    err = np.abs(got - gold).max()
+    ref = om.fid_inception_forward(sd, om.fid_preprocess(img)).numpy()
+    err_o = np.abs(got - ref).max()
+    print(f"inception exact: vs reference golden {err:.3e}, vs oracle {err_o:.3e}, max|act|={np.abs(gold).max():.3f}")
+    # fp32 evaluations of a 94-convolution network differ by their own summation order (the oracle is within 2e-5 of the
+    # golden vector, tests/test_oracle_fid.py); the exact path must sit inside the same band
+    assert err < 3e-5 * max(1.0, np.abs(gold).max()) and err_o < 3e-5 * max(1.0, np.abs(ref).max())
+
+
+def test_fid_value_exact_mode():
+    """FID of two small image sets, exact mode vs the oracle pipeline: the north-star tolerance (1e-4) on the value."""
+    sd = om.make_inception_state_dict(2)
+    net = nets.build_fid_inception(sd, max_batch=8, precision="exact")
+    real, gen = _imgs(12, 20), _imgs(12, 21)
+    got = dfid.fid_from_images(net, real, gen, batch_size=8)
+    a = om.fid_inception_forward(sd, om.fid_preprocess(real)).numpy()
+    b = om.fid_inception_forward(sd, om.fid_preprocess(gen)).numpy()
+    ref = ofid.frechet_distance(*ofid.activation_statistics(a), *ofid.activation_statistics(b))
+    print(f"fid exact: got {got:.6f} oracle {ref:.6f}")
+    assert abs(got - ref) < 1e-4 * max(1.0, abs(ref)), (got, ref)
+
+
 def test_inception_fast_mode():
     sd = om.make_inception_state_dict(0)
     img = _imgs(3, 2)

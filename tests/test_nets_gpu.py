@@ -34,6 +34,26 @@ def test_sscd_resnet50_parity_mode(mean, std):
     assert (got @ got.T - ref @ ref.T).abs().max().item() < 1e-4
 
 
+def test_sscd_resnet50_exact_mode():
+    sd = om.make_sscd_state_dict(0)
+    img = _imgs(3, 7)
+    ref = om.sscd_forward(sd, om.preprocess(img))
+    net = nets.build_sscd_resnet50(sd, max_batch=2, precision="exact")
+    got = net(img.cuda()).cpu()
+    err, cos = _report("sscd exact", got, ref)
+    assert err < 1e-5, err      # unit-norm descriptors: a few fp32 ulps of summation-order noise in the oracle itself
+
+
+def test_dino_vits16_exact_mode():
+    sd = om.make_vit_state_dict(0)
+    img = _imgs(3, 3)
+    ref = om.vit_forward(sd, om.preprocess(img))
+    net = nets.build_dino_vit(sd, max_batch=2, precision="exact")
+    got = net(img.cuda()).cpu()
+    err, cos = _report("vit exact", got, ref)
+    assert err < 3e-5 * max(1.0, ref.abs().max().item()), err
+
+
 def test_sscd_resnet50_fast_mode():
     sd = om.make_sscd_state_dict(0)
     img = _imgs(6, 2)
