@@ -943,6 +943,69 @@ __global__ void __launch_bounds__(128)
 }
 
 // ------------------------------------------------------------------------------------------------------------
+// 'splitloss' similarity (diff_retrieval.py:393-400): descriptors are cut into n_chunks equal parts and the score of
+// a pair is the MAXIMUM over the parts of the per-part dot products.  The top-k under that score is contained in the
+// union of the per-part top-k lists (if a row is in the true top-k through its best part c, fewer than k rows beat it
+// in part c), so the host runs the fused kernel once per part and this kernel finishes: per query, de-duplicate the
+// n_cand candidate rows, evaluate max_c <q_c, g_c> exactly (float64, the same fixed-order dot as the re-score
+// kernel), and select k by (score desc, row asc).
+__global__ void __launch_bounds__(128)
+    split_rescore_kernel(const float* __restrict__ q, const float* __restrict__ g, int d, int n_chunks,
+                         const long long* __restrict__ cand, int n_cand, int k, float* __restrict__ out_scores,
+                         long long* __restrict__ out_idx) {
+  extern __shared__ __align__(16) uint8_t sm[];
+  float* qs = reinterpret_cast<float*>(sm);                              // [d]
+  double* sc = reinterpret_cast<double*>(sm + ((d * 4 + 15) & ~15));      // [n_cand]
+  long long* ci = reinterpret_cast<long long*>(sc + n_cand);              // [n_cand], -1 = duplicate / taken
+  __shared__ BlockBest s_bb;
+  const int qrow = blockIdx.x;
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int c = threadIdx.x; c < d; c += blockDim.x) qs[c] = q[static_cast<size_t>(qrow) * d + c];
+  for (int c = threadIdx.x; c < n_cand; c += blockDim.x) ci[c] = cand[static_cast<size_t>(qrow) * n_cand + c];
+  __syncthreads();
+  // duplicates (a row that made the list of several parts): keep the first occurrence
+  for (int c = threadIdx.x; c < n_cand; c += blockDim.x) {
+    const long long v = ci[c];
+    bool dup = false;
+    for (int j = 0; j < c; ++j) dup |= (cand[static_cast<size_t>(qrow) * n_cand + j] == v);
+    sc[c] = dup ? 1.0 : 0.0;
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < n_cand; c += blockDim.x)
+    if (sc[c] != 0.0) ci[c] = -1;
+  __syncthreads();
+  const int p = d / n_chunks;
+  for (int c = warp; c < n_cand; c += 4) {
+    if (ci[c] < 0) continue;   // warp-uniform
+    double best = -INFINITY;
+    for (int part = 0; part < n_chunks; ++part) {
+      const double v = exact_dot_warp(qs + part * p, g + static_cast<size_t>(ci[c]) * d + part * p, p, lane);
+      best = fmax(best, v);
+    }
+    if (lane == 0) sc[c] = best;   // ranked on the float64 value (as dcr_sim_topk), reported as fp32
+  }
+  __syncthreads();
+  for (int round = 0; round < k; ++round) {
+    double bs = -INFINITY;
+    long long bi = 0x7fffffffffffffffLL;
+    int bp = -1;
+    for (int c = threadIdx.x; c < n_cand; c += blockDim.x)
+      if (ci[c] >= 0 && (bp < 0 || better(sc[c], ci[c], bs, bi))) {
+        bs = sc[c];
+        bi = ci[c];
+        bp = c;
+      }
+    block_argbest(bs, bi, bp, &s_bb, lane, warp);
+    if (threadIdx.x == 0) {
+      out_scores[static_cast<size_t>(qrow) * k + round] = bp >= 0 ? static_cast<float>(bs) : -INFINITY;
+      out_idx[static_cast<size_t>(qrow) * k + round] = bp >= 0 ? bi : -1;
+      if (bp >= 0) ci[bp] = -1;
+    }
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
 // brute-force exact path for flagged queries (batch of <= kExactBatch): scores[f][g] in fp64, then select.
 constexpr int kExactBatch = 32;
 
@@ -1256,6 +1319,21 @@ int launch_fused(const SimPlan& pl, const PassPlan& pp, const __nv_bfloat16* qb,
 }
 
 }  // namespace
+
+int split_rescore(const float* q, const float* g, int nq, int d, int n_chunks, const long long* cand, int n_cand, int k,
+                  float* out_scores, long long* out_idx, cudaStream_t stream) {
+  DCR_REQUIRE(nq >= 1 && d >= 1 && n_chunks >= 1 && d % n_chunks == 0 && (d / n_chunks) % 4 == 0,
+              "split_rescore: d=%d must split into %d parts whose length is a multiple of 4", d, n_chunks);
+  DCR_REQUIRE(n_cand >= k && k >= 1 && n_cand <= 1024, "split_rescore: need k <= n_cand <= 1024 (k=%d n_cand=%d)", k, n_cand);
+  DCR_REQUIRE((reinterpret_cast<uintptr_t>(q) & 15) == 0 && (reinterpret_cast<uintptr_t>(g) & 15) == 0,
+              "split_rescore: q/g must be 16-byte aligned");
+  const size_t smem = ((static_cast<size_t>(d) * 4 + 15) & ~size_t(15)) + static_cast<size_t>(n_cand) * 16;
+  DCR_CUDA_CHECK(cudaFuncSetAttribute(split_rescore_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  split_rescore_kernel<<<nq, 128, smem, stream>>>(q, g, d, n_chunks, cand, n_cand, k, out_scores, out_idx);
+  count_launch();
+  DCR_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
 
 size_t sim_topk_workspace_size(int nq, int ng, int d, int k) {
   const DeviceInfo* di = device_info();

@@ -19,7 +19,7 @@ import torch
 
 from . import _lib
 from .nets import DcrNet
-from .similarity import l2_normalize_, sim_topk
+from .similarity import l2_normalize_, sim_topk, sim_topk_split
 
 
 @torch.no_grad()
@@ -92,13 +92,17 @@ def retrieval_stats(main_v: torch.Tensor, bg_v: Optional[torch.Tensor] = None) -
 
 
 def run_retrieval(net: DcrNet, query_images: torch.Tensor, gallery_images: torch.Tensor, k: int = 1,
-                  with_background: bool = False, batch_size: Optional[int] = None) -> Dict[str, object]:
+                  with_background: bool = False, batch_size: Optional[int] = None,
+                  num_loss_chunks: int = 1) -> Dict[str, object]:
     """Embed both image sets and match them (the rank-0 block of diff_retrieval.py:386-419)."""
     values_features = extract_features(net, gallery_images, batch_size)       # :386
     query_features = extract_features(net, query_images, batch_size)         # :387
     l2_normalize_(values_features)                                           # :388
     l2_normalize_(query_features)                                            # :389
-    main_v, main_l = sim_topk(query_features, values_features, k)             # :402, :411, :417
+    if num_loss_chunks > 1:                                                  # :393-400 ('splitloss', aligned parts)
+        main_v, main_l = sim_topk_split(query_features, values_features, k, num_loss_chunks)
+    else:
+        main_v, main_l = sim_topk(query_features, values_features, k)         # :402, :411, :417
     out = {"values": main_v, "indices": main_l, "query_features": query_features,
            "gallery_features": values_features}
     bg_v = None

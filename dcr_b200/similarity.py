@@ -85,6 +85,40 @@ def sim_topk(query: torch.Tensor, gallery: torch.Tensor, k: int = 1, *, index_ba
     return out_s, out_i
 
 
+def sim_topk_split(q: torch.Tensor, g: torch.Tensor, k: int, num_chunks: int) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Top-k under the 'splitloss' similarity of diff_retrieval.py:393-400 (--similarity_metric splitloss,
+    --num_loss_chunks C): score(q, g) = max_c <q_c, g_c> over the C equal parts of the descriptors.
+    One fused similarity+top-k pass per part (the true top-k is contained in the union of the per-part top-k lists),
+    then dcr_split_rescore evaluates the exact split score of the <= C*k candidates per query and selects.
+    Only the aligned form is implemented; the 'cross' variant (--stype cross, every part against every part,
+    einsum_in_chunks :643-662) is not."""
+    lib = _lib.load()
+    if num_chunks == 1:
+        return sim_topk(q, g, k)
+    if not (q.is_cuda and g.is_cuda):
+        raise _lib.DcrError("sim_topk_split needs CUDA tensors")
+    q = q.contiguous().float()
+    g = g.contiguous().float()
+    nq, d = q.shape
+    if d % num_chunks or (d // num_chunks) % 4:
+        raise _lib.DcrError(f"splitloss: descriptor dim {d} must split into {num_chunks} parts of a multiple of 4 dims")
+    if num_chunks * k > 1024:
+        raise _lib.DcrError("splitloss: num_chunks * k must be <= 1024")
+    p = d // num_chunks
+    cand = torch.empty((nq, num_chunks * k), dtype=torch.int64, device=q.device)
+    for c in range(num_chunks):
+        _, idx = sim_topk(q[:, c * p:(c + 1) * p].contiguous(), g[:, c * p:(c + 1) * p].contiguous(), k)
+        cand[:, c * k:(c + 1) * k] = idx
+    out_s = torch.empty((nq, k), dtype=torch.float32, device=q.device)
+    out_i = torch.empty((nq, k), dtype=torch.int64, device=q.device)
+    with torch.cuda.device(q.device):
+        st = torch.cuda.current_stream().cuda_stream
+        rc = lib.dcr_split_rescore(q.data_ptr(), g.data_ptr(), nq, d, num_chunks, cand.data_ptr(), num_chunks * k, k,
+                                   out_s.data_ptr(), out_i.data_ptr(), st)
+        _lib.check(rc, "dcr_split_rescore")
+    return out_s, out_i
+
+
 def sim_topk_stats() -> dict:
     lib = _lib.load()
     arr = (C.c_int * 8)()

@@ -87,6 +87,14 @@ long long dcr_kernel_launch_count(void);
 int dcr_topk_merge(const float* scores, const int64_t* idx, int nq, int nlists, int k_in, int k_out,
                    float* out_scores, int64_t* out_idx, void* stream);
 
+/* Final step of the 'splitloss' similarity (diff_retrieval.py:393-400: descriptors cut into n_chunks equal parts, pair
+ * score = max over the parts of the per-part dot products).  The caller runs dcr_sim_topk once per part and passes
+ * the union of the per-part top-k rows as cand [nq][n_cand] (duplicates allowed); this evaluates the exact split
+ * score of every candidate (float64 accumulation, reported as fp32) and writes the k best per query ordered by
+ * (score desc, row asc).  d %% n_chunks == 0, (d / n_chunks) %% 4 == 0, k <= n_cand <= 1024. */
+int dcr_split_rescore(const float* q, const float* g, int nq, int d, int n_chunks, const int64_t* cand, int n_cand, int k,
+                      float* out_scores, int64_t* out_idx, void* stream);
+
 /* ---- dense contraction of the descriptor networks ------------------------------------------------------------- */
 /* y = act(scale[n] * conv2d(x, w)[.., n] + bias[n] (+ residual)) as a tcgen05 implicit GEMM.
  *   x        NHWC bf16, `x_planes` planes of B*H*W*C elements each (plane p at x + p*x_plane_stride elements);

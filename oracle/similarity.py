@@ -58,6 +58,28 @@ def sim_topk(q: np.ndarray, g: np.ndarray, k: int, chunk: int = 256):
     return vals, idx
 
 
+def sim_topk_split(q: np.ndarray, g: np.ndarray, k: int, num_chunks: int, chunk: int = 128):
+    """'splitloss' similarity, diff_retrieval.py:393-400: v,q -> [b, c, p]; chunk_dp = einsum('ncp,mcp->nmc');
+    sim = max over c; then the same top-k as sim_topk (float64 dot products per part, ranked on the float64 value,
+    reported as float32, ties by lowest gallery index)."""
+    q = np.asarray(q, dtype=np.float32)
+    g = np.asarray(g, dtype=np.float32)
+    d = q.shape[1]
+    assert d % num_chunks == 0
+    p = d // num_chunks
+    g64 = g.astype(np.float64).reshape(g.shape[0], num_chunks, p)
+    vals = np.empty((q.shape[0], k), dtype=np.float32)
+    idx = np.empty((q.shape[0], k), dtype=np.int64)
+    for s in range(0, q.shape[0], chunk):
+        qq = q[s:s + chunk].astype(np.float64).reshape(-1, num_chunks, p)
+        S = np.einsum("mcp,ncp->mnc", qq, g64).max(axis=2)          # [chunk, G]
+        for r in range(S.shape[0]):
+            top = _rank_row(S[r], k)
+            idx[s + r] = top
+            vals[s + r] = S[r, top].astype(np.float32)
+    return vals, idx
+
+
 def sim_topk_reference_fp32(q, g, k: int):
     """Literal restatement of diff_retrieval.py:402,411,417 on CPU fp32 torch (tie order unspecified)."""
     import torch

@@ -67,3 +67,23 @@ def test_stats_keys():
     assert set(st) == {"sim_mean", "sim_std", "sim_75pc", "sim_90pc", "sim_95pc", "sim_gt_05pc", "bg_mean", "bg_std",
                        "bg_75pc", "bg_90pc", "bg_95pc"}
     assert abs(st["sim_gt_05pc"] - 50 / 101) < 1e-12
+
+
+def test_splitloss_oracle_is_the_einsum_max():
+    """Literal restatement of diff_retrieval.py:396-400 with torch/einops-free numpy on a tiny case."""
+    rng = np.random.default_rng(4)
+    q = rng.standard_normal((7, 24)).astype(np.float32)
+    g = rng.standard_normal((40, 24)).astype(np.float32)
+    c = 3
+    v = g.reshape(40, c, 8)
+    qq = q.reshape(7, c, 8)
+    chunk_dp = np.einsum("ncp,mcp->nmc", v.astype(np.float64), qq.astype(np.float64))   # :398
+    sim = chunk_dp.max(axis=2)                                                            # :399  [G, Q]
+    ref_idx = np.argsort(-sim.T, axis=1, kind="stable")[:, :5]
+    vals, idx = osim.sim_topk_split(q, g, 5, c)
+    assert np.array_equal(idx, ref_idx)
+    np.testing.assert_allclose(vals, np.take_along_axis(sim.T, ref_idx, axis=1), atol=1e-6)
+    # one part == the plain dot product
+    v1, i1 = osim.sim_topk_split(q, g, 5, 1)
+    v0, i0 = osim.sim_topk(q, g, 5)
+    assert np.array_equal(i1, i0) and np.array_equal(v1, v0)

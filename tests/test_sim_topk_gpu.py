@@ -147,3 +147,17 @@ def test_rejects_bad_arguments():
         similarity.sim_topk(q.cuda(), g.cuda(), 17)  # k > 16
     with pytest.raises(DcrError):
         similarity.sim_topk(q.cuda(), g[:3].cuda(), 5)  # k > G
+
+
+@pytest.mark.parametrize("nq,ng,d,c,k", [(64, 3000, 512, 4, 10), (33, 1000, 96, 3, 1), (20, 500, 512, 32, 5)])
+def test_splitloss_topk_matches_oracle(nq, ng, d, c, k):
+    """diff_retrieval.py:393-400: score = max over the c descriptor parts of the per-part dot products."""
+    from oracle import similarity as osim
+    q, g = synthetic.descriptors(nq, ng, d, seed=11 + c)
+    g[5] = g[9]                                   # exact duplicate rows: tie -> lowest index first
+    v, i = similarity.sim_topk_split(q.cuda(), g.cuda(), k, c)
+    ov, oi = osim.sim_topk_split(q.numpy(), g.numpy(), k, c)
+    assert np.array_equal(i.cpu().numpy(), oi)
+    np.testing.assert_allclose(v.cpu().numpy(), ov, rtol=0, atol=1e-6)
+    with pytest.raises(similarity._lib.DcrError):
+        similarity.sim_topk_split(q.cuda(), g.cuda(), k, 7)       # 7 does not divide d
