@@ -217,6 +217,60 @@ __global__ void pool_kernel(const PoolParams p) {
   }
 }
 
+// Single-plane 3x3 max pool (any stride / padding): the fast-mode path of the ResNet stem and the three Inception
+// reductions.  bf16 maxima are taken directly on the packed pairs (the maximum of bf16 values is exact), the nine
+// 16-byte loads are issued unconditionally from clamped coordinates (out-of-range taps are masked with -inf after the
+// load) so they are all in flight together, and each thread produces two horizontally adjacent outputs so that the
+// shared middle column of their windows is loaded once.
+__global__ void __launch_bounds__(256) maxpool3_bf16_kernel(const PoolParams p) {
+  const int cg = p.C / 8;
+  const int OW2 = (p.OW + 1) / 2;
+  const long long total = static_cast<long long>(p.B) * p.OH * OW2 * cg;
+  const __nv_bfloat162 ninf = __floats2bfloat162_rn(-INFINITY, -INFINITY);
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c8 = static_cast<int>(i % cg);
+    const long long m2 = i / cg;
+    const int q0 = static_cast<int>(m2 % OW2) * 2;
+    const int pp = static_cast<int>((m2 / OW2) % p.OH);
+    const int b = static_cast<int>(m2 / (static_cast<long long>(OW2) * p.OH));
+    const int y0 = pp * p.stride - p.pad, x0 = q0 * p.stride - p.pad;
+    const int ncols = 3 + p.stride;                 // columns covered by the two windows (<= 5 for stride <= 2)
+    __nv_bfloat162 a0[4], a1[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) a0[e] = a1[e] = ninf;
+    const __nv_bfloat16* img = p.in + static_cast<size_t>(b) * p.H * p.W * p.C + c8 * 8;
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      const int y = y0 + r;
+      const bool yok = y >= 0 && y < p.H;
+      const __nv_bfloat16* row = img + static_cast<size_t>(min(max(y, 0), p.H - 1)) * p.W * p.C;
+      uint4 v[5];
+#pragma unroll
+      for (int s = 0; s < 5; ++s) {
+        const int x = x0 + s;
+        v[s] = __ldg(reinterpret_cast<const uint4*>(row + static_cast<size_t>(min(max(x, 0), p.W - 1)) * p.C));
+      }
+#pragma unroll
+      for (int s = 0; s < 5; ++s) {
+        const int x = x0 + s;
+        const bool ok = yok && x >= 0 && x < p.W && s < ncols;
+        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v[s]);
+        const bool in0 = ok && s < 3, in1 = ok && s >= p.stride && s < p.stride + 3;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          if (in0) a0[e] = __hmax2(a0[e], h[e]);
+          if (in1) a1[e] = __hmax2(a1[e], h[e]);
+        }
+      }
+    }
+    const size_t m = (static_cast<size_t>(b) * p.OH + pp) * p.OW + q0;
+    __nv_bfloat16* o = p.out + m * p.ld_out + p.out_col_off + c8 * 8;
+    *reinterpret_cast<uint4*>(o) = *reinterpret_cast<const uint4*>(a0);
+    if (q0 + 1 < p.OW) *reinterpret_cast<uint4*>(o + p.ld_out) = *reinterpret_cast<const uint4*>(a1);
+  }
+}
+
 // ---- GeM / global average over the spatial positions of one image --------------------------------------------
 // grid = (B, C/8 / 32 rounded up); each thread owns one 8-channel group of one image and walks HW positions.
 struct ReduceHWParams {
@@ -441,7 +495,10 @@ int pool2d(bool is_max, const __nv_bfloat16* in, long long in_plane_stride, __nv
   p.ld_out = ld_out; p.out_col_off = out_col_off;
   if (B == 0) return 0;
   const long long total = static_cast<long long>(B) * p.OH * p.OW * (C / 8);
-  if (is_max) pool_kernel<true><<<grid_for(total, 256, di->num_sms), 256, 0, stream>>>(p);
+  if (is_max && planes == 1 && k == 3 && stride <= 2 && getenv("DCR_POOL_GENERIC") == nullptr) {
+    const long long total2 = static_cast<long long>(B) * p.OH * ((p.OW + 1) / 2) * (C / 8);
+    maxpool3_bf16_kernel<<<grid_for(total2, 256, di->num_sms), 256, 0, stream>>>(p);
+  } else if (is_max) pool_kernel<true><<<grid_for(total, 256, di->num_sms), 256, 0, stream>>>(p);
   else pool_kernel<false><<<grid_for(total, 256, di->num_sms), 256, 0, stream>>>(p);
   count_launch();
   DCR_CUDA_CHECK(cudaGetLastError());

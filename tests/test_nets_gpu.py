@@ -99,3 +99,22 @@ def test_forward_rejects_cpu_and_wrong_size():
         net(_imgs(1, 0))                                  # CPU tensor
     with pytest.raises(DcrError):
         net(torch.zeros(1, 224, 224, 3, dtype=torch.uint8, device="cuda"))
+
+
+def test_maxpool_fast_path_is_bit_identical_to_generic(monkeypatch):
+    """The packed-bf16 3x3 max pool (two outputs per thread, clamped loads) against the generic pool kernel: maxima of
+    bf16 values are exact, so whole-network outputs must not differ in a single bit (ResNet stem pool: stride 2 pad 1;
+    Inception pools: stride 2 pad 0, odd widths)."""
+    img = _imgs(3, 9).cuda()
+    net = nets.build_sscd_resnet50(om.make_sscd_state_dict(2), max_batch=4, precision="fast")
+    fast = net(img).clone()
+    monkeypatch.setenv("DCR_POOL_GENERIC", "1")
+    generic = net(img).clone()
+    monkeypatch.delenv("DCR_POOL_GENERIC")
+    assert torch.equal(fast, generic)
+    img2 = torch.randint(0, 256, (2, 299, 299, 3), dtype=torch.uint8, generator=torch.Generator().manual_seed(3)).cuda()
+    inc = nets.build_fid_inception(om.make_inception_state_dict(1), max_batch=2, precision="fast")
+    fast = inc(img2).clone()
+    monkeypatch.setenv("DCR_POOL_GENERIC", "1")
+    generic = inc(img2).clone()
+    assert torch.equal(fast, generic)
