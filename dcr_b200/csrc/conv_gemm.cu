@@ -243,31 +243,41 @@ __global__ void __launch_bounds__(kThreads, 1)
                          kEvictFirst);
     };
     if (kTma && has_res && etid == 0 && static_cast<int>(blockIdx.x) < num_tiles) load_residual(blockIdx.x, 0);
+    const bool two_out = p.n_out_bufs == 2;
+    const uint32_t sb_addr = smem_u32(sb), out_addr = smem_u32(out_stage), res_addr = smem_u32(res_stage);
+    int staged_n0 = -1;
+    uint32_t sbsel = 1;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tc) {
       const int m0 = (tile % num_m_tiles) * kBM;
       const int n0 = (tile / num_m_tiles) * BN;
       const uint32_t buf = tc & 1;
-      float* s_scale = sb + buf * 2 * BN;
-      float* s_bias = s_scale + BN;
-      uint8_t* ostage = out_stage + ((p.n_out_bufs == 2) ? (tc & 1) : 0) * kStagingBytes;
-      const uint8_t* rstage = res_stage + (tc & 1) * kStagingBytes;
+      uint8_t* ostage = out_stage + (two_out ? (tc & 1) : 0) * kStagingBytes;
+      const uint32_t ostage_addr = out_addr + (two_out ? (tc & 1) : 0) * kStagingBytes;
+      const uint32_t rstage_addr = res_addr + (tc & 1) * kStagingBytes;
       if constexpr (kTma) {
         if (etid == 0) {
-          // this tile's output staging buffer is free once the store that last used it has finished READING it:
-          // with two buffers that is the store of tile tc-2 (at most the newest group may still be pending)
-          if (p.n_out_bufs == 2) tma_store_wait_read_1(); else tma_store_wait_read();
+          // single output staging tile: it is free once the store of the previous tile has finished READING it (with
+          // two tiles that wait sits before the end-of-tile barrier, see below)
+          if (!two_out) tma_store_wait_read();
           // prefetch the NEXT tile's residual; its buffer was last read in tile tc-1 (all warps passed that barrier)
           if (has_res && tile + static_cast<int>(gridDim.x) < num_tiles) load_residual(tile + gridDim.x, (tc & 1) ^ 1);
         }
       }
-      // stage the per-channel affine of this tile (buffer `buf` was last read two tiles ago; every epilogue warp has
-      // passed the barrier of the previous tile since then)
-      for (int c = etid; c < BN; c += 256) {
-        const int n = n0 + c;
-        s_scale[c] = (p.scale && n < N) ? p.scale[n] : 1.f;
-        s_bias[c] = (p.bias && n < N) ? p.bias[n] : 0.f;
+      // Per-channel affine: staged only when the column block changes (tiles are walked m-fastest, so a CTA keeps its
+      // column block for many tiles) into the buffer the previous block did not use -- warps still finishing the
+      // previous tile read the other one.  The barrier is also what orders a single output staging tile's reuse.
+      const bool restage = n0 != staged_n0;
+      if (restage) {
+        sbsel ^= 1;
+        staged_n0 = n0;
+        for (int c = etid; c < BN; c += 256) {
+          const int n = n0 + c;
+          st_shared_f32(sb_addr + (sbsel * 2 * BN + c) * 4, (p.scale && n < N) ? p.scale[n] : 1.f);
+          st_shared_f32(sb_addr + (sbsel * 2 * BN + BN + c) * 4, (p.bias && n < N) ? p.bias[n] : 0.f);
+        }
       }
-      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (restage || (kTma && !two_out)) asm volatile("bar.sync 1, 256;" ::: "memory");
+      const uint32_t s_scale = sb_addr + sbsel * 2 * BN * 4, s_bias = s_scale + BN * 4;
       mbar_wait(&t_full[buf], (tc >> 1) & 1);
       tc_fence_after();
       if (kTma && has_res) mbar_wait(&res_full[tc & 1], (tc >> 1) & 1);
@@ -290,8 +300,8 @@ __global__ void __launch_bounds__(kThreads, 1)
         float y[32];
 #pragma unroll
         for (int c = 0; c < 32; c += 4) {
-          const float4 sc = *reinterpret_cast<const float4*>(s_scale + ch * 32 + c);
-          const float4 bi = *reinterpret_cast<const float4*>(s_bias + ch * 32 + c);
+          const float4 sc = ld_shared_f4(s_scale + (ch * 32 + c) * 4);
+          const float4 bi = ld_shared_f4(s_bias + (ch * 32 + c) * 4);
           y[c + 0] = fmaf(__uint_as_float(r[c + 0]), sc.x, bi.x);
           y[c + 1] = fmaf(__uint_as_float(r[c + 1]), sc.y, bi.y);
           y[c + 2] = fmaf(__uint_as_float(r[c + 2]), sc.z, bi.z);
@@ -299,13 +309,13 @@ __global__ void __launch_bounds__(kThreads, 1)
         }
         if constexpr (kTma) {
           // this thread's 32 columns live in slab ch/2 at 16-byte chunks (ch&1)*4 .. +3 of row `row` (128B swizzle)
-          uint8_t* srow = ostage + (ch >> 1) * kBM * 128 + row * 128;
-          const uint8_t* rrow = rstage + (ch >> 1) * kBM * 128 + row * 128;
+          const uint32_t srow = ostage_addr + (ch >> 1) * kBM * 128 + row * 128;
+          const uint32_t rrow = rstage_addr + (ch >> 1) * kBM * 128 + row * 128;
           const uint32_t sw = row & 7;
           if (has_res) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-              const uint4 rv = *reinterpret_cast<const uint4*>(rrow + ((((ch & 1) * 4 + j) ^ sw) << 4));
+              const uint4 rv = ld_shared_v4(rrow + ((((ch & 1) * 4 + j) ^ sw) << 4));
               const uint32_t w[4] = {rv.x, rv.y, rv.z, rv.w};
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
@@ -323,7 +333,7 @@ __global__ void __launch_bounds__(kThreads, 1)
             v.y = pack_bf16(y[j * 8 + 2], y[j * 8 + 3]);
             v.z = pack_bf16(y[j * 8 + 4], y[j * 8 + 5]);
             v.w = pack_bf16(y[j * 8 + 6], y[j * 8 + 7]);
-            *reinterpret_cast<uint4*>(srow + ((((ch & 1) * 4 + j) ^ sw) << 4)) = v;
+            st_shared_v4(srow + ((((ch & 1) * 4 + j) ^ sw) << 4), v);
           }
         } else {
           if (!row_ok) continue;
@@ -378,6 +388,9 @@ __global__ void __launch_bounds__(kThreads, 1)
       }
       if constexpr (kTma) {
         fence_proxy_async();   // generic-proxy writes -> visible to the TMA (async proxy)
+        // two output staging tiles: the NEXT tile writes the tile the PREVIOUS store (committed a whole tile ago) reads
+        // from; that read must be over before anyone passes this barrier
+        if (two_out && etid == 0) tma_store_wait_read();
         asm volatile("bar.sync 2, 256;" ::: "memory");
         if (etid == 0) {
           for (int sl = 0; sl < BN / 64; ++sl)

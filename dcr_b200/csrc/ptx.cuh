@@ -230,6 +230,26 @@ DCR_DEVICE void tmem_st_32x32(uint32_t taddr, const uint32_t (&r)[32]) {
 }
 DCR_DEVICE void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
+// Explicit shared-state-space vector accesses (32-bit shared addresses): pointers into dynamically carved shared
+// memory whose buffer index is a run-time value otherwise compile to GENERIC loads/stores (LD.E / ST.E), which queue
+// with the global-memory operations (lg_throttle stalls) and have a longer latency than LDS / STS.
+DCR_DEVICE uint4 ld_shared_v4(uint32_t saddr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(saddr));
+  return v;
+}
+DCR_DEVICE float4 ld_shared_f4(uint32_t saddr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr));
+  return v;
+}
+DCR_DEVICE void st_shared_v4(uint32_t saddr, const uint4& v) {
+  asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+DCR_DEVICE void st_shared_f32(uint32_t saddr, float v) {
+  asm volatile("st.shared.f32 [%0], %1;" ::"r"(saddr), "f"(v) : "memory");
+}
+
 // commit all previously issued MMAs of this thread to an mbarrier (arrive::one when they retire).
 // kCG == 2 multicasts the arrive to the barrier at the same offset in both CTAs of the pair.
 template <int kCG>
