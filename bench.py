@@ -333,6 +333,11 @@ def main():
             "images_embedded_per_s": (q_total + g_total) / (ms_per_step / 1e3),
             "embed_tflops": net.flops_per_image * (q_total + g_total) / (ms_per_step / 1e3) / 1e12,
             "gpu_launches": int(launches), "clocks": sampler.summary(), "roofline": roofline}
+    # the step's time is dominated by the descriptor network (conv/linear GEMM family, many shapes): its aggregate
+    # tensor throughput over the whole step, against the same measured peak, reported beside the graded kernel's roofline
+    line["roofline_embed"] = {"kernel": "gemm_bf16_kernel family (SSCD ResNet-50 forward, all layers, per GPU)",
+                              "bound": "tensor", "achieved": line["embed_tflops"] / world, "peak": peaks["sustained"],
+                              "unit": "TFLOP/s", "frac": line["embed_tflops"] / world / peaks["sustained"]}
     if e2e is not None:
         line["e2e"] = e2e
     if world == 1:

@@ -33,7 +33,8 @@ namespace {
 constexpr int kBlockM = 128;      // query rows per CTA (TMEM lanes)
 constexpr int kBlockN = 256;      // gallery rows per tile (TMEM columns per accumulator buffer)
 constexpr int kBlockK = 64;       // bf16 elements per 128-byte swizzled smem row
-constexpr int kMaxKB = 8;         // d_pad <= 512
+constexpr int kMaxKB = 8;         // d_pad <= 512: the query tile stays resident in shared memory; larger: streamed
+constexpr int kMaxDim = 8192;     // largest descriptor dimension accepted
 constexpr int kKPMax = 32;        // max candidates kept per (query, segment)
 constexpr int kWarmTiles = 4;     // tiles replayed at the start of every segment to seed the threshold
 constexpr uint32_t kFull = 0xffffffffu;
@@ -43,6 +44,7 @@ constexpr int kMaxSlotsPerQuery = 512;  // (chunk, unit) segments that may cover
 struct SimParams {
   int nq, ng;
   int num_kb;          // d_pad / 64
+  int stream_a;        // 1 (d_pad > 512): query k-blocks travel with the gallery k-blocks instead of staying resident
   int n_qtiles;        // ceil(nq / (128*CG))
   int n_gtiles;        // ceil(ng / 256)
   int gchunk;          // gallery tiles per L2-sized chunk (all units sweep chunk c before chunk c+1)
@@ -451,9 +453,13 @@ __global__ void __launch_bounds__(64 + 128 * kSets, 1)
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   constexpr int kBRows = kBlockN / kCG;
   constexpr int kBTileBytes = kBRows * kBlockK * 2;
-  uint8_t* smem_a = smem;                                   // num_kb x 16 KB
-  uint8_t* smem_b = smem_a + p.num_kb * kATileBytes;        // stages x kBTileBytes
-  uint2* cand = reinterpret_cast<uint2*>(smem_b + p.stages * kBTileBytes);  // [kSets][cap][128]
+  // resident mode: [num_kb x 16 KB query tile][stages x gallery tile]; streamed mode (d_pad > 512, the query tile no
+  // longer fits): [stages x (gallery tile | 16 KB query k-block)] -- twice the L2->SMEM traffic per FLOP
+  const bool stream_a = p.stream_a != 0;
+  const int stage_bytes = kBTileBytes + (stream_a ? kATileBytes : 0);
+  uint8_t* smem_a = smem;                                                  // num_kb x 16 KB (resident mode)
+  uint8_t* smem_b = smem_a + (stream_a ? 0 : p.num_kb * kATileBytes);      // stages x stage_bytes
+  uint2* cand = reinterpret_cast<uint2*>(smem_b + p.stages * stage_bytes);  // [kSets][cap][128]
   uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(cand) + kSets * p.cap * 128 * 8);
   uint64_t* b_full = bars;              // [stages]
   uint64_t* b_empty = bars + 8;         // [stages]
@@ -512,13 +518,14 @@ __global__ void __launch_bounds__(64 + 128 * kSets, 1)
       while (w.next()) {
         const int qi = w.qi, g_begin = w.g_begin, ntiles = w.ntiles;
         const int warm = (p.thr_init || w.carried) ? 0 : min(kWarmTiles, ntiles);
-        // resident query tile
-        mbar_wait(a_empty, (seg & 1) ^ 1);
-        if (leader) mbar_arrive_expect_tx(a_full, p.num_kb * kATileBytes * kCG);
-        else mbar_arrive_cluster(a_full, 0);
         const int q_row = qi * rows_per_qtile + static_cast<int>(cta_rank) * kBlockM;
-        for (int kb = 0; kb < p.num_kb; ++kb)
-          tma_load_2d<kCG>(smem_a + kb * kATileBytes, &tmap_q, a_full, kb * kBlockK, q_row, kEvictNormal);
+        if (!stream_a) {   // resident query tile
+          mbar_wait(a_empty, (seg & 1) ^ 1);
+          if (leader) mbar_arrive_expect_tx(a_full, p.num_kb * kATileBytes * kCG);
+          else mbar_arrive_cluster(a_full, 0);
+          for (int kb = 0; kb < p.num_kb; ++kb)
+            tma_load_2d<kCG>(smem_a + kb * kATileBytes, &tmap_q, a_full, kb * kBlockK, q_row, kEvictNormal);
+        }
         for (int j = 0; j < warm + ntiles; ++j) {
           const int gi = g_begin + (j < warm ? j : j - warm);
           const int g_row = gi * kBlockN + static_cast<int>(cta_rank) * kBRows;
@@ -526,9 +533,11 @@ __global__ void __launch_bounds__(64 + 128 * kSets, 1)
           for (int kb = 0; kb < p.num_kb; ++kb, ++it) {
             const uint32_t s = it % p.stages, ph = (it / p.stages) & 1;
             mbar_wait(&b_empty[s], ph ^ 1);
-            if (leader) mbar_arrive_expect_tx(&b_full[s], kBTileBytes * kCG);
+            if (leader) mbar_arrive_expect_tx(&b_full[s], stage_bytes * kCG);
             else mbar_arrive_cluster(&b_full[s], 0);
-            tma_load_2d<kCG>(smem_b + s * kBTileBytes, &tmap_g, &b_full[s], kb * kBlockK, g_row, kEvictNormal);
+            tma_load_2d<kCG>(smem_b + s * stage_bytes, &tmap_g, &b_full[s], kb * kBlockK, g_row, kEvictNormal);
+            if (stream_a)
+              tma_load_2d<kCG>(smem_b + s * stage_bytes + kBTileBytes, &tmap_q, &b_full[s], kb * kBlockK, q_row, kEvictNormal);
           }
         }
         ++seg;
@@ -543,8 +552,10 @@ __global__ void __launch_bounds__(64 + 128 * kSets, 1)
       while (w.next()) {
         const int ntiles = w.ntiles;
         const int warm = (p.thr_init || w.carried) ? 0 : min(kWarmTiles, ntiles);
-        mbar_wait(a_full, seg & 1);
-        tc_fence_after();
+        if (!stream_a) {
+          mbar_wait(a_full, seg & 1);
+          tc_fence_after();
+        }
         for (int j = 0; j < warm + ntiles; ++j, ++tc) {
           const uint32_t buf = tc & 1;
           mbar_wait(&t_empty[buf], ((tc >> 1) & 1) ^ 1);
@@ -554,15 +565,15 @@ __global__ void __launch_bounds__(64 + 128 * kSets, 1)
             const uint32_t s = it % p.stages, ph = (it / p.stages) & 1;
             if (p.debug_mode != 3) mbar_wait(&b_full[s], ph);
             tc_fence_after();
-            const uint64_t da = umma_desc_sw128(smem_u32(smem_a + kb * kATileBytes));
-            const uint64_t db = umma_desc_sw128(smem_u32(smem_b + s * kBTileBytes));
+            const uint64_t da = umma_desc_sw128(smem_u32(stream_a ? smem_b + s * stage_bytes + kBTileBytes : smem_a + kb * kATileBytes));
+            const uint64_t db = umma_desc_sw128(smem_u32(smem_b + s * stage_bytes));
 #pragma unroll
             for (int k = 0; k < kBlockK / 16; ++k)
               umma_f16<kCG>(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);  // +32 B per K=16 step
             if (p.debug_mode != 3) umma_commit<kCG>(&b_empty[s]);   // frees this B stage (both CTAs) once the MMAs above retire
             if (kb == p.num_kb - 1) {
               umma_commit<kCG>(&t_full[buf]);
-              if (j == warm + ntiles - 1) umma_commit<kCG>(a_empty);
+              if (!stream_a && j == warm + ntiles - 1) umma_commit<kCG>(a_empty);
             }
           }
         }
@@ -1012,10 +1023,10 @@ constexpr int kExactBatch = 32;
 __global__ void __launch_bounds__(256)
     exact_scan_kernel(const float* __restrict__ q, const float* __restrict__ g, int ng, int d,
                       const int* __restrict__ flagged, int f_begin, const int* __restrict__ n_flagged,
-                      double* __restrict__ scores) {
+                      double* __restrict__ scores, int batch) {
   extern __shared__ __align__(16) uint8_t sm[];
   float* qs = reinterpret_cast<float*>(sm);  // [nb][d]
-  const int nb = min(kExactBatch, *n_flagged - f_begin);
+  const int nb = min(batch, *n_flagged - f_begin);
   if (nb <= 0) return;
   for (int i = threadIdx.x; i < nb * d; i += blockDim.x) {
     const int f = i / d, c = i % d;
@@ -1096,6 +1107,7 @@ struct PassPlan {
 
 struct SimPlan {
   int cg, d_pad, num_kb, ng_pad, n_gtiles, rows_per_qtile;
+  int stream_a;  // d_pad > 512: query tile streamed with the gallery k-blocks
   int max_sets;  // upper bound for PassPlan::n_sets (1 or 2)
   int gchunk, n_chunks;   // preferred gallery chunking (a pass may use fewer chunks)
   int kp0, kp1;           // candidates kept by the first pass / by the second-chance pass (0 = no second pass)
@@ -1112,8 +1124,8 @@ int plan_pass(int nq, int kp, const SimPlan& sp, int num_sms, size_t max_smem, i
   pp->nq_pad = pp->n_qtiles * sp.rows_per_qtile;
   pp->kp = kp;
   // ---- shared memory: resident A + stages*B + n_sets * cap KB of lists + barriers + carried thresholds ----
-  const size_t a_bytes = static_cast<size_t>(sp.num_kb) * kATileBytes;
-  const size_t b_tile = static_cast<size_t>(kBlockN / sp.cg) * kBlockK * 2;
+  const size_t a_bytes = sp.stream_a ? 0 : static_cast<size_t>(sp.num_kb) * kATileBytes;
+  const size_t b_tile = static_cast<size_t>(kBlockN / sp.cg) * kBlockK * 2 + (sp.stream_a ? kATileBytes : 0);
   const size_t fixed = 1024 /*align slack*/ + 256 /*barriers*/ + 4096 /*carried thresholds*/;
   auto fits = [&](int st, int cp, int sets) {
     return max_smem >= a_bytes + st * b_tile + static_cast<size_t>(cp) * 1024 * sets + fixed;
@@ -1177,14 +1189,14 @@ int env_int(const char* name, int dflt) {
 
 int make_plan(int nq, int ng, int d, int k, int cg, int num_sms, size_t max_smem, SimPlan* pl) {
   DCR_REQUIRE(nq >= 1 && ng >= 1 && d >= 1, "sim_topk: empty problem (nq=%d ng=%d d=%d)", nq, ng, d);
-  DCR_REQUIRE(d <= kMaxKB * kBlockK, "sim_topk: descriptor dim %d > %d not supported by the resident-query kernel", d,
-              kMaxKB * kBlockK);
+  DCR_REQUIRE(d <= kMaxDim, "sim_topk: descriptor dim %d > %d not supported", d, kMaxDim);
   DCR_REQUIRE(k >= 1 && k <= 16, "sim_topk: k=%d outside [1,16]", k);
   DCR_REQUIRE(k <= ng, "sim_topk: k=%d > gallery size %d", k, ng);
   DCR_REQUIRE(cg == 1 || cg == 2, "sim_topk: cta group must be 1 or 2");
   pl->cg = cg;
   pl->d_pad = static_cast<int>(align_up(d, kBlockK));
   pl->num_kb = pl->d_pad / kBlockK;
+  pl->stream_a = pl->num_kb > kMaxKB ? 1 : 0;
   pl->rows_per_qtile = kBlockM * cg;
   // DCR_SIM_SETS=2 gives every TMEM lane quadrant two epilogue warps (column halves with their own lists).  Measured
   // on B200 (10k x 100k x 512): no faster for k=1 (0.97 ms both ways) and slower for k=10 (the lists of two sets only
@@ -1270,6 +1282,7 @@ int launch_fused(const SimPlan& pl, const PassPlan& pp, const __nv_bfloat16* qb,
   p.nq = pp.nq;
   p.ng = ng;
   p.num_kb = pl.num_kb;
+  p.stream_a = pl.stream_a;
   p.n_qtiles = pp.n_qtiles;
   p.n_gtiles = pl.n_gtiles;
   p.gchunk = pp.gchunk;
@@ -1467,14 +1480,16 @@ int sim_topk(const float* q, int nq, const float* g, int ng, int d, int k, long 
 
   // brute-force fp64 path for the queries whose certificate still fails (ties beyond 32 candidates, NaNs, ...)
   if (n_exact > 0) {
-    const size_t ex_smem = static_cast<size_t>(kExactBatch) * d * 4;
+    // queries per brute-force launch: as many as fit in shared memory next to each other (32 up to d = 1536)
+    const int ex_batch = std::max(1, std::min<int>(kExactBatch, static_cast<int>(192 * 1024 / (static_cast<size_t>(d) * 4))));
+    const size_t ex_smem = static_cast<size_t>(ex_batch) * d * 4;
     DCR_CUDA_CHECK(cudaFuncSetAttribute(exact_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         static_cast<int>(ex_smem)));
     const int* n_dev = (exact_list == flag0) ? counts + 0 : counts + 1;
-    for (int done = 0; done < n_exact; done += kExactBatch) {
-      exact_scan_kernel<<<di->num_sms * 2, 256, ex_smem, stream>>>(q, g, ng, d, exact_list, done, n_dev, exact);
+    for (int done = 0; done < n_exact; done += ex_batch) {
+      exact_scan_kernel<<<di->num_sms * 2, 256, ex_smem, stream>>>(q, g, ng, d, exact_list, done, n_dev, exact, ex_batch);
       count_launch();
-      exact_select_kernel<<<kExactBatch, 256, 0, stream>>>(exact, ng, k, exact_list, done, n_dev, g_index_base,
+      exact_select_kernel<<<ex_batch, 256, 0, stream>>>(exact, ng, k, exact_list, done, n_dev, g_index_base,
                                                            g_index_stride, out_scores, out_idx);
       count_launch();
     }

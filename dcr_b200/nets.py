@@ -189,15 +189,38 @@ def _first_conv_weight(w: torch.Tensor, k_pad: int) -> torch.Tensor:
     return out
 
 
+def _dense_from_grouped(w: torch.Tensor, c_in: int) -> torch.Tensor:
+    """Grouped convolution weight [N, c_in/groups, kh, kw] -> the equivalent dense block-diagonal weight
+    [N, c_in, kh, kw].  The tensor cores then run the grouped 3x3 convs of a ResNeXt trunk as ordinary dense
+    implicit GEMMs (zeros included): `groups` times the arithmetic of the grouped form, but at the widths involved
+    (128..1024 channels) that is still tensor-bound work at full tile efficiency, where per-group GEMMs with 4..32
+    output channels would use a few percent of a UMMA tile."""
+    n, cpg, kh, kw = w.shape
+    if cpg == c_in:
+        return w
+    groups = c_in // cpg
+    if cpg * groups != c_in or n % groups:
+        raise _lib.DcrError(f"grouped conv weight {tuple(w.shape)} does not divide {c_in} input channels")
+    npg = n // groups
+    dense = torch.zeros((n, c_in, kh, kw), dtype=w.dtype)
+    for g in range(groups):
+        dense[g * npg:(g + 1) * npg, g * cpg:(g + 1) * cpg] = w[g * npg:(g + 1) * npg]
+    return dense
+
+
 # ------------------------------------------------------------------------------------------------------------------
-# SSCD: ResNet-50 trunk + GeM + Linear + L2
+# SSCD: ResNet / ResNeXt bottleneck trunk + GeM + Linear + L2
 def build_sscd_resnet50(state_dict: Dict[str, torch.Tensor], max_batch: int = 64, precision: str = "fast",
                         mean: Sequence[float] = (0.5, 0.5, 0.5), std: Sequence[float] = (0.5, 0.5, 0.5),
                         in_size: int = 256, crop: int = 224, gem_p: float = 3.0, gem_eps: float = 1e-6,
                         l2_normalize: bool = True) -> DcrNet:
-    """state_dict keys: torchvision resnet50 names, optionally prefixed 'backbone.' / 'module.'; head Linear under
+    """state_dict keys: torchvision ResNet names, optionally prefixed 'backbone.' / 'module.'; head Linear under
     'embeddings.1' (SSCD), 'fc' or 'head'.  mean/std: (0.5, 0.5) for diff_retrieval.py:329, ImageNet statistics for
-    embedding_search/utils.py:37-39."""
+    embedding_search/utils.py:37-39.
+    The trunk is read off the state_dict: blocks per stage, bottleneck width and group count are whatever the tensors
+    say, so the same builder serves sscd_disc_mixup / sscd_imagenet_mixup (ResNet-50, 512-d; `--arch resnet50`,
+    `resnet50_im`, diff_retrieval.py:278-281) and sscd_disc_large (`--arch resnet50_disc`, :282-283 -- upstream a
+    ResNeXt-101 with a 1024-d head [unverified]); grouped 3x3 convs run as dense block-diagonal GEMMs."""
     sd = _strip({k: v.detach().cpu() for k, v in state_dict.items()}, ["module.", "model."])
     sd = _strip(sd, ["backbone."])
     head_w = head_b = None
@@ -226,26 +249,35 @@ def build_sscd_resnet50(state_dict: Dict[str, torch.Tensor], max_batch: int = 64
     t = net.tensor(hw * hw, 64)
     net.op(OP_MAXPOOL, [t_stem, t, s, s, 64, 3, 2, 1, 0])
     c_in = 64
-    for li, (planes, blocks, stride) in enumerate([(64, 3, 1), (128, 4, 2), (256, 6, 2), (512, 3, 2)], start=1):
+    for li, stride in enumerate([1, 2, 2, 2], start=1):
+        blocks = 0
+        while f"layer{li}.{blocks}.conv1.weight" in sd:
+            blocks += 1
+        if blocks == 0:
+            raise _lib.DcrError(f"SSCD state_dict has no layer{li} blocks")
         for bi_ in range(blocks):
             pre = f"layer{li}.{bi_}"
             st = stride if bi_ == 0 else 1
             hw_out = (hw + 2 - 3) // st + 1
-            t1 = net.tensor(hw * hw, planes)
+            width = sd[pre + ".conv1.weight"].shape[0]        # bottleneck width (64.. for ResNet-50, 128.. for 32x4d)
+            c_out = sd[pre + ".conv3.weight"].shape[0]
+            t1 = net.tensor(hw * hw, width)
             sc, bi = _fold_bn(sd, pre + ".bn1", eps)
             net.conv(t, t1, hw, hw, c_in, sd[pre + ".conv1.weight"], scale=sc, bias=bi, act=1)
-            t2 = net.tensor(hw_out * hw_out, planes)
+            t2 = net.tensor(hw_out * hw_out, width)
             sc, bi = _fold_bn(sd, pre + ".bn2", eps)
-            net.conv(t1, t2, hw, hw, planes, sd[pre + ".conv2.weight"], stride=st, pad=(1, 1), scale=sc, bias=bi, act=1)
+            w2 = sd[pre + ".conv2.weight"]
+            net.flops_per_image -= 2.0 * hw_out * hw_out * width * 9 * (width - w2.shape[1])   # zeros of the dense form
+            net.conv(t1, t2, hw, hw, width, _dense_from_grouped(w2, width), stride=st, pad=(1, 1), scale=sc, bias=bi, act=1)
             ident = t
             if pre + ".downsample.0.weight" in sd:
-                ident = net.tensor(hw_out * hw_out, planes * 4)
+                ident = net.tensor(hw_out * hw_out, c_out)
                 sc, bi = _fold_bn(sd, pre + ".downsample.1", eps)
                 net.conv(t, ident, hw, hw, c_in, sd[pre + ".downsample.0.weight"], stride=st, scale=sc, bias=bi)
-            t3 = net.tensor(hw_out * hw_out, planes * 4)
+            t3 = net.tensor(hw_out * hw_out, c_out)
             sc, bi = _fold_bn(sd, pre + ".bn3", eps)
-            net.conv(t2, t3, hw_out, hw_out, planes, sd[pre + ".conv3.weight"], scale=sc, bias=bi, residual=ident, act=1)
-            t, c_in, hw = t3, planes * 4, hw_out
+            net.conv(t2, t3, hw_out, hw_out, width, sd[pre + ".conv3.weight"], scale=sc, bias=bi, residual=ident, act=1)
+            t, c_in, hw = t3, c_out, hw_out
     d = head_w.shape[0]
     net.set_output(d)
     t_pool = net.tensor(1, c_in)

@@ -50,3 +50,17 @@ def test_cli_flag_surface_matches_reference():
     d = p.parse_args(["--query_dir", "q", "--val_dir", "v"])
     assert (d.pt_style, d.arch, d.similarity_metric, d.workers, d.batch_size, d.dist_backend, d.layer,
             d.einsum_chunks, d.num_matches, d.imsize) == ("sscd", "resnet50", "dotproduct", 4, 128, "nccl", 1, 30, 4, 224)
+
+
+def test_dense_expansion_of_grouped_conv_weight():
+    """nets._dense_from_grouped: the block-diagonal dense weight computes the same convolution as the grouped one."""
+    import torch
+    import torch.nn.functional as F
+    from dcr_b200 import nets
+    g = torch.Generator().manual_seed(0)
+    w = torch.randn(32, 4, 3, 3, generator=g)          # 8 groups of 4 -> 4
+    x = torch.randn(2, 32, 9, 9, generator=g)
+    dense = nets._dense_from_grouped(w, 32)
+    assert dense.shape == (32, 32, 3, 3) and (dense != 0).sum() == w.numel()
+    assert torch.allclose(F.conv2d(x, dense, padding=1), F.conv2d(x, w, padding=1, groups=8), atol=1e-5)
+    assert nets._dense_from_grouped(dense, 32) is dense

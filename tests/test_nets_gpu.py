@@ -118,3 +118,23 @@ def test_maxpool_fast_path_is_bit_identical_to_generic(monkeypatch):
     monkeypatch.setenv("DCR_POOL_GENERIC", "1")
     generic = inc(img2).clone()
     assert torch.equal(fast, generic)
+
+
+def test_sscd_grouped_trunk_1024d():
+    """ResNeXt-style trunk with a 1024-d head (the sscd_disc_large family, `--arch resnet50_disc`): grouped 3x3 convs as
+    dense block-diagonal GEMMs; descriptors wider than 512 then go through the streamed-query similarity kernel."""
+    from dcr_b200 import similarity
+    from oracle import similarity as osim
+    sd = om.make_sscd_state_dict(4, dims=1024, arch="resnext_tiny")
+    img = _imgs(6, 12)
+    ref = om.sscd_forward(sd, om.preprocess(img))
+    net = nets.build_sscd_resnet50(sd, max_batch=4, precision="exact")
+    got = net(img.cuda())
+    err, cos = _report("sscd resnext exact", got.cpu(), ref)
+    assert got.shape == (6, 1024) and err < 1e-5
+    fast = nets.build_sscd_resnet50(sd, max_batch=8, precision="fast")(img.cuda()).cpu()
+    _, cosf = _report("sscd resnext fast", fast, ref)
+    assert cosf > 0.995
+    v, i = similarity.sim_topk(got[:2].contiguous(), got.contiguous(), 3)
+    ov, oi = osim.sim_topk(got[:2].cpu().numpy(), got.cpu().numpy(), 3)
+    assert np.array_equal(i.cpu().numpy(), oi)

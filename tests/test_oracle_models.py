@@ -52,3 +52,24 @@ def test_preprocess_matches_torchvision_transform():
     ref = tf(Image.fromarray(img.numpy()))
     got = om.preprocess(img[None])[0]
     assert torch.equal(got, ref)
+
+
+def test_sscd_oracle_grouped_trunk_matches_torchvision_module():
+    """ResNeXt-style trunk (grouped 3x3 convs; the family upstream documents for sscd_disc_large) through the same
+    functional restatement."""
+    from torchvision.models.resnet import Bottleneck, ResNet
+    sd = om.make_sscd_state_dict(5, dims=1024, arch="resnext_tiny")
+    m = ResNet(Bottleneck, [2, 2, 2, 2], groups=8, width_per_group=8)
+    tv = {k[len("backbone."):]: v for k, v in sd.items() if k.startswith("backbone.")}
+    tv["fc.weight"], tv["fc.bias"] = m.fc.weight.detach(), m.fc.bias.detach()
+    m.load_state_dict(tv)
+    m.eval()
+    x = torch.randn(2, 3, 224, 224, generator=torch.Generator().manual_seed(2))
+    with torch.no_grad():
+        f = m.layer4(m.layer3(m.layer2(m.layer1(m.maxpool(m.relu(m.bn1(m.conv1(x))))))))
+        f = f.clamp(min=1e-6).pow(3).mean(dim=(2, 3)).pow(1.0 / 3)
+        f = torch.nn.functional.linear(f, sd["embeddings.1.weight"], sd["embeddings.1.bias"])
+        ref = torch.nn.functional.normalize(f, dim=1)
+    got = om.sscd_forward(sd, x)
+    assert got.shape == (2, 1024)
+    np.testing.assert_allclose(got.numpy(), ref.numpy(), atol=2e-5)

@@ -36,6 +36,9 @@ def _check(q, g, k, rows=None):
     (513, 4097, 512, 5),
     (300, 20000, 512, 10),    # several gallery tiles per unit
     (2000, 3000, 256, 16),    # many q-tiles, max k
+    (300, 5000, 1024, 10),    # SSCD 'large' descriptor dim: query tile streamed instead of resident
+    (260, 3000, 768, 1),      # ViT-B dim
+    (40, 700, 2048, 3),       # Inception pool3 dim
 ])
 def test_parity_synthetic(nq, ng, d, k):
     q, g = synthetic.descriptors(nq, ng, d, seed=nq + ng)
@@ -57,6 +60,14 @@ def test_duplicates_tie_rule():
     st = _check(q, g, 10)
     v, i = _run(q, g, 10)
     assert i[3, 0] == 300 and i[3, 1] == 1500
+
+
+def test_identical_gallery_wide_descriptors():
+    """brute-force path with d > 512 (adaptive batch)"""
+    g = torch.nn.functional.normalize(torch.ones(1, 1024), dim=1).repeat(300, 1)
+    q, _ = synthetic.descriptors(40, 16, 1024, seed=3)
+    st = _check(q, g, 5)
+    assert st["n_flagged"] == 40
 
 
 def test_all_identical_gallery_forces_exact_fallback():
