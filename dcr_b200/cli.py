@@ -94,8 +94,9 @@ def build_model(args):
         sd = load_state_dict(args.weights or SSCD_FILES[args.arch])
         return nets.build_sscd_resnet50(sd, max_batch=256, precision=args.precision)
     if args.pt_style == "dino":
-        if args.arch != "vit_small":
-            raise NotImplementedError("only --arch vit_small (dino_vits16) is implemented for --pt_style dino")
+        if args.arch not in ("vit_small", "vit_base"):                                          # :251-257
+            raise NotImplementedError("--pt_style dino: --arch vit_small (dino_vits16) and vit_base (dino_vitb16) are "
+                                      "implemented; vit_base8 / resnet50 / vit_base_cifar10 are not")
         sd = load_state_dict(args.weights or args.pretrained)
         return nets.build_dino_vit(sd, max_batch=256, precision=args.precision)
     raise NotImplementedError(f"--pt_style {args.pt_style} is outside the embed->match hot path (DESIGN.md section 9)")

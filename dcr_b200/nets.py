@@ -292,10 +292,16 @@ def build_sscd_resnet50(state_dict: Dict[str, torch.Tensor], max_batch: int = 64
 # DINO ViT (dino_vits.py:171-289)
 def build_dino_vit(state_dict: Dict[str, torch.Tensor], max_batch: int = 64, precision: str = "fast",
                    mean: Sequence[float] = (0.5, 0.5, 0.5), std: Sequence[float] = (0.5, 0.5, 0.5),
-                   in_size: int = 256, crop: int = 224, patch: int = 16, heads: int = 6) -> DcrNet:
+                   in_size: int = 256, crop: int = 224, patch: Optional[int] = None,
+                   heads: Optional[int] = None) -> DcrNet:
+    """Width, depth, patch size and head count are read off the state_dict (64-dim heads, as every DINO ViT):
+    vit_small/16 (`dino_vits16`, dino_vits.py:340-352; 384-d) and vit_base/16 (`dino_vitb16`, :366-378; 768-d).
+    patch 8 variants (785 tokens) exceed the attention kernels' 256-token tile and are rejected by dcr_net_forward."""
     sd = _strip({k: v.detach().cpu() for k, v in state_dict.items()}, ["module.", "backbone."])
     dim = sd["cls_token"].shape[-1]
     depth = 1 + max(int(k.split(".")[1]) for k in sd if k.startswith("blocks."))
+    patch = int(sd["patch_embed.proj.weight"].shape[-1]) if patch is None else patch
+    heads = dim // 64 if heads is None else heads
     grid = crop // patch
     n_patch = grid * grid
     tokens = n_patch + 1

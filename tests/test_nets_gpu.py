@@ -138,3 +138,19 @@ def test_sscd_grouped_trunk_1024d():
     v, i = similarity.sim_topk(got[:2].contiguous(), got.contiguous(), 3)
     ov, oi = osim.sim_topk(got[:2].cpu().numpy(), got.cpu().numpy(), 3)
     assert np.array_equal(i.cpu().numpy(), oi)
+
+
+def test_dino_vit_base_width():
+    """vit_base/16 geometry (768-d, 12 heads; `--arch vit_base`, dino_vits.py:366-378) at reduced depth: heads and
+    patch size are inferred from the state_dict; the 768-d descriptors exceed the resident-query tile of the similarity
+    kernel (streamed mode)."""
+    sd = om.make_vit_state_dict(2, dim=768, depth=2, heads=12)
+    img = _imgs(3, 5)
+    ref = om.vit_forward(sd, om.preprocess(img), heads=12)
+    net = nets.build_dino_vit(sd, max_batch=4, precision="exact")
+    got = net(img.cuda()).cpu()
+    err, cos = _report("vit-b exact", got, ref)
+    assert got.shape == (3, 768) and err < 3e-5 * max(1.0, ref.abs().max().item())
+    fast = nets.build_dino_vit(sd, max_batch=4, precision="fast")(img.cuda()).cpu()
+    _, cosf = _report("vit-b fast", fast, ref)
+    assert cosf > 0.99
