@@ -129,3 +129,66 @@ def load_resized(path: str, size: int = 299) -> torch.Tensor:
     for i, f in enumerate(files):
         out[i] = torch.from_numpy(np.asarray(tf(Image.open(f).convert("RGB"))))
     return out
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# the reference's call signatures (metrics/fid.py:224-275)
+_FID_WEIGHTS_FILE = "pt_inception-2015-12-05-6726825d.pth"       # metrics/inception.py:13 (downloaded there; a local file here)
+
+
+def _build_inception(weights, max_batch: int, precision: str) -> DcrNet:
+    import os
+    from . import nets
+    if isinstance(weights, DcrNet):
+        return weights
+    if isinstance(weights, dict):
+        sd = weights
+    else:
+        path = weights or os.environ.get("DCR_FID_WEIGHTS", _FID_WEIGHTS_FILE)
+        if not os.path.exists(path):
+            raise FileNotFoundError(f"FID Inception weights not found: {path} (there is no network access to fetch "
+                                    f"{_FID_WEIGHTS_FILE}; pass weights= or set DCR_FID_WEIGHTS)")
+        sd = torch.load(path, map_location="cpu")
+    return nets.build_fid_inception(sd, max_batch=max_batch, precision=precision)
+
+
+def compute_statistics_of_path(path: str, net: DcrNet, batch_size: int = 50) -> Tuple[np.ndarray, np.ndarray]:
+    """metrics/fid.py:224-236: a `.npz` with mu/sigma is loaded, anything else is globbed for images."""
+    if path.endswith(".npz"):
+        with np.load(path) as f:
+            return f["mu"][:], f["sigma"][:]
+    return statistics_of_images(net, load_resized(path), batch_size)
+
+
+def calculate_fid_given_paths(paths, batch_size: int = 50, device=None, dims: int = 2048, num_workers: int = 1,
+                              weights=None, precision: str = "fast") -> float:
+    """metrics/fid.py:239-255.  `device` / `num_workers` are accepted for signature compatibility (the current CUDA
+    device is used; image decoding is sequential).  Only the pool3 features (dims = 2048, the reference's default and
+    the only block its callers request, diff_retrieval.py:597-600) are implemented."""
+    import os
+    for p in paths:
+        if not os.path.exists(p):
+            raise RuntimeError("Invalid path: %s" % p)                                       # fid.py:241-243
+    print(dims)                                                                              # fid.py:244
+    if dims != 2048:
+        raise NotImplementedError("only dims=2048 (pool3, InceptionV3.BLOCK_INDEX_BY_DIM[2048]) is implemented")
+    net = _build_inception(weights, batch_size, precision)
+    m1, s1 = compute_statistics_of_path(paths[0], net, batch_size)
+    m2, s2 = compute_statistics_of_path(paths[1], net, batch_size)
+    return frechet_distance(m1, s1, m2, s2)
+
+
+def save_fid_stats(paths, batch_size: int = 50, device=None, dims: int = 2048, num_workers: int = 1, weights=None,
+                   precision: str = "fast") -> None:
+    """metrics/fid.py:258-275: statistics of paths[0] written to the .npz paths[1]."""
+    import os
+    if not os.path.exists(paths[0]):
+        raise RuntimeError("Invalid path: %s" % paths[0])
+    if os.path.exists(paths[1]):
+        raise RuntimeError("Existing output file: %s" % paths[1])
+    if dims != 2048:
+        raise NotImplementedError("only dims=2048 (pool3) is implemented")
+    net = _build_inception(weights, batch_size, precision)
+    print(f"Saving statistics for {paths[0]}")
+    m1, s1 = compute_statistics_of_path(paths[0], net, batch_size)
+    np.savez_compressed(paths[1], mu=m1, sigma=s1)

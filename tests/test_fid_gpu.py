@@ -106,3 +106,29 @@ def test_fid_pipeline_small():
     assert np.abs(m1 - rm).max() < tol and np.abs(s1 - rs).max() < tol * np.abs(act).max()
     v = dfid.fid_from_images(net, real, gen, batch_size=8)
     assert np.isfinite(v) and v >= -1e-6
+
+
+def test_calculate_fid_given_paths_mirror(tmp_path, capsys):
+    """metrics/fid.py:224-275 call surface: folders of images, .npz statistics files, error behaviour."""
+    from PIL import Image
+    sd = om.make_inception_state_dict(3)
+    a, b = tmp_path / "real" / "sub", tmp_path / "gen"
+    a.mkdir(parents=True)
+    b.mkdir()
+    ia, ib = _imgs(10, 30), _imgs(9, 31)
+    for i in range(10):
+        Image.fromarray(ia[i].numpy()).save(a / f"{i}.png")
+    for i in range(9):
+        Image.fromarray(ib[i].numpy()).save(b / f"{i}.png")
+    net = nets.build_fid_inception(sd, max_batch=8, precision="fast")
+    v = dfid.calculate_fid_given_paths([str(tmp_path / "real"), str(b)], 8, "cuda", 2048, weights=net)
+    assert capsys.readouterr().out.strip().splitlines()[0] == "2048"              # fid.py:244
+    assert abs(v - dfid.fid_from_images(net, dfid.load_resized(str(tmp_path / "real")), dfid.load_resized(str(b)), 8)) < 1e-6
+    npz = str(tmp_path / "real_stats.npz")
+    dfid.save_fid_stats([str(tmp_path / "real"), npz], 8, "cuda", 2048, weights=net)
+    v2 = dfid.calculate_fid_given_paths([npz, str(b)], 8, "cuda", 2048, weights=net)
+    assert abs(v - v2) < 1e-6
+    with pytest.raises(RuntimeError, match="Invalid path"):
+        dfid.calculate_fid_given_paths([str(tmp_path / "missing"), str(b)], 8, "cuda", 2048, weights=net)
+    with pytest.raises(FileNotFoundError):
+        dfid.calculate_fid_given_paths([str(tmp_path / "real"), str(b)], 8, "cuda", 2048, weights=str(tmp_path / "none.pth"))
