@@ -42,6 +42,7 @@ struct GemmMaps {
   CUtensorMap w[3];
   CUtensorMap out;   // TMA-store epilogue (single-plane bf16 output)
   CUtensorMap res;   // residual tile loads for that epilogue
+  CUtensorMap a_flat; // timing experiment DCR_GEMM_DEBUG=2 only: the im2col input viewed as a plain [pixels, C] matrix
 };
 
 struct GemmParams {
@@ -65,6 +66,8 @@ struct GemmParams {
   int tma_epi;                // 1: stage the bf16 output tile in shared memory and write it with TMA stores
   int n_out_bufs;             // 1 or 2 output staging tiles (2: the TMA store of tile i drains during tile i+1)
   int n_res_bufs;             // 0 or 2 residual staging tiles (the residual of tile i+1 is prefetched during tile i)
+  int debug;                  // timing experiments (results are garbage): 1 = loads only (no MMA, no epilogue), 2 = loads only and
+                              // every im2col request replaced by a tiled request of the same size (row-shifted view)
 };
 
 DCR_DEVICE float apply_act(float y, int act) {
@@ -188,10 +191,13 @@ __global__ void __launch_bounds__(kThreads, 1)
               mbar_wait(&empty[s], ph ^ 1);
               mbar_arrive_expect_tx(&full[s], kStageBytes);
               uint8_t* sa = smem_ab + s * kStageBytes;
-              if constexpr (kIm2col)
-                tma_load_im2col_4d<1>(sa, ma, &full[s], cb * kBK, w0, h0, img, static_cast<uint16_t>(sx),
-                                      static_cast<uint16_t>(r));
-              else
+              if constexpr (kIm2col) {
+                if (p.debug == 2)
+                  tma_load_2d<1>(sa, &maps.a_flat, &full[s], cb * kBK, max(0, m0 + (r - 1) * p.Q + sx - 1), kEvictNormal);
+                else
+                  tma_load_im2col_4d<1>(sa, ma, &full[s], cb * kBK, w0, h0, img, static_cast<uint16_t>(sx),
+                                        static_cast<uint16_t>(r));
+              } else
                 tma_load_2d<1>(sa, ma, &full[s], cb * kBK, m0, kEvictNormal);
               tma_load_2d<1>(sa + kAStage, mw, &full[s], (tap * cblocks + cb) * kBK, n0, kEvictNormal);
             }
@@ -205,6 +211,14 @@ __global__ void __launch_bounds__(kThreads, 1)
       uint32_t it = 0, tc = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tc) {
         const uint32_t buf = tc & 1;
+        if (p.debug) {   // loads only: hand every stage straight back to the producer
+          for (int ki = 0; ki < k_iters; ++ki, ++it) {
+            const uint32_t s = it % stages, ph = (it / stages) & 1;
+            mbar_wait(&full[s], ph);
+            mbar_arrive(&empty[s]);
+          }
+          continue;
+        }
         mbar_wait(&t_empty[buf], ((tc >> 1) & 1) ^ 1);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + buf * BN;
@@ -242,12 +256,12 @@ __global__ void __launch_bounds__(kThreads, 1)
           tma_load_2d<1>(res_stage + rbuf * kStagingBytes + sl * kBM * 128, &maps.res, &res_full[rbuf], rn0 + sl * 64, rm0,
                          kEvictFirst);
     };
-    if (kTma && has_res && etid == 0 && static_cast<int>(blockIdx.x) < num_tiles) load_residual(blockIdx.x, 0);
+    if (kTma && has_res && etid == 0 && static_cast<int>(blockIdx.x) < num_tiles && !p.debug) load_residual(blockIdx.x, 0);
     const bool two_out = p.n_out_bufs == 2;
     const uint32_t sb_addr = smem_u32(sb), out_addr = smem_u32(out_stage), res_addr = smem_u32(res_stage);
     int staged_n0 = -1;
     uint32_t sbsel = 1;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tc) {
+    for (int tile = blockIdx.x; tile < num_tiles && !p.debug; tile += gridDim.x, ++tc) {
       const int m0 = (tile % num_m_tiles) * kBM;
       const int n0 = (tile / num_m_tiles) * BN;
       const uint32_t buf = tc & 1;
@@ -517,6 +531,12 @@ int conv_gemm(const ConvGemmDesc& d, cudaStream_t stream) {
   p.out_f32 = d.out_f32;
   p.ld_out_f32 = d.ld_out_f32;
   p.act = d.act;
+  p.debug = getenv("DCR_GEMM_DEBUG") ? atoi(getenv("DCR_GEMM_DEBUG")) : 0;
+  if (p.debug == 2 && im2col && !windowed) {
+    if (int rc = make_tmap_2d_bf16(&maps.a_flat, d.in, static_cast<uint64_t>(d.B) * d.H * d.W, d.C, d.C, kBM, kBK)) return rc;
+  } else if (p.debug == 2) {
+    p.debug = 1;
+  }
   p.tma_epi = (p.out != nullptr && p.out_planes == 1 && p.out_f32 == nullptr && (p.res == nullptr || p.res_planes == 1) &&
                getenv("DCR_GEMM_DIRECT_EPILOGUE") == nullptr)
                   ? 1
