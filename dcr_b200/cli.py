@@ -92,11 +92,18 @@ def build_model(args):
         if args.arch not in SSCD_FILES:
             raise NotImplementedError("This model type does not exist/supported for SSCD")      # :285
         sd = load_state_dict(args.weights or SSCD_FILES[args.arch])
+        if args.multiscale:                                                                   # utils_ret.py:676-698
+            from . import retrieval
+            return [nets.build_sscd_resnet50(sd, max_batch=256, precision=args.precision, scale_factor=s)
+                    for s in retrieval.MULTI_SCALES]
         return nets.build_sscd_resnet50(sd, max_batch=256, precision=args.precision)
     if args.pt_style == "dino":
         if args.arch not in ("vit_small", "vit_base"):                                          # :251-257
             raise NotImplementedError("--pt_style dino: --arch vit_small (dino_vits16) and vit_base (dino_vitb16) are "
                                       "implemented; vit_base8 / resnet50 / vit_base_cifar10 are not")
+        if args.multiscale:
+            raise NotImplementedError("--multiscale needs interpolated position embeddings for ViTs (dino_vits.py:213-233); "
+                                      "it is implemented for the convolutional SSCD trunks")
         sd = load_state_dict(args.weights or args.pretrained)
         return nets.build_dino_vit(sd, max_batch=256, precision=args.precision)
     raise NotImplementedError(f"--pt_style {args.pt_style} is outside the embed->match hot path (DESIGN.md section 9)")

@@ -78,7 +78,7 @@ int im2col_u8(const uint8_t* img, int B, int IH, int IW, int crop_y, int crop_x,
               float post_shift, __nv_bfloat16* out, long long out_plane_stride, int planes, cudaStream_t stream);
 int stem_s2d_u8(const uint8_t* img, int B, int IH, int IW, int crop_y, int crop_x, int H, int W, const float* mean3,
                 const float* std3, float post_scale, float post_shift, __nv_bfloat16* out, long long out_plane_stride,
-                int planes, cudaStream_t stream);
+                int planes, cudaStream_t stream, int RH = 0, int RW = 0, float rscale = 0.f);
 int pool2d(bool is_max, const __nv_bfloat16* in, long long in_plane_stride, __nv_bfloat16* out,
            long long out_plane_stride, int planes, int B, int H, int W, int C, int k, int stride, int pad, int ld_out,
            int out_col_off, cudaStream_t stream);

@@ -118,7 +118,9 @@ int net_add_op(Net* n, int kind, const int* iargs, int ni, const float* fargs, i
   auto param_ok = [&](int id, bool optional) { return (optional && id < 0) || (id >= 0 && id < (int)n->params.size()); };
   switch (kind) {
     case NET_OP_IM2COL_U8: DCR_REQUIRE(ni == 12 && nf == 8 && tensor_ok(op.i[0], false), "im2col_u8 op: bad args"); break;
-    case NET_OP_STEM_S2D: DCR_REQUIRE(ni == 7 && nf == 8 && tensor_ok(op.i[0], false), "stem_s2d op: bad args"); break;
+    case NET_OP_STEM_S2D:
+      DCR_REQUIRE(((ni == 7 && nf == 8) || (ni == 9 && nf == 9)) && tensor_ok(op.i[0], false), "stem_s2d op: bad args");
+      break;
     case NET_OP_CONV:
       DCR_REQUIRE((ni == 18 || ni == 20) && tensor_ok(op.i[0], false) && tensor_ok(op.i[1], true) && param_ok(op.i[5], false) &&
                       param_ok(op.i[12], true) && param_ok(op.i[13], true) && tensor_ok(op.i[14], true),
@@ -164,8 +166,9 @@ int net_forward(Net* n, const uint8_t* images, int B, float* out, cudaStream_t s
       }
       case NET_OP_STEM_S2D: {
         NetTensor& t = n->tensors[a[0]];
+        // optional 9-int / 9-float form: a[7], a[8] = size after bilinear resizing of the crop, f[8] = float(1 / scale_factor)
         rc = stem_s2d_u8(images, B, a[1], a[2], a[3], a[4], a[5], a[6], &op.f[0], &op.f[3], op.f[6], op.f[7], t.ptr,
-                         t.plane_stride, P, stream);
+                         t.plane_stride, P, stream, a[7], a[8], op.f[8]);   // unset arguments are zero = no resizing
         break;
       }
       case NET_OP_CONV: {

@@ -119,9 +119,14 @@ __global__ void __launch_bounds__(256) im2col_u8_kernel(const Im2colU8Params p) 
 // Z[b, u, v, (i*2+j)*3 + c] = xn[2u + i - 3, 2v + j - 3, c]  (zero outside the image), channels 12..15 = 0, with
 // xn the normalised crop.  A 7x7/2 convolution of xn equals a 4x4/1 convolution of Z (weights regrouped on the host),
 // which the GEMM kernel reads through an overlapping-window tensor map -- no im2col matrix in HBM.
+// Optional bilinear down-scaling of the normalised crop first (utils_ret.py:676-698 `multi_scale`:
+// F.interpolate(x, scale_factor=s, mode='bilinear', align_corners=False)): xn is then the [RH, RW] resized image,
+// sampled with torch's arithmetic (source index = rscale * (dst + 0.5) - 0.5 clamped at 0, rscale = float(1 / s)).
 struct StemS2dParams {
   const uint8_t* img;
   int B, IH, IW, crop_y, crop_x, H, W, U, V;
+  int RH, RW;        // size of xn (== H, W without resizing)
+  float rscale;      // 0 = no resizing
   float mean[3], std[3], post_scale, post_shift;
   __nv_bfloat16* out;
   long long out_plane_stride;
@@ -149,14 +154,29 @@ __global__ void __launch_bounds__(256) stem_s2d_u8_kernel(const StemS2dParams p)
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
       const int y = 2 * u + i - 3;
-      if (y < 0 || y >= p.H) continue;
+      if (y < 0 || y >= p.RH) continue;
 #pragma unroll
       for (int j = 0; j < 2; ++j) {
         const int x = 2 * v + j - 3;
-        if (x < 0 || x >= p.W) continue;
-        const uint8_t* px = img + (static_cast<size_t>(y + p.crop_y) * p.IW + (x + p.crop_x)) * 3;
+        if (x < 0 || x >= p.RW) continue;
+        if (p.rscale == 0.f) {
+          const uint8_t* px = img + (static_cast<size_t>(y + p.crop_y) * p.IW + (x + p.crop_x)) * 3;
 #pragma unroll
-        for (int c = 0; c < 3; ++c) z[(i * 2 + j) * 3 + c] = lut[c][px[c]];
+          for (int c = 0; c < 3; ++c) z[(i * 2 + j) * 3 + c] = lut[c][px[c]];
+        } else {
+          const float sy = fmaxf(p.rscale * (static_cast<float>(y) + 0.5f) - 0.5f, 0.f);
+          const float sx = fmaxf(p.rscale * (static_cast<float>(x) + 0.5f) - 0.5f, 0.f);
+          const int y0 = static_cast<int>(sy), x0 = static_cast<int>(sx);
+          const int y1 = y0 + (y0 < p.H - 1 ? 1 : 0), x1 = x0 + (x0 < p.W - 1 ? 1 : 0);
+          const float ly = sy - static_cast<float>(y0), lx = sx - static_cast<float>(x0);
+          const float hy = 1.f - ly, hx = 1.f - lx;
+          const uint8_t* r0 = img + (static_cast<size_t>(y0 + p.crop_y) * p.IW + p.crop_x) * 3;
+          const uint8_t* r1 = img + (static_cast<size_t>(y1 + p.crop_y) * p.IW + p.crop_x) * 3;
+#pragma unroll
+          for (int c = 0; c < 3; ++c)
+            z[(i * 2 + j) * 3 + c] = hy * (hx * lut[c][r0[x0 * 3 + c]] + lx * lut[c][r0[x1 * 3 + c]]) +
+                                     ly * (hx * lut[c][r1[x0 * 3 + c]] + lx * lut[c][r1[x1 * 3 + c]]);
+        }
       }
     }
     float lo[8], hi[8];
@@ -462,14 +482,16 @@ int im2col_u8(const uint8_t* img, int B, int IH, int IW, int crop_y, int crop_x,
 
 int stem_s2d_u8(const uint8_t* img, int B, int IH, int IW, int crop_y, int crop_x, int H, int W, const float* mean3,
                 const float* std3, float post_scale, float post_shift, __nv_bfloat16* out, long long out_plane_stride,
-                int planes, cudaStream_t stream) {
+                int planes, cudaStream_t stream, int RH, int RW, float rscale) {
   const DeviceInfo* di = device_info();
   if (!di) return -2;
   DCR_REQUIRE(crop_y >= 0 && crop_x >= 0 && crop_y + H <= IH && crop_x + W <= IW, "stem_s2d_u8: crop outside image");
-  DCR_REQUIRE(H % 2 == 0 && W % 2 == 0, "stem_s2d_u8: crop size must be even");
+  if (rscale == 0.f) { RH = H; RW = W; }
+  DCR_REQUIRE(RH >= 2 && RW >= 2 && RH % 2 == 0 && RW % 2 == 0, "stem_s2d_u8: network input size must be even (%d x %d)", RH, RW);
   StemS2dParams p;
   p.img = img; p.B = B; p.IH = IH; p.IW = IW; p.crop_y = crop_y; p.crop_x = crop_x; p.H = H; p.W = W;
-  p.U = (H + 6) / 2; p.V = (W + 6) / 2;
+  p.RH = RH; p.RW = RW; p.rscale = rscale;
+  p.U = (RH + 6) / 2; p.V = (RW + 6) / 2;
   for (int c = 0; c < 3; ++c) { p.mean[c] = mean3[c]; p.std[c] = std3[c]; }
   p.post_scale = post_scale; p.post_shift = post_shift;
   p.out = out; p.out_plane_stride = out_plane_stride; p.planes = planes;

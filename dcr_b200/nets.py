@@ -18,6 +18,7 @@ from __future__ import annotations
 import ctypes as C
 from typing import Dict, Optional, Sequence
 
+import numpy as np
 import torch
 
 from . import _lib
@@ -213,7 +214,7 @@ def _dense_from_grouped(w: torch.Tensor, c_in: int) -> torch.Tensor:
 def build_sscd_resnet50(state_dict: Dict[str, torch.Tensor], max_batch: int = 64, precision: str = "fast",
                         mean: Sequence[float] = (0.5, 0.5, 0.5), std: Sequence[float] = (0.5, 0.5, 0.5),
                         in_size: int = 256, crop: int = 224, gem_p: float = 3.0, gem_eps: float = 1e-6,
-                        l2_normalize: bool = True) -> DcrNet:
+                        l2_normalize: bool = True, scale_factor: Optional[float] = None) -> DcrNet:
     """state_dict keys: torchvision ResNet names, optionally prefixed 'backbone.' / 'module.'; head Linear under
     'embeddings.1' (SSCD), 'fc' or 'head'.  mean/std: (0.5, 0.5) for diff_retrieval.py:329, ImageNet statistics for
     embedding_search/utils.py:37-39.
@@ -234,13 +235,24 @@ def build_sscd_resnet50(state_dict: Dict[str, torch.Tensor], max_batch: int = 64
     net.in_shape = (in_size, in_size)
     off = (in_size - crop) // 2
     eps = 1e-5
+    src_crop = crop
+    stem_i, stem_f = [], []
+    if scale_factor is not None and scale_factor != 1:
+        # multi_scale (utils_ret.py:676-698): the transformed crop is bilinearly resized by `scale_factor` before the
+        # network; fused into the stem's input kernel.  Output size and coordinate scale as F.interpolate computes them.
+        import math
+        crop = int(math.floor(float(src_crop) * float(scale_factor)))
+        if crop % 2:
+            raise _lib.DcrError(f"scale_factor {scale_factor} gives an odd network input size {crop}")
+        stem_i = [crop, crop]
+        stem_f = [float(np.float32(1.0 / float(scale_factor)))]
     # stem: 7x7/2/pad-3 conv == 4x4/1 conv over the zero-padded 2x2 space-to-depth input (12 -> 16 channels); the
     # preprocessing (crop, ToTensor, Normalize) is fused into the space-to-depth kernel, and the GEMM kernel reads 4
     # horizontally adjacent 16-channel pixels as one 64-channel pixel through an overlapping-window tensor map
     s = (crop + 2 * 3 - 7) // 2 + 1   # 112
     u = (crop + 6) // 2               # 115 stored rows / pixels per row
     t_z = net.tensor(u * u, 16)
-    net.op(OP_STEM_S2D, [t_z, in_size, in_size, off, off, crop, crop], list(mean) + list(std) + [1.0, 0.0])
+    net.op(OP_STEM_S2D, [t_z, in_size, in_size, off, off, src_crop, src_crop] + stem_i, list(mean) + list(std) + [1.0, 0.0] + stem_f)
     sc, bi = _fold_bn(sd, "bn1", eps)
     t_stem = net.tensor(s * s, 64)
     net.conv(t_z, t_stem, u, u - 3, 64, _stem_s2d_weight(sd["conv1.weight"]), scale=sc, bias=bi, act=1, window=(16, u))

@@ -57,6 +57,26 @@ def extract_features(net: DcrNet, images: torch.Tensor, batch_size: Optional[int
     return out
 
 
+MULTI_SCALES = (1.0, 1.0 / 2 ** 0.5, 0.5)       # utils_ret.py:678 "we use 3 different scales"
+
+
+@torch.no_grad()
+def extract_features_multiscale(nets_by_scale, images: torch.Tensor, batch_size: Optional[int] = None) -> torch.Tensor:
+    """`extract_features(..., multiscale=True)` (utils_ret.py:676-698, :714-715): the mean over the three scales of the
+    model's descriptor.  `nets_by_scale`: one network per entry of MULTI_SCALES, built with
+    `build_sscd_resnet50(sd, scale_factor=s)` (the bilinear resize of the transformed crop is fused into the first
+    kernel).  The reference then divides the whole batch tensor by ITS Frobenius norm (`v /= v.norm()`, :697) -- one
+    scalar per loader batch, which the per-row normalisation of diff_retrieval.py:388-389 removes again; it is not
+    applied here.  Convolutional trunks only (a ViT would need interpolated position embeddings)."""
+    if len(nets_by_scale) != len(MULTI_SCALES):
+        raise _lib.DcrError(f"extract_features_multiscale needs {len(MULTI_SCALES)} networks (scales {MULTI_SCALES})")
+    out = None
+    for net in nets_by_scale:
+        f = extract_features(net, images, batch_size)
+        out = f if out is None else out.add_(f)
+    return out.div_(float(len(nets_by_scale)))
+
+
 def retrieve(query_features: torch.Tensor, gallery_features: torch.Tensor, k: int = 1, normalize: bool = True,
              index_base: int = 0, index_stride: int = 1) -> Tuple[torch.Tensor, torch.Tensor]:
     """(values [Q,k], indices [Q,k]) == torch.mm(normalize(G), normalize(Q).T).T.topk(k)  (diff_retrieval.py:388-417)."""
@@ -95,8 +115,12 @@ def run_retrieval(net: DcrNet, query_images: torch.Tensor, gallery_images: torch
                   with_background: bool = False, batch_size: Optional[int] = None,
                   num_loss_chunks: int = 1) -> Dict[str, object]:
     """Embed both image sets and match them (the rank-0 block of diff_retrieval.py:386-419)."""
-    values_features = extract_features(net, gallery_images, batch_size)       # :386
-    query_features = extract_features(net, query_images, batch_size)         # :387
+    if isinstance(net, (list, tuple)):                                        # multiscale=args.multiscale (:386-387)
+        values_features = extract_features_multiscale(net, gallery_images, batch_size)
+        query_features = extract_features_multiscale(net, query_images, batch_size)
+    else:
+        values_features = extract_features(net, gallery_images, batch_size)   # :386
+        query_features = extract_features(net, query_images, batch_size)     # :387
     l2_normalize_(values_features)                                           # :388
     l2_normalize_(query_features)                                            # :389
     if num_loss_chunks > 1:                                                  # :393-400 ('splitloss', aligned parts)

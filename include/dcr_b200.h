@@ -134,7 +134,9 @@ int dcr_conv2d_bf16(const void* x, int x_planes, int64_t x_plane_stride, int B, 
  *   7 VIT_TOKENS i: patch_t, out_t, n_patches, C, cls_param, pos_param
  *   8 ATTENTION  i: qkv_t, out_t, T, heads, head_dim      f: scale
  *   9 L2NORM_OUT f: eps        (row-normalise the fp32 output buffer in place)
- *  10 STEM_S2D   i: out_t, IH, IW, crop_y, crop_x, H, W     f: mean[3], std[3], post_scale, post_shift
+ *  10 STEM_S2D   i: out_t, IH, IW, crop_y, crop_x, H, W [, RH, RW]     f: mean[3], std[3], post_scale, post_shift [, rscale]
+ *                (optional RH, RW, rscale: the normalised crop is first resized to RH x RW with torch's bilinear
+ *                 F.interpolate(scale_factor=s, align_corners=False) arithmetic, rscale = float(1/s); utils_ret.py:676-698)
  *                uint8 HWC input -> normalised, zero-padded 2x2 space-to-depth tensor [(H+6)/2, (W+6)/2, 16] of the
  *                7x7/2/pad-3 stem; the following CONV passes two extra ints (elements per stored pixel, stored pixels
  *                per row) to read 4 adjacent stored pixels as one 64-channel pixel (kh = 4, kw = 1). */

@@ -154,3 +154,22 @@ def test_dino_vit_base_width():
     fast = nets.build_dino_vit(sd, max_batch=4, precision="fast")(img.cuda()).cpu()
     _, cosf = _report("vit-b fast", fast, ref)
     assert cosf > 0.99
+
+
+def test_sscd_multiscale():
+    """--multiscale (utils_ret.py:676-698): three bilinearly rescaled forward passes (224, 158, 112), averaged."""
+    from dcr_b200 import retrieval
+    sd = om.make_sscd_state_dict(6)
+    img = _imgs(3, 21)
+    x = om.preprocess(img)
+    ref = om.sscd_forward_multiscale(sd, x)
+    nets_ms = [nets.build_sscd_resnet50(sd, max_batch=4, precision="exact", scale_factor=s) for s in retrieval.MULTI_SCALES]
+    # each scale on its own against the oracle's F.interpolate + forward
+    import torch.nn.functional as F
+    for s, net in zip(retrieval.MULTI_SCALES, nets_ms):
+        inp = x if s == 1 else F.interpolate(x, scale_factor=s, mode="bilinear", align_corners=False)
+        err, _ = _report(f"sscd scale {s:.3f} ({inp.shape[-1]} px)", net(img.cuda()).cpu(), om.sscd_forward(sd, inp))
+        assert err < 2e-5, (s, err)
+    got = retrieval.extract_features_multiscale(nets_ms, img.cuda()).cpu()
+    err, cos = _report("sscd multiscale", got, ref)
+    assert err < 2e-5
