@@ -47,8 +47,8 @@ SIGNATURES = {
     "dcr_fid_destroy": (None, [C.c_void_p]),
     "dcr_fid_accumulate": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     "dcr_fid_finalize": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_int64), C.c_void_p]),
-    "dcr_split_rescore": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int,
-                                    C.c_void_p, C.c_void_p, C.c_void_p]),
+    "dcr_split_rescore": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int,
+                                    C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "dcr_topk_merge": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                  C.c_void_p]),
 }

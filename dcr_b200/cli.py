@@ -116,10 +116,8 @@ def main(argv=None) -> int:
         args.similarity_metric, args.stype = "splitloss", "cross"
     if args.similarity_metric not in ("dotproduct", "splitloss"):
         raise NotImplementedError(f"--similarity_metric {args.similarity_metric}")
-    if args.similarity_metric == "splitloss" and args.stype == "cross":
-        raise NotImplementedError("--stype cross (every part against every part, einsum_in_chunks :643-662) is not "
-                                  "implemented; the aligned splitloss metric is")
     split = args.num_loss_chunks if args.similarity_metric == "splitloss" else 1
+    cross = split > 1 and args.stype == "cross"
     from . import data, retrieval
     if args.gpu is not None:
         torch.cuda.set_device(args.gpu)
@@ -128,8 +126,12 @@ def main(argv=None) -> int:
     values_u8, v_files = data.load_folder_u8(args.val_dir, workers=args.workers)
     # splitloss: the reference never defines sim2 on that branch (:393-403) and stops at :412; background statistics
     # are only produced for the dot-product metric
-    out = retrieval.run_retrieval(net, query_u8, values_u8, k=min(args.topk, len(v_files)), with_background=(split == 1),
-                                  num_loss_chunks=split)
+    k = min(args.topk, len(v_files))
+    if cross and (k - 1) * split + 1 > 16:
+        k = 15 // split + 1
+        print(f"--stype cross with {split} parts: keeping the {k} best matches per query (kernel limit (k-1)*parts+1 <= 16)")
+    out = retrieval.run_retrieval(net, query_u8, values_u8, k=k, with_background=(split == 1), num_loss_chunks=split,
+                                  cross=cross)
     dp = os.sep.join(os.path.normpath(args.query_dir).split(os.sep)[-3:])                      # :378
     save = f"ret_plots/{dp}/images/{args.pt_style}_{args.arch}_{args.similarity_metric}{args.stype}/"   # :408
     os.makedirs(save, exist_ok=True)

@@ -111,10 +111,10 @@ int dcr_topk_merge(const float* scores, const int64_t* idx, int nq, int nlists, 
                          reinterpret_cast<long long*>(out_idx), as_stream(stream));
 }
 
-int dcr_split_rescore(const float* q, const float* g, int nq, int d, int n_chunks, const int64_t* cand, int n_cand, int k,
-                      float* out_scores, int64_t* out_idx, void* stream) {
+int dcr_split_rescore(const float* q, const float* g, int nq, int d, int n_chunks, int cross, const int64_t* cand,
+                      int n_cand, int k, float* out_scores, int64_t* out_idx, void* stream) {
   DCR_REQUIRE(q && g && cand && out_scores && out_idx, "dcr_split_rescore: null pointer argument");
-  return dcr::split_rescore(q, g, nq, d, n_chunks, reinterpret_cast<const long long*>(cand), n_cand, k, out_scores,
+  return dcr::split_rescore(q, g, nq, d, n_chunks, cross, reinterpret_cast<const long long*>(cand), n_cand, k, out_scores,
                             reinterpret_cast<long long*>(out_idx), as_stream(stream));
 }
 

@@ -28,8 +28,8 @@ int sim_topk(const float* q, int nq, const float* g, int ng, int d, int k, long 
              long long g_index_stride, float* out_scores, long long* out_idx, void* ws, size_t ws_bytes,
              cudaStream_t stream, SimStats* stats);
 
-int split_rescore(const float* q, const float* g, int nq, int d, int n_chunks, const long long* cand, int n_cand, int k,
-                  float* out_scores, long long* out_idx, cudaStream_t stream);
+int split_rescore(const float* q, const float* g, int nq, int d, int n_chunks, int cross, const long long* cand, int n_cand,
+                  int k, float* out_scores, long long* out_idx, cudaStream_t stream);
 
 int l2_normalize(float* x, int n, int d, float eps, cudaStream_t stream);
 int topk_merge(const float* scores, const long long* idx, int nq, int nlists, int k_in, int k_out, float* out_scores,

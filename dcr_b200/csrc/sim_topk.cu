@@ -961,7 +961,7 @@ __global__ void __launch_bounds__(128)
 // n_cand candidate rows, evaluate max_c <q_c, g_c> exactly (float64, the same fixed-order dot as the re-score
 // kernel), and select k by (score desc, row asc).
 __global__ void __launch_bounds__(128)
-    split_rescore_kernel(const float* __restrict__ q, const float* __restrict__ g, int d, int n_chunks,
+    split_rescore_kernel(const float* __restrict__ q, const float* __restrict__ g, int d, int n_chunks, int cross,
                          const long long* __restrict__ cand, int n_cand, int k, float* __restrict__ out_scores,
                          long long* __restrict__ out_idx) {
   extern __shared__ __align__(16) uint8_t sm[];
@@ -990,8 +990,12 @@ __global__ void __launch_bounds__(128)
     if (ci[c] < 0) continue;   // warp-uniform
     double best = -INFINITY;
     for (int part = 0; part < n_chunks; ++part) {
-      const double v = exact_dot_warp(qs + part * p, g + static_cast<size_t>(ci[c]) * d + part * p, p, lane);
-      best = fmax(best, v);
+      if (cross) {   // 'cross' (einsum_in_chunks, diff_retrieval.py:652-654): every gallery part against every query part
+        for (int qp = 0; qp < n_chunks; ++qp)
+          best = fmax(best, exact_dot_warp(qs + qp * p, g + static_cast<size_t>(ci[c]) * d + part * p, p, lane));
+      } else {
+        best = fmax(best, exact_dot_warp(qs + part * p, g + static_cast<size_t>(ci[c]) * d + part * p, p, lane));
+      }
     }
     if (lane == 0) sc[c] = best;   // ranked on the float64 value (as dcr_sim_topk), reported as fp32
   }
@@ -1334,8 +1338,8 @@ int launch_fused(const SimPlan& pl, const PassPlan& pp, const __nv_bfloat16* qb,
 
 }  // namespace
 
-int split_rescore(const float* q, const float* g, int nq, int d, int n_chunks, const long long* cand, int n_cand, int k,
-                  float* out_scores, long long* out_idx, cudaStream_t stream) {
+int split_rescore(const float* q, const float* g, int nq, int d, int n_chunks, int cross, const long long* cand, int n_cand,
+                  int k, float* out_scores, long long* out_idx, cudaStream_t stream) {
   DCR_REQUIRE(nq >= 1 && d >= 1 && n_chunks >= 1 && d % n_chunks == 0 && (d / n_chunks) % 4 == 0,
               "split_rescore: d=%d must split into %d parts whose length is a multiple of 4", d, n_chunks);
   DCR_REQUIRE(n_cand >= k && k >= 1 && n_cand <= 1024, "split_rescore: need k <= n_cand <= 1024 (k=%d n_cand=%d)", k, n_cand);
@@ -1343,7 +1347,7 @@ int split_rescore(const float* q, const float* g, int nq, int d, int n_chunks, c
               "split_rescore: q/g must be 16-byte aligned");
   const size_t smem = ((static_cast<size_t>(d) * 4 + 15) & ~size_t(15)) + static_cast<size_t>(n_cand) * 16;
   DCR_CUDA_CHECK(cudaFuncSetAttribute(split_rescore_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-  split_rescore_kernel<<<nq, 128, smem, stream>>>(q, g, d, n_chunks, cand, n_cand, k, out_scores, out_idx);
+  split_rescore_kernel<<<nq, 128, smem, stream>>>(q, g, d, n_chunks, cross, cand, n_cand, k, out_scores, out_idx);
   count_launch();
   DCR_CUDA_CHECK(cudaGetLastError());
   return 0;

@@ -113,7 +113,7 @@ def retrieval_stats(main_v: torch.Tensor, bg_v: Optional[torch.Tensor] = None) -
 
 def run_retrieval(net: DcrNet, query_images: torch.Tensor, gallery_images: torch.Tensor, k: int = 1,
                   with_background: bool = False, batch_size: Optional[int] = None,
-                  num_loss_chunks: int = 1) -> Dict[str, object]:
+                  num_loss_chunks: int = 1, cross: bool = False) -> Dict[str, object]:
     """Embed both image sets and match them (the rank-0 block of diff_retrieval.py:386-419)."""
     if isinstance(net, (list, tuple)):                                        # multiscale=args.multiscale (:386-387)
         values_features = extract_features_multiscale(net, gallery_images, batch_size)
@@ -124,7 +124,7 @@ def run_retrieval(net: DcrNet, query_images: torch.Tensor, gallery_images: torch
     l2_normalize_(values_features)                                           # :388
     l2_normalize_(query_features)                                            # :389
     if num_loss_chunks > 1:                                                  # :393-400 ('splitloss', aligned parts)
-        main_v, main_l = sim_topk_split(query_features, values_features, k, num_loss_chunks)
+        main_v, main_l = sim_topk_split(query_features, values_features, k, num_loss_chunks, cross=cross)
     else:
         main_v, main_l = sim_topk(query_features, values_features, k)         # :402, :411, :417
     out = {"values": main_v, "indices": main_l, "query_features": query_features,

@@ -85,16 +85,21 @@ def sim_topk(query: torch.Tensor, gallery: torch.Tensor, k: int = 1, *, index_ba
     return out_s, out_i
 
 
-def sim_topk_split(q: torch.Tensor, g: torch.Tensor, k: int, num_chunks: int) -> Tuple[torch.Tensor, torch.Tensor]:
+def sim_topk_split(q: torch.Tensor, g: torch.Tensor, k: int, num_chunks: int, cross: bool = False
+                   ) -> Tuple[torch.Tensor, torch.Tensor]:
     """Top-k under the 'splitloss' similarity of diff_retrieval.py:393-400 (--similarity_metric splitloss,
     --num_loss_chunks C): score(q, g) = max_c <q_c, g_c> over the C equal parts of the descriptors.
     One fused similarity+top-k pass per part (the true top-k is contained in the union of the per-part top-k lists),
     then dcr_split_rescore evaluates the exact split score of the <= C*k candidates per query and selects.
-    Only the aligned form is implemented; the 'cross' variant (--stype cross, every part against every part,
-    einsum_in_chunks :643-662) is not."""
+    cross=True is `--stype cross` (einsum_in_chunks :643-662): score = max over every (gallery part, query part) pair.
+    Candidates then come from ONE fused pass over the part matrices [Q*C, D/C] x [G*C, D/C] with
+    k' = (k-1)*C + 1 rows per query part (fewer than k' part-rows can beat the best part-row of a true top-k gallery row),
+    which must stay within the kernel's k' <= 16."""
     lib = _lib.load()
     if num_chunks == 1:
         return sim_topk(q, g, k)
+    if cross:
+        return _sim_topk_cross(lib, q, g, k, num_chunks)
     if not (q.is_cuda and g.is_cuda):
         raise _lib.DcrError("sim_topk_split needs CUDA tensors")
     q = q.contiguous().float()
@@ -113,7 +118,33 @@ def sim_topk_split(q: torch.Tensor, g: torch.Tensor, k: int, num_chunks: int) ->
     out_i = torch.empty((nq, k), dtype=torch.int64, device=q.device)
     with torch.cuda.device(q.device):
         st = torch.cuda.current_stream().cuda_stream
-        rc = lib.dcr_split_rescore(q.data_ptr(), g.data_ptr(), nq, d, num_chunks, cand.data_ptr(), num_chunks * k, k,
+        rc = lib.dcr_split_rescore(q.data_ptr(), g.data_ptr(), nq, d, num_chunks, 0, cand.data_ptr(), num_chunks * k, k,
+                                   out_s.data_ptr(), out_i.data_ptr(), st)
+        _lib.check(rc, "dcr_split_rescore")
+    return out_s, out_i
+
+
+def _sim_topk_cross(lib, q: torch.Tensor, g: torch.Tensor, k: int, c: int) -> Tuple[torch.Tensor, torch.Tensor]:
+    if not (q.is_cuda and g.is_cuda):
+        raise _lib.DcrError("sim_topk_split needs CUDA tensors")
+    q = q.contiguous().float()
+    g = g.contiguous().float()
+    nq, d = q.shape
+    ng = g.shape[0]
+    if d % c or (d // c) % 4:
+        raise _lib.DcrError(f"splitloss: descriptor dim {d} must split into {c} parts of a multiple of 4 dims")
+    kk = (k - 1) * c + 1
+    if kk > 16:
+        raise _lib.DcrError(f"splitloss cross: needs (k-1)*parts+1 = {kk} candidates per query part, the kernel keeps at most 16")
+    kk = min(kk, ng * c)
+    p = d // c
+    _, idx = sim_topk(q.view(nq * c, p), g.view(ng * c, p), kk)            # rows of the part matrices
+    cand = (idx // c).reshape(nq, c * kk).contiguous()                      # gallery rows the part-rows belong to
+    out_s = torch.empty((nq, k), dtype=torch.float32, device=q.device)
+    out_i = torch.empty((nq, k), dtype=torch.int64, device=q.device)
+    with torch.cuda.device(q.device):
+        st = torch.cuda.current_stream().cuda_stream
+        rc = lib.dcr_split_rescore(q.data_ptr(), g.data_ptr(), nq, d, c, 1, cand.data_ptr(), c * kk, k,
                                    out_s.data_ptr(), out_i.data_ptr(), st)
         _lib.check(rc, "dcr_split_rescore")
     return out_s, out_i

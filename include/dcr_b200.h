@@ -91,9 +91,12 @@ int dcr_topk_merge(const float* scores, const int64_t* idx, int nq, int nlists, 
  * score = max over the parts of the per-part dot products).  The caller runs dcr_sim_topk once per part and passes
  * the union of the per-part top-k rows as cand [nq][n_cand] (duplicates allowed); this evaluates the exact split
  * score of every candidate (float64 accumulation, reported as fp32) and writes the k best per query ordered by
- * (score desc, row asc).  d %% n_chunks == 0, (d / n_chunks) %% 4 == 0, k <= n_cand <= 1024. */
-int dcr_split_rescore(const float* q, const float* g, int nq, int d, int n_chunks, const int64_t* cand, int n_cand, int k,
-                      float* out_scores, int64_t* out_idx, void* stream);
+ * (score desc, row asc).  d %% n_chunks == 0, (d / n_chunks) %% 4 == 0, k <= n_cand <= 1024.
+ * cross != 0: the 'cross' form (--stype cross, einsum_in_chunks diff_retrieval.py:643-662): score = max over EVERY pair
+ * (gallery part, query part); the caller then collects candidates by running dcr_sim_topk on the part matrices
+ * [nq * n_chunks, d / n_chunks] x [ng * n_chunks, d / n_chunks] with k' = (k - 1) * n_chunks + 1. */
+int dcr_split_rescore(const float* q, const float* g, int nq, int d, int n_chunks, int cross, const int64_t* cand,
+                      int n_cand, int k, float* out_scores, int64_t* out_idx, void* stream);
 
 /* ---- dense contraction of the descriptor networks ------------------------------------------------------------- */
 /* y = act(scale[n] * conv2d(x, w)[.., n] + bias[n] (+ residual)) as a tcgen05 implicit GEMM.

@@ -58,7 +58,7 @@ def sim_topk(q: np.ndarray, g: np.ndarray, k: int, chunk: int = 256):
     return vals, idx
 
 
-def sim_topk_split(q: np.ndarray, g: np.ndarray, k: int, num_chunks: int, chunk: int = 128):
+def sim_topk_split(q: np.ndarray, g: np.ndarray, k: int, num_chunks: int, chunk: int = 128, cross: bool = False):
     """'splitloss' similarity, diff_retrieval.py:393-400: v,q -> [b, c, p]; chunk_dp = einsum('ncp,mcp->nmc');
     sim = max over c; then the same top-k as sim_topk (float64 dot products per part, ranked on the float64 value,
     reported as float32, ties by lowest gallery index)."""
@@ -72,7 +72,10 @@ def sim_topk_split(q: np.ndarray, g: np.ndarray, k: int, num_chunks: int, chunk:
     idx = np.empty((q.shape[0], k), dtype=np.int64)
     for s in range(0, q.shape[0], chunk):
         qq = q[s:s + chunk].astype(np.float64).reshape(-1, num_chunks, p)
-        S = np.einsum("mcp,ncp->mnc", qq, g64).max(axis=2)          # [chunk, G]
+        if cross:   # einsum_in_chunks stype='cross', diff_retrieval.py:652-654: 'ncp,mdp->nmcd' then max over (c, d)
+            S = np.einsum("mdp,ncp->mncd", qq, g64).max(axis=(2, 3))
+        else:
+            S = np.einsum("mcp,ncp->mnc", qq, g64).max(axis=2)      # [chunk, G]
         for r in range(S.shape[0]):
             top = _rank_row(S[r], k)
             idx[s + r] = top

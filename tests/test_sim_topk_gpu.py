@@ -172,3 +172,16 @@ def test_splitloss_topk_matches_oracle(nq, ng, d, c, k):
     np.testing.assert_allclose(v.cpu().numpy(), ov, rtol=0, atol=1e-6)
     with pytest.raises(similarity._lib.DcrError):
         similarity.sim_topk_split(q.cuda(), g.cuda(), k, 7)       # 7 does not divide d
+
+
+@pytest.mark.parametrize("nq,ng,d,c,k", [(50, 2000, 512, 8, 1), (21, 600, 128, 4, 3), (9, 300, 96, 2, 8)])
+def test_splitloss_cross_matches_oracle(nq, ng, d, c, k):
+    """--stype cross (einsum_in_chunks, diff_retrieval.py:643-662): score = max over every (gallery part, query part)."""
+    q, g = synthetic.descriptors(nq, ng, d, seed=23 + c)
+    g[7] = g[2]
+    v, i = similarity.sim_topk_split(q.cuda(), g.cuda(), k, c, cross=True)
+    ov, oi = osim.sim_topk_split(q.numpy(), g.numpy(), k, c, cross=True)
+    assert np.array_equal(i.cpu().numpy(), oi)
+    np.testing.assert_allclose(v.cpu().numpy(), ov, rtol=0, atol=1e-6)
+    with pytest.raises(similarity._lib.DcrError):
+        similarity.sim_topk_split(q.cuda(), g.cuda(), 10, 8, cross=True) if d % 8 == 0 else similarity.sim_topk_split(q.cuda(), g.cuda(), 16, c, cross=True)
