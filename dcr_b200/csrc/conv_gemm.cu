@@ -165,10 +165,14 @@ __global__ void __launch_bounds__(kThreads, 1)
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  // Producer and MMA roles: the WHOLE warp walks the loops (so that every value is provably warp-uniform and lives
+  // in uniform registers) and one elected lane issues the TMA / tcgen05 instructions.  Running the loops under
+  // `if (lane == 0)` makes the compiler wrap every UTMALDG / UTCHMMA in an ELECT + R2UR.BROADCAST + BRA.U.ANY loop
+  // (8-20 extra instructions each) -- and the single-thread instruction stream IS the pipeline's critical path.
   if (warp == 0) {
-    if (lane == 0) {
+    {
       const int n_terms = p.n_terms, taps = p.taps, kw = p.kw, cblocks = p.cblocks;
-      uint32_t it = 0;
+      PipeState st(stages);
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int m0 = (tile % num_m_tiles) * kBM;
         const int n0 = (tile / num_m_tiles) * BN;
@@ -186,52 +190,63 @@ __global__ void __launch_bounds__(kThreads, 1)
           const CUtensorMap* mw = &maps.w[p.term_w[t]];
           for (int tap = 0; tap < taps; ++tap) {
             const int r = tap / kw, sx = tap - r * kw;
-            for (int cb = 0; cb < cblocks; ++cb, ++it) {
-              const uint32_t s = it % stages, ph = (it / stages) & 1;
+            for (int cb = 0; cb < cblocks; ++cb, st.next()) {
+              const uint32_t s = st.s, ph = st.ph;
               mbar_wait(&empty[s], ph ^ 1);
-              mbar_arrive_expect_tx(&full[s], kStageBytes);
-              uint8_t* sa = smem_ab + s * kStageBytes;
-              if constexpr (kIm2col) {
-                if (p.debug == 2)
-                  tma_load_2d<1>(sa, &maps.a_flat, &full[s], cb * kBK, max(0, m0 + (r - 1) * p.Q + sx - 1), kEvictNormal);
-                else
-                  tma_load_im2col_4d<1>(sa, ma, &full[s], cb * kBK, w0, h0, img, static_cast<uint16_t>(sx),
-                                        static_cast<uint16_t>(r));
-              } else
-                tma_load_2d<1>(sa, ma, &full[s], cb * kBK, m0, kEvictNormal);
-              tma_load_2d<1>(sa + kAStage, mw, &full[s], (tap * cblocks + cb) * kBK, n0, kEvictNormal);
+              if (elect_one()) {
+                mbar_arrive_expect_tx(&full[s], kStageBytes);
+                uint8_t* sa = smem_ab + s * kStageBytes;
+                if constexpr (kIm2col) {
+                  if (p.debug == 2)
+                    tma_load_2d<1>(sa, &maps.a_flat, &full[s], cb * kBK, max(0, m0 + (r - 1) * p.Q + sx - 1), kEvictNormal);
+                  else
+                    tma_load_im2col_4d<1>(sa, ma, &full[s], cb * kBK, w0, h0, img, static_cast<uint16_t>(sx),
+                                          static_cast<uint16_t>(r));
+                } else
+                  tma_load_2d<1>(sa, ma, &full[s], cb * kBK, m0, kEvictNormal);
+                tma_load_2d<1>(sa + kAStage, mw, &full[s], (tap * cblocks + cb) * kBK, n0, kEvictNormal);
+              }
+              __syncwarp();
             }
           }
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {
       constexpr uint32_t idesc = umma_idesc_bf16(kBM, BN);
-      uint32_t it = 0, tc = 0;
+      uint32_t tc = 0;
+      PipeState st(stages);
+      // descriptors of stage 0; stage s adds s * kStageBytes to the 16-byte-granular start-address field (no carry out
+      // of the field: shared memory addresses stay below 256 KB)
+      const uint64_t da0 = umma_desc_sw128(smem_u32(smem_ab));
+      const uint64_t db0 = umma_desc_sw128(smem_u32(smem_ab + kAStage));
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tc) {
         const uint32_t buf = tc & 1;
         if (p.debug) {   // loads only: hand every stage straight back to the producer
-          for (int ki = 0; ki < k_iters; ++ki, ++it) {
-            const uint32_t s = it % stages, ph = (it / stages) & 1;
-            mbar_wait(&full[s], ph);
-            mbar_arrive(&empty[s]);
+          for (int ki = 0; ki < k_iters; ++ki, st.next()) {
+            mbar_wait(&full[st.s], st.ph);
+            if (elect_one()) mbar_arrive(&empty[st.s]);
+            __syncwarp();
           }
           continue;
         }
         mbar_wait(&t_empty[buf], ((tc >> 1) & 1) ^ 1);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + buf * BN;
-        for (int ki = 0; ki < k_iters; ++ki, ++it) {
-          const uint32_t s = it % stages, ph = (it / stages) & 1;
-          mbar_wait(&full[s], ph);
+        for (int ki = 0; ki < k_iters; ++ki, st.next()) {
+          const uint32_t s = st.s;
+          mbar_wait(&full[s], st.ph);
           tc_fence_after();
-          const uint64_t da = umma_desc_sw128(smem_u32(smem_ab + s * kStageBytes));
-          const uint64_t db = umma_desc_sw128(smem_u32(smem_ab + s * kStageBytes + kAStage));
+          const uint64_t da = da0 + static_cast<uint64_t>(s * (kStageBytes >> 4));
+          const uint64_t db = db0 + static_cast<uint64_t>(s * (kStageBytes >> 4));
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < kBK / 16; ++k) umma_f16<1>(tmem_d, da + 2 * k, db + 2 * k, idesc, (ki | k) != 0);
-          umma_commit<1>(&empty[s]);
-          if (ki == k_iters - 1) umma_commit<1>(&t_full[buf]);
+            for (int k = 0; k < kBK / 16; ++k) umma_f16<1>(tmem_d, da + 2 * k, db + 2 * k, idesc, (ki | k) != 0);
+            umma_commit<1>(&empty[s]);
+            if (ki == k_iters - 1) umma_commit<1>(&t_full[buf]);
+          }
+          __syncwarp();
         }
       }
     }
@@ -461,6 +476,7 @@ int conv_gemm(const ConvGemmDesc& d, cudaStream_t stream) {
   DCR_REQUIRE(d.C % 8 == 0 && d.N % 8 == 0, "conv_gemm: C (%d) and N (%d) must be multiples of 8", d.C, d.N);
   DCR_REQUIRE(d.kh >= 1 && d.kw >= 1 && d.stride >= 1, "conv_gemm: bad filter geometry");
   if (d.exact) return conv_exact(d, stream);
+  if (conv3x3_halo_eligible(d)) return conv3x3_halo(d, stream);
   const bool windowed = d.in_stride_w != 0;
   const bool im2col = windowed || !(d.kh == 1 && d.kw == 1 && d.stride == 1 && d.pad_h == 0 && d.pad_w == 0);
   const int P = (d.H + 2 * d.pad_h - d.kh) / d.stride + 1;

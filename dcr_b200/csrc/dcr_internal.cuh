@@ -70,6 +70,8 @@ struct ConvGemmDesc {
 };
 int conv_gemm(const ConvGemmDesc& d, cudaStream_t stream);
 int conv_exact(const ConvGemmDesc& d, cudaStream_t stream);
+bool conv3x3_halo_eligible(const ConvGemmDesc& d);   // 3x3 / stride 1 / pad 1, fast mode, no residual, W <= 62, N <= 256
+int conv3x3_halo(const ConvGemmDesc& d, cudaStream_t stream);
 
 
 // ---- HBM-bound kernels (pool_norm.cu, attention.cu) ---------------------------------------------------------------

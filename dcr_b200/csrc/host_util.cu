@@ -87,6 +87,25 @@ int make_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t rows, uint64_
   return 0;
 }
 
+int make_tmap_nhwc_box_bf16(CUtensorMap* out, const void* base, int n, int h, int w, int c, long long pixel_stride,
+                            uint32_t box_w, uint32_t box_h) {
+  static PFN_encodeTiled fn = reinterpret_cast<PFN_encodeTiled>(driver_fn("cuTensorMapEncodeTiled"));
+  DCR_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled driver entry point not available");
+  DCR_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, "tensor-map base must be 16-byte aligned");
+  DCR_REQUIRE(box_w >= 1 && box_w <= 256 && box_h >= 1 && box_h <= 256, "tensor-map box out of range: %u x %u", box_w, box_h);
+  DCR_REQUIRE((pixel_stride * 2) % 16 == 0, "tensor-map pixel stride must be a multiple of 16 bytes");
+  cuuint64_t gdim[4] = {(cuuint64_t)c, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)n};
+  cuuint64_t gstride[3] = {(cuuint64_t)pixel_stride * 2, (cuuint64_t)pixel_stride * 2 * w, (cuuint64_t)pixel_stride * 2 * w * h};
+  cuuint32_t box[4] = {64, box_w, box_h, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), gdim, gstride, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  DCR_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled (NHWC box) failed with CUresult %d (n=%d h=%d w=%d c=%d box=%ux%u)",
+              static_cast<int>(r), n, h, w, c, box_w, box_h);
+  return 0;
+}
+
 int make_tmap_im2col_bf16(CUtensorMap* out, const void* base, int n, int h, int w, int c, int pad_h, int pad_w,
                           int kh, int kw, int stride, int channels_per_pixel, int pixels_per_column,
                           long long stride_w, long long stride_h, long long stride_n) {

@@ -47,6 +47,10 @@ int make_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t rows, uint64_
 
 // im2col tensor map over an NHWC bf16 activation tensor (see conv_gemm.cu)
 // stride_w/h/n: element strides of the (possibly overlapping-window) NHWC view; 0 = dense
+// 4-D tiled map over an NHWC bf16 tensor (dims C, W, H, N; `pixel_stride` elements between pixels), box = 64 channels x
+// box_w x box_h x 1 image, 128B swizzle, out-of-bounds elements read as zero / are not written.
+int make_tmap_nhwc_box_bf16(CUtensorMap* out, const void* base, int n, int h, int w, int c, long long pixel_stride,
+                            uint32_t box_w, uint32_t box_h);
 int make_tmap_im2col_bf16(CUtensorMap* out, const void* base, int n, int h, int w, int c, int pad_h, int pad_w,
                           int kh, int kw, int stride, int channels_per_pixel, int pixels_per_column,
                           long long stride_w = 0, long long stride_h = 0, long long stride_n = 0);

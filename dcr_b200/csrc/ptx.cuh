@@ -65,10 +65,32 @@ DCR_DEVICE bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// The producer and MMA-issuing roles are single threads whose instruction stream runs at one dependent instruction
+// every few cycles; everything between two tcgen05.mma / TMA issues is on the critical path of the whole pipeline
+// (tools/microbench/umma_rate.cu: a handful of extra compares and branches per 4 MMAs turn 54 cycles per 128x64x16 MMA
+// into 120).  So: the wait is one tight asm loop (no predicate -> register -> branch round trip per poll) ...
 DCR_DEVICE void mbar_wait(uint64_t* bar, uint32_t parity) {
-  while (!mbar_try_wait(bar, parity)) {
-  }
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P, [%0], %1;\n\t"
+      "@P bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
 }
+// ... and ring positions advance with a compare instead of `it % stages` / `it / stages` (runtime divisions).
+struct PipeState {
+  uint32_t s, ph, n;
+  DCR_DEVICE explicit PipeState(uint32_t stages) : s(0), ph(0), n(stages) {}
+  DCR_DEVICE void next() {
+    if (++s == n) {
+      s = 0;
+      ph ^= 1;
+    }
+  }
+};
 // acquire at cluster scope: needed when the arrival came from the peer CTA / a multicast commit
 DCR_DEVICE bool mbar_try_wait_cluster(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
@@ -131,6 +153,21 @@ DCR_DEVICE void tma_load_3d(void* dst, const void* tmap, uint64_t* bar, int c0, 
         "l"(hint)
         : "memory");
   }
+}
+
+// 4-D tiled load / store (coordinates innermost first; loads may start at negative coordinates: zero fill)
+DCR_DEVICE void tma_load_4d(void* dst, const void* tmap, uint64_t* bar, int c0, int c1, int c2, int c3, uint64_t hint) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+      " [%0], [%1, {%3, %4, %5, %6}], [%2], %7;" ::"r"(smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "l"(hint)
+      : "memory");
+}
+DCR_DEVICE void tma_store_4d(const void* tmap, const void* src_smem, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(tmap)),
+               "r"(smem_u32(src_smem)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
 }
 
 // im2col-mode load of an NHWC tensor: coordinates {c, w, h, n} of the first base pixel, filter-tap offsets {w, h}

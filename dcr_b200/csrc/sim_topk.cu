@@ -512,8 +512,12 @@ __global__ void __launch_bounds__(64 + 128 * kSets, 1)
 
   if (warp == 0) {
     // ===================================== TMA producer =====================================
-    if (lane == 0) {
-      uint32_t it = 0, seg = 0;
+    // The whole warp walks the loop (warp-uniform values stay in uniform registers) and one elected lane issues: under
+    // `if (lane == 0)` every UTMALDG / UTCHMMA gets an ELECT + R2UR + BRA.U.ANY wrapper, and the single-thread
+    // instruction stream is the critical path of the pipeline (tools/microbench/umma_rate.cu).
+    {
+      uint32_t seg = 0;
+      PipeState st(p.stages);
       SegWalker w(p.n_qtiles, p.n_gtiles, p.gchunk, p.n_chunks, unit, n_units);
       while (w.next()) {
         const int qi = w.qi, g_begin = w.g_begin, ntiles = w.ntiles;
@@ -521,23 +525,29 @@ __global__ void __launch_bounds__(64 + 128 * kSets, 1)
         const int q_row = qi * rows_per_qtile + static_cast<int>(cta_rank) * kBlockM;
         if (!stream_a) {   // resident query tile
           mbar_wait(a_empty, (seg & 1) ^ 1);
-          if (leader) mbar_arrive_expect_tx(a_full, p.num_kb * kATileBytes * kCG);
-          else mbar_arrive_cluster(a_full, 0);
-          for (int kb = 0; kb < p.num_kb; ++kb)
-            tma_load_2d<kCG>(smem_a + kb * kATileBytes, &tmap_q, a_full, kb * kBlockK, q_row, kEvictNormal);
+          if (elect_one()) {
+            if (leader) mbar_arrive_expect_tx(a_full, p.num_kb * kATileBytes * kCG);
+            else mbar_arrive_cluster(a_full, 0);
+            for (int kb = 0; kb < p.num_kb; ++kb)
+              tma_load_2d<kCG>(smem_a + kb * kATileBytes, &tmap_q, a_full, kb * kBlockK, q_row, kEvictNormal);
+          }
+          __syncwarp();
         }
         for (int j = 0; j < warm + ntiles; ++j) {
           const int gi = g_begin + (j < warm ? j : j - warm);
           const int g_row = gi * kBlockN + static_cast<int>(cta_rank) * kBRows;
           if (p.debug_mode == 3) continue;   // timing experiment: no gallery loads at all
-          for (int kb = 0; kb < p.num_kb; ++kb, ++it) {
-            const uint32_t s = it % p.stages, ph = (it / p.stages) & 1;
+          for (int kb = 0; kb < p.num_kb; ++kb, st.next()) {
+            const uint32_t s = st.s, ph = st.ph;
             mbar_wait(&b_empty[s], ph ^ 1);
-            if (leader) mbar_arrive_expect_tx(&b_full[s], stage_bytes * kCG);
-            else mbar_arrive_cluster(&b_full[s], 0);
-            tma_load_2d<kCG>(smem_b + s * stage_bytes, &tmap_g, &b_full[s], kb * kBlockK, g_row, kEvictNormal);
-            if (stream_a)
-              tma_load_2d<kCG>(smem_b + s * stage_bytes + kBTileBytes, &tmap_q, &b_full[s], kb * kBlockK, q_row, kEvictNormal);
+            if (elect_one()) {
+              if (leader) mbar_arrive_expect_tx(&b_full[s], stage_bytes * kCG);
+              else mbar_arrive_cluster(&b_full[s], 0);
+              tma_load_2d<kCG>(smem_b + s * stage_bytes, &tmap_g, &b_full[s], kb * kBlockK, g_row, kEvictNormal);
+              if (stream_a)
+                tma_load_2d<kCG>(smem_b + s * stage_bytes + kBTileBytes, &tmap_q, &b_full[s], kb * kBlockK, q_row, kEvictNormal);
+            }
+            __syncwarp();
           }
         }
         ++seg;
@@ -545,9 +555,13 @@ __global__ void __launch_bounds__(64 + 128 * kSets, 1)
     }
   } else if (warp == 1) {
     // ===================================== MMA issuer (leader CTA) =====================================
-    if (leader && lane == 0) {
+    if (leader) {
       constexpr uint32_t idesc = umma_idesc_bf16(kBlockM * kCG, kBlockN);
-      uint32_t it = 0, seg = 0, tc = 0;
+      uint32_t seg = 0, tc = 0;
+      PipeState st(p.stages);
+      const uint64_t da0 = umma_desc_sw128(smem_u32(stream_a ? smem_b + kBTileBytes : smem_a));
+      const uint64_t db0 = umma_desc_sw128(smem_u32(smem_b));
+      const uint32_t stage_step = static_cast<uint32_t>(stage_bytes) >> 4;   // descriptor start-address units (16 B)
       SegWalker w(p.n_qtiles, p.n_gtiles, p.gchunk, p.n_chunks, unit, n_units);
       while (w.next()) {
         const int ntiles = w.ntiles;
@@ -561,20 +575,23 @@ __global__ void __launch_bounds__(64 + 128 * kSets, 1)
           mbar_wait(&t_empty[buf], ((tc >> 1) & 1) ^ 1);
           tc_fence_after();
           const uint32_t tmem_d = tmem_base + buf * kBlockN;
-          for (int kb = 0; kb < p.num_kb; ++kb, ++it) {
-            const uint32_t s = it % p.stages, ph = (it / p.stages) & 1;
-            if (p.debug_mode != 3) mbar_wait(&b_full[s], ph);
+          for (int kb = 0; kb < p.num_kb; ++kb, st.next()) {
+            const uint32_t s = st.s;
+            if (p.debug_mode != 3) mbar_wait(&b_full[s], st.ph);
             tc_fence_after();
-            const uint64_t da = umma_desc_sw128(smem_u32(stream_a ? smem_b + s * stage_bytes + kBTileBytes : smem_a + kb * kATileBytes));
-            const uint64_t db = umma_desc_sw128(smem_u32(smem_b + s * stage_bytes));
+            const uint64_t da = da0 + static_cast<uint64_t>(stream_a ? s * stage_step : static_cast<uint32_t>(kb) * (kATileBytes >> 4));
+            const uint64_t db = db0 + static_cast<uint64_t>(s * stage_step);
+            if (elect_one()) {
 #pragma unroll
-            for (int k = 0; k < kBlockK / 16; ++k)
-              umma_f16<kCG>(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);  // +32 B per K=16 step
-            if (p.debug_mode != 3) umma_commit<kCG>(&b_empty[s]);   // frees this B stage (both CTAs) once the MMAs above retire
-            if (kb == p.num_kb - 1) {
-              umma_commit<kCG>(&t_full[buf]);
-              if (!stream_a && j == warm + ntiles - 1) umma_commit<kCG>(a_empty);
+              for (int k = 0; k < kBlockK / 16; ++k)
+                umma_f16<kCG>(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);  // +32 B per K=16 step
+              if (p.debug_mode != 3) umma_commit<kCG>(&b_empty[s]);   // frees this B stage (both CTAs) once the MMAs above retire
+              if (kb == p.num_kb - 1) {
+                umma_commit<kCG>(&t_full[buf]);
+                if (!stream_a && j == warm + ntiles - 1) umma_commit<kCG>(a_empty);
+              }
             }
+            __syncwarp();
           }
         }
         ++seg;

@@ -82,3 +82,42 @@ def test_conv_matches_torch(shape, planes):
         ref3 = _ref(ops.merge_planes(xp), ops.merge_planes(wp).reshape(n, kh, kw, -1)[..., :c].permute(0, 3, 1, 2),
                     scale, bias, None, act, stride, (ph, pw))
         assert (ops.merge_planes(out3) - ref3).abs().max().item() < ptol
+
+
+HALO_SHAPES = [   # (B, H, W, C, N): 3x3 / stride 1 / pad 1 without residual -> halo-reuse kernel (csrc/conv3x3_halo.cu)
+    (2, 56, 56, 64, 64),       # resnet layer1: 2 output rows per tile
+    (3, 28, 28, 128, 128),     # layer2: 4 rows per tile, two channel blocks
+    (5, 14, 14, 256, 256),     # layer3: 8 rows per tile, last tile of every image half outside (14 = 8 + 6)
+    (2, 14, 14, 64, 192),      # N not a power of two (256-wide accumulator, 3 of 4 output slabs)
+    (1, 30, 62, 64, 64),       # widest supported row (62 + 2 = 64)
+    (2, 9, 20, 128, 64),       # H not a multiple of the rows per tile (5)
+    (1, 2, 8, 64, 64),         # smallest
+]
+
+
+@pytest.mark.parametrize("shape", HALO_SHAPES)
+@pytest.mark.parametrize("act", [0, 1])
+def test_conv3x3_halo_path(shape, act, monkeypatch):
+    b, h, w_, c, n = shape
+    gen = torch.Generator(device="cuda").manual_seed(b * 100 + h + c + n)
+    x = torch.randn(b, h, w_, c, device="cuda", generator=gen)
+    w = torch.randn(n, c, 3, 3, device="cuda", generator=gen) / (c * 9) ** 0.5
+    scale = 0.5 + torch.rand(n, device="cuda", generator=gen)
+    bias = torch.randn(n, device="cuda", generator=gen) * 0.1
+    xp, wp = ops.split_planes(x, 1), ops.prepare_conv_weight(w, 1)
+    l0 = None
+    out, _ = ops.conv2d(xp, wp, n, 3, 3, 1, 1, 1, scale=scale, bias=bias, act=act)
+    torch.cuda.synchronize()
+    monkeypatch.setenv("DCR_CONV_NO_HALO", "1")
+    gen_out, _ = ops.conv2d(xp, wp, n, 3, 3, 1, 1, 1, scale=scale, bias=bias, act=act)
+    torch.cuda.synchronize()
+    monkeypatch.delenv("DCR_CONV_NO_HALO")
+    ref = _ref(ops.merge_planes(xp), ops.merge_planes(wp).reshape(n, 3, 3, -1)[..., :c].permute(0, 3, 1, 2), scale, bias,
+               None, act, 1, (1, 1))
+    got, gen_got = ops.merge_planes(out), ops.merge_planes(gen_out)
+    mx = max(1.0, ref.abs().max().item())
+    err = (got - ref).abs().max().item()
+    assert err < 2 ** -8 * mx + 3e-4 * mx, f"halo path err {err}"
+    # same products, different accumulation order than the generic kernel: at most one bf16 ulp apart
+    assert (got - gen_got).abs().max().item() <= 2 ** -7 * mx
+    assert (got != gen_got).float().mean().item() < 0.02
