@@ -166,15 +166,18 @@ __global__ void __launch_bounds__(kAttnThreads, 1)
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 8) {
-    if (lane == 0) {
+    {   // control warp: all lanes walk the (warp-uniform) code, one elected lane issues (see conv_gemm.cu)
       const int cq = h * 64, ck = p.heads * 64 + h * 64, cv = 2 * p.heads * 64 + h * 64;
-      mbar_arrive_expect_tx(bar_load, 6 * 16384);
-      tma_load_2d<1>(s_q, &tmap_qkv, bar_load, cq, row0, kEvictFirst);
-      tma_load_2d<1>(s_q + 16384, &tmap_qkv, bar_load, cq, row0 + 128, kEvictFirst);
-      tma_load_2d<1>(s_k, &tmap_qkv, bar_load, ck, row0, kEvictFirst);
-      tma_load_2d<1>(s_k + 16384, &tmap_qkv, bar_load, ck, row0 + 128, kEvictFirst);
-      tma_load_2d<1>(s_v, &tmap_qkv, bar_load, cv, row0, kEvictFirst);
-      tma_load_2d<1>(s_v + 16384, &tmap_qkv, bar_load, cv, row0 + 128, kEvictFirst);
+      if (elect_one()) {
+        mbar_arrive_expect_tx(bar_load, 6 * 16384);
+        tma_load_2d<1>(s_q, &tmap_qkv, bar_load, cq, row0, kEvictFirst);
+        tma_load_2d<1>(s_q + 16384, &tmap_qkv, bar_load, cq, row0 + 128, kEvictFirst);
+        tma_load_2d<1>(s_k, &tmap_qkv, bar_load, ck, row0, kEvictFirst);
+        tma_load_2d<1>(s_k + 16384, &tmap_qkv, bar_load, ck, row0 + 128, kEvictFirst);
+        tma_load_2d<1>(s_v, &tmap_qkv, bar_load, cv, row0, kEvictFirst);
+        tma_load_2d<1>(s_v + 16384, &tmap_qkv, bar_load, cv, row0 + 128, kEvictFirst);
+      }
+      __syncwarp();
       mbar_wait(bar_load, 0);
       tc_fence_after();
       constexpr uint32_t idesc_s = umma_idesc_bf16(128, 256);
@@ -182,24 +185,30 @@ __global__ void __launch_bounds__(kAttnThreads, 1)
       for (int mt = 0; mt < n_mtiles; ++mt) {
         const uint64_t da = umma_desc_sw128(smem_u32(s_q + mt * 16384));
         const uint64_t db = umma_desc_sw128(smem_u32(s_k));
+        if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) umma_f16<1>(tmem_base + mt * 256, da + 2 * k, db + 2 * k, idesc_s, k != 0);
-        umma_commit<1>(&s_full[mt]);
+          for (int k = 0; k < 4; ++k) umma_f16<1>(tmem_base + mt * 256, da + 2 * k, db + 2 * k, idesc_s, k != 0);
+          umma_commit<1>(&s_full[mt]);
+        }
+        __syncwarp();
       }
       for (int mt = 0; mt < n_mtiles; ++mt) {
         mbar_wait(&p_ready[mt], 0);
         tc_fence_after();
-#pragma unroll 1
-        for (int kb = 0; kb < 4; ++kb) {
-          const uint64_t da = umma_desc_sw128(smem_u32(s_p + mt * 65536 + kb * 16384));
+        if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            // A: +32 B per 16 keys inside the 64-key block; B (V, MN-major): +16 rows * 128 B per 16 keys
-            const uint64_t dv = umma_desc_sw128_mn(smem_u32(s_v + (kb * 64 + k * 16) * 128));
-            umma_f16<1>(tmem_base + mt * 256, da + 2 * k, dv, idesc_o, (kb | k) != 0);
+          for (int kb = 0; kb < 4; ++kb) {
+            const uint64_t da = umma_desc_sw128(smem_u32(s_p + mt * 65536 + kb * 16384));
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              // A: +32 B per 16 keys inside the 64-key block; B (V, MN-major): +16 rows * 128 B per 16 keys
+              const uint64_t dv = umma_desc_sw128_mn(smem_u32(s_v + (kb * 64 + k * 16) * 128));
+              umma_f16<1>(tmem_base + mt * 256, da + 2 * k, dv, idesc_o, (kb | k) != 0);
+            }
           }
+          umma_commit<1>(&o_full[mt]);
         }
-        umma_commit<1>(&o_full[mt]);
+        __syncwarp();
       }
     }
   } else {

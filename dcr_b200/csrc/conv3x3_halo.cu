@@ -12,7 +12,8 @@
 // fine.)  MMA row m of the tile is padded-raster position m = pl * (W + 2) + ql; positions with ql >= W (2 per row)
 // and the rows past R * (W + 2) are junk that the epilogue drops when it compacts the tile into the [R x W] staging
 // box of the TMA store.  W + 2 <= 64 and R = 128 / (W + 2) rows: 2 rows at 56 wide (87.5 % useful MMA rows), 4 at 28,
-// 8 at 14.
+// 8 at 14.  Used for N <= 128 (measured on B200: 171 -> 89 us at 56x56x64->64, 74 -> 55 us at 28x28x128->128, batch
+// 256; at N = 256 only two 32 KB weight stages fit beside the halo buffers and the generic kernel is faster).
 //
 // Weights are streamed per (tap, channel block) exactly as in the generic kernel (all SMs read the same tiles; that
 // traffic is served at several times the rate of per-SM-unique data).  Fast (single-plane bf16) mode only, no residual:
@@ -310,7 +311,7 @@ bool conv3x3_halo_eligible(const ConvGemmDesc& d) {
   const bool shape = d.kh == 3 && d.kw == 3 && d.stride == 1 && d.pad_h == 1 && d.pad_w == 1 && d.in_stride_w == 0;
   const bool fast = d.n_terms == 1 && d.term_a[0] == 0 && d.term_w[0] == 0 && !d.exact && d.out != nullptr &&
                     d.out_planes <= 1 && d.out_f32 == nullptr && d.res == nullptr && (d.act == 0 || d.act == 1);
-  const bool dims = d.C % 64 == 0 && d.ld_in == d.C && d.N % 64 == 0 && d.N <= 256 && d.ld_out % 8 == 0 &&
+  const bool dims = d.C % 64 == 0 && d.ld_in == d.C && d.N % 64 == 0 && d.N <= (getenv("DCR_CONV_HALO_N256") ? 256 : 128) && d.ld_out % 8 == 0 &&
                     d.out_col_off % 8 == 0 && d.W + 2 <= 64 && d.W >= 8 && d.H >= 2 && d.B >= 1;
   return shape && fast && dims;
 }

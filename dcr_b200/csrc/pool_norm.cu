@@ -133,6 +133,7 @@ struct StemS2dParams {
   int planes;
 };
 
+template <bool kResize>
 __global__ void __launch_bounds__(256) stem_s2d_u8_kernel(const StemS2dParams p) {
   __shared__ float lut[3][256];
   for (int i = threadIdx.x; i < 768; i += blockDim.x) {
@@ -159,7 +160,7 @@ __global__ void __launch_bounds__(256) stem_s2d_u8_kernel(const StemS2dParams p)
       for (int j = 0; j < 2; ++j) {
         const int x = 2 * v + j - 3;
         if (x < 0 || x >= p.RW) continue;
-        if (p.rscale == 0.f) {
+        if constexpr (!kResize) {
           const uint8_t* px = img + (static_cast<size_t>(y + p.crop_y) * p.IW + (x + p.crop_x)) * 3;
 #pragma unroll
           for (int c = 0; c < 3; ++c) z[(i * 2 + j) * 3 + c] = lut[c][px[c]];
@@ -497,7 +498,8 @@ int stem_s2d_u8(const uint8_t* img, int B, int IH, int IW, int crop_y, int crop_
   p.out = out; p.out_plane_stride = out_plane_stride; p.planes = planes;
   if (B == 0) return 0;
   const long long total = static_cast<long long>(B) * p.U * p.V;
-  stem_s2d_u8_kernel<<<grid_for(total, 256, di->num_sms), 256, 0, stream>>>(p);
+  if (rscale == 0.f) stem_s2d_u8_kernel<false><<<grid_for(total, 256, di->num_sms), 256, 0, stream>>>(p);
+  else stem_s2d_u8_kernel<true><<<grid_for(total, 256, di->num_sms), 256, 0, stream>>>(p);
   count_launch();
   DCR_CUDA_CHECK(cudaGetLastError());
   return 0;
