@@ -1219,11 +1219,11 @@ int make_plan(int nq, int ng, int d, int k, int cg, int num_sms, size_t max_smem
   pl->num_kb = pl->d_pad / kBlockK;
   pl->stream_a = pl->num_kb > kMaxKB ? 1 : 0;
   pl->rows_per_qtile = kBlockM * cg;
-  // DCR_SIM_SETS=2 gives every TMEM lane quadrant two epilogue warps (column halves with their own lists).  Measured
-  // on B200 (10k x 100k x 512): no faster for k=1 (0.97 ms both ways) and slower for k=10 (the lists of two sets only
-  // fit with a small capacity) -- the filter's cost is the rare-hit slow path, which does not split by columns.  Off
-  // by default; kept for experiments.
-  pl->max_sets = (cg == 2) ? std::max(1, std::min(2, env_int("DCR_SIM_SETS", 1))) : 1;
+  // Two epilogue warp sets (two warps per TMEM lane quadrant, each with its own lists for one column half) pay off when
+  // few candidates are kept: measured on B200 (10k x 100k x 512) k = 1: 0.79 ms vs 0.82 ms and no second-chance pass
+  // (each segment keeps 2 x 4 candidates); k = 10: slower (the lists of two sets only fit with a small capacity).
+  // DCR_SIM_SETS=1|2 overrides.
+  pl->max_sets = (cg == 2) ? std::max(1, std::min(2, env_int("DCR_SIM_SETS", k <= 2 ? 2 : 1))) : 1;
   pl->n_gtiles = (ng + kBlockN - 1) / kBlockN;
   pl->ng_pad = pl->n_gtiles * kBlockN;
   // gallery chunks of ~DCR_SIM_CHUNK_MB of bf16 rows: the units sweep one chunk at a time so that it stays L2 resident
