@@ -21,6 +21,10 @@ SHAPES = [
     (2, 35, 35, 288, 384, 3, 3, 2, 0, 0),    # inception 3x3/2 no padding
     (300, 1, 1, 384, 1152, 1, 1, 1, 0, 0),   # ViT qkv Linear
     (1, 9, 9, 8, 8, 3, 3, 1, 1, 1),          # tiny
+    (2, 56, 56, 64, 256, 1, 1, 1, 0, 0),     # resnet layer1 expansion: A-resident schedule (K = 64, 2 column blocks)
+    (3, 28, 28, 128, 512, 1, 1, 1, 0, 0),    # layer2 expansion (K = 128, 4 column blocks)
+    (5, 14, 14, 256, 1024, 1, 1, 1, 0, 0),   # layer3 expansion (K = 256, 8 column blocks, single output staging tile)
+    (1, 10, 13, 192, 320, 1, 1, 1, 0, 0),    # ragged M and N with the A-resident schedule
 ]
 
 
