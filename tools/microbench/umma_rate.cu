@@ -48,6 +48,78 @@ __global__ void __launch_bounds__(128, 1) rate_kernel(int iters, int issuers, in
   if (warp == 0) tmem_dealloc<1>(tmem_base, 512);
 }
 
+// A operand from tensor memory (".ts" form): D[tmem] += A[tmem] * B[smem desc]
+__device__ __forceinline__ void umma_f16_ts_cg1(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc) {
+  const uint32_t z = 0, one = 1;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, {%5, %5, %5, %5}, p;\n\t}\n" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(one), "r"(z)
+      : "memory");
+}
+
+template <int N>
+__global__ void __launch_bounds__(128, 1) rate_ts_kernel(int iters, unsigned long long* out) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_slot;
+  const uint32_t warp = threadIdx.x >> 5;
+  for (int i = threadIdx.x; i < (N * 128) / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0x3f803f80u;
+  if (threadIdx.x == 0) { mbar_init(&bar, 1); fence_mbar_init(); }
+  if (warp == 0) { tmem_alloc<1>(&tmem_slot, 512); tmem_relinquish<1>(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_slot;
+  if (warp == 1) {
+    constexpr uint32_t idesc = umma_idesc_bf16(128, N);
+    const uint64_t db = umma_desc_sw128(smem_u32(smem));
+    const long long t0 = clock64();
+    for (int i = 0; i < iters; ++i) {
+      if (elect_one()) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_f16_ts_cg1(tmem_base + 256, tmem_base + k * 8, db + 2 * k, idesc);
+      }
+      __syncwarp();
+    }
+    if (elect_one()) umma_commit<1>(&bar);
+    __syncwarp();
+    mbar_wait(&bar, 0);
+    const long long t1 = clock64();
+    if (blockIdx.x == 0 && (threadIdx.x & 31) == 0) out[0] = static_cast<unsigned long long>(t1 - t0);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc<1>(tmem_base, 512);
+}
+
+template <int N>
+void run_ts() {
+  unsigned long long* d;
+  cudaMalloc(&d, 16);
+  cudaMemset(d, 0, 16);
+  const int iters = 2000;
+  const size_t smem = 1024 + N * 128;
+  cudaFuncSetAttribute(rate_ts_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  rate_ts_kernel<N><<<148, 128, smem>>>(iters, d);
+  cudaEventRecord(e0);
+  rate_ts_kernel<N><<<148, 128, smem>>>(iters, d);
+  cudaEventRecord(e1);
+  cudaError_t err = cudaDeviceSynchronize();
+  unsigned long long h[2];
+  cudaMemcpy(h, d, 16, cudaMemcpyDeviceToHost);
+  float ms = 0;
+  cudaEventElapsedTime(&ms, e0, e1);
+  const double mmas = 4.0 * iters;
+  printf("A-in-TMEM N=%3d: %s  cycles/MMA = %.1f  kernel %.3f ms  %.0f TFLOP/s\n", N, cudaGetErrorString(err), h[0] / mmas, ms,
+         2.0 * 128 * N * 16 * mmas * 148 / (ms * 1e-3) / 1e12);
+  cudaFree(d);
+}
+
 template <int N>
 void run(int issuers, int mode = 0) {
   unsigned long long* d;
@@ -79,5 +151,6 @@ int main() {
   // 5: commit per 4 MMAs and wait (mbarrier try_wait) for the commit of 8 groups earlier before each group
   for (int mode : {0, 1, 2, 3, 5}) { run<64>(1, mode); run<256>(1, mode); }
   run<64>(2); run<256>(2);
+  run_ts<64>(); run_ts<128>(); run_ts<256>();
   return 0;
 }
