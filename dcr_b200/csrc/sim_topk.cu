@@ -59,6 +59,8 @@ struct SimParams {
   const float* col_bias;   // [ng_pad] per-gallery-row score offset nu.(g-mu) added to every accumulator column; null = none
   int debug_mode;          // timing experiments only: 1 = epilogue loads TMEM but does not scan, 2 = does not even load
   const float* thr_init;   // per query row: start thresholds (second-chance pass); null = seed by warm-up replay
+  unsigned int* gthr;      // [nq_pad] per query row: best threshold any unit has reached so far, as an order-preserving
+                           // unsigned key (0 = none); null = no sharing
   unsigned long long* clk; // [4] clock64 / globaltimer at the start and end of CTA 0 (SM clock under this kernel); null = off
 };
 
@@ -222,6 +224,16 @@ DCR_DEVICE unsigned long long global_timer_ns() {
   unsigned long long t;
   asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
   return t;
+}
+
+// order-preserving float <-> unsigned key (0 is below every float): thresholds are shared with atomicMax
+DCR_DEVICE unsigned int thr_key(float f) {
+  const unsigned int b = __float_as_uint(f);
+  return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+DCR_DEVICE float thr_from_key(unsigned int k) {
+  if (k == 0) return -INFINITY;
+  return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
 }
 
 DCR_DEVICE float max8(const float* v) {
@@ -625,6 +637,13 @@ __global__ void __launch_bounds__(64 + 128 * kSets, 1)
       // a threshold this row reached on an earlier gallery chunk is a valid (and usually tight) start here
       if (w.carried) thr = fmaxf(thr, my_carry[(qi & 3) * kBlockM + row]);
       int cnt = 0;
+      // Threshold sharing: a threshold ANY unit reached for this query row (kp recorded scores above it exist somewhere
+      // in the gallery) is a valid drop bound for every other unit sweeping the same query tile.  Read once per tile
+      // (the load is issued before the accumulator-ready wait), published when it has risen.
+      const int qrow_s = qi * rows_per_qtile + static_cast<int>(cta_rank) * kBlockM + static_cast<int>(row);
+      unsigned int* gslot = (p.gthr && qrow_s < p.nq) ? p.gthr + qrow_s : nullptr;
+      float published = gslot ? thr_from_key(*reinterpret_cast<volatile unsigned int*>(gslot)) : INFINITY;
+      if (gslot) thr = fmaxf(thr, published);
 
       // one accumulator tile: warm-up tiles only track column-slot maxima, the others feed the candidate lists.  Two
       // separate loops so that the 32 slot registers are dead while the lists are live.
@@ -634,8 +653,21 @@ __global__ void __launch_bounds__(64 + 128 * kSets, 1)
         const bool tail = gcol0 + kSetCols > p.ng;
         const uint32_t buf = tc & 1;
         const float* sb = kBias ? colbias + gcol0 : nullptr;   // per-column offsets: warp-uniform (broadcast) loads
+        unsigned int shared_key = 0;
+        if (!kWarm && gslot) shared_key = *reinterpret_cast<volatile unsigned int*>(gslot);
         mbar_wait(&t_full[buf], (tc >> 1) & 1);
         tc_fence_after();
+        if (!kWarm && gslot) {
+          if (thr > published) {   // risen since the last publication (compaction): let the other units know
+            atomicMax(gslot, thr_key(thr));
+            published = thr;
+          }
+          const float other = thr_from_key(shared_key);
+          if (other > thr) {
+            thr = other;
+            published = other;
+          }
+        }
         const uint32_t taddr = tmem_row + buf * kBlockN + set * kSetCols;
         uint32_t ra[32], rb[32];
         auto release = [&]() {   // this warp's columns of the accumulator buffer are in registers
@@ -696,6 +728,7 @@ __global__ void __launch_bounds__(64 + 128 * kSets, 1)
       }
       __syncwarp();
       my_carry[(qi & 3) * kBlockM + row] = thr;
+      if (gslot && thr > published) atomicMax(gslot, thr_key(thr));
       const size_t slot_row0 = (static_cast<size_t>(w.slot) * kSets + set) * rows_per_qtile + cta_rank * kBlockM + quad * 32;
       for (int L = 0; L < 32; ++L) {
         const int n = __shfl_sync(kFull, cnt, L);
@@ -1135,7 +1168,7 @@ struct SimPlan {
   PassPlan p0, p1;        // p1 is sized for the worst case (every query flagged)
   // workspace offsets
   size_t off_qb, off_qb1, off_gb, off_qnh, off_qnr, off_qnx, off_gmax, off_colsum, off_mu, off_cand, off_cnt, off_thr,
-      off_flag0, off_flag1, off_thr1, off_counts, off_exact, off_nu, off_bias, off_clk;
+      off_flag0, off_flag1, off_thr1, off_counts, off_exact, off_nu, off_bias, off_clk, off_gthr;
   size_t total;
 };
 
@@ -1276,6 +1309,7 @@ int make_plan(int nq, int ng, int d, int k, int cg, int num_sms, size_t max_smem
   pl->off_thr1 = take(static_cast<size_t>(nq) * 4);
   pl->off_counts = take(16);
   pl->off_clk = take(32);
+  pl->off_gthr = take(static_cast<size_t>(std::max(big.nq_pad, pl->kp1 ? pl->p1.nq_pad : 0)) * 4);
   pl->off_exact = take(static_cast<size_t>(kExactBatch) * ng * 8);
   pl->total = off;
   return 0;
@@ -1296,7 +1330,7 @@ struct PassBuffers {
 // one fused pass: qb (bf16, padded) x gb (bf16, centred, padded) -> candidate slots
 int launch_fused(const SimPlan& pl, const PassPlan& pp, const __nv_bfloat16* qb, const __nv_bfloat16* gb, int ng,
                  const PassBuffers& pb, const float* col_bias, const int* bias_flag, const float* thr_init,
-                 unsigned long long* clk, cudaStream_t stream) {
+                 unsigned long long* clk, unsigned int* gthr, cudaStream_t stream) {
   CUtensorMap tq, tg;
   if (int rc = make_tmap_2d_bf16(&tq, qb, pp.nq_pad, pl.d_pad, pl.d_pad, kBlockM, kBlockK)) return rc;
   if (int rc = make_tmap_2d_bf16(&tg, gb, pl.ng_pad, pl.d_pad, pl.d_pad, kBlockN / pl.cg, kBlockK)) return rc;
@@ -1320,6 +1354,8 @@ int launch_fused(const SimPlan& pl, const PassPlan& pp, const __nv_bfloat16* qb,
   p.bias_flag = bias_flag;
   p.thr_init = thr_init;
   p.clk = clk;
+  p.gthr = gthr;
+  if (gthr) DCR_CUDA_CHECK(cudaMemsetAsync(gthr, 0, static_cast<size_t>(pp.nq_pad) * 4, stream));
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(pp.n_units * pl.cg);
   cfg.blockDim = dim3(64 + 128 * pp.n_sets);
@@ -1413,6 +1449,7 @@ int sim_topk(const float* q, int nq, const float* g, int ng, int d, int k, long 
   auto* counts = reinterpret_cast<int*>(w + pl.off_counts);   // [0] flagged by pass 0, [1] flagged by pass 1
   auto* exact = reinterpret_cast<double*>(w + pl.off_exact);
   auto* clk = reinterpret_cast<unsigned long long*>(w + pl.off_clk);
+  unsigned int* gthr = env_int("DCR_SIM_SHARE_THR", 1) ? reinterpret_cast<unsigned int*>(w + pl.off_gthr) : nullptr;
 
   const bool centre = env_int("DCR_SIM_CENTER", 1) != 0;
   DCR_CUDA_CHECK(cudaMemsetAsync(gmax, 0, 16, stream));
@@ -1458,7 +1495,7 @@ int sim_topk(const float* q, int nq, const float* g, int ng, int d, int k, long 
     DCR_CUDA_CHECK(cudaEventCreate(&ev1));
   }
   DCR_CUDA_CHECK(cudaEventRecord(ev0, stream));
-  if (int rc = launch_fused(pl, pl.p0, qb, gb, ng, pb, col_bias, qflag, nullptr, clk, stream)) return rc;
+  if (int rc = launch_fused(pl, pl.p0, qb, gb, ng, pb, col_bias, qflag, nullptr, clk, gthr, stream)) return rc;
   DCR_CUDA_CHECK(cudaEventRecord(ev1, stream));
 
   auto rescore = [&](const PassPlan& pp, const int* qmap, int* flagged, int* n_flagged, float* thr_next) -> int {
@@ -1492,7 +1529,7 @@ int sim_topk(const float* q, int nq, const float* g, int ng, int d, int k, long 
     gather_rows_kernel<<<std::min(di->num_sms * 8, (p1.nq_pad * (pl.d_pad / 8) + 255) / 256), 256, 0, stream>>>(
         qb, flag0, n_second, p1.nq_pad, pl.d_pad, qb1);
     count_launch();
-    if (int rc = launch_fused(pl, p1, qb1, gb, ng, pb, col_bias, qflag, thr1, nullptr, stream)) return rc;
+    if (int rc = launch_fused(pl, p1, qb1, gb, ng, pb, col_bias, qflag, thr1, nullptr, gthr, stream)) return rc;
     if (int rc = rescore(p1, flag0, flag1, counts + 1, nullptr)) return rc;
     DCR_CUDA_CHECK(cudaMemcpyAsync(h_counts, counts, 8, cudaMemcpyDeviceToHost, stream));
     DCR_CUDA_CHECK(cudaStreamSynchronize(stream));
