@@ -288,8 +288,14 @@ def main():
     # ---- end to end through the public API from pinned host memory ------------------------------------------------
     e2e = None
     if not args.no_e2e:
-        gal_h = torch.empty(gal_u8.shape, dtype=torch.uint8, pin_memory=True)
-        qry_h = torch.empty(qry_u8.shape, dtype=torch.uint8, pin_memory=True)
+        host_kind = "pinned"
+        try:
+            gal_h = torch.empty(gal_u8.shape, dtype=torch.uint8, pin_memory=True)
+            qry_h = torch.empty(qry_u8.shape, dtype=torch.uint8, pin_memory=True)
+        except RuntimeError:        # page-locking ~22 GB per rank can fail on a crowded host: pageable copies still work
+            host_kind = "pageable"
+            gal_h = torch.empty(gal_u8.shape, dtype=torch.uint8)
+            qry_h = torch.empty(qry_u8.shape, dtype=torch.uint8)
         gal_h.copy_(gal_u8)
         qry_h.copy_(qry_u8)
         torch.cuda.synchronize()
@@ -302,7 +308,7 @@ def main():
         ms_e2e, _ = timed(e2e_step, args.steps)
         e2e = {"value": q_total / (ms_e2e / args.steps / 1e3), "unit": "query images/s",
                "h2d_bytes_per_step": int(gal_h.numel() + qry_h.numel()) * world,
-               "d2h_bytes_per_step": int(q_total * K_TOP * 12) * world}
+               "d2h_bytes_per_step": int(q_total * K_TOP * 12) * world, "host_memory": host_kind}
         del gal_h, qry_h
     if rank == 0:
         sampler.stop_flag.set()
