@@ -64,3 +64,40 @@ def test_dense_expansion_of_grouped_conv_weight():
     assert dense.shape == (32, 32, 3, 3) and (dense != 0).sum() == w.numel()
     assert torch.allclose(F.conv2d(x, dense, padding=1), F.conv2d(x, w, padding=1, groups=8), atol=1e-5)
     assert nets._dense_from_grouped(dense, 32) is dense
+
+
+def test_fid_call_surface_errors_need_no_gpu(tmp_path):
+    """metrics/fid.py:239-255 / :258-275 error behaviour is checked before any device work."""
+    from dcr_b200 import fid as dfid
+    a = tmp_path / "a"
+    a.mkdir()
+    with pytest.raises(RuntimeError, match="Invalid path"):
+        dfid.calculate_fid_given_paths([str(tmp_path / "missing"), str(a)], 50, "cuda", 2048)
+    with pytest.raises(NotImplementedError):
+        dfid.calculate_fid_given_paths([str(a), str(a)], 50, "cuda", 768)
+    with pytest.raises(RuntimeError, match="Invalid path"):
+        dfid.save_fid_stats([str(tmp_path / "missing"), str(tmp_path / "x.npz")], 50, "cuda", 2048)
+    (tmp_path / "exists.npz").write_bytes(b"")
+    with pytest.raises(RuntimeError, match="Existing output file"):
+        dfid.save_fid_stats([str(a), str(tmp_path / "exists.npz")], 50, "cuda", 2048)
+
+
+def test_embedding_search_command_line_errors():
+    from dcr_b200 import embedding_search as es
+    with pytest.raises(es._lib.DcrError):
+        es.embed_main(["--parquet-fname", "x.parquet"])                      # download path: out of scope
+    with pytest.raises(RuntimeError, match="Either tar files or image folder"):
+        es.embed_main([])                                                    # embedding_search/utils.py:66
+    with pytest.raises(NotImplementedError):
+        es.embed_main(["--image-folder", "x", "--arch", "resnet18"])
+
+
+def test_cli_rejects_unknown_models_and_metrics(tmp_path):
+    q = tmp_path / "q"
+    q.mkdir()
+    with pytest.raises(NotImplementedError):
+        cli.main(["--query_dir", str(q), "--val_dir", str(q), "--similarity_metric", "cosine"])
+    with pytest.raises(NotImplementedError):
+        cli.main(["--query_dir", str(q), "--val_dir", str(q), "--pt_style", "clip"])
+    with pytest.raises(FileNotFoundError):
+        cli.main(["--query_dir", str(q), "--val_dir", str(q), "--pt_style", "sscd", "--weights", str(tmp_path / "none.pt")])
