@@ -300,6 +300,28 @@ def build_sscd_resnet50(state_dict: Dict[str, torch.Tensor], max_batch: int = 64
     return net
 
 
+def interpolate_pos_embed(pos_embed: torch.Tensor, grid_h: int, grid_w: int) -> torch.Tensor:
+    """Host-side parameter preparation for a ViT run at another input size: the reference resamples the patch position
+    embeddings bicubically at every forward (dino_vits.py:213-233, including its `+ 0.1` on the target grid); here it
+    happens once when the network is built.  pos_embed [1, 1 + n*n, dim] -> [1, 1 + grid_h * grid_w, dim]."""
+    import math
+    n = pos_embed.shape[1] - 1
+    side = int(math.sqrt(n))
+    if side * side != n:
+        raise _lib.DcrError(f"pos_embed with {n} patch positions is not a square grid")
+    if grid_h == side and grid_w == side:
+        return pos_embed
+    dim = pos_embed.shape[-1]
+    pe = pos_embed.detach().float().cpu()
+    patch_pos = pe[:, 1:].reshape(1, side, side, dim).permute(0, 3, 1, 2)
+    patch_pos = torch.nn.functional.interpolate(patch_pos, scale_factor=((grid_h + 0.1) / side, (grid_w + 0.1) / side),
+                                                mode="bicubic")
+    if patch_pos.shape[-2] != grid_h or patch_pos.shape[-1] != grid_w:
+        raise _lib.DcrError("position-embedding interpolation produced an unexpected grid")
+    patch_pos = patch_pos.permute(0, 2, 3, 1).reshape(1, grid_h * grid_w, dim)
+    return torch.cat((pe[:, :1], patch_pos), dim=1)
+
+
 # ------------------------------------------------------------------------------------------------------------------
 # DINO ViT (dino_vits.py:171-289)
 def build_dino_vit(state_dict: Dict[str, torch.Tensor], max_batch: int = 64, precision: str = "fast",
@@ -318,8 +340,10 @@ def build_dino_vit(state_dict: Dict[str, torch.Tensor], max_batch: int = 64, pre
     n_patch = grid * grid
     tokens = n_patch + 1
     if sd["pos_embed"].shape[1] != tokens:
-        raise _lib.DcrError(f"pos_embed has {sd['pos_embed'].shape[1]} positions, network input gives {tokens}; "
-                            "interpolate_pos_encoding (dino_vits.py:213-233) is not implemented")
+        # another input size than the checkpoint's: resample the position embeddings as the reference does
+        # (dino_vits.py:213-233); the hardware path for token counts other than 197 is not covered by the GPU tests yet
+        sd = dict(sd)
+        sd["pos_embed"] = interpolate_pos_embed(sd["pos_embed"], grid, grid)
     net = DcrNet(max_batch, precision)
     net.in_shape = (in_size, in_size)
     off = (in_size - crop) // 2

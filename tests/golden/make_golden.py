@@ -44,6 +44,22 @@ def make_dino(seed):
     print("dino", seed, y.shape, float(y.abs().mean()))
 
 
+def make_dino_other_size(seed, size=160):
+    """Same module at a 160 x 160 input: exercises interpolate_pos_encoding (dino_vits.py:213-233)."""
+    from oracle.models import make_vit_state_dict
+    dv = _load("ref_dino_vits", os.path.join(REF, "dino_vits.py"))
+    model = dv.vit_small(patch_size=16, num_classes=0)
+    model.load_state_dict(make_vit_state_dict(seed), strict=True)
+    model.eval()
+    x = golden_inputs(seed, size=size)
+    with torch.no_grad():
+        y = model(x)
+        pos = model.interpolate_pos_encoding(torch.zeros(1, 1 + (size // 16) ** 2, 384), size, size)
+    np.savez_compressed(os.path.join(HERE, f"dino_vits16_seed{seed}_{size}.npz"), seed=seed, out=y.numpy(),
+                        pos_embed=pos.numpy(), in_checksum=float(x.double().sum()))
+    print("dino", seed, size, y.shape, pos.shape)
+
+
 def make_fid_inception(seed):
     """metrics/inception.InceptionV3([3]) exactly as metrics/fid.py:245-247 builds it, with the URL weight load
     (inception.py:219) replaced by the seeded state_dict of oracle.models.make_inception_state_dict(seed)."""
@@ -74,4 +90,5 @@ if __name__ == "__main__":
     torch.manual_seed(0)
     for s in (0, 1):
         make_dino(s)
+    make_dino_other_size(0)
     make_fid_inception(0)

@@ -73,3 +73,23 @@ def test_sscd_oracle_grouped_trunk_matches_torchvision_module():
     got = om.sscd_forward(sd, x)
     assert got.shape == (2, 1024)
     np.testing.assert_allclose(got.numpy(), ref.numpy(), atol=2e-5)
+
+
+def test_vit_other_input_size_matches_reference_golden():
+    """160 x 160 input: position embeddings resampled as dino_vits.py:213-233 does -- oracle forward, oracle helper and
+    the host-side parameter preparation of the product (dcr_b200.nets.interpolate_pos_embed) against the reference's own
+    outputs (tests/golden/make_golden.py: make_dino_other_size)."""
+    from dcr_b200 import nets
+    g = np.load(os.path.join(GOLD, "dino_vits16_seed0_160.npz"))
+    sd = om.make_vit_state_dict(0)
+    x = _golden_inputs(0, size=160)
+    assert abs(float(x.double().sum()) - float(g["in_checksum"])) < 1e-6
+    y = om.vit_forward(sd, x).numpy()
+    np.testing.assert_allclose(y, g["out"], rtol=0, atol=2e-5)
+    pos_o = om.interpolate_pos_encoding(sd["pos_embed"], 100, 160, 160, 16).numpy()
+    pos_p = nets.interpolate_pos_embed(sd["pos_embed"], 10, 10).numpy()
+    assert pos_o.shape == g["pos_embed"].shape == pos_p.shape == (1, 101, 384)
+    np.testing.assert_array_equal(pos_o, g["pos_embed"])
+    np.testing.assert_array_equal(pos_p, g["pos_embed"])
+    # same size: untouched
+    assert nets.interpolate_pos_embed(sd["pos_embed"], 14, 14) is sd["pos_embed"]
