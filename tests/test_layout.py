@@ -46,3 +46,20 @@ def test_product_never_imports_oracle_or_reference():
                 if re.search(r"^\s*(from|import)\s+oracle\b", txt, flags=re.M) or "/root/reference" in txt:
                     bad.append(os.path.join(dirpath, f))
     assert not bad, bad
+
+
+def test_similarity_planner_accepts_the_supported_shape_range():
+    """dcr_sim_topk_workspace_size is host-only (launch planning: tiles, chunks, shared-memory budget, candidate slots):
+    every shape of the supported range must plan -- the BASELINE configs, single rows, 1M+ galleries, descriptor dims up
+    to 8192, every k <= 16 -- and out-of-range arguments must be refused with a message."""
+    import itertools
+    from dcr_b200 import _lib
+    lib = _lib.load()
+    for nq, ng, d, k in itertools.product([1, 7, 256, 10000, 50000, 1000000], [16, 1000, 100000, 1000000, 5000000],
+                                          [4, 64, 100, 384, 512, 768, 1024, 2048, 8192], [1, 2, 5, 10, 16]):
+        if k > ng:
+            continue
+        assert lib.dcr_sim_topk_workspace_size(nq, ng, d, k) > 0, (nq, ng, d, k, lib.dcr_last_error().decode())
+    for nq, ng, d, k in [(0, 10, 64, 1), (10, 10, 64, 17), (10, 5, 64, 8), (10, 10, 8200, 1), (10, 0, 64, 1)]:
+        assert lib.dcr_sim_topk_workspace_size(nq, ng, d, k) == 0
+        assert lib.dcr_last_error().decode() != ""
