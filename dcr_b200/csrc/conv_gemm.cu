@@ -524,11 +524,18 @@ int launch(const GemmMaps& maps, GemmParams& p, int num_sms, size_t max_smem, cu
   // residual-free 2-block downsample)
   p.a_resident = (!kIm2col && kEpi != 0 && p.n_terms == 1 && p.num_n_tiles >= 2 && (p.res != nullptr || p.num_n_tiles >= 4) &&
                   k_iters_h * kAStage <= 64 * 1024 && p.num_n_tiles * BN <= 4096 && getenv("DCR_GEMM_NO_ARES") == nullptr) ? 1 : 0;
+  // the resident rows, the all-blocks affine table and the staging tiles must leave at least three W stages; otherwise
+  // the layer runs with the default schedule
+  if (p.a_resident) {
+    const size_t need = 1024 + static_cast<size_t>(2) * p.num_n_tiles * BN * 4 + static_cast<size_t>(k_iters_h) * kAStage + 256 +
+                        static_cast<size_t>(1 + p.n_res_bufs) * kStagingBytes + 3 * static_cast<size_t>(BN) * kBK * 2;
+    if (need > max_smem) p.a_resident = 0;
+  }
   const size_t sb_bytes = p.a_resident ? static_cast<size_t>(2) * p.num_n_tiles * BN * 4 : static_cast<size_t>(4) * BN * 4;
   const size_t ares_bytes = p.a_resident ? static_cast<size_t>(k_iters_h) * kAStage : 0;
   auto fixed_for = [&](int nout, int nres) { return 1024 + sb_bytes + ares_bytes + 256 + static_cast<size_t>(nout + nres) * kStagingBytes; };
   const size_t stage_bytes = p.a_resident ? static_cast<size_t>(BN) * kBK * 2 : static_cast<size_t>(kStageBytes);
-  if (p.tma_epi && (max_smem - fixed_for(p.n_out_bufs, p.n_res_bufs)) / stage_bytes < 3) p.n_out_bufs = 1;
+  if (p.tma_epi && (fixed_for(p.n_out_bufs, p.n_res_bufs) + 3 * stage_bytes > max_smem)) p.n_out_bufs = 1;
   const size_t fixed = fixed_for(p.n_out_bufs, p.n_res_bufs);
   DCR_REQUIRE(max_smem > fixed + 2 * stage_bytes, "gemm: not enough shared memory");
   int stages = static_cast<int>((max_smem - fixed) / stage_bytes);
