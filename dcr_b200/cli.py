@@ -87,66 +87,137 @@ def load_state_dict(path: str):
 
 
 def build_model(args):
-    from . import nets
+    from . import nets, retrieval
     if args.pt_style == "sscd":
         if args.arch not in SSCD_FILES:
             raise NotImplementedError("This model type does not exist/supported for SSCD")      # :285
         sd = load_state_dict(args.weights or SSCD_FILES[args.arch])
         if args.multiscale:                                                                   # utils_ret.py:676-698
-            from . import retrieval
             return [nets.build_sscd_resnet50(sd, max_batch=256, precision=args.precision, scale_factor=s)
                     for s in retrieval.MULTI_SCALES]
         return nets.build_sscd_resnet50(sd, max_batch=256, precision=args.precision)
     if args.pt_style == "dino":
-        if args.arch not in ("vit_small", "vit_base"):                                          # :251-257
-            raise NotImplementedError("--pt_style dino: --arch vit_small (dino_vits16) and vit_base (dino_vitb16) are "
-                                      "implemented; vit_base8 / resnet50 / vit_base_cifar10 are not")
-        if args.multiscale:
-            raise NotImplementedError("--multiscale needs interpolated position embeddings for ViTs (dino_vits.py:213-233); "
-                                      "it is implemented for the convolutional SSCD trunks")
+        if args.arch not in ("vit_small", "vit_base", "vit_base8"):                             # :251-257
+            raise NotImplementedError("--pt_style dino: --arch vit_small (dino_vits16), vit_base (dino_vitb16) and "
+                                      "vit_base8 (dino_vitb8) are implemented; resnet50 / vit_base_cifar10 are not")
         sd = load_state_dict(args.weights or args.pretrained)
-        return nets.build_dino_vit(sd, max_batch=256, precision=args.precision)
+        # splitloss on a ViT: global_pool='' (:258-263) -> one descriptor part per token (utils_ret.py:728-737)
+        pool = "" if args.similarity_metric == "splitloss" else "token"
+        kw = dict(max_batch=64 if args.arch == "vit_base8" else 256, precision=args.precision, global_pool=pool,
+                  n_last_layers=max(1, args.layer))                                             # utils_ret.py:732,745
+        if args.multiscale:                                                                   # utils_ret.py:676-698
+            return [nets.build_dino_vit(sd, scale_factor=s, **kw) for s in retrieval.MULTI_SCALES]
+        return nets.build_dino_vit(sd, **kw)
     raise NotImplementedError(f"--pt_style {args.pt_style} is outside the embed->match hot path (DESIGN.md section 9)")
 
 
 def main(argv=None) -> int:
+    """diff_retrieval.py:183-221: parse, then one worker -- or, with --multiprocessing-distributed, one worker per GPU."""
     args = build_parser().parse_args(argv)
-    assert os.path.isdir(args.query_dir)                                                      # :187
-    if args.similarity_metric == "splitlosscross":                                            # :188-190
+    assert os.path.isdir(args.query_dir), "Query dir doesnt exist, skipping!"                   # :185
+    if args.similarity_metric == "splitlosscross":                                            # :186-188
         args.similarity_metric, args.stype = "splitloss", "cross"
     if args.similarity_metric not in ("dotproduct", "splitloss"):
         raise NotImplementedError(f"--similarity_metric {args.similarity_metric}")
-    split = args.num_loss_chunks if args.similarity_metric == "splitloss" else 1
-    cross = split > 1 and args.stype == "cross"
-    from . import data, retrieval
+    if args.dist_url == "env://" and args.world_size == -1:                                   # :204-205
+        args.world_size = int(os.environ["WORLD_SIZE"])
+    args.distributed = args.world_size > 1 or args.multiprocessing_distributed               # :207
+    ngpus_per_node = torch.cuda.device_count()
+    if args.multiprocessing_distributed:                                                     # :210-216
+        args.world_size = ngpus_per_node * max(1, args.world_size)
+        import torch.multiprocessing as mp
+        mp.spawn(main_worker, nprocs=ngpus_per_node, args=(ngpus_per_node, args))
+        return 0
+    return main_worker(args.gpu, ngpus_per_node, args)
+
+
+def _init_distributed(gpu, ngpus_per_node, args) -> None:
+    """diff_retrieval.py:237-246 (and utils_ret.init_distributed_mode for the env:// launch)."""
+    import torch.distributed as dist
+    if args.dist_url == "env://" and args.rank == -1:
+        args.rank = int(os.environ["RANK"])
+    if args.multiprocessing_distributed:
+        args.rank = max(0, args.rank) * ngpus_per_node + gpu          # global rank among all the processes (:240-243)
+    if args.gpu is None:                                              # env:// launch (torchrun): one GPU per local rank
+        args.gpu = int(os.environ.get("LOCAL_RANK", args.rank % max(1, ngpus_per_node)))
+    torch.cuda.set_device(args.gpu)
+    dist.init_process_group(backend=args.dist_backend, init_method=args.dist_url, world_size=args.world_size,
+                            rank=args.rank, device_id=torch.device("cuda", args.gpu) if args.dist_backend == "nccl" else None)
+    dist.barrier()
+
+
+def main_worker(gpu, ngpus_per_node, args) -> int:
+    """diff_retrieval.py:224-483 restricted to the hot path.  Distributed runs shard BOTH image sets contiguously over
+    the ranks (the reference shards the gallery loader with a DistributedSampler, :345-348, and funnels every batch to
+    rank 0); every rank embeds its shards, scores all queries against its gallery shard and the per-shard top-k lists
+    are all-gathered and merged (dcr_b200/dist.py) -- same result as the single-process run, on every rank."""
+    args.gpu = gpu
+    if args.multiprocessing_distributed and args.gpu != 0:                                    # :229-232
+        import builtins
+        builtins.print = lambda *a, **k: None
     if args.gpu is not None:
+        print("Use GPU: {} for training".format(args.gpu))
+    rank, world = 0, 1
+    if args.distributed:
+        import torch.distributed as dist
+        _init_distributed(gpu, ngpus_per_node, args)
+        rank, world = dist.get_rank(), dist.get_world_size()
+    elif args.gpu is not None:
         torch.cuda.set_device(args.gpu)
+    from . import data, retrieval, similarity
+    from . import dist as ddist
+    split = args.num_loss_chunks if args.similarity_metric == "splitloss" else 1
     net = build_model(args)
-    query_u8, q_files = data.load_folder_u8(args.query_dir, workers=args.workers)
-    values_u8, v_files = data.load_folder_u8(args.val_dir, workers=args.workers)
-    # splitloss: the reference never defines sim2 on that branch (:393-403) and stops at :412; background statistics
-    # are only produced for the dot-product metric
+    first = net[0] if isinstance(net, (list, tuple)) else net
+    if args.similarity_metric == "splitloss" and args.pt_style == "dino":
+        split = first.tokens                                              # args.numpatches = feats.shape[1] (utils_ret.py:736, :394-395)
+    cross = split > 1 and args.stype == "cross"
+    q_files = data.list_images(args.query_dir)
+    v_files = data.list_images(args.val_dir)
+    print(f"train: {len(v_files)} imgs / query: {len(q_files)} imgs")                         # :367
+    qlo, qhi = ddist.shard_bounds(len(q_files), rank, world)
+    vlo, vhi = ddist.shard_bounds(len(v_files), rank, world)
+    query_u8 = data.load_files_u8(q_files[qlo:qhi], workers=args.workers)
+    values_u8 = data.load_files_u8(v_files[vlo:vhi], workers=args.workers)
     k = min(args.topk, len(v_files))
-    if cross and (k - 1) * split + 1 > 16:
-        k = 15 // split + 1
-        print(f"--stype cross with {split} parts: keeping the {k} best matches per query (kernel limit (k-1)*parts+1 <= 16)")
-    out = retrieval.run_retrieval(net, query_u8, values_u8, k=k, with_background=(split == 1), num_loss_chunks=split,
-                                  cross=cross)
-    dp = os.sep.join(os.path.normpath(args.query_dir).split(os.sep)[-3:])                      # :378
-    save = f"ret_plots/{dp}/images/{args.pt_style}_{args.arch}_{args.similarity_metric}{args.stype}/"   # :408
-    os.makedirs(save, exist_ok=True)
-    torch.save({"values": out["values"].cpu(), "indices": out["indices"].cpu(), "query_files": q_files,
-                "gallery_files": v_files}, os.path.join(save, "topk.pth"))
-    print("Simscores @x% part done")                                                          # :470
-    print(out["stats"])
-    if args.fid_weights:
-        from . import fid, nets
-        inc = nets.build_fid_inception(load_state_dict(args.fid_weights), max_batch=50)
-        val = fid.fid_from_images(inc, fid.load_resized(args.val_dir), fid.load_resized(args.query_dir))   # :597-600
-        print({"fid": val})
-        out["stats"]["fid"] = val
-    with open(os.path.join(save, "stats.json"), "w") as f:
-        json.dump(out["stats"], f)
+    if world == 1:
+        # splitloss: the reference never defines sim2 on that branch (:393-403) and stops at :412; background statistics
+        # are only produced for the dot-product metric
+        out = retrieval.run_retrieval(net, query_u8, values_u8, k=k, with_background=(split == 1), num_loss_chunks=split,
+                                      cross=cross)
+    else:
+        if split > 1:
+            raise NotImplementedError("--similarity_metric splitloss runs on one GPU (the sharded path merges dot-product lists)")
+        embed = retrieval.extract_features_multiscale if isinstance(net, (list, tuple)) else retrieval.extract_features
+        gf = similarity.l2_normalize_(embed(net, values_u8))                                    # :386, :388
+        qf = similarity.l2_normalize_(embed(net, query_u8))                                     # :387, :389
+        q_sizes = [b - a for a, b in (ddist.shard_bounds(len(q_files), r, world) for r in range(world))]
+        v_sizes = [b - a for a, b in (ddist.shard_bounds(len(v_files), r, world) for r in range(world))]
+        main_v, main_l = ddist.sharded_topk(qf, gf, k, vlo, ddist.cuda_local_topk, ddist.cuda_merge, query_sizes=q_sizes)
+        bg, _ = ddist.sharded_topk(gf, gf, min(2, len(v_files)), vlo, ddist.cuda_local_topk, ddist.cuda_merge,
+                                   query_sizes=v_sizes)                                         # :403, :418
+        out = {"values": main_v, "indices": main_l, "bg_values": bg[:, -1],
+               "stats": retrieval.retrieval_stats(main_v[:, 0], bg[:, -1])}
+    if rank == 0:                                                                             # :375 only rank 0 writes
+        dp = os.sep.join(os.path.normpath(args.query_dir).split(os.sep)[-3:])                  # :378
+        save = f"ret_plots/{dp}/images/{args.pt_style}_{args.arch}_{args.similarity_metric}{args.stype}/"   # :408
+        os.makedirs(save, exist_ok=True)
+        torch.save({"values": out["values"].cpu(), "indices": out["indices"].cpu(), "query_files": q_files,
+                    "gallery_files": v_files}, os.path.join(save, "topk.pth"))
+        print("Simscores @x% part done")                                                      # :470
+        print(out["stats"])
+        if args.fid_weights:
+            from . import fid, nets
+            inc = nets.build_fid_inception(load_state_dict(args.fid_weights), max_batch=50)
+            val = fid.fid_from_images(inc, fid.load_resized(args.val_dir), fid.load_resized(args.query_dir))   # :597-600
+            print({"fid": val})
+            out["stats"]["fid"] = val
+        with open(os.path.join(save, "stats.json"), "w") as f:
+            json.dump(out["stats"], f)
+    if args.distributed:
+        import torch.distributed as dist
+        dist.barrier()
+        dist.destroy_process_group()
     return 0
 
 

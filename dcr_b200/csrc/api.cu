@@ -171,6 +171,11 @@ int dcr_net_forward(dcr_net* net, const uint8_t* images, int n, float* out, void
   return dcr::net_forward(reinterpret_cast<dcr::Net*>(net), images, n, out, as_stream(stream));
 }
 
+int dcr_net_forward_f32(dcr_net* net, const float* x_nchw, int n, float* out, void* stream) {
+  DCR_REQUIRE(x_nchw != nullptr, "dcr_net_forward_f32: null input");
+  return dcr::net_forward(reinterpret_cast<dcr::Net*>(net), nullptr, n, out, as_stream(stream), x_nchw);
+}
+
 struct dcr_fid;   // opaque alias of dcr::FidState
 int dcr_fid_create(int d, dcr_fid** out) {
   DCR_REQUIRE(out != nullptr, "dcr_fid_create: null out pointer");

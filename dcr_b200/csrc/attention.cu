@@ -104,6 +104,104 @@ __global__ void __launch_bounds__(256) attention_fp32_kernel(const AttnParams p)
   }
 }
 
+// Long sequences (patch-8 ViTs: 785 tokens, dino_vits.py:381-397): K / V no longer fit in shared memory, so they are
+// streamed in tiles of 128 keys and the softmax runs online (running max / sum per query row, output rescaled when the
+// max moves).  fp32 SIMT like the kernel above; grid = (B * heads, ceil(T / 64)), one warp owns 8 query rows.
+constexpr int kStreamQ = 64;
+constexpr int kStreamK = 128;
+__global__ void __launch_bounds__(256) attention_stream_kernel(const AttnParams p) {
+  extern __shared__ __align__(16) float sm[];
+  float* ks = sm;                          // [kStreamK][65]
+  float* vs = ks + kStreamK * 65;          // [kStreamK][64]
+  float* qs = vs + kStreamK * 64;          // [kStreamQ][64]
+  float* ps = qs + kStreamQ * 64;          // [8 warps][kStreamK]
+  const int T = p.T;
+  const int b = blockIdx.x / p.heads, h = blockIdx.x % p.heads;
+  const int q0 = blockIdx.y * kStreamQ;
+  const int ld = 3 * p.heads * 64;
+  const size_t row0 = static_cast<size_t>(b) * T;
+  for (int i = threadIdx.x; i < kStreamQ * 64; i += blockDim.x) {
+    const int t = q0 + (i >> 6), d = i & 63;
+    qs[i] = t < T ? load1(p.qkv, p.qkv_plane_stride, p.planes, (row0 + t) * ld + h * 64 + d) : 0.f;
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* pr = ps + warp * kStreamK;
+  float m[8], l[8], o0[8], o1[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    m[i] = -INFINITY;
+    l[i] = 0.f;
+    o0[i] = 0.f;
+    o1[i] = 0.f;
+  }
+  for (int kt = 0; kt < T; kt += kStreamK) {
+    __syncthreads();   // previous tile fully consumed (and the query rows staged, first iteration)
+    for (int i = threadIdx.x; i < kStreamK * 64; i += blockDim.x) {
+      const int j = i >> 6, d = i & 63;
+      const bool ok = kt + j < T;
+      ks[j * 65 + d] = ok ? load1(p.qkv, p.qkv_plane_stride, p.planes, (row0 + kt + j) * ld + p.heads * 64 + h * 64 + d) : 0.f;
+      vs[j * 64 + d] = ok ? load1(p.qkv, p.qkv_plane_stride, p.planes, (row0 + kt + j) * ld + 2 * p.heads * 64 + h * 64 + d) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int r = warp * 8 + i;
+      if (q0 + r >= T) continue;   // warp-uniform
+      const float* q = qs + r * 64;
+      float s[4];
+      float tmax = -INFINITY;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const int j = lane + 32 * c;
+        float acc = 0.f;
+#pragma unroll 16
+        for (int d = 0; d < 64; ++d) acc = fmaf(q[d], ks[j * 65 + d], acc);
+        s[c] = (kt + j < T) ? acc * p.scale : -INFINITY;
+        tmax = fmaxf(tmax, s[c]);
+      }
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) tmax = fmaxf(tmax, __shfl_xor_sync(kFull, tmax, off));
+      const float m_new = fmaxf(m[i], tmax);          // finite: every tile holds at least one valid key
+      const float corr = expf(m[i] - m_new);           // exp(-inf) = 0 on the first tile
+      float lsum = 0.f;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const float e = expf(s[c] - m_new);
+        pr[lane + 32 * c] = e;
+        lsum += e;
+      }
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) lsum += __shfl_xor_sync(kFull, lsum, off);
+      l[i] = l[i] * corr + lsum;
+      __syncwarp();
+      float a0 = o0[i] * corr, a1 = o1[i] * corr;
+      for (int j = 0; j < kStreamK; ++j) {
+        const float w = pr[j];
+        a0 = fmaf(w, vs[j * 64 + lane], a0);
+        a1 = fmaf(w, vs[j * 64 + lane + 32], a1);
+      }
+      o0[i] = a0;
+      o1[i] = a1;
+      m[i] = m_new;
+      __syncwarp();
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int t = q0 + warp * 8 + i;
+    if (t >= T) continue;
+    float a0 = o0[i] / l[i], a1 = o1[i] / l[i];
+    const size_t oidx = (row0 + t) * (p.heads * 64) + h * 64;
+    for (int pl = 0; pl < p.planes; ++pl) {
+      const __nv_bfloat16 x0 = __float2bfloat16_rn(a0), x1 = __float2bfloat16_rn(a1);
+      p.out[pl * p.out_plane_stride + oidx + lane] = x0;
+      p.out[pl * p.out_plane_stride + oidx + lane + 32] = x1;
+      a0 -= __bfloat162float(x0);
+      a1 -= __bfloat162float(x1);
+    }
+  }
+}
+
 
 // ---------------------------------------------------------------------------------------------------------------
 // tcgen05 attention
@@ -312,9 +410,9 @@ __global__ void __launch_bounds__(kAttnThreads, 1)
 int attention(const __nv_bfloat16* qkv, long long qkv_plane_stride, __nv_bfloat16* out, long long out_plane_stride,
               int planes, int B, int T, int heads, int dh, float scale, cudaStream_t stream) {
   DCR_REQUIRE(dh == 64, "attention: head dim %d not supported (64 only)", dh);
-  DCR_REQUIRE(T >= 1 && T <= 1024, "attention: sequence length %d out of range", T);
+  DCR_REQUIRE(T >= 1 && T <= 16384, "attention: sequence length %d out of range", T);
   if (B == 0) return 0;
-  if (planes == 1 && T <= 256 && getenv("DCR_ATTN_FP32") == nullptr) {
+  if (planes == 1 && T <= 256 && !tuning_flag("DCR_ATTN_FP32")) {
     const DeviceInfo* di = device_info();
     if (!di) return -2;
     CUtensorMap tm;
@@ -333,6 +431,15 @@ int attention(const __nv_bfloat16* qkv, long long qkv_plane_stride, __nv_bfloat1
   AttnParams p;
   p.qkv = qkv; p.qkv_plane_stride = qkv_plane_stride; p.out = out; p.out_plane_stride = out_plane_stride;
   p.planes = planes; p.B = B; p.T = T; p.heads = heads; p.dh = dh; p.scale = scale;
+  if (T > 256) {   // K / V streamed in tiles, online softmax (patch-8 ViTs)
+    const size_t smem_s = (static_cast<size_t>(kStreamK) * 65 + kStreamK * 64 + kStreamQ * 64 + 8 * kStreamK) * 4;
+    DCR_CUDA_CHECK(cudaFuncSetAttribute(attention_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        static_cast<int>(smem_s)));
+    attention_stream_kernel<<<dim3(B * heads, (T + kStreamQ - 1) / kStreamQ), 256, smem_s, stream>>>(p);
+    count_launch();
+    DCR_CUDA_CHECK(cudaGetLastError());
+    return 0;
+  }
   const int Tpad = (T + 31) / 32 * 32;
   const size_t smem = (static_cast<size_t>(T) * 65 + static_cast<size_t>(T) * 64 + 8 * 64 + 8 * Tpad) * 4;
   DCR_CUDA_CHECK(cudaFuncSetAttribute(attention_fp32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,

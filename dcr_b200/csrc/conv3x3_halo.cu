@@ -35,6 +35,11 @@ constexpr int kHM = 128;                    // MMA rows (padded-raster positions
 constexpr int kHK = 64;                     // channels per block = one 128-byte swizzled row
 constexpr int kSlabBytes = kHM * 128;       // one 64-channel slab of the output staging tile
 constexpr int kHThreads = 320;              // warp 0 producer, warp 1 MMA issuer, warps 2..9 epilogue
+// Timing experiments (garbage results), compile-time only: bit 0 = no weight loads, bit 1 = no halo loads.
+#ifndef DCR_HALO_TIMING_MODE
+#define DCR_HALO_TIMING_MODE 0
+#endif
+constexpr int kHaloTimingMode = DCR_HALO_TIMING_MODE;
 
 struct HaloMaps {
   CUtensorMap a;     // input  [B][H][W][C]   box 64 x (W+2) x (R+2) x 1
@@ -51,7 +56,6 @@ struct HaloParams {
   const float* scale;
   const float* bias;
   int act, out_col_off;
-  int debug;               // timing experiments (garbage results): bit 0 = no weight loads, bit 1 = no halo loads
 };
 
 DCR_DEVICE void tma_store_commit_() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
@@ -126,7 +130,7 @@ __global__ void __launch_bounds__(kHThreads, 1)
           const uint32_t sa = as.s, pha = as.ph;
           mbar_wait(&a_empty[sa], pha ^ 1);
           if (elect_one()) {
-            if ((p.debug & 2) && ai >= static_cast<uint32_t>(p.a_bufs)) {
+            if ((kHaloTimingMode & 2) && ai >= static_cast<uint32_t>(p.a_bufs)) {
               mbar_arrive(&a_full[sa]);    // timing experiment: reuse stale halo data, no load
             } else {
               mbar_arrive_expect_tx(&a_full[sa], p.halo_bytes);
@@ -139,7 +143,7 @@ __global__ void __launch_bounds__(kHThreads, 1)
             const uint32_t sw = ws.s, phw = ws.ph;
             mbar_wait(&w_empty[sw], phw ^ 1);
             if (elect_one()) {
-              if ((p.debug & 1) && wi >= static_cast<uint32_t>(p.w_stages)) {
+              if ((kHaloTimingMode & 1) && wi >= static_cast<uint32_t>(p.w_stages)) {
                 mbar_arrive(&w_full[sw]);  // timing experiment: stale weights, no load
               } else {
                 mbar_arrive_expect_tx(&w_full[sw], kWStage);
@@ -293,7 +297,10 @@ int launch_halo(const HaloMaps& maps, HaloParams& p, int num_sms, size_t max_sme
   }
   const size_t smem = fixed + static_cast<size_t>(p.a_bufs) * abuf + static_cast<size_t>(p.w_stages) * kWStage;
   auto kern = conv3x3_halo_kernel<BN>;
-  static bool attr_set = false;
+  static bool attr_set_dev[64] = {};   // per template instantiation and device (the attribute is per device)
+  int cur_dev = 0;
+  DCR_CUDA_CHECK(cudaGetDevice(&cur_dev));
+  bool& attr_set = attr_set_dev[cur_dev & 63];
   if (!attr_set) {
     DCR_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(max_smem)));
     attr_set = true;
@@ -307,11 +314,11 @@ int launch_halo(const HaloMaps& maps, HaloParams& p, int num_sms, size_t max_sme
 }  // namespace
 
 bool conv3x3_halo_eligible(const ConvGemmDesc& d) {
-  if (getenv("DCR_CONV_NO_HALO") != nullptr) return false;
+  if (tuning_flag("DCR_CONV_NO_HALO")) return false;
   const bool shape = d.kh == 3 && d.kw == 3 && d.stride == 1 && d.pad_h == 1 && d.pad_w == 1 && d.in_stride_w == 0;
   const bool fast = d.n_terms == 1 && d.term_a[0] == 0 && d.term_w[0] == 0 && !d.exact && d.out != nullptr &&
                     d.out_planes <= 1 && d.out_f32 == nullptr && d.res == nullptr && (d.act == 0 || d.act == 1);
-  const bool dims = d.C % 64 == 0 && d.ld_in == d.C && d.N % 64 == 0 && d.N <= (getenv("DCR_CONV_HALO_N256") ? 256 : 128) && d.ld_out % 8 == 0 &&
+  const bool dims = d.C % 64 == 0 && d.ld_in == d.C && d.N % 64 == 0 && d.N <= (tuning_flag("DCR_CONV_HALO_N256") ? 256 : 128) && d.ld_out % 8 == 0 &&
                     d.out_col_off % 8 == 0 && d.W + 2 <= 64 && d.W >= 8 && d.H >= 2 && d.B >= 1;
   return shape && fast && dims;
 }
@@ -329,7 +336,6 @@ int conv3x3_halo(const ConvGemmDesc& d, cudaStream_t stream) {
   p.num_tiles = d.B * p.tiles_per_img;
   p.halo_bytes = static_cast<uint32_t>(128) * p.Wp * (p.R + 2);
   p.scale = d.scale; p.bias = d.bias; p.act = d.act; p.out_col_off = d.out_col_off;
-  p.debug = getenv("DCR_HALO_DEBUG") ? atoi(getenv("DCR_HALO_DEBUG")) : 0;
   // the loaded block and the last tap's 128-row window (start row 2 * Wp + 2) must stay inside the buffer
   p.a_buf_bytes = (std::max<uint32_t>(p.halo_bytes, static_cast<uint32_t>(2 * p.Wp + 2 + kHM) * 128u) + 1023u) & ~1023u;
   HaloMaps maps;

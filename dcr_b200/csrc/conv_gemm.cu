@@ -36,6 +36,12 @@ constexpr int kBM = 128;
 constexpr int kBK = 64;
 constexpr int kThreads = 320;   // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue
 constexpr int kAStage = kBM * kBK * 2;   // 16 KB
+// Timing experiments (results are garbage), compile-time only: 1 = loads only (no MMA, no epilogue), 2 = loads only and
+// every im2col request replaced by a tiled request of the same size (row-shifted view).
+#ifndef DCR_GEMM_TIMING_MODE
+#define DCR_GEMM_TIMING_MODE 0
+#endif
+constexpr int kGemmTimingMode = DCR_GEMM_TIMING_MODE;
 
 struct GemmMaps {
   CUtensorMap a[3];
@@ -68,8 +74,6 @@ struct GemmParams {
   int n_res_bufs;             // 0 or 2 residual staging tiles (the residual of tile i+1 is prefetched during tile i)
   int a_resident;             // 1: the A rows of an m-tile (all of K) stay in shared memory while the CTA walks that m-tile's
                               //    column blocks (tiles n-fastest, contiguous tile range per CTA); stages carry only W tiles
-  int debug;                  // timing experiments (results are garbage): 1 = loads only (no MMA, no epilogue), 2 = loads only and
-                              // every im2col request replaced by a tiled request of the same size (row-shifted view)
 };
 
 DCR_DEVICE float apply_act(float y, int act) {
@@ -240,7 +244,7 @@ __global__ void __launch_bounds__(kThreads, 1)
                 mbar_arrive_expect_tx(&full[s], kStageBytes);
                 uint8_t* sa = smem_ab + s * kStageBytes;
                 if constexpr (kIm2col) {
-                  if (p.debug == 2)
+                  if constexpr (kGemmTimingMode == 2)
                     tma_load_2d<1>(sa, &maps.a_flat, &full[s], cb * kBK, max(0, m0 + (r - 1) * p.Q + sx - 1), kEvictNormal);
                   else
                     tma_load_im2col_4d<1>(sa, ma, &full[s], cb * kBK, w0, h0, img, static_cast<uint16_t>(sx),
@@ -281,7 +285,7 @@ __global__ void __launch_bounds__(kThreads, 1)
           }
           last_of_m = (tile + 1 >= t_end) || tile_m(tile + 1) != m;
         }
-        if (p.debug) {   // loads only: hand every stage straight back to the producer
+        if constexpr (kGemmTimingMode != 0) {   // loads only: hand every stage straight back to the producer
           for (int ki = 0; ki < k_iters; ++ki, st.next()) {
             mbar_wait(&full[st.s], st.ph);
             if (elect_one()) mbar_arrive(&empty[st.s]);
@@ -332,7 +336,7 @@ __global__ void __launch_bounds__(kThreads, 1)
           tma_load_2d<1>(res_stage + rbuf * kStagingBytes + sl * kBM * 128, &maps.res, &res_full[rbuf], rn0 + sl * 64, rm0,
                          kEvictFirst);
     };
-    if (kTma && has_res && etid == 0 && t_first < t_end && !p.debug) load_residual(t_first, 0);
+    if (kTma && has_res && etid == 0 && t_first < t_end && kGemmTimingMode == 0) load_residual(t_first, 0);
     const bool two_out = p.n_out_bufs == 2;
     const uint32_t sb_addr = smem_u32(sb), out_addr = smem_u32(out_stage), res_addr = smem_u32(res_stage);
     int staged_n0 = -1;
@@ -345,7 +349,7 @@ __global__ void __launch_bounds__(kThreads, 1)
       }
       asm volatile("bar.sync 1, 256;" ::: "memory");
     }
-    for (int tile = t_first; tile < t_end && !p.debug; tile += t_step, ++tc) {
+    for (int tile = t_first; tile < t_end && kGemmTimingMode == 0; tile += t_step, ++tc) {
       const int m0 = tile_m(tile) * kBM;
       const int n0 = tile_n(tile) * BN;
       const uint32_t buf = tc & 1;
@@ -523,7 +527,7 @@ int launch(const GemmMaps& maps, GemmParams& p, int num_sms, size_t max_smem, cu
   // batch 256: 177 -> 157 us for the layer1 expansion with residual, 98 -> 90 us layer2, but 103 -> 130 us for the
   // residual-free 2-block downsample)
   p.a_resident = (!kIm2col && kEpi != 0 && p.n_terms == 1 && p.num_n_tiles >= 2 && (p.res != nullptr || p.num_n_tiles >= 4) &&
-                  k_iters_h * kAStage <= 64 * 1024 && p.num_n_tiles * BN <= 4096 && getenv("DCR_GEMM_NO_ARES") == nullptr) ? 1 : 0;
+                  k_iters_h * kAStage <= 64 * 1024 && p.num_n_tiles * BN <= 4096 && !tuning_flag("DCR_GEMM_NO_ARES")) ? 1 : 0;
   // the resident rows, the all-blocks affine table and the staging tiles must leave at least three W stages; otherwise
   // the layer runs with the default schedule
   if (p.a_resident) {
@@ -543,7 +547,10 @@ int launch(const GemmMaps& maps, GemmParams& p, int num_sms, size_t max_smem, cu
   p.stages = stages;
   const size_t smem = fixed + static_cast<size_t>(stages) * stage_bytes;
   auto kern = gemm_bf16_kernel<BN, kIm2col, kEpi>;
-  static bool attr_set = false;   // per template instantiation
+  static bool attr_set_dev[64] = {};   // per template instantiation and device (the attribute is per device)
+  int cur_dev = 0;
+  DCR_CUDA_CHECK(cudaGetDevice(&cur_dev));
+  bool& attr_set = attr_set_dev[cur_dev & 63];
   if (!attr_set) {
     DCR_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(max_smem)));
     attr_set = true;
@@ -637,14 +644,11 @@ int conv_gemm(const ConvGemmDesc& d, cudaStream_t stream) {
   p.out_f32 = d.out_f32;
   p.ld_out_f32 = d.ld_out_f32;
   p.act = d.act;
-  p.debug = getenv("DCR_GEMM_DEBUG") ? atoi(getenv("DCR_GEMM_DEBUG")) : 0;
-  if (p.debug == 2 && im2col && !windowed) {
+  if (kGemmTimingMode == 2 && im2col && !windowed) {
     if (int rc = make_tmap_2d_bf16(&maps.a_flat, d.in, static_cast<uint64_t>(d.B) * d.H * d.W, d.C, d.C, kBM, kBK)) return rc;
-  } else if (p.debug == 2) {
-    p.debug = 1;
   }
   p.tma_epi = (p.out != nullptr && p.out_planes == 1 && p.out_f32 == nullptr && (p.res == nullptr || p.res_planes == 1) &&
-               getenv("DCR_GEMM_DIRECT_EPILOGUE") == nullptr)
+               !tuning_flag("DCR_GEMM_DIRECT_EPILOGUE"))
                   ? 1
                   : 0;
   if (p.tma_epi) {

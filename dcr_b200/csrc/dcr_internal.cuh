@@ -77,10 +77,12 @@ int conv3x3_halo(const ConvGemmDesc& d, cudaStream_t stream);
 // ---- HBM-bound kernels (pool_norm.cu, attention.cu) ---------------------------------------------------------------
 int im2col_u8(const uint8_t* img, int B, int IH, int IW, int crop_y, int crop_x, int H, int W, int kh, int kw,
               int stride, int pad, int k_pad, const float* mean3, const float* std3, float post_scale,
-              float post_shift, __nv_bfloat16* out, long long out_plane_stride, int planes, cudaStream_t stream);
+              float post_shift, __nv_bfloat16* out, long long out_plane_stride, int planes, cudaStream_t stream,
+              const float* img_f32 = nullptr,    // img_f32: fp32 NCHW [B,3,IH,IW] already transformed (img unused)
+              int RH = 0, int RW = 0, float rscale = 0.f);   // optional bilinear resize of the crop (multi_scale)
 int stem_s2d_u8(const uint8_t* img, int B, int IH, int IW, int crop_y, int crop_x, int H, int W, const float* mean3,
                 const float* std3, float post_scale, float post_shift, __nv_bfloat16* out, long long out_plane_stride,
-                int planes, cudaStream_t stream, int RH = 0, int RW = 0, float rscale = 0.f);
+                int planes, cudaStream_t stream, int RH = 0, int RW = 0, float rscale = 0.f, const float* img_f32 = nullptr);
 int pool2d(bool is_max, const __nv_bfloat16* in, long long in_plane_stride, __nv_bfloat16* out,
            long long out_plane_stride, int planes, int B, int H, int W, int C, int k, int stride, int pad, int ld_out,
            int out_col_off, cudaStream_t stream);
@@ -118,7 +120,9 @@ int net_add_tensor(Net* n, long long rows_per_image, int C);
 int net_add_param(Net* n, const void* host, size_t bytes);
 int net_set_output(Net* n, int dim);
 int net_add_op(Net* n, int kind, const int* iargs, int ni, const float* fargs, int nf);
-int net_forward(Net* n, const uint8_t* images, int B, float* out, cudaStream_t stream);
+// images: uint8 NHWC [B,IH,IW,3] (raw, the transform is fused) -- or, when images_f32 != nullptr, fp32 NCHW
+// [B,3,H,W] already transformed (what the reference passes to `model(samples)`, utils_ret.py:751)
+int net_forward(Net* n, const uint8_t* images, int B, float* out, cudaStream_t stream, const float* images_f32 = nullptr);
 
 
 // ---- FID statistics (fid.cu) ----------------------------------------------------------------------------------------

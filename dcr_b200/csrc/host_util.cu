@@ -1,5 +1,6 @@
 #include "host_util.cuh"
 
+#include <cstdlib>
 #include <cstring>
 #include <atomic>
 #include <mutex>
@@ -24,6 +25,17 @@ int set_error(int code, const char* fmt, ...) {
 static std::atomic<long long> g_launches{0};
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 long long launch_count() { return g_launches.load(std::memory_order_relaxed); }
+
+bool tuning_enabled() {
+  const char* e = getenv("DCR_B200_TUNING");   // read per call: the tests switch it on and off inside one process
+  return e != nullptr && e[0] == '1';
+}
+int tuning_int(const char* name, int dflt) {
+  if (!tuning_enabled()) return dflt;
+  const char* e = getenv(name);
+  return (e && *e) ? atoi(e) : dflt;
+}
+bool tuning_flag(const char* name) { return tuning_enabled() && getenv(name) != nullptr; }
 
 const DeviceInfo* device_info() {
   static DeviceInfo cache[64];

@@ -37,6 +37,14 @@ struct DeviceInfo {
 void count_launch(int n = 1);
 long long launch_count();
 
+// Tuning knobs (DCR_SIM_KP0, DCR_SIM_SETS, DCR_GEMM_NO_ARES, ...) are honoured ONLY when DCR_B200_TUNING=1 is set in the
+// environment: a stray variable cannot change what a benchmark or a test runs.  Every knob selects between variants
+// that produce identical results.  (The timing-experiment modes that produce garbage results are compile-time only:
+// -DDCR_SIM_TIMING_MODE / -DDCR_GEMM_TIMING_MODE / -DDCR_HALO_TIMING_MODE, all 0 in the shipped library.)
+bool tuning_enabled();
+int tuning_int(const char* name, int dflt);
+bool tuning_flag(const char* name);   // true when tuning is enabled and the variable is set (to anything)
+
 // cached per current device; returns nullptr and sets the error on failure
 const DeviceInfo* device_info();
 

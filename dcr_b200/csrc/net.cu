@@ -117,7 +117,9 @@ int net_add_op(Net* n, int kind, const int* iargs, int ni, const float* fargs, i
   auto tensor_ok = [&](int id, bool optional) { return (optional && id < 0) || (id >= 0 && id < (int)n->tensors.size()); };
   auto param_ok = [&](int id, bool optional) { return (optional && id < 0) || (id >= 0 && id < (int)n->params.size()); };
   switch (kind) {
-    case NET_OP_IM2COL_U8: DCR_REQUIRE(ni == 12 && nf == 8 && tensor_ok(op.i[0], false), "im2col_u8 op: bad args"); break;
+    case NET_OP_IM2COL_U8:
+      DCR_REQUIRE(((ni == 12 && nf == 8) || (ni == 14 && nf == 9)) && tensor_ok(op.i[0], false), "im2col_u8 op: bad args");
+      break;
     case NET_OP_STEM_S2D:
       DCR_REQUIRE(((ni == 7 && nf == 8) || (ni == 9 && nf == 9)) && tensor_ok(op.i[0], false), "stem_s2d op: bad args");
       break;
@@ -148,8 +150,9 @@ int net_add_op(Net* n, int kind, const int* iargs, int ni, const float* fargs, i
   return static_cast<int>(n->ops.size()) - 1;
 }
 
-int net_forward(Net* n, const uint8_t* images, int B, float* out, cudaStream_t stream) {
-  DCR_REQUIRE(n && images && out, "net_forward: null argument");
+int net_forward(Net* n, const uint8_t* images, int B, float* out, cudaStream_t stream, const float* images_f32) {
+  DCR_REQUIRE(n && (images || images_f32) && out, "net_forward: null argument");
+  const bool f32 = images_f32 != nullptr;
   DCR_REQUIRE(B >= 0 && B <= n->max_batch, "net_forward: batch %d exceeds max_batch %d", B, n->max_batch);
   DCR_REQUIRE(n->out_f32 && n->out_dim > 0, "net_forward: output not configured");
   if (B == 0) return 0;
@@ -160,15 +163,18 @@ int net_forward(Net* n, const uint8_t* images, int B, float* out, cudaStream_t s
     switch (op.kind) {
       case NET_OP_IM2COL_U8: {
         NetTensor& t = n->tensors[a[0]];
-        rc = im2col_u8(images, B, a[1], a[2], a[3], a[4], a[5], a[6], a[7], a[8], a[9], a[10], a[11], &op.f[0],
-                       &op.f[3], op.f[6], op.f[7], t.ptr, t.plane_stride, P, stream);
+        // fp32 input: the tensor is the transformed crop itself ([B,3,H,W]: no crop offset, no mean/std)
+        rc = im2col_u8(images, B, f32 ? a[5] : a[1], f32 ? a[6] : a[2], f32 ? 0 : a[3], f32 ? 0 : a[4], a[5], a[6], a[7], a[8],
+                       a[9], a[10], a[11], &op.f[0], &op.f[3], op.f[6], op.f[7], t.ptr, t.plane_stride, P, stream, images_f32,
+                       a[12], a[13], op.f[8]);   // optional 14-int / 9-float form: resized size + float(1 / scale_factor)
         break;
       }
       case NET_OP_STEM_S2D: {
         NetTensor& t = n->tensors[a[0]];
         // optional 9-int / 9-float form: a[7], a[8] = size after bilinear resizing of the crop, f[8] = float(1 / scale_factor)
-        rc = stem_s2d_u8(images, B, a[1], a[2], a[3], a[4], a[5], a[6], &op.f[0], &op.f[3], op.f[6], op.f[7], t.ptr,
-                         t.plane_stride, P, stream, a[7], a[8], op.f[8]);   // unset arguments are zero = no resizing
+        rc = stem_s2d_u8(images, B, f32 ? a[5] : a[1], f32 ? a[6] : a[2], f32 ? 0 : a[3], f32 ? 0 : a[4], a[5], a[6], &op.f[0],
+                         &op.f[3], op.f[6], op.f[7], t.ptr, t.plane_stride, P, stream, a[7], a[8], op.f[8],
+                         images_f32);   // unset arguments are zero = no resizing
         break;
       }
       case NET_OP_CONV: {

@@ -60,7 +60,10 @@ __device__ __forceinline__ void store8(__nv_bfloat16* base, long long plane_stri
 // that fall into the zero padding).  value = post_scale * ((u8/255 - mean[c]) / std[c]) + post_shift.
 struct Im2colU8Params {
   const uint8_t* img;
+  const float* img_f32;   // kF32 kernels: fp32 NCHW [B,3,IH,IW], already transformed (ToTensor/Normalize done by the caller)
   int B, IH, IW, crop_y, crop_x, H, W;   // H, W: size after the centre crop
+  int RH, RW;                            // network input size: == H, W, or the bilinearly resized crop (rscale != 0)
+  float rscale;                          // float(1 / scale_factor) of utils_ret.py:676-698 `multi_scale`, 0 = no resizing
   int kh, kw, stride, pad, OH, OW, k_pad;
   float mean[3], std[3], post_scale, post_shift;
   __nv_bfloat16* out;
@@ -71,7 +74,9 @@ struct Im2colU8Params {
 // K layout: k = r * RP + s * 3 + c with RP = ceil8(3 * KW) (each filter row padded to a multiple of 8 elements so
 // that a thread owns whole 16-byte groups and every (s, c) index is a compile-time constant).  One thread per
 // (output pixel, filter row): 3*KW contiguous image bytes -> RP normalised bf16 values.
-template <int KW>
+// kF32: the input is the tensor the reference hands to `model(samples)` (utils_ret.py:751): fp32 NCHW, already
+// normalised; only the optional post affine (FID's second 2x-1, inception.py:152-153) is applied.
+template <int KW, bool kF32, bool kResize>
 __global__ void __launch_bounds__(256) im2col_u8_kernel(const Im2colU8Params p) {
   constexpr int RP = (3 * KW + 7) / 8 * 8;
   // per-channel lookup table u8 -> normalised value, computed once per block with the reference's exact arithmetic
@@ -94,20 +99,45 @@ __global__ void __launch_bounds__(256) im2col_u8_kernel(const Im2colU8Params p) 
     const int b = static_cast<int>(m / (static_cast<long long>(p.OW) * p.OH));
     const int y = pp * p.stride - p.pad + r;           // in crop coordinates
     const int x0 = q * p.stride - p.pad;
-    const bool row_ok = r < p.kh && y >= 0 && y < p.H;
-    const uint8_t* src = p.img + ((static_cast<size_t>(b) * p.IH + (y + p.crop_y)) * p.IW + (x0 + p.crop_x)) * 3;
+    const bool row_ok = r < p.kh && y >= 0 && y < p.RH;
+    const size_t plane = static_cast<size_t>(p.IH) * p.IW;
+    const uint8_t* img = p.img + static_cast<size_t>(b) * p.IH * p.IW * 3;
+    const float* imgf = p.img_f32 + static_cast<size_t>(b) * 3 * plane;
+    // transformed value of channel c at crop coordinates (yy, xx)
+    auto px = [&](int yy, int xx, int c) -> float {
+      if constexpr (kF32) return fmaf(p.post_scale, imgf[c * plane + static_cast<size_t>(yy + p.crop_y) * p.IW + (xx + p.crop_x)], p.post_shift);
+      else return lut[c][img[(static_cast<size_t>(yy + p.crop_y) * p.IW + (xx + p.crop_x)) * 3 + c]];
+    };
+    // bilinear source rows of the resized image (torch F.interpolate, align_corners=False, scale_factor given)
+    int y0 = 0, y1 = 0;
+    float ly = 0.f, hy = 1.f;
+    if constexpr (kResize) {
+      const float sy = fmaxf(p.rscale * (static_cast<float>(y) + 0.5f) - 0.5f, 0.f);
+      y0 = min(static_cast<int>(sy), p.H - 1);
+      y1 = y0 + (y0 < p.H - 1 ? 1 : 0);
+      ly = sy - static_cast<float>(y0);
+      hy = 1.f - ly;
+    }
     __nv_bfloat16* dst = p.out + static_cast<size_t>(m) * p.k_pad + r * RP;
 #pragma unroll
     for (int g = 0; g < RP / 8; ++g) {
       float v[8];
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
-        constexpr int dummy = 0;
-        (void)dummy;
         const int j = g * 8 + e;          // compile-time after unrolling
         const int s = j / 3, c = j % 3;
         float val = 0.f;
-        if (j < 3 * KW && row_ok && x0 + s >= 0 && x0 + s < p.W) val = lut[c][src[j]];
+        if (j < 3 * KW && row_ok && x0 + s >= 0 && x0 + s < p.RW) {
+          if constexpr (kResize) {
+            const float sx = fmaxf(p.rscale * (static_cast<float>(x0 + s) + 0.5f) - 0.5f, 0.f);
+            const int xa = min(static_cast<int>(sx), p.W - 1);
+            const int xb = xa + (xa < p.W - 1 ? 1 : 0);
+            const float lx = sx - static_cast<float>(xa), hx = 1.f - lx;
+            val = hy * (hx * px(y0, xa, c) + lx * px(y0, xb, c)) + ly * (hx * px(y1, xa, c) + lx * px(y1, xb, c));
+          } else {
+            val = px(y, x0 + s, c);
+          }
+        }
         v[e] = val;
       }
       store8(dst, p.out_plane_stride, p.planes, g * 8, v);
@@ -124,6 +154,7 @@ __global__ void __launch_bounds__(256) im2col_u8_kernel(const Im2colU8Params p) 
 // sampled with torch's arithmetic (source index = rscale * (dst + 0.5) - 0.5 clamped at 0, rscale = float(1 / s)).
 struct StemS2dParams {
   const uint8_t* img;
+  const float* img_f32;   // kF32 kernels: fp32 NCHW [B,3,IH,IW], already transformed
   int B, IH, IW, crop_y, crop_x, H, W, U, V;
   int RH, RW;        // size of xn (== H, W without resizing)
   float rscale;      // 0 = no resizing
@@ -133,7 +164,7 @@ struct StemS2dParams {
   int planes;
 };
 
-template <bool kResize>
+template <bool kResize, bool kF32>
 __global__ void __launch_bounds__(256) stem_s2d_u8_kernel(const StemS2dParams p) {
   __shared__ float lut[3][256];
   for (int i = threadIdx.x; i < 768; i += blockDim.x) {
@@ -149,6 +180,13 @@ __global__ void __launch_bounds__(256) stem_s2d_u8_kernel(const StemS2dParams p)
     const int u = static_cast<int>((idx / p.V) % p.U);
     const int b = static_cast<int>(idx / (static_cast<long long>(p.V) * p.U));
     const uint8_t* img = p.img + static_cast<size_t>(b) * p.IH * p.IW * 3;
+    const size_t plane = static_cast<size_t>(p.IH) * p.IW;
+    const float* imgf = p.img_f32 + static_cast<size_t>(b) * 3 * plane;
+    // normalised value of channel c at crop coordinates (yy, xx)
+    auto px = [&](int yy, int xx, int c) -> float {
+      if constexpr (kF32) return fmaf(p.post_scale, imgf[c * plane + static_cast<size_t>(yy + p.crop_y) * p.IW + (xx + p.crop_x)], p.post_shift);
+      else return lut[c][img[(static_cast<size_t>(yy + p.crop_y) * p.IW + (xx + p.crop_x)) * 3 + c]];
+    };
     float z[16];
 #pragma unroll
     for (int e = 0; e < 16; ++e) z[e] = 0.f;
@@ -161,9 +199,8 @@ __global__ void __launch_bounds__(256) stem_s2d_u8_kernel(const StemS2dParams p)
         const int x = 2 * v + j - 3;
         if (x < 0 || x >= p.RW) continue;
         if constexpr (!kResize) {
-          const uint8_t* px = img + (static_cast<size_t>(y + p.crop_y) * p.IW + (x + p.crop_x)) * 3;
 #pragma unroll
-          for (int c = 0; c < 3; ++c) z[(i * 2 + j) * 3 + c] = lut[c][px[c]];
+          for (int c = 0; c < 3; ++c) z[(i * 2 + j) * 3 + c] = px(y, x, c);
         } else {
           const float sy = fmaxf(p.rscale * (static_cast<float>(y) + 0.5f) - 0.5f, 0.f);
           const float sx = fmaxf(p.rscale * (static_cast<float>(x) + 0.5f) - 0.5f, 0.f);
@@ -171,12 +208,10 @@ __global__ void __launch_bounds__(256) stem_s2d_u8_kernel(const StemS2dParams p)
           const int y1 = y0 + (y0 < p.H - 1 ? 1 : 0), x1 = x0 + (x0 < p.W - 1 ? 1 : 0);
           const float ly = sy - static_cast<float>(y0), lx = sx - static_cast<float>(x0);
           const float hy = 1.f - ly, hx = 1.f - lx;
-          const uint8_t* r0 = img + (static_cast<size_t>(y0 + p.crop_y) * p.IW + p.crop_x) * 3;
-          const uint8_t* r1 = img + (static_cast<size_t>(y1 + p.crop_y) * p.IW + p.crop_x) * 3;
 #pragma unroll
           for (int c = 0; c < 3; ++c)
-            z[(i * 2 + j) * 3 + c] = hy * (hx * lut[c][r0[x0 * 3 + c]] + lx * lut[c][r0[x1 * 3 + c]]) +
-                                     ly * (hx * lut[c][r1[x0 * 3 + c]] + lx * lut[c][r1[x1 * 3 + c]]);
+            z[(i * 2 + j) * 3 + c] = hy * (hx * px(y0, x0, c) + lx * px(y0, x1, c)) +
+                                     ly * (hx * px(y1, x0, c) + lx * px(y1, x1, c));
         }
       }
     }
@@ -454,18 +489,22 @@ int grid_for(long long work_items, int block, int num_sms) {
 
 int im2col_u8(const uint8_t* img, int B, int IH, int IW, int crop_y, int crop_x, int H, int W, int kh, int kw,
               int stride, int pad, int k_pad, const float* mean3, const float* std3, float post_scale,
-              float post_shift, __nv_bfloat16* out, long long out_plane_stride, int planes, cudaStream_t stream) {
+              float post_shift, __nv_bfloat16* out, long long out_plane_stride, int planes, cudaStream_t stream,
+              const float* img_f32, int RH, int RW, float rscale) {
   const DeviceInfo* di = device_info();
   if (!di) return -2;
   const int rp = (3 * kw + 7) / 8 * 8;
   DCR_REQUIRE(k_pad % rp == 0 && k_pad >= kh * rp, "im2col_u8: k_pad %d must be a multiple of %d and >= %d", k_pad, rp, kh * rp);
-  DCR_REQUIRE(kw == 3 || kw == 7 || kw == 16, "im2col_u8: filter width %d not instantiated (3, 7, 16)", kw);
+  DCR_REQUIRE(kw == 3 || kw == 7 || kw == 8 || kw == 16, "im2col_u8: filter width %d not instantiated (3, 7, 8, 16)", kw);
   DCR_REQUIRE(crop_y >= 0 && crop_x >= 0 && crop_y + H <= IH && crop_x + W <= IW, "im2col_u8: crop outside image");
   Im2colU8Params p;
-  p.img = img; p.B = B; p.IH = IH; p.IW = IW; p.crop_y = crop_y; p.crop_x = crop_x; p.H = H; p.W = W;
+  p.img = img; p.img_f32 = img_f32; p.B = B; p.IH = IH; p.IW = IW; p.crop_y = crop_y; p.crop_x = crop_x; p.H = H; p.W = W;
   p.kh = kh; p.kw = kw; p.stride = stride; p.pad = pad;
-  p.OH = (H + 2 * pad - kh) / stride + 1;
-  p.OW = (W + 2 * pad - kw) / stride + 1;
+  if (rscale == 0.f) { RH = H; RW = W; }
+  DCR_REQUIRE(RH >= kh && RW >= kw, "im2col_u8: network input %d x %d smaller than the filter", RH, RW);
+  p.RH = RH; p.RW = RW; p.rscale = rscale;
+  p.OH = (RH + 2 * pad - kh) / stride + 1;
+  p.OW = (RW + 2 * pad - kw) / stride + 1;
   p.k_pad = k_pad;
   for (int c = 0; c < 3; ++c) { p.mean[c] = mean3[c]; p.std[c] = std3[c]; }
   p.post_scale = post_scale; p.post_shift = post_shift;
@@ -473,9 +512,21 @@ int im2col_u8(const uint8_t* img, int B, int IH, int IW, int crop_y, int crop_x,
   if (B == 0) return 0;
   const long long total = static_cast<long long>(B) * p.OH * p.OW * (k_pad / rp);
   const int grid = grid_for(total, 256, di->num_sms);
-  if (kw == 7) im2col_u8_kernel<7><<<grid, 256, 0, stream>>>(p);
-  else if (kw == 3) im2col_u8_kernel<3><<<grid, 256, 0, stream>>>(p);
-  else im2col_u8_kernel<16><<<grid, 256, 0, stream>>>(p);
+#define DCR_IM2COL(KWv)                                                                             \
+  do {                                                                                              \
+    if (img_f32) {                                                                                  \
+      if (rscale == 0.f) im2col_u8_kernel<KWv, true, false><<<grid, 256, 0, stream>>>(p);           \
+      else im2col_u8_kernel<KWv, true, true><<<grid, 256, 0, stream>>>(p);                          \
+    } else {                                                                                        \
+      if (rscale == 0.f) im2col_u8_kernel<KWv, false, false><<<grid, 256, 0, stream>>>(p);          \
+      else im2col_u8_kernel<KWv, false, true><<<grid, 256, 0, stream>>>(p);                         \
+    }                                                                                               \
+  } while (0)
+  if (kw == 7) DCR_IM2COL(7);
+  else if (kw == 3) DCR_IM2COL(3);
+  else if (kw == 8) DCR_IM2COL(8);
+  else DCR_IM2COL(16);
+#undef DCR_IM2COL
   count_launch();
   DCR_CUDA_CHECK(cudaGetLastError());
   return 0;
@@ -483,14 +534,14 @@ int im2col_u8(const uint8_t* img, int B, int IH, int IW, int crop_y, int crop_x,
 
 int stem_s2d_u8(const uint8_t* img, int B, int IH, int IW, int crop_y, int crop_x, int H, int W, const float* mean3,
                 const float* std3, float post_scale, float post_shift, __nv_bfloat16* out, long long out_plane_stride,
-                int planes, cudaStream_t stream, int RH, int RW, float rscale) {
+                int planes, cudaStream_t stream, int RH, int RW, float rscale, const float* img_f32) {
   const DeviceInfo* di = device_info();
   if (!di) return -2;
   DCR_REQUIRE(crop_y >= 0 && crop_x >= 0 && crop_y + H <= IH && crop_x + W <= IW, "stem_s2d_u8: crop outside image");
   if (rscale == 0.f) { RH = H; RW = W; }
   DCR_REQUIRE(RH >= 2 && RW >= 2 && RH % 2 == 0 && RW % 2 == 0, "stem_s2d_u8: network input size must be even (%d x %d)", RH, RW);
   StemS2dParams p;
-  p.img = img; p.B = B; p.IH = IH; p.IW = IW; p.crop_y = crop_y; p.crop_x = crop_x; p.H = H; p.W = W;
+  p.img = img; p.img_f32 = img_f32; p.B = B; p.IH = IH; p.IW = IW; p.crop_y = crop_y; p.crop_x = crop_x; p.H = H; p.W = W;
   p.RH = RH; p.RW = RW; p.rscale = rscale;
   p.U = (RH + 6) / 2; p.V = (RW + 6) / 2;
   for (int c = 0; c < 3; ++c) { p.mean[c] = mean3[c]; p.std[c] = std3[c]; }
@@ -498,8 +549,14 @@ int stem_s2d_u8(const uint8_t* img, int B, int IH, int IW, int crop_y, int crop_
   p.out = out; p.out_plane_stride = out_plane_stride; p.planes = planes;
   if (B == 0) return 0;
   const long long total = static_cast<long long>(B) * p.U * p.V;
-  if (rscale == 0.f) stem_s2d_u8_kernel<false><<<grid_for(total, 256, di->num_sms), 256, 0, stream>>>(p);
-  else stem_s2d_u8_kernel<true><<<grid_for(total, 256, di->num_sms), 256, 0, stream>>>(p);
+  const int grid = grid_for(total, 256, di->num_sms);
+  if (img_f32) {
+    if (rscale == 0.f) stem_s2d_u8_kernel<false, true><<<grid, 256, 0, stream>>>(p);
+    else stem_s2d_u8_kernel<true, true><<<grid, 256, 0, stream>>>(p);
+  } else {
+    if (rscale == 0.f) stem_s2d_u8_kernel<false, false><<<grid, 256, 0, stream>>>(p);
+    else stem_s2d_u8_kernel<true, false><<<grid, 256, 0, stream>>>(p);
+  }
   count_launch();
   DCR_CUDA_CHECK(cudaGetLastError());
   return 0;
@@ -519,7 +576,7 @@ int pool2d(bool is_max, const __nv_bfloat16* in, long long in_plane_stride, __nv
   p.ld_out = ld_out; p.out_col_off = out_col_off;
   if (B == 0) return 0;
   const long long total = static_cast<long long>(B) * p.OH * p.OW * (C / 8);
-  if (is_max && planes == 1 && k == 3 && stride <= 2 && getenv("DCR_POOL_GENERIC") == nullptr) {
+  if (is_max && planes == 1 && k == 3 && stride <= 2 && !tuning_flag("DCR_POOL_GENERIC")) {
     const long long total2 = static_cast<long long>(B) * p.OH * ((p.OW + 1) / 2) * (C / 8);
     maxpool3_bf16_kernel<<<grid_for(total2, 256, di->num_sms), 256, 0, stream>>>(p);
   } else if (is_max) pool_kernel<true><<<grid_for(total, 256, di->num_sms), 256, 0, stream>>>(p);

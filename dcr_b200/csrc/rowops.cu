@@ -62,19 +62,27 @@ __global__ void topk_merge_kernel(const float* __restrict__ scores, const long l
       s_s[e] = scores[src];
       s_i[e] = idx[src];
     }
+    // fewer than k_out valid entries (a total gallery smaller than k): the remaining slots are (-inf, -1)
+    for (int r = lane; r < k_out; r += 32) {
+      out_scores[static_cast<size_t>(q) * k_out + r] = -INFINITY;
+      out_idx[static_cast<size_t>(q) * k_out + r] = -1;
+    }
     __syncwarp();
     for (int e = lane; e < m; e += 32) {
-      const float se = s_s[e];
+      const float se_raw = s_s[e];
+      const float se = (se_raw != se_raw) ? -INFINITY : se_raw;   // NaN orders last; ranks stay a permutation
       const long long ie = s_i[e];
       if (ie < 0) continue;
       int rank = 0;
       for (int o = 0; o < m; ++o) {
-        const float so = s_s[o];
+        const float so_raw = s_s[o];
+        const float so = (so_raw != so_raw) ? -INFINITY : so_raw;
         const long long io = s_i[o];
-        rank += (io >= 0) && ((so > se) || (so == se && io < ie));
+        // total order: score desc, index asc, list position asc (duplicate (score, index) pairs do not collide)
+        rank += (io >= 0) && ((so > se) || (so == se && (io < ie || (io == ie && o < e))));
       }
       if (rank < k_out) {
-        out_scores[static_cast<size_t>(q) * k_out + rank] = se;
+        out_scores[static_cast<size_t>(q) * k_out + rank] = se_raw;
         out_idx[static_cast<size_t>(q) * k_out + rank] = ie;
       }
     }

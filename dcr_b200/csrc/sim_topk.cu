@@ -40,6 +40,12 @@ constexpr int kWarmTiles = 4;     // tiles replayed at the start of every segmen
 constexpr uint32_t kFull = 0xffffffffu;
 constexpr int kATileBytes = kBlockM * kBlockK * 2;  // 16 KB
 constexpr int kMaxSlotsPerQuery = 512;  // (chunk, unit) segments that may cover one q-tile
+// Timing experiments (results are garbage), compile-time only so that the production issue loops carry no trace of them:
+// 1 = the epilogue loads TMEM but does not scan, 2 = does not even load, 3 = additionally no gallery loads at all.
+#ifndef DCR_SIM_TIMING_MODE
+#define DCR_SIM_TIMING_MODE 0
+#endif
+constexpr int kTimingMode = DCR_SIM_TIMING_MODE;
 
 struct SimParams {
   int nq, ng;
@@ -57,7 +63,6 @@ struct SimParams {
   float* cand_thr;     // [n_slots][rows_per_qtile]
   const int* bias_flag;    // device flag: 0 = ignore col_bias (query centring switched off for this data)
   const float* col_bias;   // [ng_pad] per-gallery-row score offset nu.(g-mu) added to every accumulator column; null = none
-  int debug_mode;          // timing experiments only: 1 = epilogue loads TMEM but does not scan, 2 = does not even load
   const float* thr_init;   // per query row: start thresholds (second-chance pass); null = seed by warm-up replay
   unsigned int* gthr;      // [nq_pad] per query row: best threshold any unit has reached so far, as an order-preserving
                            // unsigned key (0 = none); null = no sharing
@@ -548,7 +553,7 @@ __global__ void __launch_bounds__(64 + 128 * kSets, 1)
         for (int j = 0; j < warm + ntiles; ++j) {
           const int gi = g_begin + (j < warm ? j : j - warm);
           const int g_row = gi * kBlockN + static_cast<int>(cta_rank) * kBRows;
-          if (p.debug_mode == 3) continue;   // timing experiment: no gallery loads at all
+          if constexpr (kTimingMode == 3) continue;   // timing experiment: no gallery loads at all
           for (int kb = 0; kb < p.num_kb; ++kb, st.next()) {
             const uint32_t s = st.s, ph = st.ph;
             mbar_wait(&b_empty[s], ph ^ 1);
@@ -589,7 +594,7 @@ __global__ void __launch_bounds__(64 + 128 * kSets, 1)
           const uint32_t tmem_d = tmem_base + buf * kBlockN;
           for (int kb = 0; kb < p.num_kb; ++kb, st.next()) {
             const uint32_t s = st.s;
-            if (p.debug_mode != 3) mbar_wait(&b_full[s], st.ph);
+            if constexpr (kTimingMode != 3) mbar_wait(&b_full[s], st.ph);
             tc_fence_after();
             const uint64_t da = da0 + static_cast<uint64_t>(stream_a ? s * stage_step : static_cast<uint32_t>(kb) * (kATileBytes >> 4));
             const uint64_t db = db0 + static_cast<uint64_t>(s * stage_step);
@@ -597,7 +602,7 @@ __global__ void __launch_bounds__(64 + 128 * kSets, 1)
 #pragma unroll
               for (int k = 0; k < kBlockK / 16; ++k)
                 umma_f16<kCG>(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);  // +32 B per K=16 step
-              if (p.debug_mode != 3) umma_commit<kCG>(&b_empty[s]);   // frees this B stage (both CTAs) once the MMAs above retire
+              if constexpr (kTimingMode != 3) umma_commit<kCG>(&b_empty[s]);   // frees this B stage (both CTAs) once the MMAs above retire
               if (kb == p.num_kb - 1) {
                 umma_commit<kCG>(&t_full[buf]);
                 if (!stream_a && j == warm + ntiles - 1) umma_commit<kCG>(a_empty);
@@ -678,7 +683,7 @@ __global__ void __launch_bounds__(64 + 128 * kSets, 1)
             else mbar_arrive(&t_empty[buf]);
           }
         };
-        if (p.debug_mode >= 2) {   // timing experiment: do not even read the accumulator (results are meaningless)
+        if constexpr (kTimingMode >= 2) {   // timing experiment: do not even read the accumulator (results are meaningless)
           release();
           return;
         }
@@ -689,7 +694,7 @@ __global__ void __launch_bounds__(64 + 128 * kSets, 1)
           tmem_ld_wait_dep(ra);
           tmem_ld_32x32(taddr + (ch + 1) * 32, rb);
           if (tail) mask_tail(ra, gcol0 + ch * 32, p.ng);
-          if (p.debug_mode == 0) {
+          if constexpr (kTimingMode == 0) {
             if constexpr (kWarm) warm_chunk<false>(ra, sb ? sb + ch * 32 : nullptr, gcol0 + ch * 32, p.ng, slot);
             else scan_chunk<false>(ra, sb ? sb + ch * 32 : nullptr, gcol0 + ch * 32, p.ng, thr, cnt, my_list, warp_list, kp, cap, lane);
           } else {
@@ -699,7 +704,7 @@ __global__ void __launch_bounds__(64 + 128 * kSets, 1)
           if (ch + 2 < kSetCols / 32) tmem_ld_32x32(taddr + (ch + 2) * 32, ra);
           else release();
           if (tail) mask_tail(rb, gcol0 + (ch + 1) * 32, p.ng);
-          if (p.debug_mode == 0) {
+          if constexpr (kTimingMode == 0) {
             if constexpr (kWarm) warm_chunk<false>(rb, sb ? sb + (ch + 1) * 32 : nullptr, gcol0 + (ch + 1) * 32, p.ng, slot);
             else scan_chunk<false>(rb, sb ? sb + (ch + 1) * 32 : nullptr, gcol0 + (ch + 1) * 32, p.ng, thr, cnt, my_list, warp_list, kp, cap, lane);
           } else {
@@ -735,7 +740,7 @@ __global__ void __launch_bounds__(64 + 128 * kSets, 1)
         if (static_cast<int>(lane) < n) p.cand[(slot_row0 + L) * kKPMax + lane] = warp_list[L + lane * 128];
       }
       p.cand_cnt[slot_row0 + lane] = cnt;
-      p.cand_thr[slot_row0 + lane] = (p.debug_mode && dbg == 0x12345678u) ? 0.f : thr;   // keeps `dbg` live in the timing modes
+      p.cand_thr[slot_row0 + lane] = (kTimingMode != 0 && dbg == 0x12345678u) ? 0.f : thr;   // keeps `dbg` live in the timing modes
       __syncwarp();
     }
   }
@@ -1015,41 +1020,45 @@ __global__ void __launch_bounds__(128)
                          const long long* __restrict__ cand, int n_cand, int k, float* __restrict__ out_scores,
                          long long* __restrict__ out_idx) {
   extern __shared__ __align__(16) uint8_t sm[];
-  float* qs = reinterpret_cast<float*>(sm);                              // [d]
-  double* sc = reinterpret_cast<double*>(sm + ((d * 4 + 15) & ~15));      // [n_cand]
+  // only ONE query part is staged at a time (per-token splitloss on ViT outputs has d = 197 * 384 floats per row)
+  const int p = d / n_chunks;
+  float* qs = reinterpret_cast<float*>(sm);                              // [p]
+  double* sc = reinterpret_cast<double*>(sm + ((p * 4 + 15) & ~15));      // [n_cand]
   long long* ci = reinterpret_cast<long long*>(sc + n_cand);              // [n_cand], -1 = duplicate / taken
   __shared__ BlockBest s_bb;
   const int qrow = blockIdx.x;
   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (int c = threadIdx.x; c < d; c += blockDim.x) qs[c] = q[static_cast<size_t>(qrow) * d + c];
   for (int c = threadIdx.x; c < n_cand; c += blockDim.x) ci[c] = cand[static_cast<size_t>(qrow) * n_cand + c];
   __syncthreads();
   // duplicates (a row that made the list of several parts): keep the first occurrence
   for (int c = threadIdx.x; c < n_cand; c += blockDim.x) {
     const long long v = ci[c];
-    bool dup = false;
-    for (int j = 0; j < c; ++j) dup |= (cand[static_cast<size_t>(qrow) * n_cand + j] == v);
+    bool dup = v < 0;                                                     // negative = empty slot of the caller's list
+    for (int j = 0; j < c; ++j) dup |= (ci[j] == v);   // ci is not modified before the barrier below
     sc[c] = dup ? 1.0 : 0.0;
   }
   __syncthreads();
-  for (int c = threadIdx.x; c < n_cand; c += blockDim.x)
+  for (int c = threadIdx.x; c < n_cand; c += blockDim.x) {
     if (sc[c] != 0.0) ci[c] = -1;
-  __syncthreads();
-  const int p = d / n_chunks;
-  for (int c = warp; c < n_cand; c += 4) {
-    if (ci[c] < 0) continue;   // warp-uniform
-    double best = -INFINITY;
-    for (int part = 0; part < n_chunks; ++part) {
-      if (cross) {   // 'cross' (einsum_in_chunks, diff_retrieval.py:652-654): every gallery part against every query part
-        for (int qp = 0; qp < n_chunks; ++qp)
-          best = fmax(best, exact_dot_warp(qs + qp * p, g + static_cast<size_t>(ci[c]) * d + part * p, p, lane));
-      } else {
-        best = fmax(best, exact_dot_warp(qs + part * p, g + static_cast<size_t>(ci[c]) * d + part * p, p, lane));
-      }
-    }
-    if (lane == 0) sc[c] = best;   // ranked on the float64 value (as dcr_sim_topk), reported as fp32
+    sc[c] = -INFINITY;
   }
   __syncthreads();
+  for (int qp = 0; qp < n_chunks; ++qp) {
+    for (int c = threadIdx.x; c < p; c += blockDim.x) qs[c] = q[static_cast<size_t>(qrow) * d + qp * p + c];
+    __syncthreads();
+    for (int c = warp; c < n_cand; c += 4) {
+      if (ci[c] < 0) continue;   // warp-uniform
+      double best = sc[c];
+      if (cross) {   // 'cross' (einsum_in_chunks, diff_retrieval.py:652-654): every gallery part against every query part
+        for (int part = 0; part < n_chunks; ++part)
+          best = fmax(best, exact_dot_warp(qs, g + static_cast<size_t>(ci[c]) * d + part * p, p, lane));
+      } else {
+        best = fmax(best, exact_dot_warp(qs, g + static_cast<size_t>(ci[c]) * d + qp * p, p, lane));
+      }
+      if (lane == 0) sc[c] = best;   // ranked on the float64 value (as dcr_sim_topk), reported as fp32
+    }
+    __syncthreads();
+  }
   for (int round = 0; round < k; ++round) {
     double bs = -INFINITY;
     long long bi = 0x7fffffffffffffffLL;
@@ -1140,9 +1149,14 @@ __global__ void __launch_bounds__(256)
           s_best[0] = s_best[w];
           s_besti[0] = s_besti[w];
         }
-      out_scores[static_cast<size_t>(qrow) * k + round] = static_cast<float>(s_best[0]);
-      out_idx[static_cast<size_t>(qrow) * k + round] = g_index_base + g_index_stride * s_besti[0];
-      s[s_besti[0]] = __longlong_as_double(0x7ff8000000000000LL);  // NaN marks "taken"
+      if (s_besti[0] < 0) {   // every remaining score is NaN (NaN query row, or k > number of non-NaN scores)
+        out_scores[static_cast<size_t>(qrow) * k + round] = __int_as_float(0x7fc00000);
+        out_idx[static_cast<size_t>(qrow) * k + round] = -1;
+      } else {
+        out_scores[static_cast<size_t>(qrow) * k + round] = static_cast<float>(s_best[0]);
+        out_idx[static_cast<size_t>(qrow) * k + round] = g_index_base + g_index_stride * s_besti[0];
+        s[s_besti[0]] = __longlong_as_double(0x7ff8000000000000LL);  // NaN marks "taken"
+      }
     }
     __syncthreads();
   }
@@ -1236,10 +1250,7 @@ int plan_pass(int nq, int kp, const SimPlan& sp, int num_sms, size_t max_smem, i
   return 0;
 }
 
-int env_int(const char* name, int dflt) {
-  const char* e = getenv(name);
-  return (e && *e) ? atoi(e) : dflt;
-}
+int env_int(const char* name, int dflt) { return tuning_int(name, dflt); }   // honoured only under DCR_B200_TUNING=1
 
 int make_plan(int nq, int ng, int d, int k, int cg, int num_sms, size_t max_smem, SimPlan* pl) {
   DCR_REQUIRE(nq >= 1 && ng >= 1 && d >= 1, "sim_topk: empty problem (nq=%d ng=%d d=%d)", nq, ng, d);
@@ -1316,9 +1327,8 @@ int make_plan(int nq, int ng, int d, int k, int cg, int num_sms, size_t max_smem
 }
 
 int default_cg() {
-  const char* e = getenv("DCR_SIM_CTA_GROUP");
-  if (e && (e[0] == '1' || e[0] == '2')) return e[0] - '0';
-  return 2;
+  const int cg = tuning_int("DCR_SIM_CTA_GROUP", 2);
+  return (cg == 1 || cg == 2) ? cg : 2;
 }
 
 struct PassBuffers {
@@ -1349,7 +1359,6 @@ int launch_fused(const SimPlan& pl, const PassPlan& pp, const __nv_bfloat16* qb,
   p.cand = pb.cand;
   p.cand_cnt = pb.ccnt;
   p.cand_thr = pb.cthr;
-  p.debug_mode = env_int("DCR_SIM_DEBUG_EPILOGUE", 0);
   p.col_bias = col_bias;
   p.bias_flag = bias_flag;
   p.thr_init = thr_init;
@@ -1395,10 +1404,10 @@ int split_rescore(const float* q, const float* g, int nq, int d, int n_chunks, i
                   int k, float* out_scores, long long* out_idx, cudaStream_t stream) {
   DCR_REQUIRE(nq >= 1 && d >= 1 && n_chunks >= 1 && d % n_chunks == 0 && (d / n_chunks) % 4 == 0,
               "split_rescore: d=%d must split into %d parts whose length is a multiple of 4", d, n_chunks);
-  DCR_REQUIRE(n_cand >= k && k >= 1 && n_cand <= 1024, "split_rescore: need k <= n_cand <= 1024 (k=%d n_cand=%d)", k, n_cand);
+  DCR_REQUIRE(n_cand >= k && k >= 1 && n_cand <= 4096, "split_rescore: need k <= n_cand <= 4096 (k=%d n_cand=%d)", k, n_cand);
   DCR_REQUIRE((reinterpret_cast<uintptr_t>(q) & 15) == 0 && (reinterpret_cast<uintptr_t>(g) & 15) == 0,
               "split_rescore: q/g must be 16-byte aligned");
-  const size_t smem = ((static_cast<size_t>(d) * 4 + 15) & ~size_t(15)) + static_cast<size_t>(n_cand) * 16;
+  const size_t smem = ((static_cast<size_t>(d / n_chunks) * 4 + 15) & ~size_t(15)) + static_cast<size_t>(n_cand) * 16;
   DCR_CUDA_CHECK(cudaFuncSetAttribute(split_rescore_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   split_rescore_kernel<<<nq, 128, smem, stream>>>(q, g, d, n_chunks, cross, cand, n_cand, k, out_scores, out_idx);
   count_launch();
@@ -1489,7 +1498,10 @@ int sim_topk(const float* q, int nq, const float* g, int ng, int d, int k, long 
   const float* col_bias = centre ? bias : nullptr;
 
   // CUDA events around the first fused pass only (thread-local, created once): bench.py's roofline numerator
-  static thread_local cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  // (events belong to the device that was current when they were created: one pair per device)
+  static thread_local cudaEvent_t ev_tab[64][2] = {};
+  cudaEvent_t& ev0 = ev_tab[di->device][0];
+  cudaEvent_t& ev1 = ev_tab[di->device][1];
   if (!ev0) {
     DCR_CUDA_CHECK(cudaEventCreate(&ev0));
     DCR_CUDA_CHECK(cudaEventCreate(&ev1));

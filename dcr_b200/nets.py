@@ -45,6 +45,7 @@ class DcrNet:
         self.precision = precision
         self.out_dim = 0
         self.in_shape = None          # (IH, IW) expected uint8 input
+        self.net_input = None         # (H, W) of the transformed fp32 input (after the centre crop)
         self.flops_per_image = 0.0
         self.meta = []                # one entry per op, in launch order (tools/layer_profile.py)
         h = C.c_void_p()
@@ -117,21 +118,38 @@ class DcrNet:
 
     # ---- execution ----------------------------------------------------------------------------------------------
     @torch.no_grad()
-    def forward(self, images_u8: torch.Tensor) -> torch.Tensor:
-        """images_u8: CUDA uint8 [n, IH, IW, 3] -> fp32 [n, out_dim] (same device)."""
-        if not (images_u8.is_cuda and images_u8.dtype == torch.uint8 and images_u8.dim() == 4
-                and images_u8.shape[3] == 3):
-            raise _lib.DcrError("forward expects a CUDA uint8 tensor [n, H, W, 3]")
-        if self.in_shape is not None and tuple(images_u8.shape[1:3]) != tuple(self.in_shape):
-            raise _lib.DcrError(f"network was built for {self.in_shape} inputs, got {tuple(images_u8.shape[1:3])}")
-        images_u8 = images_u8.contiguous()
-        n = images_u8.shape[0]
-        out = torch.empty((n, self.out_dim), dtype=torch.float32, device=images_u8.device)
-        with torch.cuda.device(images_u8.device):
+    def forward(self, images: torch.Tensor) -> torch.Tensor:
+        """Two input forms, same network and kernels:
+          * CUDA uint8 [n, IH, IW, 3]: raw images; Resize/CenterCrop/ToTensor/Normalize (diff_retrieval.py:325-330) run
+            fused in the first kernel (the fast path: 3 bytes per pixel cross PCIe / HBM instead of 12);
+          * CUDA float32 [n, 3, H, W]: the tensor the reference's own loop passes to `model(samples)`
+            (utils_ret.py:751, embedding_search/utils.py:101, metrics/fid.py:126) -- already transformed by the
+            caller's torchvision pipeline; H x W must be the network's input size (self.net_input).
+        Returns fp32 [n, out_dim] on the same device."""
+        if not (isinstance(images, torch.Tensor) and images.is_cuda and images.dim() == 4):
+            raise _lib.DcrError("forward expects a CUDA tensor: uint8 [n, H, W, 3] or float32 [n, 3, H, W]")
+        f32 = images.dtype == torch.float32
+        if f32:
+            if images.shape[1] != 3:
+                raise _lib.DcrError(f"float32 input must be NCHW with 3 channels, got {tuple(images.shape)}")
+            if self.net_input is not None and tuple(images.shape[2:4]) != tuple(self.net_input):
+                raise _lib.DcrError(f"network takes {self.net_input} transformed inputs, got {tuple(images.shape[2:4])}")
+        elif images.dtype == torch.uint8:
+            if images.shape[3] != 3:
+                raise _lib.DcrError("uint8 input must be NHWC with 3 channels")
+            if self.in_shape is not None and tuple(images.shape[1:3]) != tuple(self.in_shape):
+                raise _lib.DcrError(f"network was built for {self.in_shape} inputs, got {tuple(images.shape[1:3])}")
+        else:
+            raise _lib.DcrError(f"forward expects uint8 or float32 input, got {images.dtype}")
+        images = images.contiguous()
+        n = images.shape[0]
+        out = torch.empty((n, self.out_dim), dtype=torch.float32, device=images.device)
+        fwd = self.lib.dcr_net_forward_f32 if f32 else self.lib.dcr_net_forward
+        with torch.cuda.device(images.device):
             st = torch.cuda.current_stream().cuda_stream
             for s in range(0, n, self.max_batch):
                 b = min(self.max_batch, n - s)
-                rc = self.lib.dcr_net_forward(self.handle, images_u8[s:s + b].data_ptr(), b, out[s:s + b].data_ptr(), st)
+                rc = fwd(self.handle, images[s:s + b].data_ptr(), b, out[s:s + b].data_ptr(), st)
                 _lib.check(rc, "dcr_net_forward")
         return out
 
@@ -233,6 +251,7 @@ def build_sscd_resnet50(state_dict: Dict[str, torch.Tensor], max_batch: int = 64
         raise _lib.DcrError("SSCD state_dict has no head Linear (embeddings.1 / fc / head)")
     net = DcrNet(max_batch, precision)
     net.in_shape = (in_size, in_size)
+    net.net_input = (crop, crop)
     off = (in_size - crop) // 2
     eps = 1e-5
     src_crop = crop
@@ -327,30 +346,51 @@ def interpolate_pos_embed(pos_embed: torch.Tensor, grid_h: int, grid_w: int) -> 
 def build_dino_vit(state_dict: Dict[str, torch.Tensor], max_batch: int = 64, precision: str = "fast",
                    mean: Sequence[float] = (0.5, 0.5, 0.5), std: Sequence[float] = (0.5, 0.5, 0.5),
                    in_size: int = 256, crop: int = 224, patch: Optional[int] = None,
-                   heads: Optional[int] = None) -> DcrNet:
+                   heads: Optional[int] = None, scale_factor: Optional[float] = None, n_last_layers: int = 1,
+                   global_pool: str = "token") -> DcrNet:
     """Width, depth, patch size and head count are read off the state_dict (64-dim heads, as every DINO ViT):
-    vit_small/16 (`dino_vits16`, dino_vits.py:340-352; 384-d) and vit_base/16 (`dino_vitb16`, :366-378; 768-d).
-    patch 8 variants (785 tokens) exceed the attention kernels' 256-token tile and are rejected by dcr_net_forward."""
+    vit_small/16 (`dino_vits16`, dino_vits.py:340-352; 384-d), vit_base/16 (`dino_vitb16`, :366-378; 768-d) and the
+    patch-8 variants (`dino_vitb8`, :381-393: 785 tokens, streamed-KV attention kernel).
+    scale_factor: `multi_scale` (utils_ret.py:676-698) -- the transformed crop is bilinearly resized before the patch
+      embedding (fused into the first kernel) and the position embeddings are resampled as dino_vits.py:213-233 does.
+    n_last_layers: `--layer n` (utils_ret.py:732,745): the normed output of block depth - n, i.e.
+      `get_intermediate_layers(x, n)[0]` (dino_vits.py:267-275); 1 = the ordinary forward.
+    global_pool: 'token' -> the CLS row [B, dim] (dino_vits.py:253-254); '' -> every token, flattened to
+      [B, tokens * dim] as `rearrange(feats, 'b h w -> b (h w)')` does for --similarity_metric splitloss
+      (dino_vits.py:255-256, utils_ret.py:728-737)."""
+    import math
     sd = _strip({k: v.detach().cpu() for k, v in state_dict.items()}, ["module.", "backbone."])
     dim = sd["cls_token"].shape[-1]
     depth = 1 + max(int(k.split(".")[1]) for k in sd if k.startswith("blocks."))
+    if not 1 <= n_last_layers <= depth:
+        raise _lib.DcrError(f"--layer {n_last_layers} outside [1, {depth}]")
+    if global_pool not in ("token", ""):
+        raise _lib.DcrError(f"global_pool must be 'token' or '', got {global_pool!r}")
+    depth_used = depth - n_last_layers + 1
     patch = int(sd["patch_embed.proj.weight"].shape[-1]) if patch is None else patch
     heads = dim // 64 if heads is None else heads
-    grid = crop // patch
+    net_in = crop
+    rs_i, rs_f = [], []
+    if scale_factor is not None and scale_factor != 1:
+        net_in = int(math.floor(float(crop) * float(scale_factor)))
+        rs_i = [net_in, net_in]
+        rs_f = [float(np.float32(1.0 / float(scale_factor)))]
+    grid = (net_in - patch) // patch + 1
     n_patch = grid * grid
     tokens = n_patch + 1
     if sd["pos_embed"].shape[1] != tokens:
         # another input size than the checkpoint's: resample the position embeddings as the reference does
-        # (dino_vits.py:213-233); the hardware path for token counts other than 197 is not covered by the GPU tests yet
+        # (dino_vits.py:213-233)
         sd = dict(sd)
         sd["pos_embed"] = interpolate_pos_embed(sd["pos_embed"], grid, grid)
     net = DcrNet(max_batch, precision)
     net.in_shape = (in_size, in_size)
+    net.net_input = (crop, crop)
     off = (in_size - crop) // 2
     k_pad = first_conv_k_pad(patch, patch)
     t_cols = net.tensor(n_patch, k_pad)
-    net.op(OP_IM2COL_U8, [t_cols, in_size, in_size, off, off, crop, crop, patch, patch, patch, 0, k_pad],
-           list(mean) + list(std) + [1.0, 0.0])
+    net.op(OP_IM2COL_U8, [t_cols, in_size, in_size, off, off, crop, crop, patch, patch, patch, 0, k_pad] + rs_i,
+           list(mean) + list(std) + [1.0, 0.0] + rs_f)
     t_patch = net.tensor(n_patch, dim)
     net.conv(t_cols, t_patch, n_patch, 1, k_pad, _first_conv_weight(sd["patch_embed.proj.weight"], k_pad),
              bias=sd["patch_embed.proj.bias"])
@@ -358,7 +398,7 @@ def build_dino_vit(state_dict: Dict[str, torch.Tensor], max_batch: int = 64, pre
     net.op(OP_VIT_TOKENS, [t_patch, x, n_patch, dim, net.param_f32(sd["cls_token"].reshape(-1)),
                            net.param_f32(sd["pos_embed"].reshape(tokens, dim))])
     dh = dim // heads
-    for i in range(depth):
+    for i in range(depth_used):
         pre = f"blocks.{i}"
         t_ln = net.tensor(tokens, dim)
         net.op(OP_LAYERNORM, [x, t_ln, tokens, dim, net.param_f32(sd[pre + ".norm1.weight"]),
@@ -379,10 +419,15 @@ def build_dino_vit(state_dict: Dict[str, torch.Tensor], max_batch: int = 64, pre
         x3 = net.tensor(tokens, dim)
         net.conv(t_h, x3, tokens, 1, hid, sd[pre + ".mlp.fc2.weight"], bias=sd[pre + ".mlp.fc2.bias"], residual=x2)
         x = x3
-    net.set_output(dim)
-    # final LayerNorm on the CLS rows only (dino_vits.py:252-254: norm, then x[:, 0])
-    net.op(OP_LAYERNORM, [x, -1, 1, dim, net.param_f32(sd["norm.weight"]), net.param_f32(sd["norm.bias"]), tokens, 1],
-           [1e-6])
+    gamma, beta = net.param_f32(sd["norm.weight"]), net.param_f32(sd["norm.bias"])
+    if global_pool == "token":
+        net.set_output(dim)
+        # final LayerNorm on the CLS rows only (dino_vits.py:252-254: norm, then x[:, 0])
+        net.op(OP_LAYERNORM, [x, -1, 1, dim, gamma, beta, tokens, 1], [1e-6])
+    else:
+        net.set_output(tokens * dim)
+        net.op(OP_LAYERNORM, [x, -1, tokens, dim, gamma, beta, 1, 1], [1e-6])     # every token row, [B, tokens * dim]
+    net.tokens = tokens
     return net
 
 
@@ -396,6 +441,7 @@ def build_fid_inception(state_dict: Dict[str, torch.Tensor], max_batch: int = 50
     sd = _strip({k: v.detach().cpu() for k, v in state_dict.items()}, ["module."])
     net = DcrNet(max_batch, precision)
     net.in_shape = (299, 299)
+    net.net_input = (299, 299)
     eps = 1e-3
 
     def bconv(in_t, h, w, c, name, *, stride=1, pad=(0, 0), out_t=None, out_c=None, col_off=0):

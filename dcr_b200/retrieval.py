@@ -41,6 +41,10 @@ def extract_features(net: DcrNet, images: torch.Tensor, batch_size: Optional[int
     compute = torch.cuda.current_stream(dev)
     copy = torch.cuda.Stream(device=dev)
     stage = [torch.empty((bs,) + tuple(images.shape[1:]), dtype=torch.uint8, device=dev) for _ in range(2)]
+    # The staging blocks come from the compute stream's allocator pool: a previous call's forward passes (still queued
+    # on the compute stream -- the host runs far ahead of the GPU) may be reading the very same memory.  The copy stream
+    # must not write into them before everything already queued on the compute stream has finished.
+    copy.wait_stream(compute)
     ready = [torch.cuda.Event() for _ in range(2)]
     freed = [torch.cuda.Event() for _ in range(2)]
     for i, s in enumerate(range(0, n, bs)):

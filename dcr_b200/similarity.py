@@ -93,8 +93,8 @@ def sim_topk_split(q: torch.Tensor, g: torch.Tensor, k: int, num_chunks: int, cr
     then dcr_split_rescore evaluates the exact split score of the <= C*k candidates per query and selects.
     cross=True is `--stype cross` (einsum_in_chunks :643-662): score = max over every (gallery part, query part) pair.
     Candidates then come from ONE fused pass over the part matrices [Q*C, D/C] x [G*C, D/C] with
-    k' = (k-1)*C + 1 rows per query part (fewer than k' part-rows can beat the best part-row of a true top-k gallery row),
-    which must stay within the kernel's k' <= 16."""
+    k' = (k-1)*C + 1 rows per query part (fewer than k' part-rows can beat the best part-row of a true top-k gallery row)
+    while k' <= 16, otherwise from one pass per gallery part with k' = k (no limit on the number of parts)."""
     lib = _lib.load()
     if num_chunks == 1:
         return sim_topk(q, g, k)
@@ -107,8 +107,8 @@ def sim_topk_split(q: torch.Tensor, g: torch.Tensor, k: int, num_chunks: int, cr
     nq, d = q.shape
     if d % num_chunks or (d // num_chunks) % 4:
         raise _lib.DcrError(f"splitloss: descriptor dim {d} must split into {num_chunks} parts of a multiple of 4 dims")
-    if num_chunks * k > 1024:
-        raise _lib.DcrError("splitloss: num_chunks * k must be <= 1024")
+    if num_chunks * k > 4096:
+        raise _lib.DcrError("splitloss: num_chunks * k must be <= 4096")
     p = d // num_chunks
     cand = torch.empty((nq, num_chunks * k), dtype=torch.int64, device=q.device)
     for c in range(num_chunks):
@@ -134,17 +134,32 @@ def _sim_topk_cross(lib, q: torch.Tensor, g: torch.Tensor, k: int, c: int) -> Tu
     if d % c or (d // c) % 4:
         raise _lib.DcrError(f"splitloss: descriptor dim {d} must split into {c} parts of a multiple of 4 dims")
     kk = (k - 1) * c + 1
-    if kk > 16:
-        raise _lib.DcrError(f"splitloss cross: needs (k-1)*parts+1 = {kk} candidates per query part, the kernel keeps at most 16")
-    kk = min(kk, ng * c)
     p = d // c
-    _, idx = sim_topk(q.view(nq * c, p), g.view(ng * c, p), kk)            # rows of the part matrices
-    cand = (idx // c).reshape(nq, c * kk).contiguous()                      # gallery rows the part-rows belong to
+    if kk <= 16:
+        # one fused pass over the part matrices: a gallery row of the true top-k is reached through its best
+        # (query part, gallery part) pair, and fewer than (k-1)*c + 1 part-rows can beat that part-row
+        kk = min(kk, ng * c)
+        _, idx = sim_topk(q.view(nq * c, p), g.view(ng * c, p), kk)            # rows of the part matrices
+        cand = (idx // c).reshape(nq, c * kk).contiguous()                      # gallery rows the part-rows belong to
+    else:
+        # any number of parts (the reference default topk = 10 with num_loss_chunks >= 2, diff_retrieval.py:643-662):
+        # one fused pass per GALLERY part against all query parts with k' = k.  Within the list of the pair
+        # (query part a, gallery part b) every row that beats a true top-k row also beats it in the cross score, so
+        # the union of the c*c per-pair top-k lists contains the true top-k.
+        if c * c * k > 4096:
+            raise _lib.DcrError(f"splitloss cross: {c} parts x top-{k} needs {c * c * k} candidates per query (max 4096)")
+        kq = min(k, ng)
+        cand = torch.full((nq, c, c, k), -1, dtype=torch.int64, device=q.device)
+        qparts = q.view(nq * c, p)
+        for b in range(c):
+            _, idx = sim_topk(qparts, g[:, b * p:(b + 1) * p].contiguous(), kq)   # [nq*c, kq] gallery rows
+            cand[:, :, b, :kq] = idx.view(nq, c, kq)
+        cand = cand.reshape(nq, c * c * k).contiguous()
     out_s = torch.empty((nq, k), dtype=torch.float32, device=q.device)
     out_i = torch.empty((nq, k), dtype=torch.int64, device=q.device)
     with torch.cuda.device(q.device):
         st = torch.cuda.current_stream().cuda_stream
-        rc = lib.dcr_split_rescore(q.data_ptr(), g.data_ptr(), nq, d, c, 1, cand.data_ptr(), c * kk, k,
+        rc = lib.dcr_split_rescore(q.data_ptr(), g.data_ptr(), nq, d, c, 1, cand.data_ptr(), cand.shape[1], k,
                                    out_s.data_ptr(), out_i.data_ptr(), st)
         _lib.check(rc, "dcr_split_rescore")
     return out_s, out_i

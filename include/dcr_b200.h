@@ -44,7 +44,8 @@ int dcr_l2_normalize(float* x, int n, int d, float eps, void* stream);
 size_t dcr_sim_topk_workspace_size(int nq, int ng, int d, int k);
 
 /* For every query row q[i,:] the k gallery rows with the largest dot product, ordered by (score descending,
- * gallery index ascending).  q[nq,d], g[ng,d]: device, fp32, row-major, 16-byte aligned, d % 4 == 0, d <= 512,
+ * gallery index ascending).  q[nq,d], g[ng,d]: device, fp32, row-major, 16-byte aligned, d % 4 == 0, d <= 8192 (the query tile is
+ * shared-memory resident up to d = 512 and streamed with the gallery tiles beyond),
  * 1 <= k <= 16, k <= ng.  out_scores[nq,k] fp32, out_idx[nq,k] int64 (device); reported index =
  * g_index_base + g_index_stride * row (lets a rank that holds a contiguous or strided gallery shard report global
  * indices).  Scores are the fp64-accumulated dot products of the fp32 inputs rounded to fp32; the [nq,ng] matrix
@@ -58,7 +59,8 @@ int dcr_sim_topk(const float* q, int nq, const float* g, int ng, int d, int k, i
                  size_t workspace_bytes, void* stream);
 
 /* Same computation with HOST buffers (pageable or pinned): allocates device memory, copies in, runs, copies the
- * results back, frees.  This is the call the end-to-end benchmark times. */
+ * results back, frees.  The zero-setup entry for a caller that holds numpy arrays (what diff_retrieval.py:386-417 has
+ * when use_cuda is falsy); tests/test_sim_topk_gpu.py drives it through ctypes with numpy buffers. */
 int dcr_sim_topk_host(const float* q, int nq, const float* g, int ng, int d, int k, float* out_scores,
                       int64_t* out_idx);
 
@@ -91,10 +93,12 @@ int dcr_topk_merge(const float* scores, const int64_t* idx, int nq, int nlists, 
  * score = max over the parts of the per-part dot products).  The caller runs dcr_sim_topk once per part and passes
  * the union of the per-part top-k rows as cand [nq][n_cand] (duplicates allowed); this evaluates the exact split
  * score of every candidate (float64 accumulation, reported as fp32) and writes the k best per query ordered by
- * (score desc, row asc).  d %% n_chunks == 0, (d / n_chunks) %% 4 == 0, k <= n_cand <= 1024.
+ * (score desc, row asc).  d %% n_chunks == 0, (d / n_chunks) %% 4 == 0, k <= n_cand <= 4096; negative entries of
+ * cand are empty slots.
  * cross != 0: the 'cross' form (--stype cross, einsum_in_chunks diff_retrieval.py:643-662): score = max over EVERY pair
  * (gallery part, query part); the caller then collects candidates by running dcr_sim_topk on the part matrices
- * [nq * n_chunks, d / n_chunks] x [ng * n_chunks, d / n_chunks] with k' = (k - 1) * n_chunks + 1. */
+ * [nq * n_chunks, d / n_chunks] x [ng * n_chunks, d / n_chunks] with k' = (k - 1) * n_chunks + 1 (when k' <= 16), or once
+ * per gallery part [nq * n_chunks, d / n_chunks] x [ng, d / n_chunks] with k' = k (any n_chunks; dcr_b200/similarity.py). */
 int dcr_split_rescore(const float* q, const float* g, int nq, int d, int n_chunks, int cross, const int64_t* cand,
                       int n_cand, int k, float* out_scores, int64_t* out_idx, void* stream);
 
@@ -126,7 +130,8 @@ int dcr_conv2d_bf16(const void* x, int x_planes, int64_t x_plane_stride, int B, 
  * planes: 1 = bf16 activations/weights (fast); 3 = split-bf16 planes carrying fp32 precision (parity mode).
  * Tensor ids / param ids / op ids are the non-negative return values; negative = error.
  * Op kinds and their integer / float argument vectors (all sizes per image; the batch is given at forward time):
- *   0 IM2COL_U8  i: out_t, IH, IW, crop_y, crop_x, H, W, kh, kw, stride, pad, k_pad     f: mean[3], std[3], post_scale, post_shift
+ *   0 IM2COL_U8  i: out_t, IH, IW, crop_y, crop_x, H, W, kh, kw, stride, pad, k_pad [, RH, RW]     f: mean[3], std[3], post_scale, post_shift [, rscale]
+ *                (optional RH, RW, rscale as for STEM_S2D: bilinear resize of the transformed crop, utils_ret.py:676-698)
  *                uint8 HWC input -> normalised im2col rows of the first (3-channel) convolution / patch embedding
  *   1 CONV       i: in_t, out_t|-1, H, W, C, w_param, N, kh, kw, stride, pad_h, pad_w, scale_param|-1, bias_param|-1,
  *                   residual_t|-1, act(0 none,1 relu,2 gelu), out_col_off, to_output(0/1)
@@ -156,6 +161,11 @@ int dcr_net_set_output(dcr_net* net, int dim);
 int dcr_net_add_op(dcr_net* net, int kind, const int* iargs, int n_iargs, const float* fargs, int n_fargs);
 /* images: DEVICE uint8 [n, IH, IW, 3]; out: DEVICE fp32 [n, dim]; n <= max_batch */
 int dcr_net_forward(dcr_net* net, const uint8_t* images, int n, float* out, void* stream);
+/* Same network, fed with what the reference's own loop feeds `model(samples)` (utils_ret.py:751; embedding_search/
+ * utils.py:101; metrics/fid.py:126 `model(batch)[0]`): x_nchw DEVICE fp32 [n, 3, H, W], already transformed by the
+ * caller's torchvision pipeline (H x W = the network's input size after the centre crop, e.g. 224 x 224 / 299 x 299).
+ * Only the network's own input affine is applied (FID's internal 2x-1, metrics/inception.py:152-153). */
+int dcr_net_forward_f32(dcr_net* net, const float* x_nchw, int n, float* out, void* stream);
 
 /* ---- FID statistics ---------------------------------------------------------------------------------------------- */
 /* Streaming mean / unbiased covariance (float64) of activation rows, accumulated on the device batch by batch.

@@ -60,6 +60,30 @@ def make_dino_other_size(seed, size=160):
     print("dino", seed, size, y.shape, pos.shape)
 
 
+def make_dino_variants(seed):
+    """The forward variants diff_retrieval.py selects: global_pool='' (splitloss on a ViT, :258-263 -> every normed
+    token, dino_vits.py:255-256) and get_intermediate_layers(x, n)[0] (--layer n, utils_ret.py:732,745).  Only a
+    checksum-like subsample of the [2, 197, 384] token tensor is stored to keep the fixture small."""
+    from oracle.models import make_vit_state_dict
+    dv = _load("ref_dino_vits", os.path.join(REF, "dino_vits.py"))
+    sd = make_vit_state_dict(seed)
+    x = golden_inputs(seed)
+    m_tok = dv.vit_small(patch_size=16, num_classes=0, global_pool="")
+    m_tok.load_state_dict(sd, strict=True)
+    m_tok.eval()
+    m_cls = dv.vit_small(patch_size=16, num_classes=0)
+    m_cls.load_state_dict(sd, strict=True)
+    m_cls.eval()
+    with torch.no_grad():
+        tokens = m_tok(x)                                            # [2, 197, 384]
+        inter3 = m_cls.get_intermediate_layers(x, 3)[0]              # normed output of block depth-3
+    np.savez_compressed(os.path.join(HERE, f"dino_vits16_seed{seed}_variants.npz"), seed=seed,
+                        tokens_rows=tokens[:, ::14, :].numpy(), tokens_sum=tokens.double().sum(dim=-1).numpy(),
+                        layer3_cls=inter3[:, 0, :].numpy(), layer3_tokens_sum=inter3.double().sum(dim=-1).numpy(),
+                        in_checksum=float(x.double().sum()))
+    print("dino variants", seed, tokens.shape, inter3.shape)
+
+
 def make_fid_inception(seed):
     """metrics/inception.InceptionV3([3]) exactly as metrics/fid.py:245-247 builds it, with the URL weight load
     (inception.py:219) replaced by the seeded state_dict of oracle.models.make_inception_state_dict(seed)."""
@@ -91,4 +115,5 @@ if __name__ == "__main__":
     for s in (0, 1):
         make_dino(s)
     make_dino_other_size(0)
+    make_dino_variants(0)
     make_fid_inception(0)

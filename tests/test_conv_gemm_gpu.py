@@ -112,6 +112,7 @@ def test_conv3x3_halo_path(shape, act, monkeypatch):
     l0 = None
     out, _ = ops.conv2d(xp, wp, n, 3, 3, 1, 1, 1, scale=scale, bias=bias, act=act)
     torch.cuda.synchronize()
+    monkeypatch.setenv("DCR_B200_TUNING", "1")
     monkeypatch.setenv("DCR_CONV_NO_HALO", "1")
     gen_out, _ = ops.conv2d(xp, wp, n, 3, 3, 1, 1, 1, scale=scale, bias=bias, act=act)
     torch.cuda.synchronize()

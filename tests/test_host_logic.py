@@ -101,3 +101,71 @@ def test_cli_rejects_unknown_models_and_metrics(tmp_path):
         cli.main(["--query_dir", str(q), "--val_dir", str(q), "--pt_style", "clip"])
     with pytest.raises(FileNotFoundError):
         cli.main(["--query_dir", str(q), "--val_dir", str(q), "--pt_style", "sscd", "--weights", str(tmp_path / "none.pt")])
+
+
+def test_synthdataset_caption_json_branch(tmp_path):
+    """diff_retrieval.py:64-69, 92-96: no prompts.txt + 'laion' in the path -> file list and prompts come from
+    `*combined_captions.json` next to the part of the path before 'train', in the json's key order."""
+    import json
+    root = tmp_path / "laion_10k"
+    d = root / "train" / "imgs"
+    d.mkdir(parents=True)
+    files = [str(d / n) for n in ("b10.png", "a2.png", "a1.png")]
+    with open(root / "x_combined_captions.json", "w") as f:
+        json.dump({files[0]: ["cap b10", "alt"], files[1]: ["cap a2"], files[2]: ["cap a1"]}, f)
+    imgs, prompts = data.dataset_index(str(d))
+    assert imgs == files and prompts == ["cap b10", "cap a2", "cap a1"]
+    assert data.list_images(str(d)) == files
+    # with prompts.txt present the folder branch wins
+    (d / "prompts.txt").write_text("p1\np2\n")
+    for n in ("b10.png", "a2.png"):
+        (d / n).write_bytes(b"")
+    imgs2, prompts2 = data.dataset_index(str(d))
+    assert [os.path.basename(p) for p in imgs2] == ["a2.png", "b10.png"] and prompts2 == ["p1\n", "p2\n"]
+
+
+def test_load_state_dict_reads_torchscript_and_plain_files(tmp_path):
+    """The SSCD models are TorchScript files (diff_retrieval.py:277-283: torch.jit.load).  Script an SSCD-shaped module
+    (backbone.* ResNet trunk + embeddings.1 head), save it, and read its tensors back through cli.load_state_dict --
+    the loading path a real sscd_disc_mixup.torchscript.pt takes; the builder must see the same keys and values as from
+    a plain torch.save'd state_dict."""
+    import torch
+    import torchvision
+    from dcr_b200 import cli
+    from oracle import models as om
+
+    class GeM(torch.nn.Module):
+        def forward(self, x):
+            return x.clamp(min=1e-6).pow(3.0).mean(dim=(2, 3)).pow(1.0 / 3.0)
+
+    class SscdLike(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            r = torchvision.models.resnet50(weights=None)
+            r.fc = torch.nn.Identity()
+            r.avgpool = torch.nn.Identity()
+            self.backbone = torch.nn.Sequential()
+            for name in ("conv1", "bn1", "relu", "maxpool", "layer1", "layer2", "layer3", "layer4"):
+                self.backbone.add_module(name, getattr(r, name))
+            self.embeddings = torch.nn.Sequential(GeM(), torch.nn.Linear(2048, 512))
+
+        def forward(self, x):
+            return torch.nn.functional.normalize(self.embeddings(self.backbone(x)), dim=1)
+
+    sd = om.make_sscd_state_dict(5)
+    m = SscdLike()
+    missing, unexpected = m.load_state_dict(sd, strict=False)
+    assert not unexpected and all("num_batches_tracked" in k for k in missing)
+    m.eval()
+    ts_path, pt_path = str(tmp_path / "sscd_like.torchscript.pt"), str(tmp_path / "sscd_like.pth")
+    torch.jit.script(m).save(ts_path)
+    torch.save(sd, pt_path)
+    got_ts, got_pt = cli.load_state_dict(ts_path), cli.load_state_dict(pt_path)
+    for k, v in sd.items():
+        assert k in got_ts and torch.equal(got_ts[k].cpu(), v), k
+        assert torch.equal(got_pt[k], v)
+    # and the scripted module itself agrees with the oracle restatement on an input (the only SSCD pin available)
+    x = torch.randn(1, 3, 224, 224, generator=torch.Generator().manual_seed(0))
+    with torch.no_grad():
+        ref = torch.jit.load(ts_path)(x)
+    assert (om.sscd_forward(sd, x) - ref).abs().max().item() < 2e-5

@@ -108,6 +108,7 @@ def test_maxpool_fast_path_is_bit_identical_to_generic(monkeypatch):
     img = _imgs(3, 9).cuda()
     net = nets.build_sscd_resnet50(om.make_sscd_state_dict(2), max_batch=4, precision="fast")
     fast = net(img).clone()
+    monkeypatch.setenv("DCR_B200_TUNING", "1")
     monkeypatch.setenv("DCR_POOL_GENERIC", "1")
     generic = net(img).clone()
     monkeypatch.delenv("DCR_POOL_GENERIC")
@@ -115,6 +116,7 @@ def test_maxpool_fast_path_is_bit_identical_to_generic(monkeypatch):
     img2 = torch.randint(0, 256, (2, 299, 299, 3), dtype=torch.uint8, generator=torch.Generator().manual_seed(3)).cuda()
     inc = nets.build_fid_inception(om.make_inception_state_dict(1), max_batch=2, precision="fast")
     fast = inc(img2).clone()
+    monkeypatch.setenv("DCR_B200_TUNING", "1")
     monkeypatch.setenv("DCR_POOL_GENERIC", "1")
     generic = inc(img2).clone()
     assert torch.equal(fast, generic)

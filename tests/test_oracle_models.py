@@ -93,3 +93,19 @@ def test_vit_other_input_size_matches_reference_golden():
     np.testing.assert_array_equal(pos_p, g["pos_embed"])
     # same size: untouched
     assert nets.interpolate_pos_embed(sd["pos_embed"], 14, 14) is sd["pos_embed"]
+
+
+def test_vit_oracle_variants_match_reference_golden():
+    """global_pool='' (all normed tokens; diff_retrieval.py:258-263 + dino_vits.py:255-256) and
+    get_intermediate_layers(x, 3)[0] (--layer 3; utils_ret.py:732,745) against the reference module's own outputs."""
+    g = np.load(os.path.join(GOLD, "dino_vits16_seed0_variants.npz"))
+    x = _golden_inputs(0)
+    assert abs(float(x.double().sum()) - float(g["in_checksum"])) < 1e-6
+    sd = om.make_vit_state_dict(0)
+    tok = om.vit_forward(sd, x, global_pool="").reshape(2, 197, 384)
+    np.testing.assert_allclose(tok[:, ::14, :].numpy(), g["tokens_rows"], rtol=0, atol=3e-5)
+    np.testing.assert_allclose(tok.double().sum(dim=-1).numpy(), g["tokens_sum"], rtol=0, atol=2e-3)
+    cls3 = om.vit_forward(sd, x, n_last_layers=3)
+    np.testing.assert_allclose(cls3.numpy(), g["layer3_cls"], rtol=0, atol=3e-5)
+    tok3 = om.vit_forward(sd, x, n_last_layers=3, global_pool="").reshape(2, 197, 384)
+    np.testing.assert_allclose(tok3.double().sum(dim=-1).numpy(), g["layer3_tokens_sum"], rtol=0, atol=2e-3)
