@@ -160,6 +160,9 @@ void dcr_net_destroy(dcr_net* net) { dcr::net_destroy(reinterpret_cast<dcr::Net*
 int dcr_net_add_tensor(dcr_net* net, int64_t rows_per_image, int channels) {
   return dcr::net_add_tensor(reinterpret_cast<dcr::Net*>(net), rows_per_image, channels);
 }
+int dcr_net_alias_tensor(dcr_net* net, int src_tensor, int64_t rows_per_image, int channels) {
+  return dcr::net_alias_tensor(reinterpret_cast<dcr::Net*>(net), src_tensor, rows_per_image, channels);
+}
 int dcr_net_add_param(dcr_net* net, const void* host_data, size_t bytes) {
   return dcr::net_add_param(reinterpret_cast<dcr::Net*>(net), host_data, bytes);
 }

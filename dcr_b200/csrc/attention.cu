@@ -31,6 +31,7 @@ struct AttnParams {
   long long out_plane_stride;
   int planes, B, T, heads, dh;
   float scale;
+  int causal;   // 1: query t attends to keys <= t only (CLIP text tower, clip/model.py build_attention_mask)
 };
 
 __device__ __forceinline__ float load1(const __nv_bfloat16* base, long long ps, int planes, size_t idx) {
@@ -64,8 +65,9 @@ __global__ void __launch_bounds__(256) attention_fp32_kernel(const AttnParams p)
     q[lane] = load1(p.qkv, p.qkv_plane_stride, p.planes, (row0 + t) * ld + h * 64 + lane);
     q[lane + 32] = load1(p.qkv, p.qkv_plane_stride, p.planes, (row0 + t) * ld + h * 64 + lane + 32);
     __syncwarp();
+    const int TL = p.causal ? t + 1 : T;   // keys this query may see
     float mx = -INFINITY;
-    for (int j = lane; j < T; j += 32) {
+    for (int j = lane; j < TL; j += 32) {
       float s = 0.f;
 #pragma unroll 16
       for (int d = 0; d < 64; ++d) s = fmaf(q[d], ks[j * 65 + d], s);
@@ -76,7 +78,7 @@ __global__ void __launch_bounds__(256) attention_fp32_kernel(const AttnParams p)
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) mx = fmaxf(mx, __shfl_xor_sync(kFull, mx, off));
     float sum = 0.f;
-    for (int j = lane; j < T; j += 32) {
+    for (int j = lane; j < TL; j += 32) {
       const float e = expf(pr[j] - mx);
       pr[j] = e;
       sum += e;
@@ -85,7 +87,7 @@ __global__ void __launch_bounds__(256) attention_fp32_kernel(const AttnParams p)
     for (int off = 16; off > 0; off >>= 1) sum += __shfl_xor_sync(kFull, sum, off);
     __syncwarp();
     float o0 = 0.f, o1 = 0.f;
-    for (int j = 0; j < T; ++j) {
+    for (int j = 0; j < TL; ++j) {
       const float w = pr[j];
       o0 = fmaf(w, vs[j * 64 + lane], o0);
       o1 = fmaf(w, vs[j * 64 + lane + 32], o1);
@@ -156,7 +158,7 @@ __global__ void __launch_bounds__(256) attention_stream_kernel(const AttnParams 
         float acc = 0.f;
 #pragma unroll 16
         for (int d = 0; d < 64; ++d) acc = fmaf(q[d], ks[j * 65 + d], acc);
-        s[c] = (kt + j < T) ? acc * p.scale : -INFINITY;
+        s[c] = (kt + j < T && (!p.causal || kt + j <= q0 + r)) ? acc * p.scale : -INFINITY;
         tmax = fmaxf(tmax, s[c]);
       }
 #pragma unroll
@@ -222,6 +224,7 @@ struct AttnTcParams {
   __nv_bfloat16* out;   // [B*T, heads*64]
   int B, T, heads;
   float scale_log2e;    // scale * log2(e)
+  int causal;           // 1: keys beyond the query's own position are masked
 };
 
 __global__ void __launch_bounds__(kAttnThreads, 1)
@@ -319,6 +322,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1)
       mbar_wait(&s_full[mt], 0);
       tc_fence_after();
       const uint32_t taddr = tmem_row + mt * 256;
+      const int lim = p.causal ? min(p.T, mt * 128 + static_cast<int>(row) + 1) : p.T;   // keys this query row may see
       // pass 1: row maximum over the valid keys
       float mx = -INFINITY;
 #pragma unroll 1
@@ -329,7 +333,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1)
         tmem_ld_wait_regs(r);
 #pragma unroll
         for (int c = 0; c < 32; ++c)
-          if (ch * 32 + c < p.T) mx = fmaxf(mx, __uint_as_float(r[c]));
+          if (ch * 32 + c < lim) mx = fmaxf(mx, __uint_as_float(r[c]));
       }
       const float mxs = mx * p.scale_log2e;
       // pass 2: exp, row sum, P -> shared memory (bf16, K-major, 128B swizzle)
@@ -343,7 +347,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1)
           tmem_ld_wait_regs(r);
 #pragma unroll
           for (int c = 0; c < 32; ++c) {
-            const float e = (ch * 32 + c < p.T) ? exp2f(fmaf(__uint_as_float(r[c]), p.scale_log2e, -mxs)) : 0.f;
+            const float e = (ch * 32 + c < lim) ? exp2f(fmaf(__uint_as_float(r[c]), p.scale_log2e, -mxs)) : 0.f;
             // the sum must be of the ROUNDED weights that the tensor core will use
             const float eb = __bfloat162float(__float2bfloat16_rn(e));
             pv[c] = eb;
@@ -408,7 +412,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1)
 }  // namespace
 
 int attention(const __nv_bfloat16* qkv, long long qkv_plane_stride, __nv_bfloat16* out, long long out_plane_stride,
-              int planes, int B, int T, int heads, int dh, float scale, cudaStream_t stream) {
+              int planes, int B, int T, int heads, int dh, float scale, cudaStream_t stream, int causal) {
   DCR_REQUIRE(dh == 64, "attention: head dim %d not supported (64 only)", dh);
   DCR_REQUIRE(T >= 1 && T <= 16384, "attention: sequence length %d out of range", T);
   if (B == 0) return 0;
@@ -418,7 +422,7 @@ int attention(const __nv_bfloat16* qkv, long long qkv_plane_stride, __nv_bfloat1
     CUtensorMap tm;
     if (int rc = make_tmap_2d_bf16(&tm, qkv, static_cast<uint64_t>(B) * T, 3 * heads * 64, 3 * heads * 64, 128, 64)) return rc;
     AttnTcParams tp;
-    tp.out = out; tp.B = B; tp.T = T; tp.heads = heads;
+    tp.out = out; tp.B = B; tp.T = T; tp.heads = heads; tp.causal = causal;
     tp.scale_log2e = scale * 1.4426950408889634f;
     const size_t smem = 1024 + 2 * 16384 + 32768 + 32768 + 2 * 65536 + 256;
     DCR_CUDA_CHECK(cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -430,7 +434,7 @@ int attention(const __nv_bfloat16* qkv, long long qkv_plane_stride, __nv_bfloat1
   }
   AttnParams p;
   p.qkv = qkv; p.qkv_plane_stride = qkv_plane_stride; p.out = out; p.out_plane_stride = out_plane_stride;
-  p.planes = planes; p.B = B; p.T = T; p.heads = heads; p.dh = dh; p.scale = scale;
+  p.planes = planes; p.B = B; p.T = T; p.heads = heads; p.dh = dh; p.scale = scale; p.causal = causal;
   if (T > 256) {   // K / V streamed in tiles, online softmax (patch-8 ViTs)
     const size_t smem_s = (static_cast<size_t>(kStreamK) * 65 + kStreamK * 64 + kStreamQ * 64 + 8 * kStreamK) * 4;
     DCR_CUDA_CHECK(cudaFuncSetAttribute(attention_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,

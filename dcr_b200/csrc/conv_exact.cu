@@ -51,6 +51,7 @@ struct ExactParams {
 __device__ __forceinline__ float act_exact(float y, int act) {
   if (act == 1) return fmaxf(y, 0.f);
   if (act == 2) return 0.5f * y * (1.f + erff(y * 0.70710678118654752440f));
+  if (act == 3) return y / (1.f + expf(-1.702f * y));   // QuickGELU
   return y;
 }
 

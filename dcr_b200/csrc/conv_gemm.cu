@@ -79,6 +79,7 @@ struct GemmParams {
 DCR_DEVICE float apply_act(float y, int act) {
   if (act == 1) return fmaxf(y, 0.f);
   if (act == 2) return 0.5f * y * (1.f + erff(y * 0.70710678118654752440f));
+  if (act == 3) return y / (1.f + expf(-1.702f * y));   // QuickGELU: x * sigmoid(1.702 x)  (CLIP, clip/model.py)
   return y;
 }
 
@@ -108,7 +109,7 @@ DCR_DEVICE void tma_store_wait_read_1() { asm volatile("cp.async.bulk.wait_group
 DCR_DEVICE void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
 // kEpi: 0 = direct epilogue (any number of planes, optional fp32 output, runtime activation; parity mode and final
-//           layers), 1/2/3 = TMA-store epilogue with compile-time activation none / ReLU / GELU (fast mode hot path).
+//           layers), 1/2/3/4 = TMA-store epilogue with compile-time activation none / ReLU / GELU / QuickGELU (fast mode hot path).
 // Eight epilogue warps: warps w and w+4 share a TMEM lane quadrant and split the tile's columns, so every SM
 // sub-partition has two epilogue warps to switch between (the epilogue is latency bound, not issue bound).
 template <int BN, bool kIm2col, int kEpi>
@@ -572,6 +573,7 @@ int conv_gemm(const ConvGemmDesc& d, cudaStream_t stream) {
   DCR_REQUIRE(d.n_terms >= 1 && d.n_terms <= kMaxGemmTerms, "conv_gemm: bad n_terms %d", d.n_terms);
   DCR_REQUIRE(d.C % 8 == 0 && d.N % 8 == 0, "conv_gemm: C (%d) and N (%d) must be multiples of 8", d.C, d.N);
   DCR_REQUIRE(d.kh >= 1 && d.kw >= 1 && d.stride >= 1, "conv_gemm: bad filter geometry");
+  DCR_REQUIRE(d.act >= 0 && d.act <= 3, "conv_gemm: unknown activation %d", d.act);
   if (d.exact) return conv_exact(d, stream);
   if (conv3x3_halo_eligible(d)) return conv3x3_halo(d, stream);
   const bool windowed = d.in_stride_w != 0;
@@ -671,7 +673,8 @@ int conv_gemm(const ConvGemmDesc& d, cudaStream_t stream) {
   (im2col ? launch<BNv, true, E>(maps, p, di->num_sms, di->max_smem_optin, stream)              \
           : launch<BNv, false, E>(maps, p, di->num_sms, di->max_smem_optin, stream))
 #define DCR_LAUNCH(BNv)                                                                          \
-  (epi == 0 ? DCR_LAUNCH_E(BNv, 0) : (epi == 1 ? DCR_LAUNCH_E(BNv, 1) : (epi == 2 ? DCR_LAUNCH_E(BNv, 2) : DCR_LAUNCH_E(BNv, 3))))
+  (epi == 0 ? DCR_LAUNCH_E(BNv, 0)                                                                \
+            : (epi == 1 ? DCR_LAUNCH_E(BNv, 1) : (epi == 2 ? DCR_LAUNCH_E(BNv, 2) : (epi == 3 ? DCR_LAUNCH_E(BNv, 3) : DCR_LAUNCH_E(BNv, 4)))))
   const int epi = p.tma_epi ? 1 + p.act : 0;   // compile-time activation on the TMA-store path
   switch (BN) {
     case 64: return DCR_LAUNCH(64);

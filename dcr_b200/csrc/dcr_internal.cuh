@@ -72,6 +72,9 @@ int conv_gemm(const ConvGemmDesc& d, cudaStream_t stream);
 int conv_exact(const ConvGemmDesc& d, cudaStream_t stream);
 bool conv3x3_halo_eligible(const ConvGemmDesc& d);   // 3x3 / stride 1 / pad 1, fast mode, no residual, W <= 62, N <= 256
 int conv3x3_halo(const ConvGemmDesc& d, cudaStream_t stream);
+// bottleneck_fuse.cu: `a` (1x1 expand + residual + ReLU) followed by `b` (1x1 reduce + ReLU) on a's output, fast mode
+bool expand_reduce_eligible(const ConvGemmDesc& a, const ConvGemmDesc& b, size_t max_smem);
+int expand_reduce(const ConvGemmDesc& a, const ConvGemmDesc& b, cudaStream_t stream);
 
 
 // ---- HBM-bound kernels (pool_norm.cu, attention.cu) ---------------------------------------------------------------
@@ -95,7 +98,10 @@ int layernorm(const __nv_bfloat16* in, long long in_plane_stride, int planes, in
 int vit_tokens(const __nv_bfloat16* patch, long long patch_plane_stride, const float* cls, const float* pos,
                __nv_bfloat16* out, long long out_plane_stride, int planes, int B, int NP, int C, cudaStream_t stream);
 int attention(const __nv_bfloat16* qkv, long long qkv_plane_stride, __nv_bfloat16* out, long long out_plane_stride,
-              int planes, int B, int T, int heads, int dh, float scale, cudaStream_t stream);
+              int planes, int B, int T, int heads, int dh, float scale, cudaStream_t stream, int causal = 0);
+// token ids [B, T] (int32, device) -> planes[B*T, C] = table[id] + pos[t]   (CLIP text tower input, clip/model.py encode_text)
+int embed_tokens(const int* ids, int B, int T, int C, const float* table, int vocab, const float* pos, __nv_bfloat16* out,
+                 long long out_plane_stride, int planes, cudaStream_t stream);
 
 // ---- network executor (net.cu) ------------------------------------------------------------------------------------
 enum NetOpKind {
@@ -110,13 +116,15 @@ enum NetOpKind {
   NET_OP_ATTENTION = 8,
   NET_OP_L2NORM_OUT = 9,
   NET_OP_STEM_S2D = 10,
-  NET_OP_COUNT = 11
+  NET_OP_EMBED = 11,
+  NET_OP_COUNT = 12
 };
 struct Net;
 int net_create(int max_batch, int planes, Net** out);
 int net_set_exact(Net* n, int on);
 void net_destroy(Net* n);
 int net_add_tensor(Net* n, long long rows_per_image, int C);
+int net_alias_tensor(Net* n, int src, long long rows_per_image, int C);
 int net_add_param(Net* n, const void* host, size_t bytes);
 int net_set_output(Net* n, int dim);
 int net_add_op(Net* n, int kind, const int* iargs, int ni, const float* fargs, int nf);

@@ -19,6 +19,7 @@ struct NetTensor {
   int C;
   __nv_bfloat16* ptr;
   long long plane_stride;   // elements
+  bool owned = true;        // false: a reshaped view of another tensor's buffer (net_alias_tensor)
 };
 
 struct NetOp {
@@ -66,7 +67,8 @@ int net_set_exact(Net* n, int on) {
 
 void net_destroy(Net* n) {
   if (!n) return;
-  for (auto& t : n->tensors) cudaFree(t.ptr);
+  for (auto& t : n->tensors)
+    if (t.owned) cudaFree(t.ptr);
   for (void* p : n->params) cudaFree(p);
   if (n->out_f32) cudaFree(n->out_f32);
   delete n;
@@ -84,6 +86,22 @@ int net_add_tensor(Net* n, long long rows_per_image, int C) {
   DCR_CUDA_CHECK(cudaMemset(p, 0, bytes));
   t.ptr = static_cast<__nv_bfloat16*>(p);
   n->bytes_allocated += bytes;
+  n->tensors.push_back(t);
+  return static_cast<int>(n->tensors.size()) - 1;
+}
+
+// A second shape for an existing activation buffer: same elements per image, other (rows, channels) factorisation
+// (flatten of the NHWC feature map in front of a Linear layer: VGG-16's classifier in metrics/ipr.py:139-141).
+int net_alias_tensor(Net* n, int src, long long rows_per_image, int C) {
+  DCR_REQUIRE(n && src >= 0 && src < static_cast<int>(n->tensors.size()), "net_alias_tensor: bad source tensor");
+  const NetTensor& s = n->tensors[src];
+  DCR_REQUIRE(rows_per_image >= 1 && C >= 8 && C % 8 == 0 && rows_per_image * C == s.rows_per_image * s.C,
+              "net_alias_tensor: (%lld, %d) does not hold the %lld elements per image of the source", rows_per_image, C,
+              s.rows_per_image * s.C);
+  NetTensor t = s;
+  t.rows_per_image = rows_per_image;
+  t.C = C;
+  t.owned = false;
   n->tensors.push_back(t);
   return static_cast<int>(n->tensors.size()) - 1;
 }
@@ -142,7 +160,12 @@ int net_add_op(Net* n, int kind, const int* iargs, int ni, const float* fargs, i
                       param_ok(op.i[5], false),
                   "vit_tokens op: bad args");
       break;
-    case NET_OP_ATTENTION: DCR_REQUIRE(ni == 5 && nf == 1 && tensor_ok(op.i[0], false) && tensor_ok(op.i[1], false), "attention op: bad args"); break;
+    case NET_OP_ATTENTION:
+      DCR_REQUIRE((ni == 5 || ni == 6) && nf == 1 && tensor_ok(op.i[0], false) && tensor_ok(op.i[1], false), "attention op: bad args");
+      break;
+    case NET_OP_EMBED:
+      DCR_REQUIRE(ni == 6 && tensor_ok(op.i[0], false) && param_ok(op.i[3], false) && param_ok(op.i[4], false), "embed op: bad args");
+      break;
     case NET_OP_L2NORM_OUT: DCR_REQUIRE(nf == 1, "l2norm op: bad args"); break;
     default: break;
   }
@@ -157,7 +180,43 @@ int net_forward(Net* n, const uint8_t* images, int B, float* out, cudaStream_t s
   DCR_REQUIRE(n->out_f32 && n->out_dim > 0, "net_forward: output not configured");
   if (B == 0) return 0;
   const int P = n->planes;
-  for (const NetOp& op : n->ops) {
+  auto conv_desc = [&](const NetOp& cop) {
+    const int* a = cop.i;
+    const NetTensor& in = n->tensors[a[0]];
+    ConvGemmDesc d;
+    d.in = in.ptr;
+    d.in_plane_stride = in.plane_stride;
+    d.B = B; d.H = a[2]; d.W = a[3]; d.C = a[4]; d.ld_in = in.C;
+    d.weight = static_cast<const __nv_bfloat16*>(n->params[a[5]]);
+    d.N = a[6]; d.kh = a[7]; d.kw = a[8]; d.stride = a[9]; d.pad_h = a[10]; d.pad_w = a[11];
+    if (a[18] > 0) {   // overlapping-window view: a[18] = elements per stored pixel, a[19] = stored pixels per row
+      d.in_stride_w = a[18];
+      d.in_stride_h = static_cast<long long>(a[18]) * a[19];
+      d.in_stride_n = in.rows_per_image * in.C;
+    }
+    const int cpad = (d.C + 63) / 64 * 64;
+    d.w_plane_stride = static_cast<long long>(d.N) * d.kh * d.kw * cpad;
+    d.n_terms = n->terms;
+    for (int t = 0; t < n->terms; ++t) { d.term_a[t] = kTermA[t]; d.term_w[t] = kTermW[t]; }
+    d.scale = a[12] >= 0 ? static_cast<const float*>(n->params[a[12]]) : nullptr;
+    d.bias = a[13] >= 0 ? static_cast<const float*>(n->params[a[13]]) : nullptr;
+    if (a[14] >= 0) {
+      const NetTensor& r = n->tensors[a[14]];
+      d.res = r.ptr; d.ld_res = r.C; d.res_planes = P; d.res_plane_stride = r.plane_stride;
+    }
+    d.act = a[15];
+    d.exact = n->exact;
+    if (a[1] >= 0) {
+      NetTensor& o = n->tensors[a[1]];
+      d.out = o.ptr; d.ld_out = o.C; d.out_col_off = a[16]; d.out_planes = P; d.out_plane_stride = o.plane_stride;
+    }
+    // fp32 output rows are the op's own N wide: [B, N] for a head on pooled features, [B * T, N] = [B, T * N] for a
+    // per-token projection (CLIP text tower)
+    if (a[17]) { d.out_f32 = n->out_f32; d.ld_out_f32 = d.N; }
+    return d;
+  };
+  for (size_t oi = 0; oi < n->ops.size(); ++oi) {
+    const NetOp& op = n->ops[oi];
     const int* a = op.i;
     int rc = 0;
     switch (op.kind) {
@@ -178,35 +237,18 @@ int net_forward(Net* n, const uint8_t* images, int B, float* out, cudaStream_t s
         break;
       }
       case NET_OP_CONV: {
-        const NetTensor& in = n->tensors[a[0]];
-        ConvGemmDesc d;
-        d.in = in.ptr;
-        d.in_plane_stride = in.plane_stride;
-        d.B = B; d.H = a[2]; d.W = a[3]; d.C = a[4]; d.ld_in = in.C;
-        d.weight = static_cast<const __nv_bfloat16*>(n->params[a[5]]);
-        d.N = a[6]; d.kh = a[7]; d.kw = a[8]; d.stride = a[9]; d.pad_h = a[10]; d.pad_w = a[11];
-        if (a[18] > 0) {   // overlapping-window view: a[18] = elements per stored pixel, a[19] = stored pixels per row
-          d.in_stride_w = a[18];
-          d.in_stride_h = static_cast<long long>(a[18]) * a[19];
-          d.in_stride_n = in.rows_per_image * in.C;
+        ConvGemmDesc d = conv_desc(op);
+        // peephole: conv3 (1x1 expand + residual + ReLU) directly followed by the next block's conv1 (1x1 reduce + ReLU)
+        // on its output -> one fused kernel that never re-reads the expanded activation (bottleneck_fuse.cu)
+        if (oi + 1 < n->ops.size() && n->ops[oi + 1].kind == NET_OP_CONV) {
+          const ConvGemmDesc d2 = conv_desc(n->ops[oi + 1]);
+          const DeviceInfo* di = device_info();
+          if (di && expand_reduce_eligible(d, d2, di->max_smem_optin)) {
+            rc = expand_reduce(d, d2, stream);
+            ++oi;   // the second convolution is done
+            break;
+          }
         }
-        const int cpad = (d.C + 63) / 64 * 64;
-        d.w_plane_stride = static_cast<long long>(d.N) * d.kh * d.kw * cpad;
-        d.n_terms = n->terms;
-        for (int t = 0; t < n->terms; ++t) { d.term_a[t] = kTermA[t]; d.term_w[t] = kTermW[t]; }
-        d.scale = a[12] >= 0 ? static_cast<const float*>(n->params[a[12]]) : nullptr;
-        d.bias = a[13] >= 0 ? static_cast<const float*>(n->params[a[13]]) : nullptr;
-        if (a[14] >= 0) {
-          const NetTensor& r = n->tensors[a[14]];
-          d.res = r.ptr; d.ld_res = r.C; d.res_planes = P; d.res_plane_stride = r.plane_stride;
-        }
-        d.act = a[15];
-        d.exact = n->exact;
-        if (a[1] >= 0) {
-          NetTensor& o = n->tensors[a[1]];
-          d.out = o.ptr; d.ld_out = o.C; d.out_col_off = a[16]; d.out_planes = P; d.out_plane_stride = o.plane_stride;
-        }
-        if (a[17]) { d.out_f32 = n->out_f32; d.ld_out_f32 = n->out_dim; }
         rc = conv_gemm(d, stream);
         break;
       }
@@ -246,7 +288,14 @@ int net_forward(Net* n, const uint8_t* images, int B, float* out, cudaStream_t s
       case NET_OP_ATTENTION: {
         const NetTensor& in = n->tensors[a[0]];
         NetTensor& o = n->tensors[a[1]];
-        rc = attention(in.ptr, in.plane_stride, o.ptr, o.plane_stride, P, B, a[2], a[3], a[4], op.f[0], stream);
+        rc = attention(in.ptr, in.plane_stride, o.ptr, o.plane_stride, P, B, a[2], a[3], a[4], op.f[0], stream, a[5]);
+        break;
+      }
+      case NET_OP_EMBED: {   // the network input is int32 token ids [B, T] (passed through the `images` pointer)
+        NetTensor& o = n->tensors[a[0]];
+        DCR_REQUIRE(images != nullptr && !f32, "net_forward: this network takes int32 token ids");
+        rc = embed_tokens(reinterpret_cast<const int*>(images), B, a[1], a[2], static_cast<const float*>(n->params[a[3]]), a[5],
+                          static_cast<const float*>(n->params[a[4]]), o.ptr, o.plane_stride, P, stream);
         break;
       }
       case NET_OP_L2NORM_OUT: rc = l2_normalize(n->out_f32, B, n->out_dim, op.f[0], stream); break;

@@ -480,6 +480,33 @@ __global__ void vit_tokens_kernel(const VitTokensParams p) {
   }
 }
 
+// ---- token embedding: planes[b*T + t, :] = table[ids[b, t], :] + pos[t, :]   (CLIP text tower input) ---------------------
+struct EmbedParams {
+  const int* ids;
+  const float* table;
+  const float* pos;
+  __nv_bfloat16* out;
+  long long out_plane_stride;
+  int planes, B, T, C, vocab;
+};
+__global__ void embed_tokens_kernel(const EmbedParams p) {
+  const int cg = p.C / 8;
+  const long long total = static_cast<long long>(p.B) * p.T * cg;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c8 = static_cast<int>(i % cg);
+    const long long row = i / cg;
+    const int t = static_cast<int>(row % p.T);
+    int id = p.ids[row];
+    id = id < 0 ? 0 : (id >= p.vocab ? p.vocab - 1 : id);
+    float v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e)
+      v[e] = p.table[static_cast<size_t>(id) * p.C + c8 * 8 + e] + p.pos[static_cast<size_t>(t) * p.C + c8 * 8 + e];
+    store8(p.out, p.out_plane_stride, p.planes, static_cast<size_t>(row) * p.C + c8 * 8, v);
+  }
+}
+
 int grid_for(long long work_items, int block, int num_sms) {
   long long blocks = (work_items + block - 1) / block;
   return static_cast<int>(std::min<long long>(blocks, static_cast<long long>(num_sms) * 16));
@@ -527,6 +554,21 @@ int im2col_u8(const uint8_t* img, int B, int IH, int IW, int crop_y, int crop_x,
   else if (kw == 8) DCR_IM2COL(8);
   else DCR_IM2COL(16);
 #undef DCR_IM2COL
+  count_launch();
+  DCR_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+int embed_tokens(const int* ids, int B, int T, int C, const float* table, int vocab, const float* pos, __nv_bfloat16* out,
+                 long long out_plane_stride, int planes, cudaStream_t stream) {
+  const DeviceInfo* di = device_info();
+  if (!di) return -2;
+  DCR_REQUIRE(ids && table && pos && out && C % 8 == 0 && T >= 1 && vocab >= 1, "embed_tokens: bad arguments");
+  if (B == 0) return 0;
+  EmbedParams p;
+  p.ids = ids; p.table = table; p.pos = pos; p.out = out; p.out_plane_stride = out_plane_stride;
+  p.planes = planes; p.B = B; p.T = T; p.C = C; p.vocab = vocab;
+  embed_tokens_kernel<<<grid_for(static_cast<long long>(B) * T * (C / 8), 256, di->num_sms), 256, 0, stream>>>(p);
   count_launch();
   DCR_CUDA_CHECK(cudaGetLastError());
   return 0;

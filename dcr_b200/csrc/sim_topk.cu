@@ -75,7 +75,8 @@ struct SimParams {
 // mu (optional): a vector subtracted from every row before rounding (gallery centring: q.g = q.(g-mu) + q.mu and the
 // second term does not depend on g, so the ranking is unchanged while the bf16 rounding error now scales with the
 // SPREAD of the gallery instead of its norm).
-__global__ void to_bf16_rows_kernel(const float* __restrict__ x, int n, int d, int n_pad, int d_pad,
+template <int kIter>
+__global__ void __launch_bounds__(256) to_bf16_rows_kernel(const float* __restrict__ x, int n, int d, int n_pad, int d_pad,
                                     const float* __restrict__ mu, __nv_bfloat16* __restrict__ out,
                                     float* __restrict__ norm_hat, float* __restrict__ norm_res,
                                     float* __restrict__ norm_x, unsigned int* __restrict__ gmax,
@@ -91,32 +92,43 @@ __global__ void to_bf16_rows_kernel(const float* __restrict__ x, int n, int d, i
     __nv_bfloat16* o = out + static_cast<size_t>(row) * d_pad;
     if (row < n) {
       const float* xr = x + static_cast<size_t>(row) * d;
-      for (int c = lane * 4; c < d_pad; c += 128) {
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (c + 3 < d) {
-          v = *reinterpret_cast<const float4*>(xr + c);      // d % 4 == 0 and 16-byte aligned rows (checked on the host)
-          if (mu) {
-            const float4 m = *reinterpret_cast<const float4*>(mu + c);
-            v.x -= m.x; v.y -= m.y; v.z -= m.z; v.w -= m.w;
-          }
-          if (nu) {
-            const float4 u = *reinterpret_cast<const float4*>(nu + c);
-            s_bias = fma(static_cast<double>(u.x), static_cast<double>(v.x), s_bias);
-            s_bias = fma(static_cast<double>(u.y), static_cast<double>(v.y), s_bias);
-            s_bias = fma(static_cast<double>(u.z), static_cast<double>(v.z), s_bias);
-            s_bias = fma(static_cast<double>(u.w), static_cast<double>(v.w), s_bias);
-          }
+      // kIter float4 loads per lane issued back to back (the row's whole HBM read is in flight before the first value
+      // is used: the kernel is a pure stream, 12 B/element read+written, and was latency bound with one load at a time)
+      for (int c0 = 0; c0 < d_pad; c0 += 128 * kIter) {
+        float4 v[kIter];
+#pragma unroll
+        for (int i = 0; i < kIter; ++i) {
+          const int c = c0 + i * 128 + lane * 4;
+          v[i] = (c + 3 < d) ? *reinterpret_cast<const float4*>(xr + c) : make_float4(0.f, 0.f, 0.f, 0.f);   // d % 4 == 0
         }
-        const __nv_bfloat16 h0 = __float2bfloat16_rn(v.x), h1 = __float2bfloat16_rn(v.y);
-        const __nv_bfloat16 h2 = __float2bfloat16_rn(v.z), h3 = __float2bfloat16_rn(v.w);
-        const float f0 = __bfloat162float(h0), f1 = __bfloat162float(h1), f2 = __bfloat162float(h2), f3 = __bfloat162float(h3);
-        s_hat += f0 * f0 + f1 * f1 + f2 * f2 + f3 * f3;
-        s_res += (v.x - f0) * (v.x - f0) + (v.y - f1) * (v.y - f1) + (v.z - f2) * (v.z - f2) + (v.w - f3) * (v.w - f3);
-        s_x += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
-        uint2 pk;
-        pk.x = static_cast<uint32_t>(__bfloat16_as_ushort(h0)) | (static_cast<uint32_t>(__bfloat16_as_ushort(h1)) << 16);
-        pk.y = static_cast<uint32_t>(__bfloat16_as_ushort(h2)) | (static_cast<uint32_t>(__bfloat16_as_ushort(h3)) << 16);
-        *reinterpret_cast<uint2*>(o + c) = pk;
+#pragma unroll
+        for (int i = 0; i < kIter; ++i) {
+          const int c = c0 + i * 128 + lane * 4;
+          if (c >= d_pad) continue;
+          if (c + 3 < d) {
+            if (mu) {
+              const float4 m = *reinterpret_cast<const float4*>(mu + c);
+              v[i].x -= m.x; v[i].y -= m.y; v[i].z -= m.z; v[i].w -= m.w;
+            }
+            if (nu) {
+              const float4 u = *reinterpret_cast<const float4*>(nu + c);
+              s_bias = fma(static_cast<double>(u.x), static_cast<double>(v[i].x), s_bias);
+              s_bias = fma(static_cast<double>(u.y), static_cast<double>(v[i].y), s_bias);
+              s_bias = fma(static_cast<double>(u.z), static_cast<double>(v[i].z), s_bias);
+              s_bias = fma(static_cast<double>(u.w), static_cast<double>(v[i].w), s_bias);
+            }
+          }
+          const __nv_bfloat16 h0 = __float2bfloat16_rn(v[i].x), h1 = __float2bfloat16_rn(v[i].y);
+          const __nv_bfloat16 h2 = __float2bfloat16_rn(v[i].z), h3 = __float2bfloat16_rn(v[i].w);
+          const float f0 = __bfloat162float(h0), f1 = __bfloat162float(h1), f2 = __bfloat162float(h2), f3 = __bfloat162float(h3);
+          s_hat += f0 * f0 + f1 * f1 + f2 * f2 + f3 * f3;
+          s_res += (v[i].x - f0) * (v[i].x - f0) + (v[i].y - f1) * (v[i].y - f1) + (v[i].z - f2) * (v[i].z - f2) + (v[i].w - f3) * (v[i].w - f3);
+          s_x += v[i].x * v[i].x + v[i].y * v[i].y + v[i].z * v[i].z + v[i].w * v[i].w;
+          uint2 pk;
+          pk.x = static_cast<uint32_t>(__bfloat16_as_ushort(h0)) | (static_cast<uint32_t>(__bfloat16_as_ushort(h1)) << 16);
+          pk.y = static_cast<uint32_t>(__bfloat16_as_ushort(h2)) | (static_cast<uint32_t>(__bfloat16_as_ushort(h3)) << 16);
+          *reinterpret_cast<uint2*>(o + c) = pk;
+        }
       }
     } else {
       for (int c = lane * 2; c < d_pad; c += 64) *reinterpret_cast<uint32_t*>(o + c) = 0u;
@@ -851,8 +863,8 @@ __global__ void __launch_bounds__(128)
   float* ap = reinterpret_cast<float*>(ci + max_cand);                  // [max_cand] approximate scores
   int* kc = reinterpret_cast<int*>(ap + max_cand);                      // [max_cand] gallery rows of the survivors
   __shared__ int s_n, s_overflow, s_kept, s_nslots, s_off[kMaxSlotsPerQuery], s_cnt[kMaxSlotsPerQuery], s_slot[kMaxSlotsPerQuery];
-  __shared__ float s_thr, s_eps, s_qx, s_gn;
-  __shared__ double s_qmu;
+  __shared__ float s_thr, s_eps, s_qx, s_gn, s_ak;
+  __shared__ double s_qmu, s_kth;
   __shared__ BlockBest s_bb;
 
   // blockIdx.x indexes the (possibly compacted) query matrix the fused kernel saw; qrow is the caller's row
@@ -934,58 +946,52 @@ __global__ void __launch_bounds__(128)
   const int kk = min(k, n);
 
   // ---- prune by approximate score ----
-  for (int c = threadIdx.x; c < n; c += blockDim.x) sc[c] = static_cast<double>(ap[c]);
+  // A_k = k-th largest approximate score, found by rank counting (n is a few dozen: one pass, one barrier, instead of k
+  // block-wide arg-max rounds)
+  if (threadIdx.x == 0) s_ak = -INFINITY;
   __syncthreads();
-  double a_k = -INFINITY;
-  for (int round = 0; round < kk; ++round) {
-    double bs = -INFINITY;
-    long long bi = 0x7fffffffffffffffLL;
-    int bp = -1;
-    for (int c = threadIdx.x; c < n; c += blockDim.x)
-      if (sc[c] > -INFINITY && (bp < 0 || better(sc[c], c, bs, bi))) {
-        bs = sc[c];
-        bi = c;
-        bp = c;
-      }
-    block_argbest(bs, bi, bp, &s_bb, lane, warp);
-    if (bp < 0) break;
-    a_k = bs;
-    if (threadIdx.x == 0) sc[bp] = -INFINITY;
-    __syncthreads();
+  for (int c = threadIdx.x; c < n; c += blockDim.x) {
+    const float v = ap[c];
+    int rank = 0;
+    for (int j = 0; j < n; ++j) {
+      const float o = ap[j];
+      rank += (o > v) || (o == v && j < c);
+    }
+    if (rank == kk - 1) s_ak = v;
   }
-  const float cut = static_cast<float>(a_k) - 2.f * s_eps - 1e-6f * fabsf(static_cast<float>(a_k));
+  __syncthreads();
+  const float a_k = s_ak;
+  const float cut = a_k - 2.f * s_eps - 1e-6f * fabsf(a_k);
   for (int c = threadIdx.x; c < n; c += blockDim.x)
     if (n <= k || ap[c] >= cut) kc[atomicAdd(&s_kept, 1)] = ci[c];
   __syncthreads();
   const int m = s_kept;
 
-  // ---- exact scores of the survivors, then selection ----
+  // ---- exact scores of the survivors, then selection by (score desc, index asc): again by rank counting ----
   for (int c = warp; c < m; c += 4) {
     const double v = exact_dot_warp(qs, g + static_cast<size_t>(kc[c]) * d, d, lane);
     if (lane == 0) sc[c] = v;
   }
+  if (threadIdx.x == 0) s_kth = -INFINITY;
   __syncthreads();
-  double kth = -INFINITY;
   const int km = min(k, m);
-  for (int round = 0; round < km; ++round) {
-    double bs = -INFINITY;
-    long long bi = 0x7fffffffffffffffLL;
-    int bp = -1;
-    for (int c = threadIdx.x; c < m; c += blockDim.x)
-      if (kc[c] >= 0 && (bp < 0 || better(sc[c], kc[c], bs, bi))) {
-        bs = sc[c];
-        bi = kc[c];
-        bp = c;
-      }
-    block_argbest(bs, bi, bp, &s_bb, lane, warp);
-    if (threadIdx.x == 0) {
-      out_scores[static_cast<size_t>(qrow) * k + round] = static_cast<float>(bs);
-      out_idx[static_cast<size_t>(qrow) * k + round] = g_index_base + g_index_stride * bi;
-      kc[bp] = -1 - kc[bp];   // mark taken
+  for (int c = threadIdx.x; c < m; c += blockDim.x) {
+    const double v = sc[c];
+    const int iv = kc[c];
+    int rank = 0;
+    for (int j = 0; j < m; ++j) {
+      const double o = sc[j];
+      const int io = kc[j];
+      rank += (o > v) || (o == v && (io < iv || (io == iv && j < c)));   // candidate rows are distinct; j < c only for safety
     }
-    kth = bs;
-    __syncthreads();
+    if (rank < km) {
+      out_scores[static_cast<size_t>(qrow) * k + rank] = static_cast<float>(v);
+      out_idx[static_cast<size_t>(qrow) * k + rank] = g_index_base + g_index_stride * iv;
+      if (rank == km - 1) s_kth = v;
+    }
   }
+  __syncthreads();
+  const double kth = (km > 0) ? s_kth : -INFINITY;
   if (threadIdx.x == 0) {
     // certificate: every gallery row g that is not a candidate has approximate centred score <= s_thr, hence exact
     // score q.g <= s_thr + eps + q.mu
@@ -1487,12 +1493,13 @@ int sim_topk(const float* q, int nq, const float* g, int ng, int d, int k, long 
   }
   // q' = q - nu, g' = g - mu:  q.g = q'.g' + nu.g' + q.mu  -- the tensor cores see only the centred parts, nu.g' is a
   // per-gallery-row offset added to the accumulator columns, q.mu a per-query constant that cannot change the ranking
-  to_bf16_rows_kernel<<<conv_blocks, 256, 0, stream>>>(q, nq, d, pl.p0.nq_pad, pl.d_pad, centre ? nu : nullptr, qb, qnh,
-                                                      qnr, qnx, nullptr, nullptr, nullptr, qflag, nullptr);
+  // d_pad <= 256: 2 loads per lane cover the row; otherwise 4 per round (512 dims = one round)
+  auto convert = (pl.d_pad <= 256) ? to_bf16_rows_kernel<2> : to_bf16_rows_kernel<4>;
+  convert<<<conv_blocks, 256, 0, stream>>>(q, nq, d, pl.p0.nq_pad, pl.d_pad, centre ? nu : nullptr, qb, qnh, qnr, qnx, nullptr,
+                                           nullptr, nullptr, qflag, nullptr);
   count_launch();
-  to_bf16_rows_kernel<<<conv_blocks, 256, 0, stream>>>(g, ng, d, pl.ng_pad, pl.d_pad, centre ? mu : nullptr, gb, nullptr,
-                                                      nullptr, nullptr, gmax, centre ? nu : nullptr,
-                                                      centre ? bias : nullptr, nullptr, qflag);
+  convert<<<conv_blocks, 256, 0, stream>>>(g, ng, d, pl.ng_pad, pl.d_pad, centre ? mu : nullptr, gb, nullptr, nullptr, nullptr,
+                                           gmax, centre ? nu : nullptr, centre ? bias : nullptr, nullptr, qflag);
   count_launch();
   DCR_CUDA_CHECK(cudaGetLastError());
   const float* col_bias = centre ? bias : nullptr;

@@ -108,6 +108,89 @@ def generate_embeddings(net, image_folder: str, dump_path: Optional[str] = None,
     return feats, names
 
 
+def expand_tar_urls(patterns: Sequence[str]) -> List[str]:
+    """webdataset-style brace ranges: 'dir/{000000..000012}.tar' -> 13 paths (download_and_generate_embedding.py:85-87
+    builds exactly this pattern); plain paths and globs pass through."""
+    import glob
+    import re
+    out: List[str] = []
+    for pat in patterns:
+        m = re.search(r"\{(\d+)\.\.(\d+)\}", pat)
+        if m:
+            lo, hi, width = int(m.group(1)), int(m.group(2)), len(m.group(1))
+            out.extend(pat[:m.start()] + str(i).zfill(width) + pat[m.end():] for i in range(lo, hi + 1))
+        elif any(ch in pat for ch in "*?["):
+            out.extend(sorted(glob.glob(pat)))
+        else:
+            out.append(pat)
+    return out
+
+
+def iter_tar_samples(tar_paths: Sequence[str], size: int = 256):
+    """(uint8 [size,size,3] image, key) per webdataset sample, in shard order: the `jpg` member decoded with PIL and the
+    `key` field of the `json` member -- `.decode("pil").rename(image="jpg", json="json")` + `json_preproc`
+    (embedding_search/utils.py:52-62).  Resize(256) + centre crop happen here on uint8; ToTensor / Normalize are fused
+    into the network's first kernel."""
+    import io
+    import json
+    import tarfile
+
+    import numpy as np
+    from PIL import Image, ImageFile
+    from torchvision import transforms
+    ImageFile.LOAD_TRUNCATED_IMAGES = True                                   # utils.py:13
+    tf = transforms.Compose([transforms.Resize(size), transforms.CenterCrop(size)])
+    for path in tar_paths:
+        with tarfile.open(path, "r") as tar:
+            cur, img, key = None, None, None
+            for m in tar:
+                if not m.isfile():
+                    continue
+                base, _, ext = m.name.partition(".")
+                if base != cur:
+                    if cur is not None and img is not None:
+                        yield img, (key if key is not None else cur)
+                    cur, img, key = base, None, None
+                ext = ext.lower()
+                if ext in ("jpg", "jpeg"):
+                    pil = Image.open(io.BytesIO(tar.extractfile(m).read())).convert("RGB")
+                    img = torch.from_numpy(np.asarray(tf(pil)).copy())
+                elif ext == "json":
+                    key = json.loads(tar.extractfile(m).read().decode("utf-8")).get("key")
+            if cur is not None and img is not None:
+                yield img, (key if key is not None else cur)
+
+
+def generate_embeddings_from_tars(net, tars: Sequence[str], dump_path: Optional[str] = None, batch_size: int = 128,
+                                  chunk: int = 4096) -> Tuple[torch.Tensor, List[str]]:
+    """The `--tars` branch of get_dataloader (embedding_search/utils.py:56-62): webdataset shards streamed through the
+    descriptor network in chunks of `chunk` decoded images (bounded host memory), keys from the json members."""
+    from . import retrieval
+    paths = expand_tar_urls(tars)
+    feats, keys = [], []
+    buf = torch.empty((chunk, 256, 256, 3), dtype=torch.uint8)
+    if torch.cuda.is_available():
+        buf = buf.pin_memory()
+    n = 0
+    for img, key in iter_tar_samples(paths):
+        buf[n] = img
+        keys.append(key)
+        n += 1
+        if n == chunk:
+            feats.append(retrieval.extract_features(net, buf, batch_size).clone())
+            torch.cuda.synchronize()      # the pinned chunk is refilled next
+            n = 0
+    if n:
+        feats.append(retrieval.extract_features(net, buf[:n], batch_size).clone())
+        torch.cuda.synchronize()
+    if not feats:
+        raise _lib.DcrError(f"no jpg samples in {list(paths)}")
+    out = torch.cat(feats, dim=0)
+    if dump_path is not None:
+        write_embedding_pkl(os.path.join(dump_path, "embedding.pkl"), out, keys)
+    return out, keys
+
+
 # ---------------------------------------------------------------------------------------------------------------
 # search
 def merge_folder_best(best_scores: torch.Tensor, best_folder: torch.Tensor, best_row: torch.Tensor,
@@ -280,10 +363,10 @@ SSCD_FILES = {  # embedding_search/utils.py:18-23
 
 def embed_main(argv=None) -> int:
     args = build_embed_parser().parse_args(argv)
-    if args.parquet_fname or args.tars:
-        # img2dataset download and webdataset tar reading are data acquisition, outside the accelerated path
-        raise _lib.DcrError("only --image-folder input is supported (parquet download / tar shards are out of scope)")
-    if args.image_folder is None:
+    if args.parquet_fname and not args.skip_download:
+        # img2dataset download (download_and_generate_embedding.py:55-83) is data acquisition over the network
+        raise _lib.DcrError("--parquet-fname download is out of scope (no network): pass the downloaded shards with --tars")
+    if args.image_folder is None and not args.tars:
         raise RuntimeError("Either tar files or image folder must be specified")    # embedding_search/utils.py:66
     if args.pt_style != "sscd" or args.arch not in SSCD_FILES:
         raise NotImplementedError("This model type does not exist for SSCD")        # utils.py:25-27 (constructed there, raised here)
@@ -294,7 +377,10 @@ def embed_main(argv=None) -> int:
     torch.cuda.set_device(args.gpu)
     net = nets.build_sscd_resnet50(sd, max_batch=min(256, max(1, args.batch_size)), mean=IMAGENET_MEAN, std=IMAGENET_STD)
     start = time.time()
-    generate_embeddings(net, args.image_folder, args.dump_path, args.batch_size, args.workers)
+    if args.tars:
+        generate_embeddings_from_tars(net, args.tars, args.dump_path, args.batch_size)
+    else:
+        generate_embeddings(net, args.image_folder, args.dump_path, args.batch_size, args.workers)
     print(f"Embedding processing + dumping took: {time.time() - start:.2f}s")
     return 0
 

@@ -84,6 +84,13 @@ def frechet_distance(mu1, sigma1, mu2, sigma2, eps: float = 1e-6, device: Option
         ra = (v * torch.sqrt(w.clamp_min(0))) @ v.T            # a^(1/2)
         m = ra @ b @ ra
         ev = torch.linalg.eigvalsh((m + m.T) * 0.5)
+        # sqrtm(s1 s2) has the spectrum sqrt(ev): a negative eigenvalue is an imaginary component of the reference's
+        # covmean.  fid.py:187-191 tolerates |imag| <= 1e-3 on the diagonal and raises otherwise.
+        neg = ev[ev < 0]
+        if neg.numel() and torch.isfinite(neg).all():
+            worst = float(torch.sqrt(-neg.min()))
+            if worst > 1e-3:
+                raise ValueError("Imaginary component {}".format(worst))
         return torch.sqrt(ev.clamp_min(0)).sum()
 
     tr = tr_sqrt_product(s1, s2)
@@ -136,9 +143,16 @@ def load_resized(path: str, size: int = 299) -> torch.Tensor:
 _FID_WEIGHTS_FILE = "pt_inception-2015-12-05-6726825d.pth"       # metrics/inception.py:13 (downloaded there; a local file here)
 
 
-def _build_inception(weights, max_batch: int, precision: str) -> DcrNet:
+# InceptionV3.BLOCK_INDEX_BY_DIM (metrics/inception.py:22-28): the feature block each `dims` selects; blocks that end in
+# a feature map are average pooled to 1x1 (metrics/fid.py:130-133), which the builder's GAP op does
+_STOP_AFTER_BY_DIM = {64: "pool1", 192: "pool2", 768: "Mixed_6e", 2048: None}
+
+
+def _build_inception(weights, max_batch: int, precision: str, dims: int = 2048) -> DcrNet:
     import os
     from . import nets
+    if dims not in _STOP_AFTER_BY_DIM:
+        raise KeyError(dims)                                   # InceptionV3.BLOCK_INDEX_BY_DIM[dims], fid.py:245
     if isinstance(weights, DcrNet):
         return weights
     if isinstance(weights, dict):
@@ -149,7 +163,7 @@ def _build_inception(weights, max_batch: int, precision: str) -> DcrNet:
             raise FileNotFoundError(f"FID Inception weights not found: {path} (there is no network access to fetch "
                                     f"{_FID_WEIGHTS_FILE}; pass weights= or set DCR_FID_WEIGHTS)")
         sd = torch.load(path, map_location="cpu")
-    return nets.build_fid_inception(sd, max_batch=max_batch, precision=precision)
+    return nets.build_fid_inception(sd, max_batch=max_batch, precision=precision, stop_after=_STOP_AFTER_BY_DIM[dims])
 
 
 def compute_statistics_of_path(path: str, net: DcrNet, batch_size: int = 50) -> Tuple[np.ndarray, np.ndarray]:
@@ -163,16 +177,14 @@ def compute_statistics_of_path(path: str, net: DcrNet, batch_size: int = 50) -> 
 def calculate_fid_given_paths(paths, batch_size: int = 50, device=None, dims: int = 2048, num_workers: int = 1,
                               weights=None, precision: str = "fast") -> float:
     """metrics/fid.py:239-255.  `device` / `num_workers` are accepted for signature compatibility (the current CUDA
-    device is used; image decoding is sequential).  Only the pool3 features (dims = 2048, the reference's default and
-    the only block its callers request, diff_retrieval.py:597-600) are implemented."""
+    device is used; image decoding is sequential).  dims in {64, 192, 768, 2048} select the feature block as
+    InceptionV3.BLOCK_INDEX_BY_DIM does (metrics/inception.py:22-28); 2048 is what diff_retrieval.py:597-600 asks for."""
     import os
     for p in paths:
         if not os.path.exists(p):
             raise RuntimeError("Invalid path: %s" % p)                                       # fid.py:241-243
     print(dims)                                                                              # fid.py:244
-    if dims != 2048:
-        raise NotImplementedError("only dims=2048 (pool3, InceptionV3.BLOCK_INDEX_BY_DIM[2048]) is implemented")
-    net = _build_inception(weights, batch_size, precision)
+    net = _build_inception(weights, batch_size, precision, dims)
     m1, s1 = compute_statistics_of_path(paths[0], net, batch_size)
     m2, s2 = compute_statistics_of_path(paths[1], net, batch_size)
     return frechet_distance(m1, s1, m2, s2)
@@ -186,9 +198,7 @@ def save_fid_stats(paths, batch_size: int = 50, device=None, dims: int = 2048, n
         raise RuntimeError("Invalid path: %s" % paths[0])
     if os.path.exists(paths[1]):
         raise RuntimeError("Existing output file: %s" % paths[1])
-    if dims != 2048:
-        raise NotImplementedError("only dims=2048 (pool3) is implemented")
-    net = _build_inception(weights, batch_size, precision)
+    net = _build_inception(weights, batch_size, precision, dims)
     print(f"Saving statistics for {paths[0]}")
     m1, s1 = compute_statistics_of_path(paths[0], net, batch_size)
     np.savez_compressed(paths[1], mu=m1, sigma=s1)

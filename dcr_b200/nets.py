@@ -25,7 +25,7 @@ from . import _lib
 from .ops import prepare_conv_weight
 
 OP_IM2COL_U8, OP_CONV, OP_MAXPOOL, OP_AVGPOOL, OP_GEM, OP_GAP, OP_LAYERNORM, OP_VIT_TOKENS, OP_ATTENTION, \
-    OP_L2NORM_OUT, OP_STEM_S2D = range(11)
+    OP_L2NORM_OUT, OP_STEM_S2D, OP_EMBED = range(12)
 
 # fast/bf16: one bf16 plane, tensor cores.  parity/fp32: three planes (exact fp32 values), 6 tensor-core cross terms.
 # exact: three planes, products accumulated in float64 on the CUDA cores (correctly rounded fp32 layer outputs).
@@ -69,6 +69,12 @@ class DcrNet:
             r = self.lib.dcr_net_add_tensor(self.handle, rows_per_image, channels)
         if r < 0:
             raise _lib.DcrError(f"dcr_net_add_tensor: {_lib.last_error()}")
+        return r
+
+    def alias(self, src: int, rows_per_image: int, channels: int) -> int:
+        r = self.lib.dcr_net_alias_tensor(self.handle, src, rows_per_image, channels)
+        if r < 0:
+            raise _lib.DcrError(f"dcr_net_alias_tensor: {_lib.last_error()}")
         return r
 
     def param(self, t: torch.Tensor) -> int:
@@ -154,6 +160,22 @@ class DcrNet:
         return out
 
     __call__ = forward
+
+    @torch.no_grad()
+    def forward_tokens(self, ids: torch.Tensor) -> torch.Tensor:
+        """Text networks (first op EMBED): ids CUDA int32/int64 [n, T] -> fp32 [n, out_dim]."""
+        if not (isinstance(ids, torch.Tensor) and ids.is_cuda and ids.dim() == 2):
+            raise _lib.DcrError("forward_tokens expects a CUDA integer tensor [n, T]")
+        ids = ids.to(torch.int32).contiguous()
+        n = ids.shape[0]
+        out = torch.empty((n, self.out_dim), dtype=torch.float32, device=ids.device)
+        with torch.cuda.device(ids.device):
+            st = torch.cuda.current_stream().cuda_stream
+            for s in range(0, n, self.max_batch):
+                b = min(self.max_batch, n - s)
+                rc = self.lib.dcr_net_forward(self.handle, ids[s:s + b].data_ptr(), b, out[s:s + b].data_ptr(), st)
+                _lib.check(rc, "dcr_net_forward")
+        return out
 
 
 def _fold_bn(sd: Dict[str, torch.Tensor], prefix: str, eps: float):
@@ -428,6 +450,143 @@ def build_dino_vit(state_dict: Dict[str, torch.Tensor], max_batch: int = 64, pre
         net.set_output(tokens * dim)
         net.op(OP_LAYERNORM, [x, -1, tokens, dim, gamma, beta, 1, 1], [1e-6])     # every token row, [B, tokens * dim]
     net.tokens = tokens
+    return net
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# CLIP ViT-B/16 towers for the CLIP score (utils_ret.py:1046-1066: clip.load("ViT-B/16"), encode_image / encode_text)
+def _clip_blocks(net: DcrNet, sd, prefix: str, x: int, tokens: int, dim: int, causal: bool) -> int:
+    """clip/model.py ResidualAttentionBlock x N: x += attn(ln_1(x)); x += c_proj(QuickGELU(c_fc(ln_2(x)))); LayerNorm eps
+    1e-5, packed in_proj [q | k | v] (the same column order as the DINO qkv Linear), 64-dim heads."""
+    heads = dim // 64
+    i = 0
+    while f"{prefix}resblocks.{i}.ln_1.weight" in sd:
+        p = f"{prefix}resblocks.{i}."
+        t_ln = net.tensor(tokens, dim)
+        net.op(OP_LAYERNORM, [x, t_ln, tokens, dim, net.param_f32(sd[p + "ln_1.weight"]), net.param_f32(sd[p + "ln_1.bias"]), 1, 0], [1e-5])
+        t_qkv = net.tensor(tokens, 3 * dim)
+        net.conv(t_ln, t_qkv, tokens, 1, dim, sd[p + "attn.in_proj_weight"], bias=sd[p + "attn.in_proj_bias"])
+        t_att = net.tensor(tokens, dim)
+        net.op(OP_ATTENTION, [t_qkv, t_att, tokens, heads, 64, 1 if causal else 0], [64 ** -0.5])
+        net.flops_per_image += 4.0 * heads * tokens * tokens * 64
+        x2 = net.tensor(tokens, dim)
+        net.conv(t_att, x2, tokens, 1, dim, sd[p + "attn.out_proj.weight"], bias=sd[p + "attn.out_proj.bias"], residual=x)
+        t_ln2 = net.tensor(tokens, dim)
+        net.op(OP_LAYERNORM, [x2, t_ln2, tokens, dim, net.param_f32(sd[p + "ln_2.weight"]), net.param_f32(sd[p + "ln_2.bias"]), 1, 0], [1e-5])
+        hid = sd[p + "mlp.c_fc.weight"].shape[0]
+        t_h = net.tensor(tokens, hid)
+        net.conv(t_ln2, t_h, tokens, 1, dim, sd[p + "mlp.c_fc.weight"], bias=sd[p + "mlp.c_fc.bias"], act=3)
+        x3 = net.tensor(tokens, dim)
+        net.conv(t_h, x3, tokens, 1, hid, sd[p + "mlp.c_proj.weight"], bias=sd[p + "mlp.c_proj.bias"], residual=x2)
+        x = x3
+        i += 1
+    return x
+
+
+def build_clip_visual(state_dict: Dict[str, torch.Tensor], max_batch: int = 64, precision: str = "fast",
+                      mean: Sequence[float] = (0.5, 0.5, 0.5), std: Sequence[float] = (0.5, 0.5, 0.5),
+                      in_size: int = 256, crop: int = 224) -> DcrNet:
+    """`model.encode_image` of clip.load("ViT-B/16") (utils_ret.py:1048, :1056): conv1 patch embedding (no bias),
+    class + positional embeddings, ln_pre, the transformer, ln_post on the class token, @ proj -> [n, 512].
+    gen_clipscore feeds the loader's tensors as they are, i.e. the 0.5/0.5-normalised 224 crop (diff_retrieval.py:325-330)
+    -- hence the default mean/std; pass CLIP's own statistics when the caller preprocesses with clip's transform."""
+    sd = {k: v.detach().cpu().float() for k, v in state_dict.items()}
+    w = sd["visual.conv1.weight"]
+    dim, patch = w.shape[0], w.shape[-1]
+    grid = crop // patch
+    n_patch, tokens = grid * grid, grid * grid + 1
+    if sd["visual.positional_embedding"].shape[0] != tokens:
+        raise _lib.DcrError("CLIP visual tower: positional embedding does not match the input size")
+    net = DcrNet(max_batch, precision)
+    net.in_shape, net.net_input = (in_size, in_size), (crop, crop)
+    off = (in_size - crop) // 2
+    k_pad = first_conv_k_pad(patch, patch)
+    t_cols = net.tensor(n_patch, k_pad)
+    net.op(OP_IM2COL_U8, [t_cols, in_size, in_size, off, off, crop, crop, patch, patch, patch, 0, k_pad],
+           list(mean) + list(std) + [1.0, 0.0])
+    t_patch = net.tensor(n_patch, dim)
+    net.conv(t_cols, t_patch, n_patch, 1, k_pad, _first_conv_weight(w, k_pad))
+    x0 = net.tensor(tokens, dim)
+    net.op(OP_VIT_TOKENS, [t_patch, x0, n_patch, dim, net.param_f32(sd["visual.class_embedding"].reshape(-1)),
+                           net.param_f32(sd["visual.positional_embedding"].reshape(tokens, dim))])
+    x = net.tensor(tokens, dim)
+    net.op(OP_LAYERNORM, [x0, x, tokens, dim, net.param_f32(sd["visual.ln_pre.weight"]), net.param_f32(sd["visual.ln_pre.bias"]), 1, 0], [1e-5])
+    x = _clip_blocks(net, sd, "visual.transformer.", x, tokens, dim, causal=False)
+    t_cls = net.tensor(1, dim)
+    net.op(OP_LAYERNORM, [x, t_cls, 1, dim, net.param_f32(sd["visual.ln_post.weight"]), net.param_f32(sd["visual.ln_post.bias"]), tokens, 0], [1e-5])
+    proj = sd["visual.proj"]                                   # [dim, embed]: x @ proj == Linear with weight proj.T
+    net.set_output(proj.shape[1])
+    net.conv(t_cls, -1, 1, 1, dim, proj.T.contiguous(), to_output=True)
+    net.tokens = tokens
+    return net
+
+
+def build_clip_text(state_dict: Dict[str, torch.Tensor], max_batch: int = 64, precision: str = "fast") -> DcrNet:
+    """`model.encode_text` (utils_ret.py:1057) up to the per-token projection: token + positional embeddings, the causal
+    transformer, ln_final on every token, @ text_projection -> float32 [n, 77 * 512]; the caller picks the row of the
+    end-of-text token (`x[arange, text.argmax(-1)]`, clip/model.py).  Input: int32 token ids [n, 77] (DcrNet.forward_tokens)."""
+    sd = {k: v.detach().cpu().float() for k, v in state_dict.items()}
+    table = sd["token_embedding.weight"]
+    vocab, dim = table.shape
+    ctx = sd["positional_embedding"].shape[0]
+    net = DcrNet(max_batch, precision)
+    x = net.tensor(ctx, dim)
+    net.op(OP_EMBED, [x, ctx, dim, net.param_f32(table), net.param_f32(sd["positional_embedding"]), vocab])
+    x = _clip_blocks(net, sd, "transformer.", x, ctx, dim, causal=True)
+    t_ln = net.tensor(ctx, dim)
+    net.op(OP_LAYERNORM, [x, t_ln, ctx, dim, net.param_f32(sd["ln_final.weight"]), net.param_f32(sd["ln_final.bias"]), 1, 0], [1e-5])
+    proj = sd["text_projection"]
+    net.set_output(ctx * proj.shape[1])
+    net.conv(t_ln, -1, ctx, 1, dim, proj.T.contiguous(), to_output=True)
+    net.tokens, net.context_length, net.embed_dim = ctx, ctx, proj.shape[1]
+    return net
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# VGG-16 fc2 features for Improved Precision & Recall (metrics/ipr.py:37-41, 124-147)
+_VGG16_CFG = (64, 64, "M", 128, 128, "M", 256, 256, 256, "M", 512, 512, 512, "M", 512, 512, 512, "M")
+
+
+def build_vgg16_fc2(state_dict: Dict[str, torch.Tensor], max_batch: int = 50, precision: str = "fast",
+                    mean: Sequence[float] = (0.485, 0.456, 0.406), std: Sequence[float] = (0.229, 0.224, 0.225)) -> DcrNet:
+    """torchvision VGG-16 up to classifier[3] (the 4096-d `fc2` features of metrics/ipr.py:139-141:
+    `vgg16.features(x)` -> view(-1, 7*7*512) -> `classifier[:4]` = Linear, ReLU, Dropout(eval: identity), Linear).
+    Input: uint8 [n,224,224,3] (the caller resizes with PIL as get_custom_loader does, ipr.py:300-306; ToTensor +
+    ImageNet Normalize are fused into the first kernel) or the already transformed float32 [n,3,224,224]."""
+    sd = _strip({k: v.detach().cpu() for k, v in state_dict.items()}, ["module."])
+    net = DcrNet(max_batch, precision)
+    net.in_shape = (224, 224)
+    net.net_input = (224, 224)
+    h = 224
+    k_pad = first_conv_k_pad(3, 3)
+    t_cols = net.tensor(h * h, k_pad)
+    net.op(OP_IM2COL_U8, [t_cols, 224, 224, 0, 0, 224, 224, 3, 3, 1, 1, k_pad], list(mean) + list(std) + [1.0, 0.0])
+    w0 = sd["features.0.weight"]
+    t = net.tensor(h * h, 64)
+    net.conv(t_cols, t, h * h, 1, k_pad, _first_conv_weight(w0, k_pad), bias=sd["features.0.bias"], act=1)
+    net.flops_per_image += 2.0 * h * h * 64 * (27 - k_pad)
+    c, li = 64, 2                       # features.0 = conv, .1 = ReLU
+    for v in _VGG16_CFG[1:]:
+        if v == "M":
+            ho = h // 2
+            o = net.tensor(ho * ho, c)
+            net.op(OP_MAXPOOL, [t, o, h, h, c, 2, 2, 0, 0])
+            t, h = o, ho
+            li += 1
+        else:
+            o = net.tensor(h * h, v)
+            net.conv(t, o, h, h, c, sd[f"features.{li}.weight"], pad=(1, 1), bias=sd[f"features.{li}.bias"], act=1)
+            t, c = o, v
+            li += 2
+    # before_fc.view(-1, 7*7*512) flattens NCHW as (c, h, w); the activation here is NHWC -> permute fc1's columns
+    flat = net.alias(t, 1, h * h * c)
+    w1 = sd["classifier.0.weight"].detach().float()
+    w1 = w1.reshape(w1.shape[0], c, h * h).permute(0, 2, 1).reshape(w1.shape[0], h * h * c).contiguous()
+    t_fc1 = net.tensor(1, w1.shape[0])
+    net.conv(flat, t_fc1, 1, 1, h * h * c, w1, bias=sd["classifier.0.bias"], act=1)
+    w2 = sd["classifier.3.weight"]
+    net.set_output(w2.shape[0])
+    net.conv(t_fc1, -1, 1, 1, w1.shape[0], w2, bias=sd["classifier.3.bias"], to_output=True)
     return net
 
 

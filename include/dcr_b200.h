@@ -140,14 +140,18 @@ int dcr_conv2d_bf16(const void* x, int x_planes, int64_t x_plane_stride, int B, 
  *   5 GAP        i: in_t, out_t|-1, HW, C, to_output     (global average pool)
  *   6 LAYERNORM  i: in_t, out_t|-1, rows_out_per_image, C, gamma_param, beta_param, in_row_stride(rows), to_output   f: eps
  *   7 VIT_TOKENS i: patch_t, out_t, n_patches, C, cls_param, pos_param
- *   8 ATTENTION  i: qkv_t, out_t, T, heads, head_dim      f: scale
+ *   8 ATTENTION  i: qkv_t, out_t, T, heads, head_dim [, causal(0/1)]      f: scale
  *   9 L2NORM_OUT f: eps        (row-normalise the fp32 output buffer in place)
  *  10 STEM_S2D   i: out_t, IH, IW, crop_y, crop_x, H, W [, RH, RW]     f: mean[3], std[3], post_scale, post_shift [, rscale]
  *                (optional RH, RW, rscale: the normalised crop is first resized to RH x RW with torch's bilinear
  *                 F.interpolate(scale_factor=s, align_corners=False) arithmetic, rscale = float(1/s); utils_ret.py:676-698)
  *                uint8 HWC input -> normalised, zero-padded 2x2 space-to-depth tensor [(H+6)/2, (W+6)/2, 16] of the
  *                7x7/2/pad-3 stem; the following CONV passes two extra ints (elements per stored pixel, stored pixels
- *                per row) to read 4 adjacent stored pixels as one 64-channel pixel (kh = 4, kw = 1). */
+ *                per row) to read 4 adjacent stored pixels as one 64-channel pixel (kh = 4, kw = 1).
+ *  11 EMBED      i: out_t, T, C, table_param, pos_param, vocab
+ *                the network input is DEVICE int32 token ids [n, T] (pass them as the `images` pointer of dcr_net_forward):
+ *                rows table[id] + pos[t]  (CLIP text tower; utils_ret.py:1046-1066 `model.encode_text`)
+ * CONV act: 0 none, 1 ReLU, 2 GELU (erf), 3 QuickGELU x*sigmoid(1.702x). */
 typedef struct dcr_net dcr_net;
 int dcr_net_create(int max_batch, int planes, dcr_net** out);
 /* on != 0: every CONV op accumulates its products in float64 on the CUDA cores (correctly rounded fp32 layer outputs,
@@ -155,6 +159,8 @@ int dcr_net_create(int max_batch, int planes, dcr_net** out);
 int dcr_net_set_exact(dcr_net* net, int on);
 void dcr_net_destroy(dcr_net* net);
 int dcr_net_add_tensor(dcr_net* net, int64_t rows_per_image, int channels);
+/* another (rows_per_image, channels) factorisation of an existing tensor's buffer (flatten in front of a Linear layer) */
+int dcr_net_alias_tensor(dcr_net* net, int src_tensor, int64_t rows_per_image, int channels);
 /* copies `bytes` from HOST memory to a new device buffer */
 int dcr_net_add_param(dcr_net* net, const void* host_data, size_t bytes);
 int dcr_net_set_output(dcr_net* net, int dim);

@@ -110,6 +110,24 @@ def make_fid_inception(seed):
     print("inception", seed, y.shape, float(y.abs().mean()))
 
 
+def make_ipr(seed):
+    """metrics/ipr.py's own numpy functions (compute_pairwise_distances, distances2radii, compute_metric, realism) on
+    seeded feature sets; the VGG-16 extractor needs CUDA in the reference (ipr.py:139 `.cuda()`) and is not run."""
+    sys.path.insert(0, REF)
+    ipr = _load("ref_ipr", os.path.join(REF, "metrics", "ipr.py"))
+    rng = np.random.default_rng(900 + seed)
+    ref = (rng.standard_normal((300, 64)) * 3 + 1).astype(np.float32)
+    sub = (rng.standard_normal((200, 64)) * 3.3 + 1.2).astype(np.float32)
+    man_ref = ipr.Manifold(ref, ipr.distances2radii(ipr.compute_pairwise_distances(ref), k=3))
+    man_sub = ipr.Manifold(sub, ipr.distances2radii(ipr.compute_pairwise_distances(sub), k=3))
+    precision = ipr.compute_metric(man_ref, sub)
+    recall = ipr.compute_metric(man_sub, ref)
+    real = np.array([ipr.realism(man_ref, sub[i:i + 1]) for i in range(8)])
+    np.savez_compressed(os.path.join(HERE, f"ipr_seed{seed}.npz"), seed=seed, radii_ref=man_ref.radii, radii_sub=man_sub.radii,
+                        precision=precision, recall=recall, realism=real)
+    print("ipr", seed, precision, recall, real[:3])
+
+
 if __name__ == "__main__":
     torch.manual_seed(0)
     for s in (0, 1):
@@ -117,3 +135,4 @@ if __name__ == "__main__":
     make_dino_other_size(0)
     make_dino_variants(0)
     make_fid_inception(0)
+    make_ipr(0)

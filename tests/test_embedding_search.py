@@ -155,3 +155,35 @@ def test_generate_embeddings_imagenet_norm(tmp_path):
     got = feats.cpu().numpy()
     cos = (got * ref).sum(1) / (np.linalg.norm(got, axis=1) * np.linalg.norm(ref, axis=1))
     assert cos.min() > 0.999, cos
+
+
+def test_webdataset_tar_reader(tmp_path):
+    """embedding_search/utils.py:52-62: samples of a webdataset shard = members sharing a basename; the image is the `jpg`
+    member, the index the `key` field of the `json` member; 'x/{000000..000001}.tar' expands to the shard list."""
+    import io
+    import json
+    import tarfile
+
+    import numpy as np
+    from PIL import Image
+    from dcr_b200 import embedding_search as es
+    rng = np.random.default_rng(0)
+    want = []
+    for shard in range(2):
+        with tarfile.open(tmp_path / f"{shard:06d}.tar", "w") as tar:
+            for i in range(3):
+                base = f"{shard:05d}{i:04d}"
+                arr = rng.integers(0, 255, (300, 280, 3), dtype=np.uint8)
+                buf = io.BytesIO()
+                Image.fromarray(arr).save(buf, format="JPEG")
+                for ext, payload in (("jpg", buf.getvalue()), ("json", json.dumps({"key": base, "url": "u"}).encode()),
+                                     ("txt", b"caption")):
+                    info = tarfile.TarInfo(f"{base}.{ext}")
+                    info.size = len(payload)
+                    tar.addfile(info, io.BytesIO(payload))
+                want.append(base)
+    urls = es.expand_tar_urls([str(tmp_path) + "/{000000..000001}.tar"])
+    assert urls == [str(tmp_path / "000000.tar"), str(tmp_path / "000001.tar")]
+    got = list(es.iter_tar_samples(urls))
+    assert [k for _, k in got] == want
+    assert all(tuple(img.shape) == (256, 256, 3) and img.dtype == torch.uint8 for img, _ in got)

@@ -132,3 +132,42 @@ def test_calculate_fid_given_paths_mirror(tmp_path, capsys):
         dfid.calculate_fid_given_paths([str(tmp_path / "missing"), str(b)], 8, "cuda", 2048, weights=net)
     with pytest.raises(FileNotFoundError):
         dfid.calculate_fid_given_paths([str(tmp_path / "real"), str(b)], 8, "cuda", 2048, weights=str(tmp_path / "none.pth"))
+
+
+@pytest.mark.parametrize("dims,stop", [(64, "pool1"), (192, "pool2"), (768, "Mixed_6e")])
+def test_fid_feature_blocks_by_dims(dims, stop, tmp_path):
+    """InceptionV3.BLOCK_INDEX_BY_DIM (metrics/inception.py:22-28): dims 64 / 192 / 768 select earlier blocks, average
+    pooled to 1x1 (metrics/fid.py:130-133); calculate_fid_given_paths(dims=...) builds the matching network."""
+    from PIL import Image
+    sd = om.make_inception_state_dict(0)
+    net = dfid._build_inception(sd, 4, "exact", dims)
+    assert net.out_dim == dims
+    img = _imgs(3, 30 + dims)
+    ref = om.fid_inception_forward(sd, om.fid_preprocess(img), stop_after=stop)
+    got = net(img.cuda()).cpu()
+    assert (got - ref).abs().max().item() < 3e-5 * max(1.0, ref.abs().max().item())
+    if dims == 64:      # the path-level entry with a non-default dims, on PNG folders
+        for name, seed in (("real", 1), ("gen", 2)):
+            d = tmp_path / name
+            d.mkdir()
+            for i, im in enumerate(_imgs(70, seed)):
+                Image.fromarray(im.numpy()).save(d / f"{i}.png")
+        val = dfid.calculate_fid_given_paths([str(tmp_path / "real"), str(tmp_path / "gen")], 50, "cuda", 64, 1, weights=sd,
+                                             precision="exact")
+        acts = [om.fid_inception_forward(sd, om.fid_preprocess(dfid.load_resized(str(tmp_path / n))), stop_after="pool1").numpy()
+                for n in ("real", "gen")]
+        want = ofid.frechet_distance(*ofid.activation_statistics(acts[0]), *ofid.activation_statistics(acts[1]))
+        assert abs(val - want) < 1e-4 * max(1.0, abs(want)), (val, want)
+    with pytest.raises(KeyError):
+        dfid._build_inception(sd, 4, "fast", 100)
+
+
+def test_frechet_raises_on_imaginary_component():
+    """metrics/fid.py:187-191: a covariance product with a clearly negative eigenvalue has no real square root."""
+    rng = np.random.default_rng(0)
+    a = rng.standard_normal((8, 8))
+    s1 = a @ a.T + np.eye(8)
+    s2 = -np.eye(8)                                    # not a covariance: sqrtm(s1 s2) is purely imaginary
+    with pytest.raises(ValueError, match="Imaginary component"):
+        dfid.frechet_distance(np.zeros(8), s1, np.zeros(8), s2)
+    assert dfid.frechet_distance(np.zeros(8), s1, np.zeros(8), s1) < 1e-8

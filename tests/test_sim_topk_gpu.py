@@ -184,4 +184,4 @@ def test_splitloss_cross_matches_oracle(nq, ng, d, c, k):
     assert np.array_equal(i.cpu().numpy(), oi)
     np.testing.assert_allclose(v.cpu().numpy(), ov, rtol=0, atol=1e-6)
     with pytest.raises(similarity._lib.DcrError):
-        similarity.sim_topk_split(q.cuda(), g.cuda(), 10, 8, cross=True) if d % 8 == 0 else similarity.sim_topk_split(q.cuda(), g.cuda(), 16, c, cross=True)
+        similarity.sim_topk_split(q.cuda(), g.cuda(), k, 7, cross=True)        # 7 does not divide d
