@@ -103,6 +103,15 @@ int attention(const __nv_bfloat16* qkv, long long qkv_plane_stride, __nv_bfloat1
 int embed_tokens(const int* ids, int B, int T, int C, const float* table, int vocab, const float* pos, __nv_bfloat16* out,
                  long long out_plane_stride, int planes, cudaStream_t stream);
 
+// ---- fused ResNet stem (stem_fused.cu): overlapping-window (Toeplitz) A operand, fast mode ------------------------------
+int stem_fused_pitch(int out_w);                              // units (16-byte pixels) per stored pair-row
+long long stem_fused_plane_units(int out_h, int out_w);       // units per column-parity plane and image (incl. slack)
+int stem_rows(const uint8_t* img, const float* img_f32, int B, int IH, int IW, int crop_y, int crop_x, int H, int W, int RH, int RW,
+              float rscale, const float* mean3, const float* std3, float post_scale, float post_shift, __nv_bfloat16* out,
+              cudaStream_t stream);
+int stem_conv(const __nv_bfloat16* planes, int B, int OH, int OW, const __nv_bfloat16* weight, const float* scale, const float* bias,
+              __nv_bfloat16* out, cudaStream_t stream);
+
 // ---- network executor (net.cu) ------------------------------------------------------------------------------------
 enum NetOpKind {
   NET_OP_IM2COL_U8 = 0,
@@ -117,7 +126,9 @@ enum NetOpKind {
   NET_OP_L2NORM_OUT = 9,
   NET_OP_STEM_S2D = 10,
   NET_OP_EMBED = 11,
-  NET_OP_COUNT = 12
+  NET_OP_STEM_ROWS = 12,
+  NET_OP_STEM_CONV = 13,
+  NET_OP_COUNT = 14
 };
 struct Net;
 int net_create(int max_batch, int planes, Net** out);

@@ -167,6 +167,14 @@ int net_add_op(Net* n, int kind, const int* iargs, int ni, const float* fargs, i
       DCR_REQUIRE(ni == 6 && tensor_ok(op.i[0], false) && param_ok(op.i[3], false) && param_ok(op.i[4], false), "embed op: bad args");
       break;
     case NET_OP_L2NORM_OUT: DCR_REQUIRE(nf == 1, "l2norm op: bad args"); break;
+    case NET_OP_STEM_ROWS:
+      DCR_REQUIRE(((ni == 7 && nf == 8) || (ni == 9 && nf == 9)) && tensor_ok(op.i[0], false) && n->planes == 1, "stem_rows op: bad args");
+      break;
+    case NET_OP_STEM_CONV:
+      DCR_REQUIRE(ni == 7 && tensor_ok(op.i[0], false) && tensor_ok(op.i[1], false) && param_ok(op.i[4], false) &&
+                      param_ok(op.i[5], true) && param_ok(op.i[6], true) && n->planes == 1,
+                  "stem_conv op: bad args");
+      break;
     default: break;
   }
   n->ops.push_back(op);
@@ -234,6 +242,23 @@ int net_forward(Net* n, const uint8_t* images, int B, float* out, cudaStream_t s
         rc = stem_s2d_u8(images, B, f32 ? a[5] : a[1], f32 ? a[6] : a[2], f32 ? 0 : a[3], f32 ? 0 : a[4], a[5], a[6], &op.f[0],
                          &op.f[3], op.f[6], op.f[7], t.ptr, t.plane_stride, P, stream, a[7], a[8], op.f[8],
                          images_f32);   // unset arguments are zero = no resizing
+        break;
+      }
+      case NET_OP_STEM_ROWS: {
+        NetTensor& t = n->tensors[a[0]];
+        rc = stem_rows(images, images_f32, B, f32 ? a[5] : a[1], f32 ? a[6] : a[2], f32 ? 0 : a[3], f32 ? 0 : a[4], a[5], a[6], a[7],
+                       a[8], op.f[8], &op.f[0], &op.f[3], op.f[6], op.f[7], t.ptr, stream);
+        break;
+      }
+      case NET_OP_STEM_CONV: {
+        const NetTensor& in = n->tensors[a[0]];
+        NetTensor& o = n->tensors[a[1]];
+        DCR_REQUIRE(in.rows_per_image == 2 * stem_fused_plane_units(a[2], a[3]) && in.C == 8 && o.C == 64 &&
+                        o.rows_per_image == static_cast<long long>(a[2]) * a[3],
+                    "stem_conv op: tensor shapes do not match the %d x %d output", a[2], a[3]);
+        rc = stem_conv(in.ptr, B, a[2], a[3], static_cast<const __nv_bfloat16*>(n->params[a[4]]),
+                       a[5] >= 0 ? static_cast<const float*>(n->params[a[5]]) : nullptr,
+                       a[6] >= 0 ? static_cast<const float*>(n->params[a[6]]) : nullptr, o.ptr, stream);
         break;
       }
       case NET_OP_CONV: {

@@ -25,10 +25,13 @@ from . import _lib
 from .ops import prepare_conv_weight
 
 OP_IM2COL_U8, OP_CONV, OP_MAXPOOL, OP_AVGPOOL, OP_GEM, OP_GAP, OP_LAYERNORM, OP_VIT_TOKENS, OP_ATTENTION, \
-    OP_L2NORM_OUT, OP_STEM_S2D, OP_EMBED = range(12)
+    OP_L2NORM_OUT, OP_STEM_S2D, OP_EMBED, OP_STEM_ROWS, OP_STEM_CONV = range(14)
 
 # fast/bf16: one bf16 plane, tensor cores.  parity/fp32: three planes (exact fp32 values), 6 tensor-core cross terms.
 # exact: three planes, products accumulated in float64 on the CUDA cores (correctly rounded fp32 layer outputs).
+# "s2d": 7x7/2 stem as a 4x4 window convolution over a space-to-depth tensor (conv_gemm.cu, every mode);
+# "toeplitz": fused stem kernel with overlapping-window operand descriptors (stem_fused.cu, fast mode)
+DEFAULT_STEM = "s2d"
 PRECISION_PLANES = {"fast": 1, "bf16": 1, "parity": 3, "fp32": 3, "bf16x3": 2, "exact": 3}
 
 
@@ -213,6 +216,24 @@ def _stem_s2d_weight(w: torch.Tensor) -> torch.Tensor:
     return out
 
 
+def _stem_toeplitz_weight(w: torch.Tensor) -> torch.Tensor:
+    """[N,3,7,7] -> [N, 256] for csrc/stem_fused.cu: k = ((a*2 + e)*4 + b)*8 + i*3 + c holds w[n, c, 2a+i, 2b+e]
+    (a, b: filter row / column pair, i, e: row / column parity; zero where 2a+i or 2b+e exceeds 6 and for the two
+    padding channels of every 8-channel unit)."""
+    n = w.shape[0]
+    out = torch.zeros((n, 256), dtype=torch.float32)
+    wf = w.detach().float()
+    for a in range(4):
+        for e in range(2):
+            for b in range(4):
+                for i in range(2):
+                    r, s = 2 * a + i, 2 * b + e
+                    if r < 7 and s < 7:
+                        k0 = ((a * 2 + e) * 4 + b) * 8 + i * 3
+                        out[:, k0:k0 + 3] = wf[:, :, r, s]
+    return out
+
+
 def first_conv_k_pad(kh: int, kw: int) -> int:
     """K of the im2col rows the IM2COL_U8 op emits: each filter row padded to ceil8(3*kw), total padded to 64."""
     rp = (3 * kw + 7) // 8 * 8
@@ -254,7 +275,8 @@ def _dense_from_grouped(w: torch.Tensor, c_in: int) -> torch.Tensor:
 def build_sscd_resnet50(state_dict: Dict[str, torch.Tensor], max_batch: int = 64, precision: str = "fast",
                         mean: Sequence[float] = (0.5, 0.5, 0.5), std: Sequence[float] = (0.5, 0.5, 0.5),
                         in_size: int = 256, crop: int = 224, gem_p: float = 3.0, gem_eps: float = 1e-6,
-                        l2_normalize: bool = True, scale_factor: Optional[float] = None) -> DcrNet:
+                        l2_normalize: bool = True, scale_factor: Optional[float] = None,
+                        stem: Optional[str] = None) -> DcrNet:
     """state_dict keys: torchvision ResNet names, optionally prefixed 'backbone.' / 'module.'; head Linear under
     'embeddings.1' (SSCD), 'fc' or 'head'.  mean/std: (0.5, 0.5) for diff_retrieval.py:329, ImageNet statistics for
     embedding_search/utils.py:37-39.
@@ -292,12 +314,27 @@ def build_sscd_resnet50(state_dict: Dict[str, torch.Tensor], max_batch: int = 64
     # horizontally adjacent 16-channel pixels as one 64-channel pixel through an overlapping-window tensor map
     s = (crop + 2 * 3 - 7) // 2 + 1   # 112
     u = (crop + 6) // 2               # 115 stored rows / pixels per row
-    t_z = net.tensor(u * u, 16)
-    net.op(OP_STEM_S2D, [t_z, in_size, in_size, off, off, src_crop, src_crop] + stem_i, list(mean) + list(std) + [1.0, 0.0] + stem_f)
     sc, bi = _fold_bn(sd, "bn1", eps)
     t_stem = net.tensor(s * s, 64)
-    net.conv(t_z, t_stem, u, u - 3, 64, _stem_s2d_weight(sd["conv1.weight"]), scale=sc, bias=bi, act=1, window=(16, u))
-    net.flops_per_image += 2.0 * s * s * 64 * (147 - 256)   # count the real 147-tap work, not the zero padding
+    if stem is None:
+        stem = DEFAULT_STEM if (net.planes == 1 and sd["conv1.weight"].shape[0] == 64) else "s2d"
+    if stem == "toeplitz":
+        # fused stem (csrc/stem_fused.cu): the input is stored once as two column-parity planes of 16-byte pixels and the
+        # tensor cores read overlapping windows of it -- each pixel enters shared memory ~1.7 times instead of 16
+        if net.planes != 1 or sd["conv1.weight"].shape[0] != 64:
+            raise _lib.DcrError("stem='toeplitz' needs the one-plane (fast) mode and a 64-channel stem")
+        units = int(net.lib.dcr_stem_plane_units(s, s))
+        t_rows = net.tensor(2 * units, 8)
+        net.op(OP_STEM_ROWS, [t_rows, in_size, in_size, off, off, src_crop, src_crop] + stem_i,
+               list(mean) + list(std) + [1.0, 0.0] + stem_f)
+        w_id = net.param(_stem_toeplitz_weight(sd["conv1.weight"]).to(torch.bfloat16))
+        net.op(OP_STEM_CONV, [t_rows, t_stem, s, s, w_id, net.param_f32(sc), net.param_f32(bi)])
+        net.flops_per_image += 2.0 * s * s * 64 * 147
+    else:
+        t_z = net.tensor(u * u, 16)
+        net.op(OP_STEM_S2D, [t_z, in_size, in_size, off, off, src_crop, src_crop] + stem_i, list(mean) + list(std) + [1.0, 0.0] + stem_f)
+        net.conv(t_z, t_stem, u, u - 3, 64, _stem_s2d_weight(sd["conv1.weight"]), scale=sc, bias=bi, act=1, window=(16, u))
+        net.flops_per_image += 2.0 * s * s * 64 * (147 - 256)   # count the real 147-tap work, not the zero padding
     hw = (s + 2 - 3) // 2 + 1         # 56
     t = net.tensor(hw * hw, 64)
     net.op(OP_MAXPOOL, [t_stem, t, s, s, 64, 3, 2, 1, 0])

@@ -151,6 +151,12 @@ int dcr_conv2d_bf16(const void* x, int x_planes, int64_t x_plane_stride, int B, 
  *  11 EMBED      i: out_t, T, C, table_param, pos_param, vocab
  *                the network input is DEVICE int32 token ids [n, T] (pass them as the `images` pointer of dcr_net_forward):
  *                rows table[id] + pos[t]  (CLIP text tower; utils_ret.py:1046-1066 `model.encode_text`)
+ *  12 STEM_ROWS  i: out_t, IH, IW, crop_y, crop_x, H, W [, RH, RW]     f: as STEM_S2D
+ *                uint8 HWC (or fp32 NCHW) input -> the two column-parity planes of 16-byte pixel units the fused stem
+ *                kernel reads through overlapping-window descriptors (csrc/stem_fused.cu); out_t has
+ *                2 * dcr_stem_plane_units(H/2, W/2) rows of 8 channels per image.  One-plane (fast) networks only.
+ *  13 STEM_CONV  i: planes_t, out_t, OH, OW, w_param ([64][256] bf16, k = ((a*2+e)*4+b)*8 + i*3+c), scale_param|-1, bias_param|-1
+ *                7x7/2/pad-3 convolution + BN + ReLU -> NHWC [OH*OW, 64]
  * CONV act: 0 none, 1 ReLU, 2 GELU (erf), 3 QuickGELU x*sigmoid(1.702x). */
 typedef struct dcr_net dcr_net;
 int dcr_net_create(int max_batch, int planes, dcr_net** out);
@@ -167,6 +173,8 @@ int dcr_net_set_output(dcr_net* net, int dim);
 int dcr_net_add_op(dcr_net* net, int kind, const int* iargs, int n_iargs, const float* fargs, int n_fargs);
 /* images: DEVICE uint8 [n, IH, IW, 3]; out: DEVICE fp32 [n, dim]; n <= max_batch */
 int dcr_net_forward(dcr_net* net, const uint8_t* images, int n, float* out, void* stream);
+/* units (16-byte pixels) per image and plane of the STEM_ROWS tensor for an OH x OW stem output (includes read slack) */
+int64_t dcr_stem_plane_units(int out_h, int out_w);
 /* Same network, fed with what the reference's own loop feeds `model(samples)` (utils_ret.py:751; embedding_search/
  * utils.py:101; metrics/fid.py:126 `model(batch)[0]`): x_nchw DEVICE fp32 [n, 3, H, W], already transformed by the
  * caller's torchvision pipeline (H x W = the network's input size after the centre crop, e.g. 224 x 224 / 299 x 299).

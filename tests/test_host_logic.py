@@ -73,8 +73,8 @@ def test_fid_call_surface_errors_need_no_gpu(tmp_path):
     a.mkdir()
     with pytest.raises(RuntimeError, match="Invalid path"):
         dfid.calculate_fid_given_paths([str(tmp_path / "missing"), str(a)], 50, "cuda", 2048)
-    with pytest.raises(NotImplementedError):
-        dfid.calculate_fid_given_paths([str(a), str(a)], 50, "cuda", 768)
+    with pytest.raises(KeyError):                      # InceptionV3.BLOCK_INDEX_BY_DIM[dims] (metrics/fid.py:245)
+        dfid.calculate_fid_given_paths([str(a), str(a)], 50, "cuda", 100)
     with pytest.raises(RuntimeError, match="Invalid path"):
         dfid.save_fid_stats([str(tmp_path / "missing"), str(tmp_path / "x.npz")], 50, "cuda", 2048)
     (tmp_path / "exists.npz").write_bytes(b"")

@@ -17,7 +17,7 @@ def describe(meta, batch):
             byt = 2 * (batch * h * w * c + m * n + (m * n if a[14] >= 0 else 0)) + 2 * n * k
             out.append(dict(op="conv", M=m, N=n, K=k, kh=kh, kw=kw, stride=st, flops=2.0 * m * n * k, bytes=byt))
         else:
-            names = {0: "im2col_u8", 10: "stem_s2d", 2: "maxpool", 3: "avgpool", 4: "gem", 5: "gap", 6: "layernorm", 7: "tokens", 8: "attention", 9: "l2norm"}
+            names = {0: "im2col_u8", 10: "stem_s2d", 2: "maxpool", 3: "avgpool", 4: "gem", 5: "gap", 6: "layernorm", 7: "tokens", 8: "attention", 9: "l2norm", 11: "embed", 12: "stem_rows", 13: "stem_conv"}
             out.append(dict(op=names.get(kind, str(kind)), M=0, N=0, K=0, flops=0.0, bytes=0))
     return out
 
