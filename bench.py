@@ -116,7 +116,7 @@ def gen_images_cuda(n: int, seed: int, device, copies_of=None, copy_frac: float 
     return out
 
 
-def synthetic_sscd_weights(dev):
+def synthetic_sscd_weights(dev, whiten_floor: float = 1e-2):
     """Seeded random-init SSCD ResNet-50 weights (no network access, no checkpoints), made data-consistent the way
     a freshly initialised PyTorch model becomes after its first training-mode batches: the BatchNorm running
     statistics are set from 512 synthetic images (torch ops, set-up only -- nothing of this runs in a timed region),
@@ -152,7 +152,10 @@ def synthetic_sscd_weights(dev):
     mean = emb.mean(dim=0)
     cov = torch.cov((emb - mean).T)
     lam, u = torch.linalg.eigh(cov)
-    lam = lam.clamp_min(lam.max() * 1e-6)
+    # floor on the whitened spectrum: directions with less than `whiten_floor` of the top variance are numerical noise of
+    # the random trunk; amplifying them to unit variance (floor 1e-6) makes the descriptor an amplifier of rounding error
+    # -- no trained model behaves like that -- so they are capped at a 10x gain
+    lam = lam.clamp_min(lam.max() * whiten_floor)
     wh = (u / lam.sqrt()).T                                    # Lambda^-1/2 U^T
     w, bias = sd["embeddings.1.weight"].double(), sd["embeddings.1.bias"].double()
     sd["embeddings.1.weight"] = (wh @ w).float()

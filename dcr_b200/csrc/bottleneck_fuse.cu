@@ -78,9 +78,13 @@ DCR_DEVICE void tma_store_2d_(const void* tmap, uint32_t src_smem, int c0, int c
                : "memory");
 }
 
+// N2 = 0: expansion only (no following reduce convolution to fuse with) -- the same in-place residual / three rotating
+// tile pipeline for the 1x1 expansions whose separate staging tiles do not fit beside the resident A rows in conv_gemm.cu
+// (K = 256: layer3 of the ResNet-50, where that kernel has to serialise on a single output staging tile).
 template <int N2>
 __global__ void __launch_bounds__(kFThreads, 1) expand_reduce_kernel(const __grid_constant__ FuseMaps maps, const FuseParams p) {
-  static_assert(N2 == 64 || N2 == 128, "second GEMM width");
+  static_assert(N2 == 0 || N2 == 64 || N2 == 128, "second GEMM width");
+  constexpr bool kSecond = N2 != 0;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int k_iters1 = p.k_iters1, nb = p.nb;
@@ -166,7 +170,7 @@ __global__ void __launch_bounds__(kFThreads, 1) expand_reduce_kernel(const __gri
             __syncwarp();
           }
         }
-        if (j >= 1) {   // W1 slabs matching the two 64-column slabs of Y block j-1
+        if (kSecond && j >= 1) {   // W1 slabs matching the two 64-column slabs of Y block j-1
           for (int sl = 0; sl < 2; ++sl, ws.next()) {
             mbar_wait(&w_empty[ws.s], ws.ph ^ 1);
             if (elect_one()) {
@@ -181,7 +185,7 @@ __global__ void __launch_bounds__(kFThreads, 1) expand_reduce_kernel(const __gri
   } else if (warp == 1) {
     // ===================================== MMA issuer =====================================
     constexpr uint32_t idesc1 = umma_idesc_bf16(kFM, kFN);
-    constexpr uint32_t idesc2 = umma_idesc_bf16(kFM, N2);
+    constexpr uint32_t idesc2 = umma_idesc_bf16(kFM, kSecond ? N2 : 64);
     PipeState ws(p.w_stages), as(p.a_bufs), xs(kXBufs);
     const uint64_t da0 = umma_desc_sw128(smem_u32(smem_a));
     const uint64_t dw0 = umma_desc_sw128(smem_u32(smem_w));
@@ -216,7 +220,7 @@ __global__ void __launch_bounds__(kFThreads, 1) expand_reduce_kernel(const __gri
           }
           ++g;
         }
-        if (j >= 1) {   // second GEMM: acc2 += Y block j-1 (in X buffer xs.s) x W1 slabs
+        if (kSecond && j >= 1) {   // second GEMM: acc2 += Y block j-1 (in X buffer xs.s) x W1 slabs
           mbar_wait(&y_ready[xs.s], xs.ph);
           if (j == 1) mbar_wait(acc2_empty, (mt & 1) ^ 1);   // previous m-tile's T1 epilogue has drained acc2
           tc_fence_after();
@@ -281,8 +285,10 @@ __global__ void __launch_bounds__(kFThreads, 1) expand_reduce_kernel(const __gri
             const uint32_t xn = (xb + 1 == kXBufs) ? 0 : xb + 1;
             if (g >= 2) {
               store_wait_read_1();
-              const uint32_t ph_prev = (xb >= 2) ? xs.ph : (xs.ph ^ 1);   // parity of use (g-2)/3 of buffer xn
-              mbar_wait(&y_free[xn], ph_prev);
+              if constexpr (kSecond) {
+                const uint32_t ph_prev = (xb >= 2) ? xs.ph : (xs.ph ^ 1);   // parity of use (g-2)/3 of buffer xn
+                mbar_wait(&y_free[xn], ph_prev);
+              }
             }
             const int nm0 = (j + 1 < nb) ? m0 : (tile + static_cast<int>(gridDim.x)) * kFM;
             const int nn0 = (j + 1 < nb) ? (j + 1) * kFN : 0;
@@ -342,9 +348,10 @@ __global__ void __launch_bounds__(kFThreads, 1) expand_reduce_kernel(const __gri
           for (int sl = 0; sl < 2; ++sl)
             tma_store_2d_(&maps.out, x_addr + xb * kXTile + sl * kSlab, j * kFN + sl * kFK, m0);
           store_commit();
-          mbar_arrive(&y_ready[xb]);
+          if constexpr (kSecond) mbar_arrive(&y_ready[xb]);
         }
       }
+      if constexpr (!kSecond) continue;
       // ---- T1 tile of this m-tile: acc2 -> BN + ReLU -> bf16 -> staging -> TMA store ----
       if (etid == 0) store_wait_read_1();   // the previous m-tile's T1 store has finished reading the staging slabs
       asm volatile("bar.sync 1, 256;" ::: "memory");
@@ -404,6 +411,18 @@ __global__ void __launch_bounds__(kFThreads, 1) expand_reduce_kernel(const __gri
 
 }  // namespace
 
+bool expand_only_eligible(const ConvGemmDesc& a, size_t max_smem) {
+  if (tuning_flag("DCR_NO_BLOCK_FUSION") || tuning_flag("DCR_NO_EXPAND_ONLY")) return false;
+  const bool plain = a.kh == 1 && a.kw == 1 && a.stride == 1 && a.pad_h == 0 && a.pad_w == 0 && a.in_stride_w == 0 && a.n_terms == 1 &&
+                     a.term_a[0] == 0 && a.term_w[0] == 0 && !a.exact && a.out != nullptr && a.out_planes <= 1 && a.out_f32 == nullptr &&
+                     a.out_col_off == 0 && a.act == 1;
+  if (!plain || a.res == nullptr || a.res_planes > 1) return false;
+  // K = 64 / 128 expansions keep double-buffered staging in conv_gemm.cu and run at the HBM roofline there already
+  if (a.C != 256 || a.ld_in != a.C || a.N % 128 != 0 || a.N > 2048 || a.ld_out != a.N || a.ld_res != a.N) return false;
+  const size_t need = 1024 + static_cast<size_t>(a.C / 64) * kSlab + 3 * kWStage + kXBufs * kXTile + 2 * a.N * 4 + 512;
+  return need <= max_smem;
+}
+
 bool expand_reduce_eligible(const ConvGemmDesc& a, const ConvGemmDesc& b, size_t max_smem) {
   if (tuning_flag("DCR_NO_BLOCK_FUSION")) return false;
   auto plain = [](const ConvGemmDesc& d) {
@@ -422,31 +441,54 @@ bool expand_reduce_eligible(const ConvGemmDesc& a, const ConvGemmDesc& b, size_t
   return need <= max_smem;
 }
 
-int expand_reduce(const ConvGemmDesc& a, const ConvGemmDesc& b, cudaStream_t stream) {
+namespace {
+template <int N2>
+int launch_fused(const FuseMaps& maps, const FuseParams& p, int grid, size_t smem, const DeviceInfo* di, cudaStream_t stream) {
+  static bool attr_set[64] = {};
+  if (!attr_set[di->device & 63]) {
+    DCR_CUDA_CHECK(cudaFuncSetAttribute(expand_reduce_kernel<N2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        static_cast<int>(di->max_smem_optin)));
+    attr_set[di->device & 63] = true;
+  }
+  expand_reduce_kernel<N2><<<grid, kFThreads, smem, stream>>>(maps, p);
+  count_launch();
+  DCR_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+}  // namespace
+
+// b == nullptr: expansion only
+static int expand_reduce_impl(const ConvGemmDesc& a, const ConvGemmDesc* b, cudaStream_t stream) {
   const DeviceInfo* di = device_info();
   if (!di) return -2;
   DCR_REQUIRE(di->cc_major == 10, "expand_reduce: this build targets sm_100a; device reports sm_%d%d", di->cc_major, di->cc_minor);
-  DCR_REQUIRE(expand_reduce_eligible(a, b, di->max_smem_optin), "expand_reduce: layer pair not eligible for fusion");
   const long long M = static_cast<long long>(a.B) * a.H * a.W;
   DCR_REQUIRE(M > 0 && M < (1ll << 31), "expand_reduce: M out of range");
+  const int n2 = b ? b->N : 0;
   FuseMaps maps;
   memset(&maps, 0, sizeof(maps));
   if (int rc = make_tmap_2d_bf16(&maps.a, a.in, M, a.C, a.ld_in, kFM, kFK)) return rc;
   if (int rc = make_tmap_2d_bf16(&maps.w3, a.weight, a.N, a.C, a.C, kFN, kFK)) return rc;
   if (int rc = make_tmap_2d_bf16(&maps.res, a.res, M, a.N, a.ld_res, kFM, kFK)) return rc;
   if (int rc = make_tmap_2d_bf16(&maps.out, a.out, M, a.N, a.ld_out, kFM, kFK)) return rc;
-  if (int rc = make_tmap_2d_bf16(&maps.w1, b.weight, b.N, b.C, b.C, b.N, kFK)) return rc;
-  if (int rc = make_tmap_2d_bf16(&maps.out2, b.out, M, b.N, b.ld_out, kFM, kFK)) return rc;
+  if (b) {
+    if (int rc = make_tmap_2d_bf16(&maps.w1, b->weight, b->N, b->C, b->C, b->N, kFK)) return rc;
+    if (int rc = make_tmap_2d_bf16(&maps.out2, b->out, M, b->N, b->ld_out, kFM, kFK)) return rc;
+  } else {
+    maps.w1 = maps.w3;
+    maps.out2 = maps.out;
+  }
   FuseParams p;
   memset(&p, 0, sizeof(p));
   p.M = static_cast<int>(M);
   p.N1 = a.N;
-  p.N2 = b.N;
+  p.N2 = n2;
   p.k_iters1 = a.C / 64;
   p.nb = a.N / kFN;
   p.num_m_tiles = static_cast<int>((M + kFM - 1) / kFM);
-  p.scale3 = a.scale; p.bias3 = a.bias; p.scale1 = b.scale; p.bias1 = b.bias;
-  const size_t fixed = 1024 + kXBufs * kXTile + static_cast<size_t>(b.N / 64) * kSlab + (2 * a.N + 2 * b.N) * 4 + 512;
+  p.scale3 = a.scale; p.bias3 = a.bias;
+  p.scale1 = b ? b->scale : nullptr; p.bias1 = b ? b->bias : nullptr;
+  const size_t fixed = 1024 + kXBufs * kXTile + static_cast<size_t>(n2 / 64) * kSlab + (2 * a.N + 2 * n2) * 4 + 512;
   const size_t a_buf = static_cast<size_t>(p.k_iters1) * kSlab;
   // a second buffer for the resident T2 rows when four W stages still fit beside it
   p.a_bufs = (fixed + 2 * a_buf + 4 * kWStage <= di->max_smem_optin) ? 2 : 1;
@@ -454,23 +496,23 @@ int expand_reduce(const ConvGemmDesc& a, const ConvGemmDesc& b, cudaStream_t str
   DCR_REQUIRE(p.w_stages >= 3, "expand_reduce: not enough shared memory");
   const size_t smem = fixed + p.a_bufs * a_buf + static_cast<size_t>(p.w_stages) * kWStage;
   const int grid = std::min(p.num_m_tiles, di->num_sms);
-  static bool attr_set[64][2] = {};
-  if (b.N == 64) {
-    if (!attr_set[di->device & 63][0]) {
-      DCR_CUDA_CHECK(cudaFuncSetAttribute(expand_reduce_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(di->max_smem_optin)));
-      attr_set[di->device & 63][0] = true;
-    }
-    expand_reduce_kernel<64><<<grid, kFThreads, smem, stream>>>(maps, p);
-  } else {
-    if (!attr_set[di->device & 63][1]) {
-      DCR_CUDA_CHECK(cudaFuncSetAttribute(expand_reduce_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(di->max_smem_optin)));
-      attr_set[di->device & 63][1] = true;
-    }
-    expand_reduce_kernel<128><<<grid, kFThreads, smem, stream>>>(maps, p);
-  }
-  count_launch();
-  DCR_CUDA_CHECK(cudaGetLastError());
-  return 0;
+  if (n2 == 0) return launch_fused<0>(maps, p, grid, smem, di, stream);
+  if (n2 == 64) return launch_fused<64>(maps, p, grid, smem, di, stream);
+  return launch_fused<128>(maps, p, grid, smem, di, stream);
+}
+
+int expand_reduce(const ConvGemmDesc& a, const ConvGemmDesc& b, cudaStream_t stream) {
+  const DeviceInfo* di = device_info();
+  if (!di) return -2;
+  DCR_REQUIRE(expand_reduce_eligible(a, b, di->max_smem_optin), "expand_reduce: layer pair not eligible for fusion");
+  return expand_reduce_impl(a, &b, stream);
+}
+
+int expand_only(const ConvGemmDesc& a, cudaStream_t stream) {
+  const DeviceInfo* di = device_info();
+  if (!di) return -2;
+  DCR_REQUIRE(expand_only_eligible(a, di->max_smem_optin), "expand_only: layer not eligible");
+  return expand_reduce_impl(a, nullptr, stream);
 }
 
 }  // namespace dcr

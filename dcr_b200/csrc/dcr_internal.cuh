@@ -75,6 +75,9 @@ int conv3x3_halo(const ConvGemmDesc& d, cudaStream_t stream);
 // bottleneck_fuse.cu: `a` (1x1 expand + residual + ReLU) followed by `b` (1x1 reduce + ReLU) on a's output, fast mode
 bool expand_reduce_eligible(const ConvGemmDesc& a, const ConvGemmDesc& b, size_t max_smem);
 int expand_reduce(const ConvGemmDesc& a, const ConvGemmDesc& b, cudaStream_t stream);
+// the same pipeline without a second convolution: K = 256 expansions with residual (ResNet-50 layer3)
+bool expand_only_eligible(const ConvGemmDesc& a, size_t max_smem);
+int expand_only(const ConvGemmDesc& a, cudaStream_t stream);
 
 
 // ---- HBM-bound kernels (pool_norm.cu, attention.cu) ---------------------------------------------------------------

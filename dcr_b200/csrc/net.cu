@@ -274,6 +274,13 @@ int net_forward(Net* n, const uint8_t* images, int B, float* out, cudaStream_t s
             break;
           }
         }
+        {
+          const DeviceInfo* di = device_info();
+          if (di && expand_only_eligible(d, di->max_smem_optin)) {
+            rc = expand_only(d, stream);
+            break;
+          }
+        }
         rc = conv_gemm(d, stream);
         break;
       }

@@ -526,7 +526,8 @@ __global__ void __launch_bounds__(64 + 128 * kSets, 1)
     tmem_relinquish<kCG>();
   }
   tc_fence_before();
-  if constexpr (kCG == 2) cluster_sync(); else __syncthreads();
+  __syncthreads();   // CTA-local ordering of the set-up writes (mbarrier init, TMEM slot) for this CTA's own readers ...
+  if constexpr (kCG == 2) cluster_sync();   // ... and the peer CTA's barriers are initialised before any remote arrive
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   if (p.clk && blockIdx.x == 0 && threadIdx.x == 0) {

@@ -7,9 +7,9 @@ its 1/N of the gallery descriptors resident, every rank scores ALL queries again
 and one all-gather of the [Q,k] (score, index) pairs + a merge gives every rank the global top-k:
 
     rank r: embeds gallery rows [r*G/N, (r+1)*G/N) and queries [r*Q/N, (r+1)*Q/N)
-    all_gather(query descriptors)                       Q*D*4 bytes total            (one collective)
+    all_gather_into_tensor(query descriptors, f32)      Q*D*4 bytes total            (one collective)
     local fused sim+top-k with global index = base + local
-    all_gather(scores f32[Q,k], indices i64[Q,k])       N*Q*k*12 bytes               (one collective)
+    all_gather_into_tensor(packed (score, index))       N*Q*k*12 bytes               (one collective)
     merge N lists -> top-k by (score desc, index asc)   == top-k over the concatenated gallery
 
 There is no data-path collective inside the kernels: the exchange is two small all-gathers per run (message sizes
@@ -32,21 +32,42 @@ def shard_bounds(n: int, rank: int, world: int) -> Tuple[int, int]:
 
 
 def all_gather_rows(x: torch.Tensor, sizes: Optional[list] = None) -> torch.Tensor:
-    """Concatenate row blocks of every rank (blocks may differ in length by one)."""
+    """Concatenate row blocks of every rank (blocks may differ in length by one).  One collective into one pre-sized
+    buffer (`all_gather_into_tensor`): equal blocks land in place, ragged blocks are padded to the longest and compacted
+    afterwards.  Descriptors travel as float32: the scores are float64-accumulated products of the float32 inputs, and
+    rounding the queries to bf16 for the wire (3x fewer bytes of a transfer that is already < 0.5 ms over NVLink at
+    50k x 512) would change them."""
     world = dist.get_world_size()
     if world == 1:
         return x
     if sizes is None:
         n = torch.tensor([x.shape[0]], device=x.device, dtype=torch.int64)
-        ns = [torch.zeros_like(n) for _ in range(world)]
-        dist.all_gather(ns, n)
-        sizes = [int(v.item()) for v in ns]
+        ns = torch.empty(world, device=x.device, dtype=torch.int64)
+        dist.all_gather_into_tensor(ns, n)
+        sizes = [int(v) for v in ns.tolist()]
     mx = max(sizes)
-    pad = torch.zeros((mx,) + tuple(x.shape[1:]), dtype=x.dtype, device=x.device)
-    pad[:x.shape[0]] = x
-    bufs = [torch.empty_like(pad) for _ in range(world)]
-    dist.all_gather(bufs, pad)
-    return torch.cat([b[:s] for b, s in zip(bufs, sizes)], dim=0)
+    x = x.contiguous()
+    if x.shape[0] != mx:
+        pad = torch.zeros((mx,) + tuple(x.shape[1:]), dtype=x.dtype, device=x.device)
+        pad[:x.shape[0]] = x
+        x = pad
+    buf = torch.empty((world * mx,) + tuple(x.shape[1:]), dtype=x.dtype, device=x.device)
+    dist.all_gather_into_tensor(buf, x)
+    if all(s == mx for s in sizes):
+        return buf
+    return torch.cat([buf[r * mx:r * mx + s] for r, s in enumerate(sizes)], dim=0)
+
+
+def _pack_topk(s: torch.Tensor, i: torch.Tensor) -> torch.Tensor:
+    """(scores f32 [Q,k], indices i64 [Q,k]) -> one int32 [Q,k,3] message: score bits, index low / high words."""
+    iv = i.contiguous().view(torch.int32).view(i.shape[0], i.shape[1], 2)
+    return torch.cat([s.contiguous().view(torch.int32).unsqueeze(-1), iv], dim=-1).contiguous()
+
+
+def _unpack_topk(p: torch.Tensor):
+    s = p[..., 0].contiguous().view(torch.float32)
+    i = p[..., 1:].contiguous().view(torch.int64).squeeze(-1)
+    return s, i
 
 
 def sharded_topk(query_local: torch.Tensor, gallery_local: torch.Tensor, k: int, gallery_base: int,
@@ -65,11 +86,12 @@ def sharded_topk(query_local: torch.Tensor, gallery_local: torch.Tensor, k: int,
         s, i = torch.cat([s, pad_s], 1), torch.cat([i, pad_i], 1)
     if world == 1:
         return s, i
-    ss = [torch.empty_like(s) for _ in range(world)]
-    ii = [torch.empty_like(i) for _ in range(world)]
-    dist.all_gather(ss, s.contiguous())
-    dist.all_gather(ii, i.contiguous())
-    return merge(torch.stack(ss), torch.stack(ii), k)
+    # ONE collective for the per-shard lists: (score, index) packed into 12 bytes per entry
+    msg = _pack_topk(s, i)
+    allmsg = torch.empty((world * msg.shape[0],) + tuple(msg.shape[1:]), dtype=msg.dtype, device=msg.device)
+    dist.all_gather_into_tensor(allmsg, msg)                   # rank-major concatenation along dim 0
+    ss, ii = _unpack_topk(allmsg.view((world,) + tuple(msg.shape)))
+    return merge(ss.contiguous(), ii.contiguous(), k)
 
 
 def cuda_local_topk(q, g, k, index_base):

@@ -97,3 +97,38 @@ def test_embedding_search_cli_end_to_end(tmp_path, monkeypatch):
     ref = oes.similarity_search(str(laion), str(tmp_path / "gen_emb" / "embedding.pkl"))
     assert out["keys"].tolist() == ref["keys"].tolist()
     np.testing.assert_allclose(out["scores"], ref["scores"], atol=1e-6)
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs (run with gpurun --gpus 2)")
+def test_diff_retrieval_cli_multiprocessing_distributed(tmp_path, monkeypatch):
+    """`--multiprocessing-distributed --world-size 1 --rank 0 --dist-url tcp://...` (diff_retrieval.py:205-246): one worker
+    per GPU, gallery and queries sharded, per-shard top-k merged over NCCL -- same topk.pth and statistics as the
+    single-process run of the same command."""
+    import subprocess
+    import sys
+    monkeypatch.chdir(tmp_path)
+    q_dir, v_dir = str(tmp_path / "runs" / "exp" / "generations"), str(tmp_path / "train")
+    _write_images(q_dir, 11, 21)
+    _write_images(v_dir, 37, 22)
+    sd = om.make_sscd_state_dict(7)
+    wpath = str(tmp_path / "sscd.pt")
+    torch.save(sd, wpath)
+    common = ["--query_dir", q_dir, "--val_dir", v_dir, "--pt_style", "sscd", "--arch", "resnet50", "--weights", wpath,
+              "--precision", "parity", "--topk", "5"]
+    save = os.path.join("ret_plots", "runs", "exp", "generations", "images", "sscd_resnet50_dotproduct")
+    assert cli.main(common) == 0
+    single = torch.load(os.path.join(save, "topk.pth"))
+    single_stats = json.load(open(os.path.join(save, "stats.json")))
+    os.remove(os.path.join(save, "topk.pth"))
+    port = 29500 + os.getpid() % 1000
+    env = dict(os.environ, PYTHONPATH=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    r = subprocess.run([sys.executable, "-m", "dcr_b200.cli", *common, "--multiprocessing-distributed", "--world-size", "1",
+                        "--rank", "0", "--dist-url", f"tcp://127.0.0.1:{port}"], env=env, capture_output=True, text=True,
+                       timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    multi = torch.load(os.path.join(save, "topk.pth"))
+    assert torch.equal(multi["indices"], single["indices"])
+    assert torch.allclose(multi["values"], single["values"], atol=1e-6)
+    stats = json.load(open(os.path.join(save, "stats.json")))
+    for k, v in single_stats.items():
+        assert abs(stats[k] - v) < 1e-6, (k, stats[k], v)

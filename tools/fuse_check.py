@@ -15,12 +15,15 @@ sd = om.make_sscd_state_dict(0)
 batch = int(sys.argv[1]) if len(sys.argv) > 1 else 256
 
 
-def run(fused: bool, img, reps: int):
+def run(fused, img, reps: int):
+    """fused: False = separate launches, "pairs" = conv3+conv1 pairs only, True = pairs + expand-only (K = 256)"""
     os.environ["DCR_B200_TUNING"] = "1"
-    if fused:
-        os.environ.pop("DCR_NO_BLOCK_FUSION", None)
-    else:
+    os.environ.pop("DCR_NO_BLOCK_FUSION", None)
+    os.environ.pop("DCR_NO_EXPAND_ONLY", None)
+    if fused is False:
         os.environ["DCR_NO_BLOCK_FUSION"] = "1"
+    elif fused == "pairs":
+        os.environ["DCR_NO_EXPAND_ONLY"] = "1"
     net = nets.build_sscd_resnet50(sd, max_batch=img.shape[0], precision="fast")
     l0 = similarity.kernel_launch_count()
     out = net(img).clone()
@@ -44,6 +47,7 @@ b, _, lb = run(True, small, 1)
 print("fused small ok, launches", lb, "bit-identical:", bool(torch.equal(a, b)), "max diff", float((a - b).abs().max()), flush=True)
 big = synthetic.images(batch, seed=4).cuda()
 a, ta, _ = run(False, big, 10)
+c, tc, _ = run("pairs", big, 10)
 b, tb, _ = run(True, big, 10)
-print(f"batch {batch}: unfused {ta:.3f} ms ({batch / ta * 1e3:.0f} img/s)  fused {tb:.3f} ms ({batch / tb * 1e3:.0f} img/s)  "
-      f"bit-identical: {bool(torch.equal(a, b))}", flush=True)
+print(f"batch {batch}: unfused {ta:.3f} ms ({batch / ta * 1e3:.0f} img/s)  pairs fused {tc:.3f} ms ({batch / tc * 1e3:.0f} img/s)  "
+      f"pairs + expand-only {tb:.3f} ms ({batch / tb * 1e3:.0f} img/s)  bit-identical: {bool(torch.equal(a, b) and torch.equal(a, c))}", flush=True)

@@ -59,7 +59,9 @@ else:
         us = float(r["Metric Value"].replace(",", "")) / 1000
         tot += us
         o = dict(ops[oi])
-        if "expand_reduce_kernel" in r["Kernel Name"]:      # conv3 (+residual) fused with the next block's conv1
+        if "expand_reduce_kernel<0>" in r["Kernel Name"].replace("(int)", ""):
+            o["op"] = "conv3(x3)"                               # expansion-only variant of the fused kernel (in-place residual)
+        elif "expand_reduce_kernel" in r["Kernel Name"]:     # conv3 (+residual) fused with the next block's conv1
             o2 = ops[oi + 1]
             # the expanded activation is written once and never re-read: drop its read from the second conv's bytes
             o = dict(op="conv3+conv1", M=o["M"], N=o["N"], K=o["K"], flops=o["flops"] + o2["flops"],
