@@ -113,7 +113,7 @@ int stem_rows(const uint8_t* img, const float* img_f32, int B, int IH, int IW, i
               float rscale, const float* mean3, const float* std3, float post_scale, float post_shift, __nv_bfloat16* out,
               cudaStream_t stream);
 int stem_conv(const __nv_bfloat16* planes, int B, int OH, int OW, const __nv_bfloat16* weight, const float* scale, const float* bias,
-              __nv_bfloat16* out, cudaStream_t stream);
+              __nv_bfloat16* out, cudaStream_t stream, int pool = 0);   // pool: fuse the 3x3/2/pad-1 max pool, out = [OHp*OWp, 64]
 
 // ---- network executor (net.cu) ------------------------------------------------------------------------------------
 enum NetOpKind {

@@ -171,7 +171,7 @@ int net_add_op(Net* n, int kind, const int* iargs, int ni, const float* fargs, i
       DCR_REQUIRE(((ni == 7 && nf == 8) || (ni == 9 && nf == 9)) && tensor_ok(op.i[0], false) && n->planes == 1, "stem_rows op: bad args");
       break;
     case NET_OP_STEM_CONV:
-      DCR_REQUIRE(ni == 7 && tensor_ok(op.i[0], false) && tensor_ok(op.i[1], false) && param_ok(op.i[4], false) &&
+      DCR_REQUIRE((ni == 7 || ni == 8) && tensor_ok(op.i[0], false) && tensor_ok(op.i[1], false) && param_ok(op.i[4], false) &&
                       param_ok(op.i[5], true) && param_ok(op.i[6], true) && n->planes == 1,
                   "stem_conv op: bad args");
       break;
@@ -253,12 +253,12 @@ int net_forward(Net* n, const uint8_t* images, int B, float* out, cudaStream_t s
       case NET_OP_STEM_CONV: {
         const NetTensor& in = n->tensors[a[0]];
         NetTensor& o = n->tensors[a[1]];
-        DCR_REQUIRE(in.rows_per_image == 2 * stem_fused_plane_units(a[2], a[3]) && in.C == 8 && o.C == 64 &&
-                        o.rows_per_image == static_cast<long long>(a[2]) * a[3],
+        const long long out_rows = a[7] ? static_cast<long long>((a[2] - 1) / 2 + 1) * ((a[3] - 1) / 2 + 1) : static_cast<long long>(a[2]) * a[3];
+        DCR_REQUIRE(in.rows_per_image == 2 * stem_fused_plane_units(a[2], a[3]) && in.C == 8 && o.C == 64 && o.rows_per_image == out_rows,
                     "stem_conv op: tensor shapes do not match the %d x %d output", a[2], a[3]);
         rc = stem_conv(in.ptr, B, a[2], a[3], static_cast<const __nv_bfloat16*>(n->params[a[4]]),
                        a[5] >= 0 ? static_cast<const float*>(n->params[a[5]]) : nullptr,
-                       a[6] >= 0 ? static_cast<const float*>(n->params[a[6]]) : nullptr, o.ptr, stream);
+                       a[6] >= 0 ? static_cast<const float*>(n->params[a[6]]) : nullptr, o.ptr, stream, a[7]);
         break;
       }
       case NET_OP_CONV: {

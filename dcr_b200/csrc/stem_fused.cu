@@ -44,7 +44,11 @@ struct StemParams {
   long long img_stride;          // elements between images (2 * alloc_units * 8)
   long long plane_stride;        // elements between the two planes (alloc_units * 8)
   int B, OH, OW, PW;
-  int tiles_per_img, num_tiles;
+  // work units: a unit is `tiles_per_unit` consecutive 512-position tiles of one image, starting at position
+  // unit_begin(part).  Without pooling: unit = one tile.  With pooling: unit = 1/parts of an image (one extra conv row on top).
+  int units_per_img, tiles_per_unit, num_units;
+  int part_rows;                 // pooling: conv rows owned per part (2 * pooled rows per part)
+  int OHp, OWp, prow_per_part;   // pooling: pooled output size, pooled rows per part
   int win_units;                 // units copied per plane and tile: 512 + 3 * PW + 3, rounded up to 8
   int win_stages;
   const float* scale;
@@ -73,6 +77,17 @@ DCR_DEVICE uint32_t pack2s(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&p);
 }
 
+// first position of a unit
+DCR_DEVICE int unit_begin(const StemParams& p, int part, bool pool) {
+  if (!pool) return part * kSTile;
+  const int row_lo = max(0, part * p.part_rows - 1);     // one conv row above the part's first pooled window
+  return row_lo * p.PW;
+}
+
+// kPool: the 3x3 / stride 2 / pad 1 max pool that follows the stem (torchvision ResNet.maxpool) is taken in the epilogue:
+// conv outputs (post BN + ReLU, bf16) go into a ring of 8 conv rows in shared memory and a pooled row is emitted as soon
+// as its three conv rows are complete -- the 112 x 112 x 64 stem activation (411 MB at batch 256) never reaches HBM.
+template <bool kPool>
 __global__ void __launch_bounds__(kSThreads, 1) stem_conv_kernel(const __grid_constant__ CUtensorMap tmap_w, const StemParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -80,8 +95,9 @@ __global__ void __launch_bounds__(kSThreads, 1) stem_conv_kernel(const __grid_co
   const int stage_bytes = (2 * win_bytes + 1023) & ~1023;
   uint8_t* s_w = smem;                                          // 32 KB, 4 k-blocks
   uint8_t* s_win = s_w + kWBytes;                               // win_stages x [even | odd]
-  uint8_t* s_out = s_win + p.win_stages * stage_bytes;          // 2 x [128 positions x 128 B]
-  float* sb = reinterpret_cast<float*>(s_out + 2 * 16384);      // scale[64] | bias[64]
+  uint8_t* s_out = s_win + p.win_stages * stage_bytes;          // 2 x [128 positions x 128 B] | kPool: ring of 8 conv rows
+  const int ring_row_bytes = p.OW * 128;
+  float* sb = reinterpret_cast<float*>(s_out + (kPool ? ((8 * ring_row_bytes + 1023) & ~1023) : 2 * 16384));   // scale[64] | bias[64]
   uint64_t* bars = reinterpret_cast<uint64_t*>(sb + 128);
   uint64_t* w_full = bars;
   uint64_t* win_full = bars + 1;      // [4]
@@ -119,17 +135,20 @@ __global__ void __launch_bounds__(kSThreads, 1) stem_conv_kernel(const __grid_co
     }
     __syncwarp();
     PipeState ws(p.win_stages);
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ws.next()) {
-      const int b = tile / p.tiles_per_img;
-      const int m0 = (tile - b * p.tiles_per_img) * kSTile;
-      mbar_wait(&win_empty[ws.s], ws.ph ^ 1);
-      if (elect_one()) {
-        mbar_arrive_expect_tx(&win_full[ws.s], 2 * win_bytes);
-        const __nv_bfloat16* src = p.planes + static_cast<size_t>(b) * p.img_stride + static_cast<size_t>(m0) * 8;
-        bulk_load(s_win + ws.s * stage_bytes, src, win_bytes, &win_full[ws.s]);
-        bulk_load(s_win + ws.s * stage_bytes + win_bytes, src + p.plane_stride, win_bytes, &win_full[ws.s]);
+    for (int unit = blockIdx.x; unit < p.num_units; unit += gridDim.x) {
+      const int b = unit / p.units_per_img;
+      const int mu = unit_begin(p, unit - b * p.units_per_img, kPool);
+      for (int t = 0; t < p.tiles_per_unit; ++t, ws.next()) {
+        const int m0 = mu + t * kSTile;
+        mbar_wait(&win_empty[ws.s], ws.ph ^ 1);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(&win_full[ws.s], 2 * win_bytes);
+          const __nv_bfloat16* src = p.planes + static_cast<size_t>(b) * p.img_stride + static_cast<size_t>(m0) * 8;
+          bulk_load(s_win + ws.s * stage_bytes, src, win_bytes, &win_full[ws.s]);
+          bulk_load(s_win + ws.s * stage_bytes + win_bytes, src + p.plane_stride, win_bytes, &win_full[ws.s]);
+        }
+        __syncwarp();
       }
-      __syncwarp();
     }
   } else if (warp == 1) {
     // ===================================== MMA issuer =====================================
@@ -141,7 +160,9 @@ __global__ void __launch_bounds__(kSThreads, 1) stem_conv_kernel(const __grid_co
     PipeState ws(p.win_stages);
     uint32_t tc = 0;
     const uint32_t PW = static_cast<uint32_t>(p.PW);
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++tc, ws.next()) {
+    int my_tiles = 0;
+    for (int unit = blockIdx.x; unit < p.num_units; unit += gridDim.x) my_tiles += p.tiles_per_unit;
+    for (int it = 0; it < my_tiles; ++it, ++tc, ws.next()) {
       const uint32_t buf = tc & 1;
       mbar_wait(&win_full[ws.s], ws.ph);
       mbar_wait(&t_empty[buf], ((tc >> 1) & 1) ^ 1);
@@ -195,55 +216,110 @@ __global__ void __launch_bounds__(kSThreads, 1) stem_conv_kernel(const __grid_co
     }
     const int positions = p.OH * p.PW;
     uint32_t tc = 0, blk = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++tc) {
-      const int b = tile / p.tiles_per_img;
-      const int m0 = (tile - b * p.tiles_per_img) * kSTile;
-      const uint32_t buf = tc & 1;
+    for (int unit = blockIdx.x; unit < p.num_units; unit += gridDim.x) {
+      const int b = unit / p.units_per_img;
+      const int part = unit - b * p.units_per_img;
+      const int mu = unit_begin(p, part, kPool);
+      // pooling state of this unit: conv rows [row_lo, row_hi) are produced here, pooled rows [next_yp, yp_end) emitted
+      const int row_lo = kPool ? max(0, part * p.part_rows - 1) : 0;
+      const int row_hi = kPool ? min(p.OH, (part + 1) * p.part_rows) : p.OH;
+      int next_yp = part * p.prow_per_part;
+      const int yp_end = min(p.OHp, next_yp + p.prow_per_part);
+      if constexpr (kPool) asm volatile("bar.sync 2, 256;" ::: "memory");   // nobody still pools the previous unit's rows
+      for (int t = 0; t < p.tiles_per_unit; ++t, ++tc) {
+        const int m0 = mu + t * kSTile;
+        const uint32_t buf = tc & 1;
 #pragma unroll 1
-      for (int mb = 0; mb < kSBlocks; ++mb, ++blk) {
-        const uint32_t stage = so_addr + (blk & 1) * 16384;
-        mbar_wait(&t_full[buf * kSBlocks + mb], (tc >> 1) & 1);
-        tc_fence_after();
-        uint32_t r[32];
-        tmem_ld_32x32(tmem_row + (buf * kSBlocks + mb) * kSN + half * 32, r);
-        tmem_ld_wait_regs(r);
-        if (mb == kSBlocks - 1) {
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&t_empty[buf]);
-        }
-        // staging row = position inside the block, 128 B per position, 16-byte chunks XOR-swizzled by the row
-        const uint32_t srow = stage + row * 128;
-        const uint32_t sw = row & 7;
+        for (int mb = 0; mb < kSBlocks; ++mb, ++blk) {
+          mbar_wait(&t_full[buf * kSBlocks + mb], (tc >> 1) & 1);
+          tc_fence_after();
+          uint32_t r[32];
+          tmem_ld_32x32(tmem_row + (buf * kSBlocks + mb) * kSN + half * 32, r);
+          tmem_ld_wait_regs(r);
+          if (mb == kSBlocks - 1) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&t_empty[buf]);
+          }
+          uint4 v[4];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          uint4 v;
-          v.x = pack2s(fmaxf(fmaf(__uint_as_float(r[q * 8 + 0]), sc[q * 8 + 0], bi[q * 8 + 0]), 0.f),
-                       fmaxf(fmaf(__uint_as_float(r[q * 8 + 1]), sc[q * 8 + 1], bi[q * 8 + 1]), 0.f));
-          v.y = pack2s(fmaxf(fmaf(__uint_as_float(r[q * 8 + 2]), sc[q * 8 + 2], bi[q * 8 + 2]), 0.f),
-                       fmaxf(fmaf(__uint_as_float(r[q * 8 + 3]), sc[q * 8 + 3], bi[q * 8 + 3]), 0.f));
-          v.z = pack2s(fmaxf(fmaf(__uint_as_float(r[q * 8 + 4]), sc[q * 8 + 4], bi[q * 8 + 4]), 0.f),
-                       fmaxf(fmaf(__uint_as_float(r[q * 8 + 5]), sc[q * 8 + 5], bi[q * 8 + 5]), 0.f));
-          v.w = pack2s(fmaxf(fmaf(__uint_as_float(r[q * 8 + 6]), sc[q * 8 + 6], bi[q * 8 + 6]), 0.f),
-                       fmaxf(fmaf(__uint_as_float(r[q * 8 + 7]), sc[q * 8 + 7], bi[q * 8 + 7]), 0.f));
-          st_shared_v4(srow + (((half * 4 + q) ^ sw) << 4), v);
-        }
-        asm volatile("bar.sync 2, 256;" ::: "memory");
-        // coalesced copy-out: 8 threads per position (16 B each), 32 positions per pass; junk positions are skipped
-        const int mblk = m0 + mb * 128;
+          for (int q = 0; q < 4; ++q) {
+            v[q].x = pack2s(fmaxf(fmaf(__uint_as_float(r[q * 8 + 0]), sc[q * 8 + 0], bi[q * 8 + 0]), 0.f),
+                            fmaxf(fmaf(__uint_as_float(r[q * 8 + 1]), sc[q * 8 + 1], bi[q * 8 + 1]), 0.f));
+            v[q].y = pack2s(fmaxf(fmaf(__uint_as_float(r[q * 8 + 2]), sc[q * 8 + 2], bi[q * 8 + 2]), 0.f),
+                            fmaxf(fmaf(__uint_as_float(r[q * 8 + 3]), sc[q * 8 + 3], bi[q * 8 + 3]), 0.f));
+            v[q].z = pack2s(fmaxf(fmaf(__uint_as_float(r[q * 8 + 4]), sc[q * 8 + 4], bi[q * 8 + 4]), 0.f),
+                            fmaxf(fmaf(__uint_as_float(r[q * 8 + 5]), sc[q * 8 + 5], bi[q * 8 + 5]), 0.f));
+            v[q].w = pack2s(fmaxf(fmaf(__uint_as_float(r[q * 8 + 6]), sc[q * 8 + 6], bi[q * 8 + 6]), 0.f),
+                            fmaxf(fmaf(__uint_as_float(r[q * 8 + 7]), sc[q * 8 + 7], bi[q * 8 + 7]), 0.f));
+          }
+          const int mblk = m0 + mb * 128;
+          if constexpr (!kPool) {
+            // staging row = position inside the block, 128 B per position, 16-byte chunks XOR-swizzled by the row
+            const uint32_t stage = so_addr + (blk & 1) * 16384;
+            const uint32_t srow = stage + row * 128;
+            const uint32_t sw = row & 7;
 #pragma unroll
-        for (int it = 0; it < 4; ++it) {
-          const int pos = it * 32 + static_cast<int>(etid >> 3);
-          const int ch16 = static_cast<int>(etid & 7);
-          const int m = mblk + pos;
-          const int y = m / p.PW, x = m - y * p.PW;
-          if (m < positions && x < p.OW) {
-            const uint4 v = ld_shared_v4(stage + pos * 128 + ((ch16 ^ (pos & 7)) << 4));
-            __nv_bfloat16* dst = p.out + ((static_cast<size_t>(b) * p.OH + y) * p.OW + x) * kSN + ch16 * 8;
-            *reinterpret_cast<uint4*>(dst) = v;
+            for (int q = 0; q < 4; ++q) st_shared_v4(srow + (((half * 4 + q) ^ sw) << 4), v[q]);
+            asm volatile("bar.sync 2, 256;" ::: "memory");
+            // coalesced copy-out: 8 threads per position (16 B each), 32 positions per pass; junk positions are skipped
+#pragma unroll
+            for (int it = 0; it < 4; ++it) {
+              const int pos = it * 32 + static_cast<int>(etid >> 3);
+              const int ch16 = static_cast<int>(etid & 7);
+              const int m = mblk + pos;
+              const int y = m / p.PW, x = m - y * p.PW;
+              if (m < positions && x < p.OW) {
+                const uint4 o = ld_shared_v4(stage + pos * 128 + ((ch16 ^ (pos & 7)) << 4));
+                __nv_bfloat16* dst = p.out + ((static_cast<size_t>(b) * p.OH + y) * p.OW + x) * kSN + ch16 * 8;
+                *reinterpret_cast<uint4*>(dst) = o;
+              }
+            }
+            // the staging buffer (blk & 1) is rewritten two blocks later: the barrier of the next block orders that
+          } else {
+            // conv row ring: ring[(y & 7)][x][64 ch], 16-byte chunks XOR-swizzled by x
+            const int m = mblk + static_cast<int>(row);
+            const int y = m / p.PW, x = m - y * p.PW;
+            if (x < p.OW && y >= row_lo && y < row_hi) {
+              const uint32_t rrow = so_addr + (y & 7) * ring_row_bytes + x * 128;
+#pragma unroll
+              for (int q = 0; q < 4; ++q) st_shared_v4(rrow + (((half * 4 + q) ^ (x & 7)) << 4), v[q]);
+            }
+            asm volatile("bar.sync 2, 256;" ::: "memory");
+            // rows <= yc are complete; emit every pooled row whose last conv row is in (ring depth 8 keeps the rows a slower
+            // thread is still pooling apart from the rows the next block writes)
+            const int yc = min((mblk + 128) / p.PW - 1, row_hi - 1);
+            while (next_yp < yp_end && min(2 * next_yp + 1, p.OH - 1) <= yc) {
+              for (int idx = etid; idx < p.OWp * 8; idx += 256) {
+                const int xp = idx >> 3, c = idx & 7;
+                __nv_bfloat162 a0 = __floats2bfloat162_rn(0.f, 0.f), a1 = a0, a2 = a0, a3 = a0;   // ReLU outputs are >= 0
+#pragma unroll
+                for (int dy = -1; dy <= 1; ++dy) {
+                  const int yy = 2 * next_yp + dy;
+                  if (yy < 0 || yy >= p.OH) continue;
+#pragma unroll
+                  for (int dx = -1; dx <= 1; ++dx) {
+                    const int xx = 2 * xp + dx;
+                    if (xx < 0 || xx >= p.OW) continue;
+                    const uint4 w = ld_shared_v4(so_addr + (yy & 7) * ring_row_bytes + xx * 128 + ((c ^ (xx & 7)) << 4));
+                    a0 = __hmax2(a0, *reinterpret_cast<const __nv_bfloat162*>(&w.x));
+                    a1 = __hmax2(a1, *reinterpret_cast<const __nv_bfloat162*>(&w.y));
+                    a2 = __hmax2(a2, *reinterpret_cast<const __nv_bfloat162*>(&w.z));
+                    a3 = __hmax2(a3, *reinterpret_cast<const __nv_bfloat162*>(&w.w));
+                  }
+                }
+                uint4 o;
+                o.x = *reinterpret_cast<uint32_t*>(&a0);
+                o.y = *reinterpret_cast<uint32_t*>(&a1);
+                o.z = *reinterpret_cast<uint32_t*>(&a2);
+                o.w = *reinterpret_cast<uint32_t*>(&a3);
+                __nv_bfloat16* dst = p.out + ((static_cast<size_t>(b) * p.OHp + next_yp) * p.OWp + xp) * kSN + c * 8;
+                *reinterpret_cast<uint4*>(dst) = o;
+              }
+              ++next_yp;
+            }
           }
         }
-        // the staging buffer (blk & 1) is rewritten two blocks later: the barrier of the next block orders that
       }
     }
   }
@@ -331,7 +407,7 @@ int stem_fused_pitch(int out_w) { return out_w + 4; }
 long long stem_fused_plane_units(int out_h, int out_w) {
   const int PW = stem_fused_pitch(out_w);
   const long long tiles = (static_cast<long long>(out_h) * PW + kSTile - 1) / kSTile;
-  return tiles * kSTile + 3ll * PW + 16;
+  return tiles * kSTile + 3ll * PW + 16 + 2 * kSTile;   // read slack: tiles of the pooled schedule may start past a tile boundary
 }
 
 int stem_rows(const uint8_t* img, const float* img_f32, int B, int IH, int IW, int crop_y, int crop_x, int H, int W, int RH, int RW,
@@ -369,7 +445,7 @@ int stem_rows(const uint8_t* img, const float* img_f32, int B, int IH, int IW, i
 }
 
 int stem_conv(const __nv_bfloat16* planes, int B, int OH, int OW, const __nv_bfloat16* weight, const float* scale, const float* bias,
-              __nv_bfloat16* out, cudaStream_t stream) {
+              __nv_bfloat16* out, cudaStream_t stream, int pool) {
   const DeviceInfo* di = device_info();
   if (!di) return -2;
   DCR_REQUIRE(di->cc_major == 10, "stem_conv: this build targets sm_100a; device reports sm_%d%d", di->cc_major, di->cc_minor);
@@ -380,23 +456,51 @@ int stem_conv(const __nv_bfloat16* planes, int B, int OH, int OW, const __nv_bfl
   p.PW = stem_fused_pitch(OW);
   p.plane_stride = stem_fused_plane_units(OH, OW) * 8;
   p.img_stride = 2 * p.plane_stride;
-  p.tiles_per_img = static_cast<int>((static_cast<long long>(OH) * p.PW + kSTile - 1) / kSTile);
-  p.num_tiles = B * p.tiles_per_img;
+  const int tiles_per_img = static_cast<int>((static_cast<long long>(OH) * p.PW + kSTile - 1) / kSTile);
   p.win_units = (kSTile + 3 * p.PW + 3 + 7) & ~7;
   p.scale = scale; p.bias = bias; p.out = out;
+  p.OHp = (OH - 1) / 2 + 1;
+  p.OWp = (OW - 1) / 2 + 1;
+  if (pool) {
+    const int parts = (p.OHp % 4 == 0) ? 4 : ((p.OHp % 2 == 0) ? 2 : 1);
+    p.units_per_img = parts;
+    p.prow_per_part = p.OHp / parts;
+    p.part_rows = 2 * p.prow_per_part;
+    p.tiles_per_unit = static_cast<int>((static_cast<long long>(p.part_rows + 1) * p.PW + kSTile - 1) / kSTile);
+    // the last part's tiles may run past the image's last conv row: the planes carry zero slack for those reads
+    const long long last_unit = static_cast<long long>(std::max(0, (parts - 1) * p.part_rows - 1)) * p.PW;
+    DCR_REQUIRE(last_unit + static_cast<long long>(p.tiles_per_unit) * kSTile + 3ll * p.PW + 8 <= stem_fused_plane_units(OH, OW),
+                "stem_conv: plane slack too small for the pooled schedule (%d x %d)", OH, OW);
+  } else {
+    p.units_per_img = tiles_per_img;
+    p.tiles_per_unit = 1;
+    p.prow_per_part = 0;
+    p.part_rows = 0;
+  }
+  p.num_units = B * p.units_per_img;
   CUtensorMap tw;
   if (int rc = make_tmap_2d_bf16(&tw, weight, kSN, 256, 256, kSN, 64)) return rc;
   const size_t stage = (static_cast<size_t>(2) * p.win_units * 16 + 1023) & ~size_t(1023);
-  const size_t fixed = 1024 + kWBytes + 2 * 16384 + 512 + 256;
+  const size_t out_bytes = pool ? ((static_cast<size_t>(8) * OW * 128 + 1023) & ~size_t(1023)) : 2 * 16384;
+  const size_t fixed = 1024 + kWBytes + out_bytes + 512 + 256;
   DCR_REQUIRE(fixed + 2 * stage <= di->max_smem_optin, "stem_conv: image too wide for the window buffers (OW = %d)", OW);
   p.win_stages = static_cast<int>(std::min<size_t>(4, (di->max_smem_optin - fixed) / stage));
   const size_t smem = fixed + p.win_stages * stage;
-  static bool attr_set[64] = {};
-  if (!attr_set[di->device & 63]) {
-    DCR_CUDA_CHECK(cudaFuncSetAttribute(stem_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(di->max_smem_optin)));
-    attr_set[di->device & 63] = true;
+  static bool attr_set[64][2] = {};
+  const int grid = std::min(p.num_units, di->num_sms);
+  if (pool) {
+    if (!attr_set[di->device & 63][1]) {
+      DCR_CUDA_CHECK(cudaFuncSetAttribute(stem_conv_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(di->max_smem_optin)));
+      attr_set[di->device & 63][1] = true;
+    }
+    stem_conv_kernel<true><<<grid, kSThreads, smem, stream>>>(tw, p);
+  } else {
+    if (!attr_set[di->device & 63][0]) {
+      DCR_CUDA_CHECK(cudaFuncSetAttribute(stem_conv_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(di->max_smem_optin)));
+      attr_set[di->device & 63][0] = true;
+    }
+    stem_conv_kernel<false><<<grid, kSThreads, smem, stream>>>(tw, p);
   }
-  stem_conv_kernel<<<std::min(p.num_tiles, di->num_sms), kSThreads, smem, stream>>>(tw, p);
   count_launch();
   DCR_CUDA_CHECK(cudaGetLastError());
   return 0;

@@ -315,12 +315,13 @@ def build_sscd_resnet50(state_dict: Dict[str, torch.Tensor], max_batch: int = 64
     s = (crop + 2 * 3 - 7) // 2 + 1   # 112
     u = (crop + 6) // 2               # 115 stored rows / pixels per row
     sc, bi = _fold_bn(sd, "bn1", eps)
-    t_stem = net.tensor(s * s, 64)
+    hw = (s + 2 - 3) // 2 + 1         # 56
     if stem is None:
         stem = DEFAULT_STEM if (net.planes == 1 and sd["conv1.weight"].shape[0] == 64) else "s2d"
-    if stem == "toeplitz":
+    if stem in ("toeplitz", "toeplitz_pool"):
         # fused stem (csrc/stem_fused.cu): the input is stored once as two column-parity planes of 16-byte pixels and the
-        # tensor cores read overlapping windows of it -- each pixel enters shared memory ~1.7 times instead of 16
+        # tensor cores read overlapping windows of it -- each pixel enters shared memory ~1.7 times instead of 16.
+        # "toeplitz_pool" also takes the 3x3/2 max pool in the epilogue: the 112x112x64 activation never reaches HBM.
         if net.planes != 1 or sd["conv1.weight"].shape[0] != 64:
             raise _lib.DcrError("stem='toeplitz' needs the one-plane (fast) mode and a 64-channel stem")
         units = int(net.lib.dcr_stem_plane_units(s, s))
@@ -328,16 +329,23 @@ def build_sscd_resnet50(state_dict: Dict[str, torch.Tensor], max_batch: int = 64
         net.op(OP_STEM_ROWS, [t_rows, in_size, in_size, off, off, src_crop, src_crop] + stem_i,
                list(mean) + list(std) + [1.0, 0.0] + stem_f)
         w_id = net.param(_stem_toeplitz_weight(sd["conv1.weight"]).to(torch.bfloat16))
-        net.op(OP_STEM_CONV, [t_rows, t_stem, s, s, w_id, net.param_f32(sc), net.param_f32(bi)])
+        pooled = stem == "toeplitz_pool"
+        t_stem = net.tensor(hw * hw if pooled else s * s, 64)
+        net.op(OP_STEM_CONV, [t_rows, t_stem, s, s, w_id, net.param_f32(sc), net.param_f32(bi), 1 if pooled else 0])
         net.flops_per_image += 2.0 * s * s * 64 * 147
+        if pooled:
+            t = t_stem
+        else:
+            t = net.tensor(hw * hw, 64)
+            net.op(OP_MAXPOOL, [t_stem, t, s, s, 64, 3, 2, 1, 0])
     else:
+        t_stem = net.tensor(s * s, 64)
         t_z = net.tensor(u * u, 16)
         net.op(OP_STEM_S2D, [t_z, in_size, in_size, off, off, src_crop, src_crop] + stem_i, list(mean) + list(std) + [1.0, 0.0] + stem_f)
         net.conv(t_z, t_stem, u, u - 3, 64, _stem_s2d_weight(sd["conv1.weight"]), scale=sc, bias=bi, act=1, window=(16, u))
         net.flops_per_image += 2.0 * s * s * 64 * (147 - 256)   # count the real 147-tap work, not the zero padding
-    hw = (s + 2 - 3) // 2 + 1         # 56
-    t = net.tensor(hw * hw, 64)
-    net.op(OP_MAXPOOL, [t_stem, t, s, s, 64, 3, 2, 1, 0])
+        t = net.tensor(hw * hw, 64)
+        net.op(OP_MAXPOOL, [t_stem, t, s, s, 64, 3, 2, 1, 0])
     c_in = 64
     for li, stride in enumerate([1, 2, 2, 2], start=1):
         blocks = 0

@@ -155,8 +155,9 @@ int dcr_conv2d_bf16(const void* x, int x_planes, int64_t x_plane_stride, int B, 
  *                uint8 HWC (or fp32 NCHW) input -> the two column-parity planes of 16-byte pixel units the fused stem
  *                kernel reads through overlapping-window descriptors (csrc/stem_fused.cu); out_t has
  *                2 * dcr_stem_plane_units(H/2, W/2) rows of 8 channels per image.  One-plane (fast) networks only.
- *  13 STEM_CONV  i: planes_t, out_t, OH, OW, w_param ([64][256] bf16, k = ((a*2+e)*4+b)*8 + i*3+c), scale_param|-1, bias_param|-1
- *                7x7/2/pad-3 convolution + BN + ReLU -> NHWC [OH*OW, 64]
+ *  13 STEM_CONV  i: planes_t, out_t, OH, OW, w_param ([64][256] bf16, k = ((a*2+e)*4+b)*8 + i*3+c), scale_param|-1, bias_param|-1 [, pool]
+ *                7x7/2/pad-3 convolution + BN + ReLU -> NHWC [OH*OW, 64]; pool = 1: the following 3x3/2/pad-1 max pool is
+ *                taken in the epilogue and out_t is [((OH-1)/2+1) * ((OW-1)/2+1), 64]
  * CONV act: 0 none, 1 ReLU, 2 GELU (erf), 3 QuickGELU x*sigmoid(1.702x). */
 typedef struct dcr_net dcr_net;
 int dcr_net_create(int max_batch, int planes, dcr_net** out);

@@ -15,19 +15,22 @@ batch = int(sys.argv[1]) if len(sys.argv) > 1 else 256
 small = synthetic.images(5, seed=3)
 ref = om.sscd_forward(sd, om.preprocess(small), bf16_points=True)
 outs = {}
-for stem in ("s2d", "toeplitz"):
+for stem in ("s2d", "toeplitz", "toeplitz_pool"):
     net = nets.build_sscd_resnet50(sd, max_batch=8, precision="fast", stem=stem)
     outs[stem] = net(small.cuda()).cpu()
     print(stem, "max |d| vs bf16-point oracle", float((outs[stem] - ref).abs().max()), flush=True)
     del net
 print("toeplitz vs s2d: max |d|", float((outs["toeplitz"] - outs["s2d"]).abs().max()),
       "min cos", float(torch.nn.functional.cosine_similarity(outs["toeplitz"], outs["s2d"], dim=1).min()), flush=True)
-for sf in (0.5,):      # multiscale input size (112 -> 56 x 56 stem output): exercises partial tiles / another pitch
+print("toeplitz_pool vs toeplitz: bit-identical", bool(torch.equal(outs["toeplitz_pool"], outs["toeplitz"])),
+      "max |d|", float((outs["toeplitz_pool"] - outs["toeplitz"]).abs().max()), flush=True)
+for sf in (0.5, 1 / 2 ** 0.5):      # multiscale input size (112 -> 56 x 56 stem output): exercises partial tiles / another pitch
     a = nets.build_sscd_resnet50(sd, max_batch=8, precision="fast", stem="s2d", scale_factor=sf)(small.cuda()).cpu()
     b = nets.build_sscd_resnet50(sd, max_batch=8, precision="fast", stem="toeplitz", scale_factor=sf)(small.cuda()).cpu()
-    print(f"scale {sf}: toeplitz vs s2d max |d|", float((a - b).abs().max()), flush=True)
+    c = nets.build_sscd_resnet50(sd, max_batch=8, precision="fast", stem="toeplitz_pool", scale_factor=sf)(small.cuda()).cpu()
+    print(f"scale {sf:.3f}: toeplitz vs s2d max |d|", float((a - b).abs().max()), " pooled == unpooled:", bool(torch.equal(b, c)), flush=True)
 big = synthetic.images(32, seed=4).cuda().repeat((batch + 31) // 32, 1, 1, 1)[:batch].contiguous()
-for stem in ("s2d", "toeplitz"):
+for stem in ("s2d", "toeplitz", "toeplitz_pool"):
     net = nets.build_sscd_resnet50(sd, max_batch=batch, precision="fast", stem=stem)
     for _ in range(3):
         net(big)
