@@ -16,9 +16,10 @@
 // K-chunk b+1 address the same bytes.  tools/microbench/toeplitz_probe.cu verifies the hardware accepts this.
 // Positions with x >= OW (PW - OW per row) are junk and dropped by the epilogue.
 //
-// Roles (320 threads, persistent over tiles of 512 positions = 4 MMA row blocks):
+// Roles (352 threads, persistent over tiles of 512 positions = 4 MMA row blocks):
 //   warp 0   producer: two cp.async.bulk copies per tile (the even / odd plane windows, 512 + 3*PW + 3 units each)
-//   warp 1   tcgen05.mma issuer: 16 x (128 x 64 x 16) per row block, weights (64 x 256, 32 KB, 128B swizzle) resident
+//   warps 1, 10   tcgen05.mma issuers (alternate row blocks): 16 x (128 x 64 x 16) per row block, weights (64 x 256, 32 KB,
+//            128B swizzle) resident
 //   warps 2-9 epilogue: TMEM -> BN affine + ReLU -> bf16 -> staging -> coalesced NHWC stores of the valid positions
 #include <cuda_bf16.h>
 
@@ -36,7 +37,7 @@ namespace {
 constexpr int kSN = 64;                   // output channels
 constexpr int kSTile = 512;               // positions per tile
 constexpr int kSBlocks = kSTile / 128;    // MMA row blocks per tile
-constexpr int kSThreads = 320;
+constexpr int kSThreads = 352;             // warp 0 producer, warps 1 and 10 MMA issuers, warps 2-9 epilogue
 constexpr int kWBytes = kSN * 256 * 2;    // resident weights: 4 k-blocks of [64 rows x 128 B]
 
 struct StemParams {
@@ -112,7 +113,7 @@ __global__ void __launch_bounds__(kSThreads, 1) stem_conv_kernel(const __grid_co
     mbar_init(w_full, 1);
     for (int s = 0; s < 4; ++s) {
       mbar_init(&win_full[s], 1);
-      mbar_init(&win_empty[s], 1);
+      mbar_init(&win_empty[s], 2);   // both MMA issuers commit once per tile
     }
     for (int s = 0; s < 8; ++s) mbar_init(&t_full[s], 1);
     for (int s = 0; s < 2; ++s) mbar_init(&t_empty[s], 8);
@@ -150,8 +151,11 @@ __global__ void __launch_bounds__(kSThreads, 1) stem_conv_kernel(const __grid_co
         __syncwarp();
       }
     }
-  } else if (warp == 1) {
-    // ===================================== MMA issuer =====================================
+  } else if (warp == 1 || warp == 10) {
+    // ===================================== MMA issuers =====================================
+    // Two issuing warps on separate accumulators: one thread issues a 128x64x16 tcgen05.mma every ~90 cycles at best (the
+    // tensor core needs 32), so the row blocks of a tile alternate between two issuers (tools/microbench/umma_rate.cu).
+    const int issuer = (warp == 1) ? 0 : 1;
     constexpr uint32_t idesc = umma_idesc_bf16(128, kSN);
     mbar_wait(w_full, 0);
     tc_fence_after();
@@ -169,7 +173,7 @@ __global__ void __launch_bounds__(kSThreads, 1) stem_conv_kernel(const __grid_co
       tc_fence_after();
       const uint32_t wbase = win0 + ws.s * stage_bytes;
 #pragma unroll 1
-      for (int mb = 0; mb < kSBlocks; ++mb) {
+      for (int mb = issuer; mb < kSBlocks; mb += 2) {
         const uint32_t tmem_d = tmem_base + (buf * kSBlocks + mb) * kSN;
         if (elect_one()) {
 #pragma unroll
@@ -187,12 +191,12 @@ __global__ void __launch_bounds__(kSThreads, 1) stem_conv_kernel(const __grid_co
             }
           }
           umma_commit<1>(&t_full[buf * kSBlocks + mb]);
-          if (mb == kSBlocks - 1) umma_commit<1>(&win_empty[ws.s]);
+          if (mb + 2 >= kSBlocks) umma_commit<1>(&win_empty[ws.s]);   // this issuer's last row block of the tile
         }
         __syncwarp();
       }
     }
-  } else {
+  } else if (warp < 10) {
     // ===================================== epilogue warps =====================================
     const uint32_t ewarp = warp - 2;
     const uint32_t quad = warp & 3;
@@ -290,29 +294,37 @@ __global__ void __launch_bounds__(kSThreads, 1) stem_conv_kernel(const __grid_co
             // thread is still pooling apart from the rows the next block writes)
             const int yc = min((mblk + 128) / p.PW - 1, row_hi - 1);
             while (next_yp < yp_end && min(2 * next_yp + 1, p.OH - 1) <= yc) {
+              // taps outside the image are replaced by the nearest tap INSIDE the window (the maximum is idempotent), so
+              // there is no branching and the nine 16-byte loads of an item are independent and all in flight together
+              const int y1 = 2 * next_yp;
+              const uint32_t r0 = so_addr + (max(y1 - 1, 0) & 7) * ring_row_bytes;
+              const uint32_t r1 = so_addr + (y1 & 7) * ring_row_bytes;
+              const uint32_t r2 = so_addr + (min(y1 + 1, p.OH - 1) & 7) * ring_row_bytes;
               for (int idx = etid; idx < p.OWp * 8; idx += 256) {
                 const int xp = idx >> 3, c = idx & 7;
-                __nv_bfloat162 a0 = __floats2bfloat162_rn(0.f, 0.f), a1 = a0, a2 = a0, a3 = a0;   // ReLU outputs are >= 0
-#pragma unroll
-                for (int dy = -1; dy <= 1; ++dy) {
-                  const int yy = 2 * next_yp + dy;
-                  if (yy < 0 || yy >= p.OH) continue;
-#pragma unroll
-                  for (int dx = -1; dx <= 1; ++dx) {
-                    const int xx = 2 * xp + dx;
-                    if (xx < 0 || xx >= p.OW) continue;
-                    const uint4 w = ld_shared_v4(so_addr + (yy & 7) * ring_row_bytes + xx * 128 + ((c ^ (xx & 7)) << 4));
-                    a0 = __hmax2(a0, *reinterpret_cast<const __nv_bfloat162*>(&w.x));
-                    a1 = __hmax2(a1, *reinterpret_cast<const __nv_bfloat162*>(&w.y));
-                    a2 = __hmax2(a2, *reinterpret_cast<const __nv_bfloat162*>(&w.z));
-                    a3 = __hmax2(a3, *reinterpret_cast<const __nv_bfloat162*>(&w.w));
-                  }
-                }
+                const int x1 = 2 * xp, x0 = max(x1 - 1, 0), x2 = min(x1 + 1, p.OW - 1);
+                const uint32_t o0 = x0 * 128 + ((c ^ (x0 & 7)) << 4), o1 = x1 * 128 + ((c ^ (x1 & 7)) << 4),
+                               o2 = x2 * 128 + ((c ^ (x2 & 7)) << 4);
+                uint4 w[9];
+                w[0] = ld_shared_v4(r0 + o0); w[1] = ld_shared_v4(r0 + o1); w[2] = ld_shared_v4(r0 + o2);
+                w[3] = ld_shared_v4(r1 + o0); w[4] = ld_shared_v4(r1 + o1); w[5] = ld_shared_v4(r1 + o2);
+                w[6] = ld_shared_v4(r2 + o0); w[7] = ld_shared_v4(r2 + o1); w[8] = ld_shared_v4(r2 + o2);
                 uint4 o;
-                o.x = *reinterpret_cast<uint32_t*>(&a0);
-                o.y = *reinterpret_cast<uint32_t*>(&a1);
-                o.z = *reinterpret_cast<uint32_t*>(&a2);
-                o.w = *reinterpret_cast<uint32_t*>(&a3);
+                {
+                  auto mx = [](uint32_t a, uint32_t b) {
+                    __nv_bfloat162 r = __hmax2(*reinterpret_cast<const __nv_bfloat162*>(&a), *reinterpret_cast<const __nv_bfloat162*>(&b));
+                    return *reinterpret_cast<uint32_t*>(&r);
+                  };
+                  auto mx9 = [&](auto get) {
+                    const uint32_t a = mx(mx(get(w[0]), get(w[1])), mx(get(w[2]), get(w[3])));
+                    const uint32_t b = mx(mx(get(w[4]), get(w[5])), mx(get(w[6]), get(w[7])));
+                    return mx(mx(a, b), get(w[8]));
+                  };
+                  o.x = mx9([](const uint4& v) { return v.x; });
+                  o.y = mx9([](const uint4& v) { return v.y; });
+                  o.z = mx9([](const uint4& v) { return v.z; });
+                  o.w = mx9([](const uint4& v) { return v.w; });
+                }
                 __nv_bfloat16* dst = p.out + ((static_cast<size_t>(b) * p.OHp + next_yp) * p.OWp + xp) * kSN + c * 8;
                 *reinterpret_cast<uint4*>(dst) = o;
               }
