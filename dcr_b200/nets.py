@@ -30,8 +30,10 @@ OP_IM2COL_U8, OP_CONV, OP_MAXPOOL, OP_AVGPOOL, OP_GEM, OP_GAP, OP_LAYERNORM, OP_
 # fast/bf16: one bf16 plane, tensor cores.  parity/fp32: three planes (exact fp32 values), 6 tensor-core cross terms.
 # exact: three planes, products accumulated in float64 on the CUDA cores (correctly rounded fp32 layer outputs).
 # "s2d": 7x7/2 stem as a 4x4 window convolution over a space-to-depth tensor (conv_gemm.cu, every mode);
-# "toeplitz": fused stem kernel with overlapping-window operand descriptors (stem_fused.cu, fast mode)
-DEFAULT_STEM = "s2d"
+# "toeplitz": fused stem kernel with overlapping-window operand descriptors (stem_fused.cu, fast mode);
+# "toeplitz_pool": the same with the 3x3/2 max pool taken in its epilogue (default of the fast mode: measured on B200 at
+# batch 256, input kernel + conv + pool: 471 us (s2d) -> 300 us (toeplitz) -> 230 us (toeplitz_pool))
+DEFAULT_STEM = "toeplitz_pool"
 PRECISION_PLANES = {"fast": 1, "bf16": 1, "parity": 3, "fp32": 3, "bf16x3": 2, "exact": 3}
 
 

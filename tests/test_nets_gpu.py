@@ -175,3 +175,42 @@ def test_sscd_multiscale():
     got = retrieval.extract_features_multiscale(nets_ms, img.cuda()).cpu()
     err, cos = _report("sscd multiscale", got, ref)
     assert err < 2e-5
+
+
+def test_fused_stem_variants_agree():
+    """stem_fused.cu: the overlapping-window (Toeplitz) stem against the space-to-depth stem of conv_gemm.cu -- same bf16
+    inputs, another summation order (fp32 noise only) -- and its pooled variant, which must be bit-identical to the
+    unpooled one (a maximum of bf16 values is exact).  Also at the multi-scale input sizes (odd 79 x 79 stem output)."""
+    sd = om.make_sscd_state_dict(0)
+    img = _imgs(5, 3)
+    ref = om.sscd_forward(sd, om.preprocess(img), bf16_points=True)
+    out = {st: nets.build_sscd_resnet50(sd, max_batch=4, precision="fast", stem=st)(img.cuda()).cpu()
+           for st in ("s2d", "toeplitz", "toeplitz_pool")}
+    assert torch.equal(out["toeplitz"], out["toeplitz_pool"])
+    assert (out["toeplitz"] - out["s2d"]).abs().max().item() < 2e-3
+    assert (out["toeplitz_pool"] - ref).abs().max().item() < 1.5e-2
+    for sf in (0.5, 1 / 2 ** 0.5):
+        a = nets.build_sscd_resnet50(sd, max_batch=8, precision="fast", stem="s2d", scale_factor=sf)(img.cuda())
+        b = nets.build_sscd_resnet50(sd, max_batch=8, precision="fast", stem="toeplitz", scale_factor=sf)(img.cuda())
+        c = nets.build_sscd_resnet50(sd, max_batch=8, precision="fast", stem="toeplitz_pool", scale_factor=sf)(img.cuda())
+        assert torch.equal(b, c) and (a - b).abs().max().item() < 2e-3
+    assert nets.build_sscd_resnet50(sd, max_batch=2, precision="parity").meta[0][0] == nets.OP_STEM_S2D   # other modes keep s2d
+
+
+def test_block_fusion_is_bit_identical(monkeypatch):
+    """bottleneck_fuse.cu: conv3 + residual + ReLU fused with the next block's conv1 (and the expansion-only variant)
+    against the separate launches of conv_gemm.cu: same K order and epilogue arithmetic -> the same bits."""
+    sd = om.make_sscd_state_dict(1)
+    img = _imgs(6, 5).cuda()
+    net = nets.build_sscd_resnet50(sd, max_batch=4, precision="fast")
+    from dcr_b200 import similarity
+    l0 = similarity.kernel_launch_count()
+    fused = net(img).clone()
+    n_fused = similarity.kernel_launch_count() - l0
+    monkeypatch.setenv("DCR_B200_TUNING", "1")
+    monkeypatch.setenv("DCR_NO_BLOCK_FUSION", "1")
+    l0 = similarity.kernel_launch_count()
+    plain = net(img).clone()
+    n_plain = similarity.kernel_launch_count() - l0
+    assert torch.equal(fused, plain)
+    assert n_plain - n_fused == 2 * 6          # two forward chunks (4 + 2 images), six fused pairs each
