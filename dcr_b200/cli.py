@@ -62,8 +62,8 @@ def build_parser() -> argparse.ArgumentParser:
     # additions of this implementation (all optional)
     p.add_argument("--weights", default="", type=str, help="state_dict / TorchScript file of the descriptor model "
                    "(default: the reference's hard-coded ./pretrainedmodels/ paths)")
-    p.add_argument("--precision", default="fast", choices=["fast", "parity", "exact"],
-                   help="fast: bf16 tensor cores; parity: split-bf16 tensor cores (fp32-level); exact: float64 accumulation")
+    p.add_argument("--precision", default="fast", choices=["fast", "bf16x3", "parity", "exact"],
+                   help="fast: bf16 tensor cores; bf16x3 / parity: 3- / 6-term split-bf16 tensor cores (fp32-level); exact: float64 accumulation")
     p.add_argument("--topk", default=10, type=int, help="matches kept per query (reference: 1 for the statistics, 10 for the galleries)")
     p.add_argument("--fid_weights", default="", type=str, help="pt_inception-2015-12-05 state_dict; enables FID")
     return p
@@ -93,9 +93,9 @@ def build_model(args):
             raise NotImplementedError("This model type does not exist/supported for SSCD")      # :285
         sd = load_state_dict(args.weights or SSCD_FILES[args.arch])
         if args.multiscale:                                                                   # utils_ret.py:676-698
-            return [nets.build_sscd_resnet50(sd, max_batch=256, precision=args.precision, scale_factor=s)
+            return [nets.build_sscd_resnet50(sd, max_batch=384, precision=args.precision, scale_factor=s)
                     for s in retrieval.MULTI_SCALES]
-        return nets.build_sscd_resnet50(sd, max_batch=256, precision=args.precision)
+        return nets.build_sscd_resnet50(sd, max_batch=384, precision=args.precision)
     if args.pt_style == "dino":
         if args.arch not in ("vit_small", "vit_base", "vit_base8"):                             # :251-257
             raise NotImplementedError("--pt_style dino: --arch vit_small (dino_vits16), vit_base (dino_vitb16) and "

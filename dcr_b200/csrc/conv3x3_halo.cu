@@ -34,7 +34,7 @@ namespace {
 constexpr int kHM = 128;                    // MMA rows (padded-raster positions) per tile
 constexpr int kHK = 64;                     // channels per block = one 128-byte swizzled row
 constexpr int kSlabBytes = kHM * 128;       // one 64-channel slab of the output staging tile
-constexpr int kHThreads = 320;              // warp 0 producer, warp 1 MMA issuer, warps 2..9 epilogue
+constexpr int kHThreads = 352;              // warp 0 producer, warp 1 (and 10) MMA issuers, warps 2..9 epilogue
 // Timing experiments (garbage results), compile-time only: bit 0 = no weight loads, bit 1 = no halo loads.
 #ifndef DCR_HALO_TIMING_MODE
 #define DCR_HALO_TIMING_MODE 0
@@ -66,7 +66,11 @@ DCR_DEVICE uint32_t pack_bf16_(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&p);
 }
 
-template <int BN>
+// kRW: ALL filter taps stay resident in shared memory (9 * cblocks tiles of [BN x 64]; fits for the 64 -> 64 convolutions of
+// ResNet layer1: 72 KB) and TWO warps issue the MMAs, alternating tiles on the two TMEM accumulators.  One thread issues a
+// 128 x 64 x 16 tcgen05.mma every ~90 cycles in this loop while the tensor core needs 32 (tools/microbench/umma_rate.cu), and
+// with the weight ring gone the two issuers only share the halo buffers, one per tile.
+template <int BN, bool kRW>
 __global__ void __launch_bounds__(kHThreads, 1)
     conv3x3_halo_kernel(const __grid_constant__ HaloMaps maps, const HaloParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -75,8 +79,8 @@ __global__ void __launch_bounds__(kHThreads, 1)
   constexpr uint32_t kTmemCols = (2 * BN <= 128) ? 128 : (2 * BN <= 256 ? 256 : 512);
   constexpr int kChunksPerWarp = BN / 64;
   uint8_t* a_ring = smem;
-  uint8_t* w_ring = a_ring + p.a_bufs * p.a_buf_bytes;
-  uint8_t* out_stage = w_ring + p.w_stages * kWStage;                 // BN/64 slabs
+  uint8_t* w_ring = a_ring + p.a_bufs * p.a_buf_bytes;                // kRW: 9 * cblocks resident tiles, tap-major
+  uint8_t* out_stage = w_ring + (kRW ? 9 * p.cblocks : p.w_stages) * kWStage;                 // BN/64 slabs
   float* sb = reinterpret_cast<float*>(out_stage + (BN / 64) * kSlabBytes);   // [scale | bias][BN]
   uint64_t* bars = reinterpret_cast<uint64_t*>(sb + 2 * BN);
   uint64_t* a_full = bars;          // [4]
@@ -98,7 +102,7 @@ __global__ void __launch_bounds__(kHThreads, 1)
       mbar_init(&a_full[s], 1);
       mbar_init(&a_empty[s], 1);
     }
-    for (int s = 0; s < p.w_stages; ++s) {
+    for (int s = 0; s < (kRW ? 1 : p.w_stages); ++s) {
       mbar_init(&w_full[s], 1);
       mbar_init(&w_empty[s], 1);
     }
@@ -122,7 +126,15 @@ __global__ void __launch_bounds__(kHThreads, 1)
     // (whole warp walks the loop, one elected lane issues: see conv_gemm.cu)
     {
       uint32_t ai = 0, wi = 0;
-      PipeState as(p.a_bufs), ws(p.w_stages);
+      PipeState as(p.a_bufs), ws(kRW ? 1 : p.w_stages);
+      if constexpr (kRW) {   // every filter tap once
+        if (elect_one()) {
+          mbar_arrive_expect_tx(&w_full[0], 9 * p.cblocks * kWStage);
+          for (int t = 0; t < 9 * p.cblocks; ++t)
+            tma_load_2d<1>(w_ring + t * kWStage, &maps.w, &w_full[0], t * kHK, 0, kEvictLast);
+        }
+        __syncwarp();
+      }
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
         const int b = tile / p.tiles_per_img;
         const int p0 = (tile - b * p.tiles_per_img) * p.R;
@@ -139,6 +151,7 @@ __global__ void __launch_bounds__(kHThreads, 1)
             }
           }
           __syncwarp();
+          if constexpr (kRW) continue;
           for (int tap = 0; tap < 9; ++tap, ++wi, ws.next()) {
             const uint32_t sw = ws.s, phw = ws.ph;
             mbar_wait(&w_empty[sw], phw ^ 1);
@@ -155,17 +168,26 @@ __global__ void __launch_bounds__(kHThreads, 1)
         }
       }
     }
-  } else if (warp == 1) {
-    // ===================================== MMA issuer =====================================
+  } else if (warp == 1 || (kRW && warp == 10)) {
+    // ===================================== MMA issuer(s) =====================================
     {
       constexpr uint32_t idesc = umma_idesc_bf16(kHM, BN);
+      const uint32_t issuer = (warp == 1) ? 0u : 1u;
       uint32_t tc = 0;
-      PipeState as(p.a_bufs), ws(p.w_stages);
+      PipeState as(p.a_bufs), ws(kRW ? 1 : p.w_stages);
       const uint64_t da0 = umma_desc_sw128(smem_u32(a_ring));
       const uint64_t db0 = umma_desc_sw128(smem_u32(w_ring));
       const uint32_t row_step = static_cast<uint32_t>(p.Wp) * 8u;   // one padded image row in 16-byte units (128 B / pixel)
+      if constexpr (kRW) {
+        mbar_wait(&w_full[0], 0);
+        tc_fence_after();
+      }
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++tc) {
         const uint32_t buf = tc & 1;
+        if (kRW && buf != issuer) {   // the other issuer's tile: only keep the halo ring position in step
+          for (int cb = 0; cb < p.cblocks; ++cb) as.next();
+          continue;
+        }
         mbar_wait(&t_empty[buf], ((tc >> 1) & 1) ^ 1);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + buf * BN;
@@ -178,17 +200,22 @@ __global__ void __launch_bounds__(kHThreads, 1)
 #pragma unroll
           for (int r = 0; r < 3; ++r) {
 #pragma unroll
-            for (int s = 0; s < 3; ++s, ws.next()) {
-              const uint32_t sw = ws.s;
-              mbar_wait(&w_full[sw], ws.ph);
-              tc_fence_after();
+            for (int s = 0; s < 3; ++s) {
+              uint32_t sw = 0;
+              if constexpr (!kRW) {
+                sw = ws.s;
+                mbar_wait(&w_full[sw], ws.ph);
+                tc_fence_after();
+              } else {
+                sw = static_cast<uint32_t>((r * 3 + s) * p.cblocks + cb);   // resident tile of this (tap, channel block)
+              }
               // the tap's view of the halo block: same buffer, start shifted by r padded rows + s pixels (128 B each)
               const uint64_t da = da_buf + static_cast<uint64_t>(r * row_step + s * 8);
               const uint64_t db = db0 + static_cast<uint64_t>(sw * (kWStage >> 4));
               if (elect_one()) {
 #pragma unroll
                 for (int k = 0; k < kHK / 16; ++k) umma_f16<1>(tmem_d, da + 2 * k, db + 2 * k, idesc, accumulate | k);
-                umma_commit<1>(&w_empty[sw]);
+                if constexpr (!kRW) umma_commit<1>(&w_empty[sw]);
                 if (r == 2 && s == 2) {
                   umma_commit<1>(&a_empty[sa]);
                   if (cb == p.cblocks - 1) umma_commit<1>(&t_full[buf]);
@@ -196,12 +223,13 @@ __global__ void __launch_bounds__(kHThreads, 1)
               }
               __syncwarp();
               accumulate = 1;
+              if constexpr (!kRW) ws.next();
             }
           }
         }
       }
     }
-  } else {
+  } else if (warp < 10) {
     // ===================================== epilogue warps =====================================
     const uint32_t ewarp = warp - 2;
     const uint32_t quad = warp & 3;
@@ -282,21 +310,30 @@ __global__ void __launch_bounds__(kHThreads, 1)
   if (warp == 2) tmem_dealloc<1>(tmem_base, kTmemCols);
 }
 
-template <int BN>
+template <int BN, bool kRW>
 int launch_halo(const HaloMaps& maps, HaloParams& p, int num_sms, size_t max_smem, cudaStream_t stream) {
   constexpr size_t kWStage = static_cast<size_t>(BN) * 128;
   const size_t fixed = 1024 + static_cast<size_t>(BN / 64) * kSlabBytes + 2 * BN * 4 + 256;
-  // two halo buffers and 3..8 weight stages; a third halo buffer if 6 weight stages still fit beside it
   const size_t abuf = p.a_buf_bytes;
-  p.a_bufs = 2;
-  DCR_REQUIRE(max_smem >= fixed + 2 * abuf + 3 * kWStage, "conv3x3_halo: not enough shared memory");
-  p.w_stages = static_cast<int>(std::min<size_t>(8, (max_smem - fixed - 2 * abuf) / kWStage));
-  if (max_smem >= fixed + 3 * abuf + 6 * kWStage) {
-    p.a_bufs = 3;
-    p.w_stages = static_cast<int>(std::min<size_t>(8, (max_smem - fixed - 3 * abuf) / kWStage));
+  size_t smem = 0;
+  if constexpr (kRW) {
+    const size_t wres = static_cast<size_t>(9) * p.cblocks * kWStage;
+    DCR_REQUIRE(max_smem >= fixed + wres + 2 * abuf, "conv3x3_halo: resident weights do not fit");
+    p.a_bufs = static_cast<int>(std::min<size_t>(4, (max_smem - fixed - wres) / abuf));
+    p.w_stages = 0;
+    smem = fixed + wres + static_cast<size_t>(p.a_bufs) * abuf;
+  } else {
+    // two halo buffers and 3..8 weight stages; a third halo buffer if 6 weight stages still fit beside it
+    p.a_bufs = 2;
+    DCR_REQUIRE(max_smem >= fixed + 2 * abuf + 3 * kWStage, "conv3x3_halo: not enough shared memory");
+    p.w_stages = static_cast<int>(std::min<size_t>(8, (max_smem - fixed - 2 * abuf) / kWStage));
+    if (max_smem >= fixed + 3 * abuf + 6 * kWStage) {
+      p.a_bufs = 3;
+      p.w_stages = static_cast<int>(std::min<size_t>(8, (max_smem - fixed - 3 * abuf) / kWStage));
+    }
+    smem = fixed + static_cast<size_t>(p.a_bufs) * abuf + static_cast<size_t>(p.w_stages) * kWStage;
   }
-  const size_t smem = fixed + static_cast<size_t>(p.a_bufs) * abuf + static_cast<size_t>(p.w_stages) * kWStage;
-  auto kern = conv3x3_halo_kernel<BN>;
+  auto kern = conv3x3_halo_kernel<BN, kRW>;
   static bool attr_set_dev[64] = {};   // per template instantiation and device (the attribute is per device)
   int cur_dev = 0;
   DCR_CUDA_CHECK(cudaGetDevice(&cur_dev));
@@ -345,9 +382,12 @@ int conv3x3_halo(const ConvGemmDesc& d, cudaStream_t stream) {
   const int ktot = 9 * p.cblocks * 64;
   if (int rc = make_tmap_2d_bf16(&maps.w, d.weight, d.N, ktot, ktot, BN, 64)) return rc;
   if (int rc = make_tmap_nhwc_box_bf16(&maps.out, d.out, d.B, d.H, d.W, d.ld_out, d.ld_out, d.W, p.R)) return rc;
-  if (BN == 64) return launch_halo<64>(maps, p, di->num_sms, di->max_smem_optin, stream);
-  if (BN == 128) return launch_halo<128>(maps, p, di->num_sms, di->max_smem_optin, stream);
-  return launch_halo<256>(maps, p, di->num_sms, di->max_smem_optin, stream);
+  // all taps resident + two MMA issuers when the weights are small (ResNet layer1: 9 x [64 x 64] = 72 KB)
+  const bool resident = BN == 64 && static_cast<size_t>(9) * p.cblocks * BN * 128 <= 80 * 1024 && !tuning_flag("DCR_HALO_NO_RESIDENT");
+  if (BN == 64) return resident ? launch_halo<64, true>(maps, p, di->num_sms, di->max_smem_optin, stream)
+                                : launch_halo<64, false>(maps, p, di->num_sms, di->max_smem_optin, stream);
+  if (BN == 128) return launch_halo<128, false>(maps, p, di->num_sms, di->max_smem_optin, stream);
+  return launch_halo<256, false>(maps, p, di->num_sms, di->max_smem_optin, stream);
 }
 
 }  // namespace dcr

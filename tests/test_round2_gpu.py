@@ -100,7 +100,7 @@ def test_precision_mode_contracts_against_fp32_mode(weights):
         assert bool(agree[safe].all())                          # the stated contract
         assert bool((i_f[:128, 0] == replica_rows).all())       # every replica is the best match ...
         assert vf[:128, 0].min().item() > 0.9999                # ... with score 1
-    assert report["parity"][1] <= report["bf16x3"][1] * 1.5 and report["bf16x3"][1] < report["fast"][1]
+    assert max(report["parity"][1], report["bf16x3"][1]) * 10 < report["fast"][1]
 
 
 # ---- full BASELINE sizes -----------------------------------------------------------------------------------------------
