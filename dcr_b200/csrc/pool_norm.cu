@@ -387,6 +387,79 @@ struct LayerNormParams {
   float* out_f32;             // [rows, C] or null
 };
 
+// Single-plane fast path for C = kChunks * 128 (384, 512, 768, 1024): HALF a warp per row, kChunks 16-byte loads per lane
+// all in flight at once (balanced: the generic kernel gives C = 384 to 32 + 16 lanes), gamma / beta held in registers across
+// the rows a half-warp walks, 4-step reductions.  The generic kernel ran at ~2 TB/s (37 us for the 50k x 384 rows of a
+// ViT-S/16 batch); this one is a pure stream.
+template <int kChunks>
+__global__ void __launch_bounds__(256) layernorm_fast_kernel(const LayerNormParams p) {
+  const int lane16 = threadIdx.x & 15;
+  const uint32_t hmask = 0xffffu << (threadIdx.x & 16);                   // this half-warp's lanes (the halves may run out of rows separately)
+  const int hw = (blockIdx.x * blockDim.x + threadIdx.x) >> 4;           // global half-warp index
+  const int n_hw = (gridDim.x * blockDim.x) >> 4;
+  float gm[kChunks][8], bt[kChunks][8];
+#pragma unroll
+  for (int g = 0; g < kChunks; ++g) {
+    const int c = (g * 16 + lane16) * 8;
+    const float4 g0 = *reinterpret_cast<const float4*>(p.gamma + c), g1 = *reinterpret_cast<const float4*>(p.gamma + c + 4);
+    const float4 b0 = *reinterpret_cast<const float4*>(p.beta + c), b1 = *reinterpret_cast<const float4*>(p.beta + c + 4);
+    gm[g][0] = g0.x; gm[g][1] = g0.y; gm[g][2] = g0.z; gm[g][3] = g0.w; gm[g][4] = g1.x; gm[g][5] = g1.y; gm[g][6] = g1.z; gm[g][7] = g1.w;
+    bt[g][0] = b0.x; bt[g][1] = b0.y; bt[g][2] = b0.z; bt[g][3] = b0.w; bt[g][4] = b1.x; bt[g][5] = b1.y; bt[g][6] = b1.z; bt[g][7] = b1.w;
+  }
+  constexpr float kInvC = 1.f / static_cast<float>(kChunks * 128);
+  for (int row = hw; row < p.rows; row += n_hw) {
+    const __nv_bfloat16* src = p.in + static_cast<size_t>(row) * p.in_row_stride;
+    uint4 raw[kChunks];
+#pragma unroll
+    for (int g = 0; g < kChunks; ++g) raw[g] = *reinterpret_cast<const uint4*>(src + (g * 16 + lane16) * 8);
+    float v[kChunks][8];
+    float s = 0.f;
+#pragma unroll
+    for (int g = 0; g < kChunks; ++g) {
+      const uint32_t w[4] = {raw[g].x, raw[g].y, raw[g].z, raw[g].w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        v[g][2 * j] = __uint_as_float(w[j] << 16);
+        v[g][2 * j + 1] = __uint_as_float(w[j] & 0xffff0000u);
+        s += v[g][2 * j] + v[g][2 * j + 1];
+      }
+    }
+#pragma unroll
+    for (int off = 8; off > 0; off >>= 1) s += __shfl_xor_sync(hmask, s, off);    // within the half-warp
+    const float mean = s * kInvC;
+    float ss = 0.f;
+#pragma unroll
+    for (int g = 0; g < kChunks; ++g)
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const float d = v[g][e] - mean;
+        ss += d * d;
+      }
+#pragma unroll
+    for (int off = 8; off > 0; off >>= 1) ss += __shfl_xor_sync(hmask, ss, off);
+    const float rstd = 1.f / sqrtf(ss * kInvC + p.eps);                             // biased variance, as nn.LayerNorm
+#pragma unroll
+    for (int g = 0; g < kChunks; ++g) {
+      float y[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) y[e] = (v[g][e] - mean) * rstd * gm[g][e] + bt[g][e];
+      const size_t o = static_cast<size_t>(row) * (kChunks * 128) + (g * 16 + lane16) * 8;
+      if (p.out_f32) {
+        *reinterpret_cast<float4*>(p.out_f32 + o) = make_float4(y[0], y[1], y[2], y[3]);
+        *reinterpret_cast<float4*>(p.out_f32 + o + 4) = make_float4(y[4], y[5], y[6], y[7]);
+      }
+      if (p.out) {
+        uint4 q;
+        __nv_bfloat162 t0 = __floats2bfloat162_rn(y[0], y[1]), t1 = __floats2bfloat162_rn(y[2], y[3]);
+        __nv_bfloat162 t2 = __floats2bfloat162_rn(y[4], y[5]), t3 = __floats2bfloat162_rn(y[6], y[7]);
+        q.x = *reinterpret_cast<uint32_t*>(&t0); q.y = *reinterpret_cast<uint32_t*>(&t1);
+        q.z = *reinterpret_cast<uint32_t*>(&t2); q.w = *reinterpret_cast<uint32_t*>(&t3);
+        *reinterpret_cast<uint4*>(p.out + o) = q;
+      }
+    }
+  }
+}
+
 __global__ void layernorm_kernel(const LayerNormParams p) {
   const int lane = threadIdx.x & 31;
   const int wpb = blockDim.x >> 5;
@@ -656,6 +729,19 @@ int layernorm(const __nv_bfloat16* in, long long in_plane_stride, int planes, in
   p.in_row_stride = in_row_stride; p.gamma = gamma; p.beta = beta; p.eps = eps;
   p.out = out; p.out_plane_stride = out_plane_stride; p.out_f32 = out_f32;
   if (rows == 0) return 0;
+  if (planes == 1 && C % 128 == 0 && C / 128 >= 3 && C / 128 <= 8 && in_row_stride % 8 == 0 && !tuning_flag("DCR_LN_GENERIC")) {
+    const int blocks = std::min((rows + 15) / 16, di->num_sms * 8);        // 16 half-warps per 256-thread block
+    switch (C / 128) {
+      case 3: layernorm_fast_kernel<3><<<blocks, 256, 0, stream>>>(p); break;
+      case 4: layernorm_fast_kernel<4><<<blocks, 256, 0, stream>>>(p); break;
+      case 6: layernorm_fast_kernel<6><<<blocks, 256, 0, stream>>>(p); break;
+      case 8: layernorm_fast_kernel<8><<<blocks, 256, 0, stream>>>(p); break;
+      default: layernorm_kernel<<<std::min((rows + 3) / 4, di->num_sms * 32), 128, 0, stream>>>(p); break;
+    }
+    count_launch();
+    DCR_CUDA_CHECK(cudaGetLastError());
+    return 0;
+  }
   layernorm_kernel<<<std::min((rows + 3) / 4, di->num_sms * 32), 128, 0, stream>>>(p);
   count_launch();
   DCR_CUDA_CHECK(cudaGetLastError());
