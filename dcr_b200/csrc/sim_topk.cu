@@ -86,6 +86,11 @@ __global__ void __launch_bounds__(256) to_bf16_rows_kernel(const float* __restri
   if (nu_flag && *nu_flag == 0) nu = nullptr;
   const int warps_per_block = blockDim.x >> 5;
   const int lane = threadIdx.x & 31;
+  // gmax: one global atomic per BLOCK (100k same-address atomics, one per row, serialise in L2 and dominated this kernel)
+  __shared__ unsigned int s_gmax[2];
+  if (threadIdx.x < 2) s_gmax[threadIdx.x] = 0u;
+  __syncthreads();
+  unsigned int w_nx = 0u, w_nr = 0u;   // this warp's running maxima (lane 0)
   for (int row = blockIdx.x * warps_per_block + (threadIdx.x >> 5); row < n_pad; row += gridDim.x * warps_per_block) {
     float s_hat = 0.f, s_res = 0.f, s_x = 0.f;
     double s_bias = 0.0;   // nu . (x - mu) in fp64: the per-gallery-row score offset of query centring
@@ -147,11 +152,17 @@ __global__ void __launch_bounds__(256) to_bf16_rows_kernel(const float* __restri
       if (norm_hat) norm_hat[row] = nh;
       if (norm_res) norm_res[row] = nr;
       if (norm_x) norm_x[row] = nx;
-      if (gmax) {
-        atomicMax(gmax + 0, __float_as_uint(nx));  // non-negative floats order like their bit patterns
-        atomicMax(gmax + 1, __float_as_uint(nr));
-      }
+      w_nx = max(w_nx, __float_as_uint(nx));     // non-negative floats order like their bit patterns
+      w_nr = max(w_nr, __float_as_uint(nr));
     }
+  }
+  if (gmax) {
+    if (lane == 0) {
+      atomicMax(&s_gmax[0], w_nx);
+      atomicMax(&s_gmax[1], w_nr);
+    }
+    __syncthreads();
+    if (threadIdx.x < 2) atomicMax(gmax + threadIdx.x, s_gmax[threadIdx.x]);
   }
 }
 
