@@ -339,37 +339,57 @@ struct ReduceHWParams {
   float* out_f32;            // [B, C] or null
 };
 
+// block = 64 channel groups x kSlices position slices: every thread streams HW / kSlices positions of its 8 channels
+// (independent 16-byte loads, several in flight), the slices meet in shared memory.  (One thread per channel group walked
+// all HW positions serially before: 41 us for the 51 MB layer4 output of a ResNet-50 batch.)
+constexpr int kRedSlices = 4;
 template <bool kGem>
-__global__ void reduce_hw_kernel(const ReduceHWParams p) {
+__global__ void __launch_bounds__(64 * kRedSlices) reduce_hw_kernel(const ReduceHWParams p) {
+  __shared__ float part[kRedSlices][64][8];
   const int cg = p.C / 8;
   const int b = blockIdx.x;
-  for (int c8 = blockIdx.y * blockDim.x + threadIdx.x; c8 < cg; c8 += gridDim.y * blockDim.x) {
+  const int tc = threadIdx.x & 63, slice = threadIdx.x >> 6;
+  for (int c0 = blockIdx.y * 64; c0 < cg; c0 += gridDim.y * 64) {
+    const int c8 = c0 + tc;
     float acc[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) acc[e] = 0.f;
-    for (int i = 0; i < p.HW; ++i) {
-      float v[8];
-      load8(p.in, p.in_plane_stride, p.planes, (static_cast<size_t>(b) * p.HW + i) * p.C + c8 * 8, v);
+    if (c8 < cg) {
+#pragma unroll 4
+      for (int i = slice; i < p.HW; i += kRedSlices) {
+        float v[8];
+        load8(p.in, p.in_plane_stride, p.planes, (static_cast<size_t>(b) * p.HW + i) * p.C + c8 * 8, v);
 #pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        if (kGem) {
-          const float t = fmaxf(v[e], p.eps);
-          acc[e] += (p.p_exp == 3.f) ? t * t * t : powf(t, p.p_exp);
-        } else {
-          acc[e] += v[e];
+        for (int e = 0; e < 8; ++e) {
+          if (kGem) {
+            const float t = fmaxf(v[e], p.eps);
+            acc[e] += (p.p_exp == 3.f) ? t * t * t : powf(t, p.p_exp);
+          } else {
+            acc[e] += v[e];
+          }
         }
       }
     }
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      acc[e] = acc[e] / static_cast<float>(p.HW);
-      if (kGem) acc[e] = (p.p_exp == 3.f) ? cbrtf(acc[e]) : powf(acc[e], 1.f / p.p_exp);
-    }
-    if (p.out_f32) {
+    for (int e = 0; e < 8; ++e) part[slice][tc][e] = acc[e];
+    __syncthreads();
+    if (slice == 0 && c8 < cg) {
 #pragma unroll
-      for (int e = 0; e < 8; ++e) p.out_f32[static_cast<size_t>(b) * p.C + c8 * 8 + e] = acc[e];
+      for (int e = 0; e < 8; ++e) {
+        float t = part[0][tc][e];
+#pragma unroll
+        for (int sl = 1; sl < kRedSlices; ++sl) t += part[sl][tc][e];   // fixed order: deterministic
+        t = t / static_cast<float>(p.HW);
+        if (kGem) t = (p.p_exp == 3.f) ? cbrtf(t) : powf(t, 1.f / p.p_exp);
+        acc[e] = t;
+      }
+      if (p.out_f32) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) p.out_f32[static_cast<size_t>(b) * p.C + c8 * 8 + e] = acc[e];
+      }
+      if (p.out) store8(p.out, p.out_plane_stride, p.planes, static_cast<size_t>(b) * p.C + c8 * 8, acc);
     }
-    if (p.out) store8(p.out, p.out_plane_stride, p.planes, static_cast<size_t>(b) * p.C + c8 * 8, acc);
+    __syncthreads();
   }
 }
 
@@ -711,8 +731,8 @@ int reduce_hw(bool gem, const __nv_bfloat16* in, long long in_plane_stride, int 
   if (B == 0) return 0;
   const int cg = C / 8;
   dim3 grid(B, (cg + 63) / 64);
-  if (gem) reduce_hw_kernel<true><<<grid, 64, 0, stream>>>(p);
-  else reduce_hw_kernel<false><<<grid, 64, 0, stream>>>(p);
+  if (gem) reduce_hw_kernel<true><<<grid, 64 * kRedSlices, 0, stream>>>(p);
+  else reduce_hw_kernel<false><<<grid, 64 * kRedSlices, 0, stream>>>(p);
   count_launch();
   DCR_CUDA_CHECK(cudaGetLastError());
   return 0;
