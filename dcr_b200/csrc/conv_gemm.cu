@@ -598,9 +598,8 @@ int conv_gemm(const ConvGemmDesc& d, cudaStream_t stream) {
   // double buffered; compute-bound shapes keep 256 (fewer re-reads of A)
   const bool single_plane = d.out && d.out_planes <= 1 && !d.out_f32 && (!d.res || d.res_planes <= 1);
   if (BN == 256 && single_plane && (d.res != nullptr || static_cast<long long>(d.kh) * d.kw * d.C <= 256)) BN = 128;
-  // experiment knob: residual layers with a long K (ResNet layer4 expansions, K = 512: A cannot stay resident, so 128-wide
-  // tiles re-read it 16 times from L2) keep the 256-wide tile
-  if (d.N >= 256 && single_plane && d.res != nullptr && d.C >= tuning_int("DCR_GEMM_RES_BN256_MIN_C", 1 << 30)) BN = 256;
+  // (256-wide tiles for the long-K residual layers -- ResNet layer4 expansions, K = 512 -- were tried in round 2: the output
+  // and residual staging tiles of a 128 x 256 tile do not fit beside three pipeline stages)
   if (d.force_bn) BN = d.force_bn;
   for (int pl = 0; pl < 3; ++pl) {
     const int pa = std::min(pl, a_planes - 1), pw = std::min(pl, w_planes - 1);
