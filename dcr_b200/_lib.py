@@ -25,6 +25,9 @@ SIGNATURES = {
                                C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "dcr_sim_topk_host": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p,
                                     C.c_void_p]),
+    "dcr_sim_topk_sharded_workspace_size": (C.c_size_t, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
+    "dcr_sim_topk_sharded": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int64, C.c_int,
+                                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "dcr_sim_topk_last_stats": (C.c_int, [C.POINTER(C.c_int)]),
     "dcr_sim_topk_last_kernel_ms": (C.c_float, []),
     "dcr_sim_topk_last_sm_mhz": (C.c_float, []),
@@ -55,6 +58,9 @@ SIGNATURES = {
     "dcr_topk_merge": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                  C.c_void_p]),
 }
+
+# the all-gather callback of dcr_sim_topk_sharded: int (*)(const void* send, void* recv, size_t bytes_per_rank, void* ctx, void* stream)
+ALLGATHER_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p)
 
 _lib = None
 

@@ -32,6 +32,9 @@ int split_rescore(const float* q, const float* g, int nq, int d, int n_chunks, i
                   int k, float* out_scores, long long* out_idx, cudaStream_t stream);
 
 int l2_normalize(float* x, int n, int d, float eps, cudaStream_t stream);
+// [nq, k_in] lists -> [nq, k_out >= k_in] with (-inf, -1) in the extra slots
+int pad_topk_lists(const float* s_in, const long long* i_in, int nq, int k_in, int k_out, float* s_out, long long* i_out,
+                   cudaStream_t stream);
 int topk_merge(const float* scores, const long long* idx, int nq, int nlists, int k_in, int k_out, float* out_scores,
                long long* out_idx, cudaStream_t stream);
 

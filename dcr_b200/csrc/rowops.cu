@@ -89,7 +89,28 @@ __global__ void topk_merge_kernel(const float* __restrict__ scores, const long l
     __syncwarp();
   }
 }
+__global__ void pad_topk_lists_kernel(const float* __restrict__ s_in, const long long* __restrict__ i_in, int nq, int k_in, int k_out,
+                                      float* __restrict__ s_out, long long* __restrict__ i_out) {
+  const long long total = static_cast<long long>(nq) * k_out;
+  for (long long t = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; t < total;
+       t += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int q = static_cast<int>(t / k_out), j = static_cast<int>(t % k_out);
+    s_out[t] = j < k_in ? s_in[static_cast<size_t>(q) * k_in + j] : -INFINITY;
+    i_out[t] = j < k_in ? i_in[static_cast<size_t>(q) * k_in + j] : -1;
+  }
+}
 }  // namespace
+
+int pad_topk_lists(const float* s_in, const long long* i_in, int nq, int k_in, int k_out, float* s_out, long long* i_out,
+                   cudaStream_t stream) {
+  DCR_REQUIRE(nq >= 1 && k_in >= 1 && k_out >= k_in, "pad_topk_lists: bad arguments");
+  const long long total = static_cast<long long>(nq) * k_out;
+  pad_topk_lists_kernel<<<static_cast<int>(std::min<long long>((total + 255) / 256, 1184)), 256, 0, stream>>>(s_in, i_in, nq, k_in, k_out,
+                                                                                                       s_out, i_out);
+  count_launch();
+  DCR_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
 
 int l2_normalize(float* x, int n, int d, float eps, cudaStream_t stream) {
   DCR_REQUIRE(n >= 0 && d >= 1, "l2_normalize: bad shape (%d,%d)", n, d);

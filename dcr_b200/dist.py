@@ -102,3 +102,62 @@ def cuda_local_topk(q, g, k, index_base):
 def cuda_merge(scores, idx, k):
     from .similarity import topk_merge
     return topk_merge(scores, idx, k)
+
+
+def sharded_topk_c(query_all: torch.Tensor, gallery_local: torch.Tensor, k: int, gallery_base: int,
+                   allgather: Optional[Callable] = None, world: Optional[int] = None, index_stride: int = 1
+                   ) -> Tuple[torch.Tensor, torch.Tensor]:
+    """The same exchange through the C entry `dcr_sim_topk_sharded` (include/dcr_b200.h): local fused top-k, ONE all-gather
+    of the packed lists, merge -- all enqueued by the library on the current stream.  `query_all`: every query descriptor
+    (already all-gathered); `allgather(send_ptr, recv_ptr, bytes_per_rank, stream_ptr) -> int` performs the collective
+    (default: torch.distributed.all_gather_into_tensor over uint8 views of the two device buffers)."""
+    import ctypes as C
+    from . import _lib
+    from .similarity import _aligned_ptr, _check_cuda_f32
+    lib = _lib.load()
+    q = _check_cuda_f32("query_all", query_all)
+    g = _check_cuda_f32("gallery_local", gallery_local)
+    if world is None:
+        world = dist.get_world_size() if dist.is_initialized() else 1
+    nq, d = q.shape
+    ng = g.shape[0]
+    holders = []
+
+    def default_allgather(send, recv, nbytes, stream):
+        # zero-copy uint8 views of the library's device buffers
+        sv = device_bytes(send, nbytes, q.device)
+        rv = device_bytes(recv, nbytes * world, q.device)
+        holders.extend([sv, rv])
+        dist.all_gather_into_tensor(rv, sv)
+        return 0
+
+    fn = allgather or default_allgather
+
+    def trampoline(send, recv, nbytes, ctx, stream):
+        try:
+            return int(fn(send, recv, nbytes, stream))
+        except Exception as e:                      # never unwind through the C frame
+            print(f"dcr_b200.dist.sharded_topk_c: all-gather callback raised {e!r}")
+            return 1
+
+    cb = _lib.ALLGATHER_FN(trampoline)
+    with torch.cuda.device(q.device):
+        nbytes = lib.dcr_sim_topk_sharded_workspace_size(nq, ng, d, k, world)
+        if nbytes == 0:
+            raise _lib.DcrError(f"dcr_sim_topk_sharded_workspace_size: {_lib.last_error()}")
+        ws = torch.empty(nbytes + 256, dtype=torch.uint8, device=q.device)
+        out_s = torch.empty((nq, k), dtype=torch.float32, device=q.device)
+        out_i = torch.empty((nq, k), dtype=torch.int64, device=q.device)
+        st = torch.cuda.current_stream().cuda_stream
+        rc = lib.dcr_sim_topk_sharded(q.data_ptr(), nq, g.data_ptr(), ng, d, k, gallery_base, index_stride, world,
+                                      C.cast(cb, C.c_void_p), None, out_s.data_ptr(), out_i.data_ptr(), _aligned_ptr(ws), nbytes, st)
+        _lib.check(rc, "dcr_sim_topk_sharded")
+        torch.cuda.current_stream().synchronize()    # the workspace and the views above die with this frame
+    return out_s, out_i
+
+
+def device_bytes(ptr: int, nbytes: int, device: torch.device) -> torch.Tensor:
+    """Zero-copy uint8 tensor over a raw device pointer (the library's workspace), for handing it to torch.distributed."""
+    iface = {"shape": (int(nbytes),), "typestr": "|u1", "data": (int(ptr), False), "version": 2}
+    holder = type("_DevicePtr", (), {"__cuda_array_interface__": iface})()
+    return torch.as_tensor(holder, device=device)

@@ -89,6 +89,21 @@ long long dcr_kernel_launch_count(void);
 int dcr_topk_merge(const float* scores, const int64_t* idx, int nq, int nlists, int k_in, int k_out,
                    float* out_scores, int64_t* out_idx, void* stream);
 
+/* Gallery-sharded form (replaces the per-batch all_gather pair of utils_ret.py:763-779 and the rank-0-only
+ * mm/topk of diff_retrieval.py:402-417): this rank scores ALL queries q[nq,d] against ITS gallery shard g[ng_local,d] (global
+ * index of local row r = g_index_base + g_index_stride * r), the per-shard (score, index) lists are exchanged by ONE
+ * all-gather and merged, and out_scores / out_idx [nq,k] receive the global top-k on every rank.
+ * The library does not link a communication library: the caller supplies the all-gather as a callback that must enqueue,
+ * on `stream`, an all-gather of `bytes_per_rank` bytes from device buffer `send` into device buffer `recv`
+ * (world * bytes_per_rank bytes, rank-major) -- one ncclAllGather(send, recv, bytes_per_rank, ncclUint8, comm, stream)
+ * call, or torch.distributed.all_gather_into_tensor from Python (dcr_b200/dist.py).  Returns non-zero to abort.
+ * workspace: dcr_sim_topk_sharded_workspace_size(nq, ng_local, d, k, world) bytes. */
+typedef int (*dcr_allgather_fn)(const void* send, void* recv, size_t bytes_per_rank, void* ctx, void* stream);
+size_t dcr_sim_topk_sharded_workspace_size(int nq, int ng_local, int d, int k, int world);
+int dcr_sim_topk_sharded(const float* q, int nq, const float* g, int ng_local, int d, int k, int64_t g_index_base,
+                         int64_t g_index_stride, int world, dcr_allgather_fn allgather, void* allgather_ctx,
+                         float* out_scores, int64_t* out_idx, void* workspace, size_t workspace_bytes, void* stream);
+
 /* Final step of the 'splitloss' similarity (diff_retrieval.py:393-400: descriptors cut into n_chunks equal parts, pair
  * score = max over the parts of the per-part dot products).  The caller runs dcr_sim_topk once per part and passes
  * the union of the per-part top-k rows as cand [nq][n_cand] (duplicates allowed); this evaluates the exact split

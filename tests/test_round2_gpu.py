@@ -297,3 +297,61 @@ def test_vit_patch8_785_tokens():
     fast = nets.build_dino_vit(sd, max_batch=2, precision="fast")
     gq = fast(img.cuda()).cpu()
     assert (gq - refq).abs().max().item() < 6e-2 * max(1.0, refq.abs().max().item())
+
+
+# ---- dcr_sim_topk_sharded: the C entry with an all-gather callback -------------------------------------------------------------
+def test_sim_topk_sharded_c_entry_emulated_two_ranks():
+    """One process plays both ranks: rank 1's packed list is computed first; rank 0's call gets it through the callback
+    (which writes [own block | peer block] into the receive buffer).  Result == the unsharded top-k == the oracle.  Also the
+    shard-smaller-than-k padding and world = 1."""
+    from dcr_b200 import dist as ddist
+    q, g = synthetic.descriptors(130, 4000, 256, seed=77)
+    qc = q.cuda()
+    k = 10
+    lo, hi = 0, 1997                       # ragged split
+    v1, i1 = similarity.sim_topk(qc, g[hi:].cuda(), k, index_base=hi)
+    peer = torch.cat([v1.contiguous().view(torch.uint8).reshape(-1), i1.contiguous().view(torch.uint8).reshape(-1)])
+
+    def fake_allgather(send, recv, nbytes, stream):
+        assert nbytes == 130 * k * 12 == peer.numel()
+        own = ddist.device_bytes(send, nbytes, qc.device)
+        out = ddist.device_bytes(recv, 2 * nbytes, qc.device)
+        out[:nbytes].copy_(own)
+        out[nbytes:].copy_(peer)
+        return 0
+
+    v, i = ddist.sharded_topk_c(qc, g[lo:hi].cuda(), k, lo, allgather=fake_allgather, world=2)
+    ov, oi = osim.sim_topk(q.numpy(), g.numpy(), k)
+    assert np.array_equal(i.cpu().numpy(), oi)
+    np.testing.assert_allclose(v.cpu().numpy(), ov, rtol=0, atol=1.2e-7)
+    # world = 1 and a shard smaller than k
+    v, i = ddist.sharded_topk_c(qc, g[:6].cuda(), k, 100, world=1)
+    ov6, oi6 = osim.sim_topk(q.numpy(), g[:6].numpy(), 6)
+    assert np.array_equal(i.cpu().numpy()[:, :6], oi6 + 100) and (i.cpu().numpy()[:, 6:] == -1).all()
+    assert torch.isinf(v[:, 6:]).all()
+
+
+def _nccl_worker_c(rank, world, port, out_dir):
+    import torch.distributed as dist
+    from dcr_b200 import dist as ddist
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    q, g = synthetic.descriptors(300, 9001, 384, seed=91)
+    glo, ghi = ddist.shard_bounds(9001, rank, world)
+    v, i = ddist.sharded_topk_c(q.cuda(), g[glo:ghi].cuda(), 10, glo)
+    np.savez(os.path.join(out_dir, f"c{rank}.npz"), v=v.cpu().numpy(), i=i.cpu().numpy())
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs (run with gpurun --gpus 2)")
+def test_sim_topk_sharded_c_entry_two_ranks_nccl(tmp_path):
+    import torch.multiprocessing as mp
+    mp.spawn(_nccl_worker_c, args=(2, 29100 + (os.getpid() % 800), str(tmp_path)), nprocs=2, join=True)
+    q, g = synthetic.descriptors(300, 9001, 384, seed=91)
+    ov, oi = osim.sim_topk(q.numpy(), g.numpy(), 10)
+    for r in range(2):
+        got = np.load(os.path.join(str(tmp_path), f"c{r}.npz"))
+        assert np.array_equal(got["i"], oi), f"rank {r}"
+        np.testing.assert_allclose(got["v"], ov, rtol=0, atol=1.2e-7)
