@@ -409,6 +409,181 @@ __global__ void __launch_bounds__(kAttnThreads, 1)
   if (warp == 0) tmem_dealloc<1>(tmem_base, 512);
 }
 
+// One query tile per CTA, two CTAs per SM.  The kernel above keeps Q (2 tiles), K, V and both P tiles resident (224 KB):
+// one CTA per SM, and inside a CTA load -> QK^T -> softmax -> PV -> store is a serial chain, so the SM idles through every
+// latency in turn (144 us per ViT-S/16 layer at batch 256, ~106 TFLOP/s).  Here a CTA owns ONE 128-row query tile of one
+// (image, head); its P tile (128 x 256 bf16 = 64 KB) is written over the Q and K tiles, which are dead once the S MMAs
+// have retired, so a CTA needs 96 KB and two of them share an SM (and its 512 TMEM columns, 256 each): one CTA's loads and
+// MMAs run under the other's softmax.  K / V of an (image, head) are fetched by both of its CTAs (second fetch: L2).
+constexpr int kAttn1Threads = 160;   // warps 0-3 softmax + epilogue, warp 4 TMA + MMA issue
+__global__ void __launch_bounds__(kAttn1Threads, 2)
+    attention_tc1_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnTcParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* s_q = smem;                 // [128 x 64] bf16          } the P tile (4 k-blocks x [128 x 64]) overwrites
+  uint8_t* s_k = s_q + 16384;          // [256 x 64]               } these 64 KB after S = Q K^T
+  uint8_t* s_v = s_k + 32768 + 16384;  // [256 x 64] (after 16 KB that only P uses)
+  uint8_t* s_p = s_q;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_v + 32768);
+  uint64_t* bar_load = bars;
+  uint64_t* s_full = bars + 1;
+  uint64_t* p_ready = bars + 2;        // 128 arrivals
+  uint64_t* o_full = bars + 3;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
+
+  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_mtiles = (p.T + 127) / 128;
+  const int mt = blockIdx.x % n_mtiles;
+  const int bh = blockIdx.x / n_mtiles;
+  const int b = bh / p.heads, h = bh % p.heads;
+  const int row0 = b * p.T;
+
+  if (warp == 4 && lane == 0) {
+    tma_prefetch_desc(&tmap_qkv);
+    mbar_init(bar_load, 1);
+    mbar_init(s_full, 1);
+    mbar_init(p_ready, 128);
+    mbar_init(o_full, 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) {
+    tmem_alloc<1>(tmem_slot, 256);
+    tmem_relinquish<1>();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 4) {
+    const int cq = h * 64, ck = p.heads * 64 + h * 64, cv = 2 * p.heads * 64 + h * 64;
+    if (elect_one()) {
+      mbar_arrive_expect_tx(bar_load, 5 * 16384);
+      tma_load_2d<1>(s_q, &tmap_qkv, bar_load, cq, row0 + mt * 128, kEvictFirst);
+      tma_load_2d<1>(s_k, &tmap_qkv, bar_load, ck, row0, kEvictNormal);
+      tma_load_2d<1>(s_k + 16384, &tmap_qkv, bar_load, ck, row0 + 128, kEvictNormal);
+      tma_load_2d<1>(s_v, &tmap_qkv, bar_load, cv, row0, kEvictNormal);
+      tma_load_2d<1>(s_v + 16384, &tmap_qkv, bar_load, cv, row0 + 128, kEvictNormal);
+    }
+    __syncwarp();
+    mbar_wait(bar_load, 0);
+    tc_fence_after();
+    constexpr uint32_t idesc_s = umma_idesc_bf16(128, 256);
+    constexpr uint32_t idesc_o = umma_idesc_bf16(128, 64) | (1u << 16);   // B operand MN-major
+    {
+      const uint64_t da = umma_desc_sw128(smem_u32(s_q));
+      const uint64_t db = umma_desc_sw128(smem_u32(s_k));
+      if (elect_one()) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_f16<1>(tmem_base, da + 2 * k, db + 2 * k, idesc_s, k != 0);
+        umma_commit<1>(s_full);
+      }
+      __syncwarp();
+    }
+    mbar_wait(p_ready, 0);
+    tc_fence_after();
+    if (elect_one()) {
+#pragma unroll
+      for (int kb = 0; kb < 4; ++kb) {
+        const uint64_t da = umma_desc_sw128(smem_u32(s_p + kb * 16384));
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const uint64_t dv = umma_desc_sw128_mn(smem_u32(s_v + (kb * 64 + k * 16) * 128));
+          umma_f16<1>(tmem_base, da + 2 * k, dv, idesc_o, (kb | k) != 0);
+        }
+      }
+      umma_commit<1>(o_full);
+    }
+    __syncwarp();
+  } else {
+    const uint32_t quad = warp & 3;
+    const uint32_t row = quad * 32 + lane;
+    const uint32_t taddr = tmem_base + ((quad * 32u) << 16);
+    const uint32_t sw = row & 7;
+    mbar_wait(s_full, 0);     // S complete: the MMAs have finished reading Q and K, P may overwrite them
+    tc_fence_after();
+    const int lim = p.causal ? min(p.T, mt * 128 + static_cast<int>(row) + 1) : p.T;
+    float mx = -INFINITY;
+#pragma unroll 1
+    for (int ch = 0; ch < 8; ++ch) {
+      if (ch * 32 >= p.T) break;
+      uint32_t r[32];
+      tmem_ld_32x32(taddr + ch * 32, r);
+      tmem_ld_wait_regs(r);
+#pragma unroll
+      for (int c = 0; c < 32; ++c)
+        if (ch * 32 + c < lim) mx = fmaxf(mx, __uint_as_float(r[c]));
+    }
+    const float mxs = mx * p.scale_log2e;
+    float sum = 0.f;
+#pragma unroll 1
+    for (int ch = 0; ch < 8; ++ch) {
+      uint32_t r[32];
+      float pv[32];
+      if (ch * 32 < p.T) {
+        tmem_ld_32x32(taddr + ch * 32, r);
+        tmem_ld_wait_regs(r);
+#pragma unroll
+        for (int c = 0; c < 32; ++c) {
+          const float e = (ch * 32 + c < lim) ? exp2f(fmaf(__uint_as_float(r[c]), p.scale_log2e, -mxs)) : 0.f;
+          const float eb = __bfloat162float(__float2bfloat16_rn(e));   // the sum must be of the ROUNDED weights
+          pv[c] = eb;
+          sum += eb;
+        }
+      } else {
+#pragma unroll
+        for (int c = 0; c < 32; ++c) pv[c] = 0.f;
+      }
+      uint8_t* prow = s_p + (ch >> 1) * 16384 + row * 128;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        uint4 v;
+        __nv_bfloat162 t0 = __floats2bfloat162_rn(pv[j * 8 + 0], pv[j * 8 + 1]);
+        __nv_bfloat162 t1 = __floats2bfloat162_rn(pv[j * 8 + 2], pv[j * 8 + 3]);
+        __nv_bfloat162 t2 = __floats2bfloat162_rn(pv[j * 8 + 4], pv[j * 8 + 5]);
+        __nv_bfloat162 t3 = __floats2bfloat162_rn(pv[j * 8 + 6], pv[j * 8 + 7]);
+        v.x = *reinterpret_cast<uint32_t*>(&t0);
+        v.y = *reinterpret_cast<uint32_t*>(&t1);
+        v.z = *reinterpret_cast<uint32_t*>(&t2);
+        v.w = *reinterpret_cast<uint32_t*>(&t3);
+        *reinterpret_cast<uint4*>(prow + ((((ch & 1) * 4 + j) ^ sw) << 4)) = v;
+      }
+    }
+    fence_proxy_async();     // P (generic proxy) -> visible to the tensor core's async proxy
+    tc_fence_before();
+    mbar_arrive(p_ready);
+    mbar_wait(o_full, 0);
+    tc_fence_after();
+    const int t = mt * 128 + static_cast<int>(row);
+    const float inv = 1.f / sum;
+#pragma unroll 1
+    for (int ch = 0; ch < 2; ++ch) {
+      uint32_t r[32];
+      tmem_ld_32x32(taddr + ch * 32, r);
+      tmem_ld_wait_regs(r);
+      if (t < p.T) {
+        __nv_bfloat16* op = p.out + static_cast<size_t>(row0 + t) * (p.heads * 64) + h * 64 + ch * 32;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          uint4 v;
+          __nv_bfloat162 t0 = __floats2bfloat162_rn(__uint_as_float(r[j * 8 + 0]) * inv, __uint_as_float(r[j * 8 + 1]) * inv);
+          __nv_bfloat162 t1 = __floats2bfloat162_rn(__uint_as_float(r[j * 8 + 2]) * inv, __uint_as_float(r[j * 8 + 3]) * inv);
+          __nv_bfloat162 t2 = __floats2bfloat162_rn(__uint_as_float(r[j * 8 + 4]) * inv, __uint_as_float(r[j * 8 + 5]) * inv);
+          __nv_bfloat162 t3 = __floats2bfloat162_rn(__uint_as_float(r[j * 8 + 6]) * inv, __uint_as_float(r[j * 8 + 7]) * inv);
+          v.x = *reinterpret_cast<uint32_t*>(&t0);
+          v.y = *reinterpret_cast<uint32_t*>(&t1);
+          v.z = *reinterpret_cast<uint32_t*>(&t2);
+          v.w = *reinterpret_cast<uint32_t*>(&t3);
+          *reinterpret_cast<uint4*>(op + j * 8) = v;
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc<1>(tmem_base, 256);
+}
+
 }  // namespace
 
 int attention(const __nv_bfloat16* qkv, long long qkv_plane_stride, __nv_bfloat16* out, long long out_plane_stride,
@@ -424,6 +599,15 @@ int attention(const __nv_bfloat16* qkv, long long qkv_plane_stride, __nv_bfloat1
     AttnTcParams tp;
     tp.out = out; tp.B = B; tp.T = T; tp.heads = heads; tp.causal = causal;
     tp.scale_log2e = scale * 1.4426950408889634f;
+    if (!tuning_flag("DCR_ATTN_ONE_CTA")) {   // one query tile per CTA, two CTAs per SM
+      const size_t smem1 = 1024 + 16384 + 32768 + 16384 + 32768 + 256;
+      DCR_CUDA_CHECK(cudaFuncSetAttribute(attention_tc1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          static_cast<int>(smem1)));
+      attention_tc1_kernel<<<B * heads * ((T + 127) / 128), kAttn1Threads, smem1, stream>>>(tm, tp);
+      count_launch();
+      DCR_CUDA_CHECK(cudaGetLastError());
+      return 0;
+    }
     const size_t smem = 1024 + 2 * 16384 + 32768 + 32768 + 2 * 65536 + 256;
     DCR_CUDA_CHECK(cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         static_cast<int>(smem)));

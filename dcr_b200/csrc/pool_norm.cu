@@ -273,6 +273,60 @@ __global__ void pool_kernel(const PoolParams p) {
   }
 }
 
+// Single-plane 3x3 average pool, count_include_pad = False (the patched pools of the FID Inception blocks,
+// metrics/inception.py:241,269,302): nine clamped 16-byte loads in flight per thread, fp32 sum of the in-bounds taps in the
+// generic kernel's order (bit-identical results), one division.  The generic kernel walked the taps serially: 1.4 ms of a
+// 5.5 ms Inception forward at batch 128 (profiles/r02_layers_inception.txt) for data HBM moves in ~0.15 ms.
+__global__ void __launch_bounds__(256) avgpool3_bf16_kernel(const PoolParams p) {
+  const int cg = p.C / 8;
+  const long long total = static_cast<long long>(p.B) * p.OH * p.OW * cg;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c8 = static_cast<int>(i % cg);
+    const long long m = i / cg;
+    const int q = static_cast<int>(m % p.OW);
+    const int pp = static_cast<int>((m / p.OW) % p.OH);
+    const int b = static_cast<int>(m / (static_cast<long long>(p.OW) * p.OH));
+    const int y0 = pp * p.stride - p.pad, x0 = q * p.stride - p.pad;
+    const __nv_bfloat16* img = p.in + static_cast<size_t>(b) * p.H * p.W * p.C + c8 * 8;
+    uint4 v[9];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      const __nv_bfloat16* row = img + static_cast<size_t>(min(max(y0 + r, 0), p.H - 1)) * p.W * p.C;
+#pragma unroll
+      for (int s = 0; s < 3; ++s)
+        v[r * 3 + s] = __ldg(reinterpret_cast<const uint4*>(row + static_cast<size_t>(min(max(x0 + s, 0), p.W - 1)) * p.C));
+    }
+    float acc[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+    int cnt = 0;
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+#pragma unroll
+      for (int s = 0; s < 3; ++s) {
+        const int y = y0 + r, x = x0 + s;
+        if (y >= 0 && y < p.H && x >= 0 && x < p.W) {
+          const uint32_t w[4] = {v[r * 3 + s].x, v[r * 3 + s].y, v[r * 3 + s].z, v[r * 3 + s].w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            acc[2 * j] += __uint_as_float(w[j] << 16);
+            acc[2 * j + 1] += __uint_as_float(w[j] & 0xffff0000u);
+          }
+          ++cnt;
+        }
+      }
+    }
+    const float fc = static_cast<float>(cnt);
+    uint4 o;
+    __nv_bfloat162 t0 = __floats2bfloat162_rn(acc[0] / fc, acc[1] / fc), t1 = __floats2bfloat162_rn(acc[2] / fc, acc[3] / fc);
+    __nv_bfloat162 t2 = __floats2bfloat162_rn(acc[4] / fc, acc[5] / fc), t3 = __floats2bfloat162_rn(acc[6] / fc, acc[7] / fc);
+    o.x = *reinterpret_cast<uint32_t*>(&t0); o.y = *reinterpret_cast<uint32_t*>(&t1);
+    o.z = *reinterpret_cast<uint32_t*>(&t2); o.w = *reinterpret_cast<uint32_t*>(&t3);
+    *reinterpret_cast<uint4*>(p.out + static_cast<size_t>(m) * p.ld_out + p.out_col_off + c8 * 8) = o;
+  }
+}
+
 // Single-plane 3x3 max pool (any stride / padding): the fast-mode path of the ResNet stem and the three Inception
 // reductions.  bf16 maxima are taken directly on the packed pairs (the maximum of bf16 values is exact), the nine
 // 16-byte loads are issued unconditionally from clamped coordinates (out-of-range taps are masked with -inf after the
@@ -714,6 +768,8 @@ int pool2d(bool is_max, const __nv_bfloat16* in, long long in_plane_stride, __nv
   if (is_max && planes == 1 && k == 3 && stride <= 2 && !tuning_flag("DCR_POOL_GENERIC")) {
     const long long total2 = static_cast<long long>(B) * p.OH * ((p.OW + 1) / 2) * (C / 8);
     maxpool3_bf16_kernel<<<grid_for(total2, 256, di->num_sms), 256, 0, stream>>>(p);
+  } else if (!is_max && planes == 1 && k == 3 && !tuning_flag("DCR_POOL_GENERIC")) {
+    avgpool3_bf16_kernel<<<grid_for(total, 256, di->num_sms), 256, 0, stream>>>(p);
   } else if (is_max) pool_kernel<true><<<grid_for(total, 256, di->num_sms), 256, 0, stream>>>(p);
   else pool_kernel<false><<<grid_for(total, 256, di->num_sms), 256, 0, stream>>>(p);
   count_launch();
