@@ -503,36 +503,39 @@ __global__ void __launch_bounds__(kAttn1Threads, 2)
     mbar_wait(s_full, 0);     // S complete: the MMAs have finished reading Q and K, P may overwrite them
     tc_fence_after();
     const int lim = p.causal ? min(p.T, mt * 128 + static_cast<int>(row) + 1) : p.T;
+    // Both passes over the S row are software pipelined: the TMEM load of chunk i+1 is in flight while chunk i is processed
+    // (tcgen05.ld is asynchronous until tcgen05.wait::ld; the waits are tied to the registers they guard).
+    const int nch = (p.T + 31) / 32;                       // 32-column chunks that hold valid keys (<= 8)
     float mx = -INFINITY;
+    {
+      uint32_t ra[32], rb[32];
+      tmem_ld_32x32(taddr, ra);
 #pragma unroll 1
-    for (int ch = 0; ch < 8; ++ch) {
-      if (ch * 32 >= p.T) break;
-      uint32_t r[32];
-      tmem_ld_32x32(taddr + ch * 32, r);
-      tmem_ld_wait_regs(r);
+      for (int ch = 0; ch < nch; ch += 2) {
+        tmem_ld_wait_regs(ra);
+        if (ch + 1 < nch) tmem_ld_32x32(taddr + (ch + 1) * 32, rb);
 #pragma unroll
-      for (int c = 0; c < 32; ++c)
-        if (ch * 32 + c < lim) mx = fmaxf(mx, __uint_as_float(r[c]));
+        for (int c = 0; c < 32; ++c)
+          if (ch * 32 + c < lim) mx = fmaxf(mx, __uint_as_float(ra[c]));
+        if (ch + 1 < nch) {
+          tmem_ld_wait_regs(rb);
+          if (ch + 2 < nch) tmem_ld_32x32(taddr + (ch + 2) * 32, ra);
+#pragma unroll
+          for (int c = 0; c < 32; ++c)
+            if ((ch + 1) * 32 + c < lim) mx = fmaxf(mx, __uint_as_float(rb[c]));
+        }
+      }
     }
     const float mxs = mx * p.scale_log2e;
     float sum = 0.f;
-#pragma unroll 1
-    for (int ch = 0; ch < 8; ++ch) {
-      uint32_t r[32];
+    auto emit = [&](int ch, const uint32_t (&r)[32], bool valid) {   // exp2, row sum, P chunk -> shared memory
       float pv[32];
-      if (ch * 32 < p.T) {
-        tmem_ld_32x32(taddr + ch * 32, r);
-        tmem_ld_wait_regs(r);
 #pragma unroll
-        for (int c = 0; c < 32; ++c) {
-          const float e = (ch * 32 + c < lim) ? exp2f(fmaf(__uint_as_float(r[c]), p.scale_log2e, -mxs)) : 0.f;
-          const float eb = __bfloat162float(__float2bfloat16_rn(e));   // the sum must be of the ROUNDED weights
-          pv[c] = eb;
-          sum += eb;
-        }
-      } else {
-#pragma unroll
-        for (int c = 0; c < 32; ++c) pv[c] = 0.f;
+      for (int c = 0; c < 32; ++c) {
+        const float e = (valid && ch * 32 + c < lim) ? exp2f(fmaf(__uint_as_float(r[c]), p.scale_log2e, -mxs)) : 0.f;
+        const float eb = __bfloat162float(__float2bfloat16_rn(e));   // the sum must be of the ROUNDED weights
+        pv[c] = eb;
+        sum += eb;
       }
       uint8_t* prow = s_p + (ch >> 1) * 16384 + row * 128;
 #pragma unroll
@@ -547,6 +550,20 @@ __global__ void __launch_bounds__(kAttn1Threads, 2)
         v.z = *reinterpret_cast<uint32_t*>(&t2);
         v.w = *reinterpret_cast<uint32_t*>(&t3);
         *reinterpret_cast<uint4*>(prow + ((((ch & 1) * 4 + j) ^ sw) << 4)) = v;
+      }
+    };
+    {
+      uint32_t ra[32], rb[32];
+      tmem_ld_32x32(taddr, ra);
+#pragma unroll 1
+      for (int ch = 0; ch < 8; ch += 2) {
+        const bool va = ch < nch, vb = ch + 1 < nch;
+        if (va) tmem_ld_wait_regs(ra);
+        if (vb) tmem_ld_32x32(taddr + (ch + 1) * 32, rb);
+        emit(ch, ra, va);
+        if (vb) tmem_ld_wait_regs(rb);
+        if (ch + 2 < nch) tmem_ld_32x32(taddr + (ch + 2) * 32, ra);
+        emit(ch + 1, rb, vb);
       }
     }
     fence_proxy_async();     // P (generic proxy) -> visible to the tensor core's async proxy
