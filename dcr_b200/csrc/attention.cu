@@ -416,6 +416,28 @@ __global__ void __launch_bounds__(kAttnThreads, 1)
 // have retired, so a CTA needs 96 KB and two of them share an SM (and its 512 TMEM columns, 256 each): one CTA's loads and
 // MMAs run under the other's softmax.  K / V of an (image, head) are fetched by both of its CTAs (second fetch: L2).
 constexpr int kAttn1Threads = 160;   // warps 0-3 softmax + epilogue, warp 4 TMA + MMA issue
+DCR_DEVICE float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+DCR_DEVICE uint32_t pack_bf16x2(float lo, float hi) {
+  uint32_t w;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(w) : "f"(hi), "f"(lo));   // upper half <- first source
+  return w;
+}
+// running maximum over one 32-column chunk of a score row; columns >= lim are not part of the row
+DCR_DEVICE float chunk_max(const uint32_t (&r)[32], int c0, int lim, float mx) {
+  if (c0 + 32 <= lim) {
+#pragma unroll
+    for (int c = 0; c < 32; c += 2) mx = fmaxf(mx, fmaxf(__uint_as_float(r[c]), __uint_as_float(r[c + 1])));
+  } else {
+#pragma unroll
+    for (int c = 0; c < 32; ++c)
+      if (c0 + c < lim) mx = fmaxf(mx, __uint_as_float(r[c]));
+  }
+  return mx;
+}
 __global__ void __launch_bounds__(kAttn1Threads, 2)
     attention_tc1_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnTcParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -514,43 +536,44 @@ __global__ void __launch_bounds__(kAttn1Threads, 2)
       for (int ch = 0; ch < nch; ch += 2) {
         tmem_ld_wait_regs(ra);
         if (ch + 1 < nch) tmem_ld_32x32(taddr + (ch + 1) * 32, rb);
-#pragma unroll
-        for (int c = 0; c < 32; ++c)
-          if (ch * 32 + c < lim) mx = fmaxf(mx, __uint_as_float(ra[c]));
+        mx = chunk_max(ra, ch * 32, lim, mx);
         if (ch + 1 < nch) {
           tmem_ld_wait_regs(rb);
           if (ch + 2 < nch) tmem_ld_32x32(taddr + (ch + 2) * 32, ra);
-#pragma unroll
-          for (int c = 0; c < 32; ++c)
-            if ((ch + 1) * 32 + c < lim) mx = fmaxf(mx, __uint_as_float(rb[c]));
+          mx = chunk_max(rb, (ch + 1) * 32, lim, mx);
         }
       }
     }
     const float mxs = mx * p.scale_log2e;
     float sum = 0.f;
-    auto emit = [&](int ch, const uint32_t (&r)[32], bool valid) {   // exp2, row sum, P chunk -> shared memory
-      float pv[32];
+    // exp2, row sum, P chunk -> shared memory.  ~5 instructions per element: FFMA, MUFU.EX2 (approx), half a bf16x2 pack, one
+    // shift / mask to get the ROUNDED weight back (the sum must be of the values the tensor core will use) and the add.
+    auto emit = [&](int ch, const uint32_t (&r)[32], bool valid) {
+      uint32_t pk[16];
+      const int c0 = ch * 32;
+      if (valid && c0 + 32 <= lim) {               // whole chunk visible: no per-element masks
 #pragma unroll
-      for (int c = 0; c < 32; ++c) {
-        const float e = (valid && ch * 32 + c < lim) ? exp2f(fmaf(__uint_as_float(r[c]), p.scale_log2e, -mxs)) : 0.f;
-        const float eb = __bfloat162float(__float2bfloat16_rn(e));   // the sum must be of the ROUNDED weights
-        pv[c] = eb;
-        sum += eb;
+        for (int c = 0; c < 32; c += 2) {
+          const float e0 = ex2_approx(fmaf(__uint_as_float(r[c]), p.scale_log2e, -mxs));
+          const float e1 = ex2_approx(fmaf(__uint_as_float(r[c + 1]), p.scale_log2e, -mxs));
+          const uint32_t w = pack_bf16x2(e0, e1);
+          pk[c >> 1] = w;
+          sum += __uint_as_float(w << 16) + __uint_as_float(w & 0xffff0000u);
+        }
+      } else {
+#pragma unroll
+        for (int c = 0; c < 32; c += 2) {
+          const float e0 = (valid && c0 + c < lim) ? ex2_approx(fmaf(__uint_as_float(r[c]), p.scale_log2e, -mxs)) : 0.f;
+          const float e1 = (valid && c0 + c + 1 < lim) ? ex2_approx(fmaf(__uint_as_float(r[c + 1]), p.scale_log2e, -mxs)) : 0.f;
+          const uint32_t w = pack_bf16x2(e0, e1);
+          pk[c >> 1] = w;
+          sum += __uint_as_float(w << 16) + __uint_as_float(w & 0xffff0000u);
+        }
       }
       uint8_t* prow = s_p + (ch >> 1) * 16384 + row * 128;
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        uint4 v;
-        __nv_bfloat162 t0 = __floats2bfloat162_rn(pv[j * 8 + 0], pv[j * 8 + 1]);
-        __nv_bfloat162 t1 = __floats2bfloat162_rn(pv[j * 8 + 2], pv[j * 8 + 3]);
-        __nv_bfloat162 t2 = __floats2bfloat162_rn(pv[j * 8 + 4], pv[j * 8 + 5]);
-        __nv_bfloat162 t3 = __floats2bfloat162_rn(pv[j * 8 + 6], pv[j * 8 + 7]);
-        v.x = *reinterpret_cast<uint32_t*>(&t0);
-        v.y = *reinterpret_cast<uint32_t*>(&t1);
-        v.z = *reinterpret_cast<uint32_t*>(&t2);
-        v.w = *reinterpret_cast<uint32_t*>(&t3);
-        *reinterpret_cast<uint4*>(prow + ((((ch & 1) * 4 + j) ^ sw) << 4)) = v;
-      }
+      for (int j = 0; j < 4; ++j)
+        *reinterpret_cast<uint4*>(prow + ((((ch & 1) * 4 + j) ^ sw) << 4)) = make_uint4(pk[j * 4], pk[j * 4 + 1], pk[j * 4 + 2], pk[j * 4 + 3]);
     };
     {
       uint32_t ra[32], rb[32];
