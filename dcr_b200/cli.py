@@ -108,6 +108,16 @@ def build_model(args):
         if args.multiscale:                                                                   # utils_ret.py:676-698
             return [nets.build_dino_vit(sd, scale_factor=s, **kw) for s in retrieval.MULTI_SCALES]
         return nets.build_dino_vit(sd, **kw)
+    if args.pt_style == "clip":
+        # diff_retrieval.py:264-271 loads clip.load({'vit_large': 'ViT-L/14', 'vit_base': 'ViT-B/16', 'resnet50': 'RN50x16'}[arch]);
+        # the descriptor is `model.encode_image(samples)` (the branch utils_ret.py:725-726 spells out).  The ViT image
+        # towers are built from the CLIP state_dict; the ResNet tower (RN50x16) is not.
+        if args.arch not in ("vit_base", "vit_large"):
+            raise NotImplementedError("--pt_style clip: --arch vit_base (ViT-B/16) and vit_large (ViT-L/14) are implemented")
+        sd = load_state_dict(args.weights or args.pretrained)
+        if args.multiscale or args.similarity_metric == "splitloss":
+            raise NotImplementedError("--pt_style clip supports the dot-product metric at the native input size")
+        return nets.build_clip_visual(sd, max_batch=64 if args.arch == "vit_large" else 256, precision=args.precision)
     raise NotImplementedError(f"--pt_style {args.pt_style} is outside the embed->match hot path (DESIGN.md section 9)")
 
 

@@ -669,7 +669,7 @@ int im2col_u8(const uint8_t* img, int B, int IH, int IW, int crop_y, int crop_x,
   if (!di) return -2;
   const int rp = (3 * kw + 7) / 8 * 8;
   DCR_REQUIRE(k_pad % rp == 0 && k_pad >= kh * rp, "im2col_u8: k_pad %d must be a multiple of %d and >= %d", k_pad, rp, kh * rp);
-  DCR_REQUIRE(kw == 3 || kw == 7 || kw == 8 || kw == 16, "im2col_u8: filter width %d not instantiated (3, 7, 8, 16)", kw);
+  DCR_REQUIRE(kw == 3 || kw == 7 || kw == 8 || kw == 14 || kw == 16, "im2col_u8: filter width %d not instantiated (3, 7, 8, 14, 16)", kw);
   DCR_REQUIRE(crop_y >= 0 && crop_x >= 0 && crop_y + H <= IH && crop_x + W <= IW, "im2col_u8: crop outside image");
   Im2colU8Params p;
   p.img = img; p.img_f32 = img_f32; p.B = B; p.IH = IH; p.IW = IW; p.crop_y = crop_y; p.crop_x = crop_x; p.H = H; p.W = W;
@@ -699,6 +699,7 @@ int im2col_u8(const uint8_t* img, int B, int IH, int IW, int crop_y, int crop_x,
   if (kw == 7) DCR_IM2COL(7);
   else if (kw == 3) DCR_IM2COL(3);
   else if (kw == 8) DCR_IM2COL(8);
+  else if (kw == 14) DCR_IM2COL(14);
   else DCR_IM2COL(16);
 #undef DCR_IM2COL
   count_launch();

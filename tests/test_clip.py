@@ -133,3 +133,21 @@ def test_clip_towers_and_score_on_gpu():
     fi, ft = fast.encode_image(img.cuda()).cpu(), fast.encode_text(tok.cuda()).cpu()
     assert (fi - fq_i).abs().max().item() < 6e-2 * max(1.0, fq_i.abs().max().item())
     assert (ft - fq_t).abs().max().item() < 6e-2 * max(1.0, fq_t.abs().max().item())
+
+
+@pytest.mark.gpu
+def test_clip_vit_l14_geometry_through_the_cli_builder():
+    """--pt_style clip --arch vit_large (diff_retrieval.py:264-271: ViT-L/14): patch 14 -> 257 tokens (the streamed-KV
+    attention kernel), width 1024 / 16 heads; a 2-layer seeded model against the oracle."""
+    from dcr_b200 import nets, synthetic
+    from oracle import models as om
+    sd = oc.make_clip_state_dict(3, layers=2, vision_width=1024, embed_dim=768, patch=14)
+    img = synthetic.images(2, seed=72)
+    ref = oc.encode_image(sd, om.preprocess(img))
+    net = nets.build_clip_visual(sd, max_batch=2, precision="exact")
+    assert net.tokens == 257
+    got = net(img.cuda()).cpu()
+    assert (got - ref).abs().max().item() < 5e-5 * max(1.0, ref.abs().max().item())
+    fast = nets.build_clip_visual(sd, max_batch=2, precision="fast")(img.cuda()).cpu()
+    refq = oc.encode_image(sd, om.preprocess(img), bf16_points=True)
+    assert (fast - refq).abs().max().item() < 6e-2 * max(1.0, refq.abs().max().item())

@@ -98,7 +98,9 @@ def test_cli_rejects_unknown_models_and_metrics(tmp_path):
     with pytest.raises(NotImplementedError):
         cli.main(["--query_dir", str(q), "--val_dir", str(q), "--similarity_metric", "cosine"])
     with pytest.raises(NotImplementedError):
-        cli.main(["--query_dir", str(q), "--val_dir", str(q), "--pt_style", "clip"])
+        cli.main(["--query_dir", str(q), "--val_dir", str(q), "--pt_style", "clip", "--arch", "resnet50"])     # RN50x16 tower
+    with pytest.raises(NotImplementedError):
+        cli.main(["--query_dir", str(q), "--val_dir", str(q), "--pt_style", "vicregl"])
     with pytest.raises(FileNotFoundError):
         cli.main(["--query_dir", str(q), "--val_dir", str(q), "--pt_style", "sscd", "--weights", str(tmp_path / "none.pt")])
 
