@@ -76,15 +76,8 @@ struct GemmParams {
                               //    column blocks (tiles n-fastest, contiguous tile range per CTA); stages carry only W tiles
 };
 
-DCR_DEVICE float apply_act(float y, int act) {
-  if (act == 1) return fmaxf(y, 0.f);
-  if (act == 2) return 0.5f * y * (1.f + erff(y * 0.70710678118654752440f));
-  if (act == 3) return y / (1.f + expf(-1.702f * y));   // QuickGELU: x * sigmoid(1.702 x)  (CLIP, clip/model.py)
-  return y;
-}
-
-// exact-erf GELU for the bf16 (TMA-store) epilogue: erf by Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7 absolute, far inside
-// the bf16 rounding of the stored activation) -- about half the instructions of erff(), whose two-branch evaluation made
+// exact-erf GELU of the tensor-core epilogues: erf by Abramowitz-Stegun 7.1.26 (|error| <= 2e-7 absolute: below the bf16
+// rounding of a stored activation and at the level of the split-bf16 modes' own accumulation error) -- about half the instructions of erff(), whose two-branch evaluation made
 // the fc1 + GELU layers of the ViTs ALU bound in their epilogue (129 us at 461 TFLOP/s for 50k x 1536 x 384).
 DCR_DEVICE float gelu_erf_fast(float y) {
   const float ax = fabsf(y) * 0.70710678118654752440f;
@@ -98,6 +91,13 @@ DCR_DEVICE float gelu_erf_fast(float y) {
   poly = fmaf(poly, t, 0.254829592f);
   const float erf_abs = fmaf(-poly * t, e, 1.f);               // erf(|y| / sqrt 2)
   return 0.5f * y + 0.5f * fabsf(y) * erf_abs;                 // 0.5 y (1 + erf(y / sqrt 2)),  y erf(..) = |y| erf(|..|)
+}
+
+DCR_DEVICE float apply_act(float y, int act) {
+  if (act == 1) return fmaxf(y, 0.f);
+  if (act == 2) return gelu_erf_fast(y);                 // every tensor-core epilogue; the float64 mode (conv_exact.cu) keeps erff
+  if (act == 3) return y / (1.f + expf(-1.702f * y));   // QuickGELU: x * sigmoid(1.702 x)  (CLIP, clip/model.py)
+  return y;
 }
 
 DCR_DEVICE uint32_t pack_bf16(float a, float b) {
