@@ -88,7 +88,7 @@ __global__ void __launch_bounds__(256) im2col_u8_kernel(const Im2colU8Params p) 
     lut[c][u] = p.post_scale * val + p.post_shift;
   }
   __syncthreads();
-  const int rows_k = p.k_pad / RP;   // kh filter rows + zero rows up to k_pad
+  const int rows_k = (p.k_pad + RP - 1) / RP;   // kh filter rows + zero rows up to k_pad (the last one may be partial)
   const long long total = static_cast<long long>(p.B) * p.OH * p.OW * rows_k;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -121,6 +121,7 @@ __global__ void __launch_bounds__(256) im2col_u8_kernel(const Im2colU8Params p) 
     __nv_bfloat16* dst = p.out + static_cast<size_t>(m) * p.k_pad + r * RP;
 #pragma unroll
     for (int g = 0; g < RP / 8; ++g) {
+      if (r * RP + g * 8 >= p.k_pad) break;   // partial last zero row (k_pad is a multiple of 8, not always of RP)
       float v[8];
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
@@ -668,7 +669,7 @@ int im2col_u8(const uint8_t* img, int B, int IH, int IW, int crop_y, int crop_x,
   const DeviceInfo* di = device_info();
   if (!di) return -2;
   const int rp = (3 * kw + 7) / 8 * 8;
-  DCR_REQUIRE(k_pad % rp == 0 && k_pad >= kh * rp, "im2col_u8: k_pad %d must be a multiple of %d and >= %d", k_pad, rp, kh * rp);
+  DCR_REQUIRE(k_pad % 8 == 0 && k_pad >= kh * rp, "im2col_u8: k_pad %d must be a multiple of 8 and >= %d", k_pad, kh * rp);
   DCR_REQUIRE(kw == 3 || kw == 7 || kw == 8 || kw == 14 || kw == 16, "im2col_u8: filter width %d not instantiated (3, 7, 8, 14, 16)", kw);
   DCR_REQUIRE(crop_y >= 0 && crop_x >= 0 && crop_y + H <= IH && crop_x + W <= IW, "im2col_u8: crop outside image");
   Im2colU8Params p;
@@ -684,7 +685,7 @@ int im2col_u8(const uint8_t* img, int B, int IH, int IW, int crop_y, int crop_x,
   p.post_scale = post_scale; p.post_shift = post_shift;
   p.out = out; p.out_plane_stride = out_plane_stride; p.planes = planes;
   if (B == 0) return 0;
-  const long long total = static_cast<long long>(B) * p.OH * p.OW * (k_pad / rp);
+  const long long total = static_cast<long long>(B) * p.OH * p.OW * ((k_pad + rp - 1) / rp);
   const int grid = grid_for(total, 256, di->num_sms);
 #define DCR_IM2COL(KWv)                                                                             \
   do {                                                                                              \
