@@ -41,6 +41,7 @@ SIGNATURES = {
     "dcr_net_create": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
     "dcr_net_set_exact": (C.c_int, [C.c_void_p, C.c_int]),
     "dcr_net_destroy": (None, [C.c_void_p]),
+    "dcr_net_fork": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
     "dcr_net_add_tensor": (C.c_int, [C.c_void_p, C.c_int64, C.c_int]),
     "dcr_net_alias_tensor": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_int]),
     "dcr_net_add_param": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),

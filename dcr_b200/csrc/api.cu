@@ -219,6 +219,10 @@ int dcr_net_create(int max_batch, int planes, dcr_net** out) {
 }
 int dcr_net_set_exact(dcr_net* net, int on) { return dcr::net_set_exact(reinterpret_cast<dcr::Net*>(net), on); }
 void dcr_net_destroy(dcr_net* net) { dcr::net_destroy(reinterpret_cast<dcr::Net*>(net)); }
+int dcr_net_fork(const dcr_net* net, dcr_net** out) {
+  DCR_REQUIRE(net != nullptr && out != nullptr, "dcr_net_fork: null argument");
+  return dcr::net_fork(reinterpret_cast<const dcr::Net*>(net), reinterpret_cast<dcr::Net**>(out));
+}
 int dcr_net_add_tensor(dcr_net* net, int64_t rows_per_image, int channels) {
   return dcr::net_add_tensor(reinterpret_cast<dcr::Net*>(net), rows_per_image, channels);
 }

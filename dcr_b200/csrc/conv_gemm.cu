@@ -617,6 +617,12 @@ int conv_gemm(const ConvGemmDesc& d, cudaStream_t stream) {
   if (BN == 256 && single_plane && (d.res != nullptr || static_cast<long long>(d.kh) * d.kw * d.C <= 256)) BN = 128;
   // (256-wide tiles for the long-K residual layers -- ResNet layer4 expansions, K = 512 -- were tried in round 2: the output
   // and residual staging tiles of a 128 x 256 tile do not fit beside three pipeline stages)
+  // few output tiles and a long K (the SSCD head: 256 x 512 x 2048 is four 128 x 256 tiles, each CTA streaming 1.5 MB through
+  // one SM's L2 port: 22 us): narrower tiles put more CTAs -- more L2 ports -- on the same K stream
+  {
+    const long long m_tiles = (M + kBM - 1) / kBM;
+    while (BN > 64 && ktot >= 1024 && m_tiles * ((d.N + BN - 1) / BN) * 4 <= di->num_sms) BN /= 2;
+  }
   if (d.force_bn) BN = d.force_bn;
   for (int pl = 0; pl < 3; ++pl) {
     const int pa = std::min(pl, a_planes - 1), pw = std::min(pl, w_planes - 1);

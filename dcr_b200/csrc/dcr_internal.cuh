@@ -140,6 +140,7 @@ struct Net;
 int net_create(int max_batch, int planes, Net** out);
 int net_set_exact(Net* n, int on);
 void net_destroy(Net* n);
+int net_fork(const Net* src, Net** out);
 int net_add_tensor(Net* n, long long rows_per_image, int C);
 int net_alias_tensor(Net* n, int src, long long rows_per_image, int C);
 int net_add_param(Net* n, const void* host, size_t bytes);

@@ -398,7 +398,9 @@ struct ReduceHWParams {
 // (independent 16-byte loads, several in flight), the slices meet in shared memory.  (One thread per channel group walked
 // all HW positions serially before: 41 us for the 51 MB layer4 output of a ResNet-50 batch.)
 constexpr int kRedSlices = 4;
-template <bool kGem>
+// kCube: GeM with p = 3 (the SSCD head): t*t*t and cbrtf; the general exponent keeps powf out of this instantiation (inlined
+// into the unrolled loop it made the kernel instruction-fetch bound: 39 us, 26 % of the warp samples on `no_inst`).
+template <bool kGem, bool kCube>
 __global__ void __launch_bounds__(64 * kRedSlices) reduce_hw_kernel(const ReduceHWParams p) {
   __shared__ float part[kRedSlices][64][8];
   const int cg = p.C / 8;
@@ -418,7 +420,7 @@ __global__ void __launch_bounds__(64 * kRedSlices) reduce_hw_kernel(const Reduce
         for (int e = 0; e < 8; ++e) {
           if (kGem) {
             const float t = fmaxf(v[e], p.eps);
-            acc[e] += (p.p_exp == 3.f) ? t * t * t : powf(t, p.p_exp);
+            acc[e] += kCube ? t * t * t : powf(t, p.p_exp);
           } else {
             acc[e] += v[e];
           }
@@ -435,7 +437,7 @@ __global__ void __launch_bounds__(64 * kRedSlices) reduce_hw_kernel(const Reduce
 #pragma unroll
         for (int sl = 1; sl < kRedSlices; ++sl) t += part[sl][tc][e];   // fixed order: deterministic
         t = t / static_cast<float>(p.HW);
-        if (kGem) t = (p.p_exp == 3.f) ? cbrtf(t) : powf(t, 1.f / p.p_exp);
+        if (kGem) t = kCube ? cbrtf(t) : powf(t, 1.f / p.p_exp);
         acc[e] = t;
       }
       if (p.out_f32) {
@@ -789,8 +791,9 @@ int reduce_hw(bool gem, const __nv_bfloat16* in, long long in_plane_stride, int 
   if (B == 0) return 0;
   const int cg = C / 8;
   dim3 grid(B, (cg + 63) / 64);
-  if (gem) reduce_hw_kernel<true><<<grid, 64 * kRedSlices, 0, stream>>>(p);
-  else reduce_hw_kernel<false><<<grid, 64 * kRedSlices, 0, stream>>>(p);
+  if (gem && p_exp == 3.f) reduce_hw_kernel<true, true><<<grid, 64 * kRedSlices, 0, stream>>>(p);
+  else if (gem) reduce_hw_kernel<true, false><<<grid, 64 * kRedSlices, 0, stream>>>(p);
+  else reduce_hw_kernel<false, false><<<grid, 64 * kRedSlices, 0, stream>>>(p);
   count_launch();
   DCR_CUDA_CHECK(cudaGetLastError());
   return 0;

@@ -68,6 +68,25 @@ class DcrNet:
         except Exception:
             pass
 
+    def fork(self) -> "DcrNet":
+        """A second executor of this (fully built) network: own activation buffers, the same device weights.  Two batches
+        can then be in flight on two streams (retrieval.extract_features does that)."""
+        import copy
+        twin = copy.copy(self)
+        twin.handle = None
+        h = C.c_void_p()
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.dcr_net_fork(self.handle, C.byref(h)), "dcr_net_fork")
+        twin.handle = h
+        twin._twin = None
+        return twin
+
+    def twin(self) -> "DcrNet":
+        """The cached fork extract_features alternates with."""
+        if getattr(self, "_twin", None) is None:
+            self._twin = self.fork()
+        return self._twin
+
     # ---- graph construction -------------------------------------------------------------------------------------
     def tensor(self, rows_per_image: int, channels: int) -> int:
         with torch.cuda.device(self.device):

@@ -180,6 +180,10 @@ int dcr_net_create(int max_batch, int planes, dcr_net** out);
  * the mode the parity tests use against the fp32 oracle); needs planes == 3.  Default 0: tcgen05 tensor cores. */
 int dcr_net_set_exact(dcr_net* net, int on);
 void dcr_net_destroy(dcr_net* net);
+/* A second executor of a fully described network: its own activation buffers, the same uploaded parameters (reference
+ * counted: either handle may be destroyed first).  Lets two batches be in flight on two streams, which is how
+ * extract_features (utils_ret.py:704-787 replacement) keeps all SMs busy across the kernels' wave tails. */
+int dcr_net_fork(const dcr_net* net, dcr_net** out);
 int dcr_net_add_tensor(dcr_net* net, int64_t rows_per_image, int channels);
 /* another (rows_per_image, channels) factorisation of an existing tensor's buffer (flatten in front of a Linear layer) */
 int dcr_net_alias_tensor(dcr_net* net, int src_tensor, int64_t rows_per_image, int channels);

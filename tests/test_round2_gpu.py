@@ -355,3 +355,28 @@ def test_sim_topk_sharded_c_entry_two_ranks_nccl(tmp_path):
         got = np.load(os.path.join(str(tmp_path), f"c{r}.npz"))
         assert np.array_equal(got["i"], oi), f"rank {r}"
         np.testing.assert_allclose(got["v"], ov, rtol=0, atol=1.2e-7)
+
+
+@pytest.mark.gpu
+def test_fork_shares_weights_and_two_batches_in_flight_give_identical_rows():
+    """dcr_net_fork: a second executor (own activations, same parameters).  extract_features alternates batches between
+    the network and its fork on two streams; rows must equal the one-stream result bit for bit, for device and host
+    inputs, ragged last batch included -- and the fork must stay usable after the parent handle is destroyed."""
+    from dcr_b200 import nets, retrieval, synthetic
+    from oracle import models as om
+    sd = om.make_sscd_state_dict(11)
+    net = nets.build_sscd_resnet50(sd, max_batch=8, precision="fast")
+    imgs = synthetic.images(37, seed=91)
+    one = retrieval.extract_features(net, imgs.cuda(), 8, two_in_flight=False)
+    two = retrieval.extract_features(net, imgs.cuda(), 8, two_in_flight=True)
+    host = retrieval.extract_features(net, imgs.pin_memory(), 8)            # default: two in flight when > 1 batch
+    again = retrieval.extract_features(net, imgs.pin_memory(), 8)           # back to back: staging / fork buffers reused
+    assert torch.equal(one, two) and torch.equal(one, host) and torch.equal(one, again)
+    assert retrieval.extract_features(net, imgs[:0].cuda(), 8).shape == (0, net.out_dim)
+    fork = net.fork()
+    ref = net(imgs[:8].cuda())
+    del net
+    import gc
+    gc.collect()
+    torch.cuda.synchronize()
+    assert torch.equal(fork(imgs[:8].cuda()), ref)
