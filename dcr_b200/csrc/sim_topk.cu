@@ -1049,6 +1049,220 @@ __global__ void __launch_bounds__(128)
   }
 }
 
+// stage 3, one WARP per query (four queries per block, no block-wide barrier): the same steps and the same arithmetic
+// as rescore_select_kernel -- identical candidate sets, eps, exact scores, order and certificate -- for passes whose
+// q-tiles are covered by at most 32 candidate slots (a lane per slot; kKPMax = 32 entries per slot: a lane per entry).
+// The block form spent a third of its warp time on barriers behind one thread's slot walk and fetched one gallery row
+// per warp at a time: 171 us for 10k queries x ~14 surviving rows (1.7 TB/s of gathers).
+constexpr int kRescoreWarps = 4;
+
+// two rows, each with exactly the association of exact_dot_warp_qd; both rows' loads are issued before the first fma
+DCR_DEVICE void exact_dot_warp_qd2(const double* __restrict__ a_smem, const float* __restrict__ b0,
+                                   const float* __restrict__ b1, int d, uint32_t lane, double& out0, double& out1) {
+  double acc0 = 0.0, acc1 = 0.0;
+#pragma unroll 4
+  for (int c = lane * 4; c < d; c += 128) {
+    if (c + 3 < d) {
+      const float4 v0 = *reinterpret_cast<const float4*>(b0 + c);
+      const float4 v1 = *reinterpret_cast<const float4*>(b1 + c);
+      const double2 a01 = *reinterpret_cast<const double2*>(a_smem + c);
+      const double2 a23 = *reinterpret_cast<const double2*>(a_smem + c + 2);
+      acc0 = fma(a01.x, static_cast<double>(v0.x), acc0);
+      acc0 = fma(a01.y, static_cast<double>(v0.y), acc0);
+      acc0 = fma(a23.x, static_cast<double>(v0.z), acc0);
+      acc0 = fma(a23.y, static_cast<double>(v0.w), acc0);
+      acc1 = fma(a01.x, static_cast<double>(v1.x), acc1);
+      acc1 = fma(a01.y, static_cast<double>(v1.y), acc1);
+      acc1 = fma(a23.x, static_cast<double>(v1.z), acc1);
+      acc1 = fma(a23.y, static_cast<double>(v1.w), acc1);
+    } else {
+      for (int e = c; e < d; ++e) {
+        acc0 = fma(a_smem[e], static_cast<double>(b0[e]), acc0);
+        acc1 = fma(a_smem[e], static_cast<double>(b1[e]), acc1);
+      }
+    }
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    acc0 += __shfl_xor_sync(kFull, acc0, off);
+    acc1 += __shfl_xor_sync(kFull, acc1, off);
+  }
+  out0 = acc0;
+  out1 = acc1;
+}
+
+__global__ void __launch_bounds__(32 * kRescoreWarps)
+    rescore_select_warp_kernel(const float* __restrict__ q, const float* __restrict__ g, int nq_pass, int d, int k,
+                               int n_qtiles, int n_gtiles, int gchunk, int n_chunks, int n_units, int rows_per_qtile,
+                               int n_sets, int d_pad, const uint2* __restrict__ cand, const int* __restrict__ cand_cnt,
+                               const float* __restrict__ cand_thr, const int* __restrict__ qmap,
+                               const float* __restrict__ mu, const float* __restrict__ nu, const int* __restrict__ nu_flag,
+                               const float* __restrict__ q_norm_hat, const float* __restrict__ q_norm_res,
+                               const float* __restrict__ q_norm_x, const unsigned int* __restrict__ g_max,
+                               long long g_index_base, long long g_index_stride, float* __restrict__ out_scores,
+                               long long* __restrict__ out_idx, int* __restrict__ flagged, int* __restrict__ n_flagged,
+                               float* __restrict__ thr_next, int max_cand) {
+  extern __shared__ __align__(16) uint8_t sm[];
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int crow = blockIdx.x * kRescoreWarps + static_cast<int>(warp);
+  if (crow >= nq_pass) return;   // whole warps leave; nothing below synchronises the block
+  const int d2 = (d + 1) & ~1, mc = (max_cand + 3) & ~3;
+  uint8_t* base = sm + static_cast<size_t>(warp) * (static_cast<size_t>(d2) * 8 + static_cast<size_t>(mc) * 20);
+  double* qs = reinterpret_cast<double*>(base);     // [d2] the query row, widened once
+  double* sc = qs + d2;                              // [mc] exact scores of the survivors
+  int* ci = reinterpret_cast<int*>(sc + mc);         // [mc] gallery rows of all candidates
+  float* ap = reinterpret_cast<float*>(ci + mc);     // [mc] approximate scores
+  int* kc = reinterpret_cast<int*>(ap + mc);         // [mc] gallery rows of the survivors
+  const int qrow = qmap ? qmap[crow] : crow;
+  for (int c = lane; c < d; c += 32) qs[c] = static_cast<double>(q[static_cast<size_t>(qrow) * d + c]);
+
+  // ---- which (chunk, unit, set) slots cover this q-tile (mirror of SegWalker): lane c owns chunk c, then lane s slot s ----
+  const int qi = crow / rows_per_qtile, r = crow % rows_per_qtile;
+  int my_lo = 0, my_cnt = 0;
+  if (static_cast<int>(lane) < n_chunks) {
+    const int g_lo = lane * gchunk;
+    const int ncg = min(gchunk, n_gtiles - g_lo);
+    const long long T = static_cast<long long>(n_qtiles) * ncg;
+    const long long u_lo = owner_unit(static_cast<long long>(qi) * ncg, T, n_units);
+    const long long u_hi = owner_unit(static_cast<long long>(qi + 1) * ncg - 1, T, n_units);
+    my_lo = static_cast<int>(u_lo);
+    my_cnt = static_cast<int>(u_hi - u_lo + 1) * n_sets;
+  }
+  int ns = 0, my_slot = -1;
+  for (int c = 0; c < n_chunks; ++c) {
+    const int lo = __shfl_sync(kFull, my_lo, c), cnt = __shfl_sync(kFull, my_cnt, c);
+    const int rel = static_cast<int>(lane) - ns;
+    if (rel >= 0 && rel < cnt) my_slot = (c * (n_units + n_qtiles) + lo + rel / n_sets + qi) * n_sets + rel % n_sets;
+    ns += cnt;
+  }
+  int cc = 0;
+  float thr = -INFINITY;
+  if (my_slot >= 0) {
+    const size_t sr = static_cast<size_t>(my_slot) * rows_per_qtile + r;
+    cc = cand_cnt[sr];
+    thr = cand_thr[sr];
+  }
+  int off = cc;   // inclusive prefix sum of the slot counts
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_up_sync(kFull, off, o);
+    if (static_cast<int>(lane) >= o) off += t;
+  }
+  const int n_total = __shfl_sync(kFull, off, 31);
+  off -= cc;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) thr = fmaxf(thr, __shfl_xor_sync(kFull, thr, o));
+  const bool overflow = ns > 32 || n_total > max_cand;   // cannot happen: the host picks this kernel for <= 32 slots
+  const int n = overflow ? 0 : n_total;
+  const int nsl = min(ns, 32);
+#pragma unroll 4
+  for (int s = 0; s < nsl; ++s) {
+    const int c_s = overflow ? 0 : __shfl_sync(kFull, cc, s), off_s = __shfl_sync(kFull, off, s);
+    const int slot_s = __shfl_sync(kFull, my_slot, s);
+    if (static_cast<int>(lane) < c_s) {
+      const uint2 e = cand[(static_cast<size_t>(slot_s) * rows_per_qtile + r) * kKPMax + lane];
+      ci[off_s + lane] = static_cast<int>(e.y);
+      ap[off_s + lane] = __uint_as_float(e.x);
+    }
+  }
+
+  // eps bounds |tensor-core score of (bf16 q, bf16 (g-mu)) - q.(g-mu)| for this query from the measured norms
+  // (DESIGN.md section 4); same expression, same order of operations as the block form
+  const float g_norm = __uint_as_float(g_max[0]), g_res = __uint_as_float(g_max[1]);
+  const float qh = q_norm_hat[qrow], qr = q_norm_res[qrow], qx = q_norm_x[qrow];
+  float eps = 1.001f * (qh * g_res + qr * g_norm) + d_pad * 2.4e-7f * qh * (g_norm + g_res) + 1e-30f;
+  {
+    float acc = 0.f;
+    if (nu && nu_flag && *nu_flag)
+      for (int c = lane; c < d; c += 32) acc += nu[c] * nu[c];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(kFull, acc, o);
+    eps += 3e-7f * (qx + sqrtf(acc) * 1.001f) * g_norm;
+  }
+  __syncwarp();
+  double qmu = 0.0;   // q . mu in fp64: the constant the centred approximate scores are offset by
+  if (mu) {
+    for (int c = lane; c < d; c += 32) qmu = fma(qs[c], static_cast<double>(mu[c]), qmu);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) qmu += __shfl_xor_sync(kFull, qmu, o);
+  }
+
+  // ---- prune by approximate score: A_k by rank counting ----
+  const int kk = min(k, n);
+  float a_k = -INFINITY;
+  for (int c = lane; c < n; c += 32) {
+    const float v = ap[c];
+    int rank = 0;
+    for (int j = 0; j < n; ++j) {
+      const float o = ap[j];
+      rank += (o > v) || (o == v && j < c);
+    }
+    if (rank == kk - 1) a_k = v;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) a_k = fmaxf(a_k, __shfl_xor_sync(kFull, a_k, o));
+  const float cut = a_k - 2.f * eps - 1e-6f * fabsf(a_k);
+  int m = 0;
+  for (int c0 = 0; c0 < n; c0 += 32) {
+    const int c = c0 + lane;
+    const bool keep = c < n && (n <= k || ap[c] >= cut);
+    const uint32_t mask = __ballot_sync(kFull, keep);
+    if (keep) kc[m + __popc(mask & ((1u << lane) - 1u))] = ci[c];
+    m += __popc(mask);
+  }
+  __syncwarp();
+
+  // ---- exact scores of the survivors (two rows in flight), then selection by (score desc, index asc) ----
+  for (int c = 0; c < m; c += 2) {
+    double v0, v1 = 0.0;
+    if (c + 1 < m) exact_dot_warp_qd2(qs, g + static_cast<size_t>(kc[c]) * d, g + static_cast<size_t>(kc[c + 1]) * d, d, lane, v0, v1);
+    else v0 = exact_dot_warp_qd(qs, g + static_cast<size_t>(kc[c]) * d, d, lane);
+    if (lane == 0) {
+      sc[c] = v0;
+      if (c + 1 < m) sc[c + 1] = v1;
+    }
+  }
+  __syncwarp();
+  const int km = min(k, m);
+  double kth = -INFINITY;
+  for (int c = lane; c < m; c += 32) {
+    const double v = sc[c];
+    const int iv = kc[c];
+    int rank = 0;
+    for (int j = 0; j < m; ++j) {
+      const double o = sc[j];
+      const int io = kc[j];
+      rank += (o > v) || (o == v && (io < iv || (io == iv && j < c)));
+    }
+    if (rank < km) {
+      out_scores[static_cast<size_t>(qrow) * k + rank] = static_cast<float>(v);
+      out_idx[static_cast<size_t>(qrow) * k + rank] = g_index_base + g_index_stride * iv;
+      if (rank == km - 1) kth = v;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) kth = fmax(kth, __shfl_xor_sync(kFull, kth, o));   // one lane holds it (NaN -> -inf: flagged)
+  if (lane == 0) {
+    // certificate: every gallery row that is not a candidate has approximate centred score <= thr, hence exact score
+    // q.g <= thr + eps + q.mu
+    const bool closed = thr > -INFINITY;
+    const bool ok = (n >= k) && (m >= k) && !overflow &&
+                    (!closed || kth > static_cast<double>(thr) + static_cast<double>(eps) + qmu);
+    if (!ok) {
+      const int pos = atomicAdd(n_flagged, 1);
+      flagged[pos] = qrow;
+      if (thr_next) {
+        float t = -INFINITY;
+        if (m >= k && kth > -INFINITY) {
+          const double lo = kth - qmu - static_cast<double>(eps);
+          t = static_cast<float>(lo) - 2e-6f * fabsf(static_cast<float>(lo)) - 1e-7f;
+        }
+        thr_next[pos] = t;
+      }
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------------------
 // 'splitloss' similarity (diff_retrieval.py:393-400): descriptors are cut into n_chunks equal parts and the score of
 // a pair is the MAXIMUM over the parts of the per-part dot products.  The top-k under that score is contained in the
@@ -1553,6 +1767,21 @@ int sim_topk(const float* q, int nq, const float* g, int ng, int d, int k, long 
   DCR_CUDA_CHECK(cudaEventRecord(ev1, stream));
 
   auto rescore = [&](const PassPlan& pp, const int* qmap, int* flagged, int* n_flagged, float* thr_next) -> int {
+    // one warp per query when a q-tile's candidate slots fit a lane each and four queries' rows fit a block's shared memory
+    const size_t per_warp = ((static_cast<size_t>(d) + 1) & ~size_t(1)) * 8 + ((static_cast<size_t>(pp.max_cand) + 3) & ~size_t(3)) * 20;
+    const bool warp_form = pp.kp > 0 && pp.max_cand / pp.kp <= 32 && pp.n_chunks <= 32 && kRescoreWarps * per_warp <= 56 * 1024 &&
+                           !tuning_flag("DCR_SIM_RESCORE_BLOCK");
+    if (warp_form) {
+      const size_t smem = kRescoreWarps * per_warp;
+      DCR_CUDA_CHECK(cudaFuncSetAttribute(rescore_select_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+      rescore_select_warp_kernel<<<(pp.nq + kRescoreWarps - 1) / kRescoreWarps, 32 * kRescoreWarps, smem, stream>>>(
+          q, g, pp.nq, d, k, pp.n_qtiles, pl.n_gtiles, pp.gchunk, pp.n_chunks, pp.n_units, pl.rows_per_qtile, pp.n_sets, pl.d_pad,
+          pb.cand, pb.ccnt, pb.cthr, qmap, centre ? mu : nullptr, centre ? nu : nullptr, qflag, qnh, qnr, qnx, gmax, g_index_base,
+          g_index_stride, out_scores, out_idx, flagged, n_flagged, thr_next, pp.max_cand);
+      count_launch();
+      DCR_CUDA_CHECK(cudaGetLastError());
+      return 0;
+    }
     const size_t rs_smem = ((static_cast<size_t>(d) + 1) & ~size_t(1)) * 8 + static_cast<size_t>(pp.max_cand) * 20 + 16;
     DCR_CUDA_CHECK(cudaFuncSetAttribute(rescore_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         static_cast<int>(rs_smem)));

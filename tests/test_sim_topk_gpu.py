@@ -185,3 +185,18 @@ def test_splitloss_cross_matches_oracle(nq, ng, d, c, k):
     np.testing.assert_allclose(v.cpu().numpy(), ov, rtol=0, atol=1e-6)
     with pytest.raises(similarity._lib.DcrError):
         similarity.sim_topk_split(q.cuda(), g.cuda(), k, 7, cross=True)        # 7 does not divide d
+
+
+@pytest.mark.parametrize("nq,ng,d,k", [(1000, 20000, 512, 10), (300, 5000, 384, 1), (129, 3000, 100, 2), (700, 9000, 515, 10)])
+def test_rescore_warp_and_block_forms_agree(nq, ng, d, k, monkeypatch):
+    """The one-warp-per-query re-score kernel and the one-block-per-query form it replaces for small slot counts: same
+    candidates, same fp64 association, same selection -> identical scores (bitwise) and indices, and both equal the oracle."""
+    q, g = synthetic.descriptors(nq, ng, d, seed=31)
+    g[7] = g[3]                                                   # an exact tie between two gallery rows
+    v_w, i_w = _run(q, g, k)
+    monkeypatch.setenv("DCR_B200_TUNING", "1")
+    monkeypatch.setenv("DCR_SIM_RESCORE_BLOCK", "1")
+    v_b, i_b = _run(q, g, k)
+    assert np.array_equal(i_w, i_b) and np.array_equal(v_w, v_b)
+    monkeypatch.delenv("DCR_SIM_RESCORE_BLOCK")
+    _check(q, g, k)
