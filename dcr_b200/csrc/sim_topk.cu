@@ -1060,25 +1060,52 @@ constexpr int kRescoreWarps = 4;
 DCR_DEVICE void exact_dot_warp_qd2(const double* __restrict__ a_smem, const float* __restrict__ b0,
                                    const float* __restrict__ b1, int d, uint32_t lane, double& out0, double& out1) {
   double acc0 = 0.0, acc1 = 0.0;
-#pragma unroll 4
-  for (int c = lane * 4; c < d; c += 128) {
-    if (c + 3 < d) {
-      const float4 v0 = *reinterpret_cast<const float4*>(b0 + c);
-      const float4 v1 = *reinterpret_cast<const float4*>(b1 + c);
-      const double2 a01 = *reinterpret_cast<const double2*>(a_smem + c);
-      const double2 a23 = *reinterpret_cast<const double2*>(a_smem + c + 2);
-      acc0 = fma(a01.x, static_cast<double>(v0.x), acc0);
-      acc0 = fma(a01.y, static_cast<double>(v0.y), acc0);
-      acc0 = fma(a23.x, static_cast<double>(v0.z), acc0);
-      acc0 = fma(a23.y, static_cast<double>(v0.w), acc0);
-      acc1 = fma(a01.x, static_cast<double>(v1.x), acc1);
-      acc1 = fma(a01.y, static_cast<double>(v1.y), acc1);
-      acc1 = fma(a23.x, static_cast<double>(v1.z), acc1);
-      acc1 = fma(a23.y, static_cast<double>(v1.w), acc1);
-    } else {
-      for (int e = c; e < d; ++e) {
-        acc0 = fma(a_smem[e], static_cast<double>(b0[e]), acc0);
-        acc1 = fma(a_smem[e], static_cast<double>(b1[e]), acc1);
+  if ((d & 127) == 0 && d <= 512) {
+    // every lane owns d/128 whole 16-byte granules of each row: all (up to eight) loads are issued before the first fma --
+    // written as a loop, each 128-column step waited for its own two loads (40 serial memory latencies per query)
+    float4 v0[4], v1[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      if (i * 128 < d) {
+        v0[i] = *reinterpret_cast<const float4*>(b0 + lane * 4 + i * 128);
+        v1[i] = *reinterpret_cast<const float4*>(b1 + lane * 4 + i * 128);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      if (i * 128 < d) {
+        const double2 a01 = *reinterpret_cast<const double2*>(a_smem + lane * 4 + i * 128);
+        const double2 a23 = *reinterpret_cast<const double2*>(a_smem + lane * 4 + i * 128 + 2);
+        acc0 = fma(a01.x, static_cast<double>(v0[i].x), acc0);
+        acc0 = fma(a01.y, static_cast<double>(v0[i].y), acc0);
+        acc0 = fma(a23.x, static_cast<double>(v0[i].z), acc0);
+        acc0 = fma(a23.y, static_cast<double>(v0[i].w), acc0);
+        acc1 = fma(a01.x, static_cast<double>(v1[i].x), acc1);
+        acc1 = fma(a01.y, static_cast<double>(v1[i].y), acc1);
+        acc1 = fma(a23.x, static_cast<double>(v1[i].z), acc1);
+        acc1 = fma(a23.y, static_cast<double>(v1[i].w), acc1);
+      }
+    }
+  } else {
+    for (int c = lane * 4; c < d; c += 128) {
+      if (c + 3 < d) {
+        const float4 v0 = *reinterpret_cast<const float4*>(b0 + c);
+        const float4 v1 = *reinterpret_cast<const float4*>(b1 + c);
+        const double2 a01 = *reinterpret_cast<const double2*>(a_smem + c);
+        const double2 a23 = *reinterpret_cast<const double2*>(a_smem + c + 2);
+        acc0 = fma(a01.x, static_cast<double>(v0.x), acc0);
+        acc0 = fma(a01.y, static_cast<double>(v0.y), acc0);
+        acc0 = fma(a23.x, static_cast<double>(v0.z), acc0);
+        acc0 = fma(a23.y, static_cast<double>(v0.w), acc0);
+        acc1 = fma(a01.x, static_cast<double>(v1.x), acc1);
+        acc1 = fma(a01.y, static_cast<double>(v1.y), acc1);
+        acc1 = fma(a23.x, static_cast<double>(v1.z), acc1);
+        acc1 = fma(a23.y, static_cast<double>(v1.w), acc1);
+      } else {
+        for (int e = c; e < d; ++e) {
+          acc0 = fma(a_smem[e], static_cast<double>(b0[e]), acc0);
+          acc1 = fma(a_smem[e], static_cast<double>(b1[e]), acc1);
+        }
       }
     }
   }
@@ -1114,7 +1141,15 @@ __global__ void __launch_bounds__(32 * kRescoreWarps)
   float* ap = reinterpret_cast<float*>(ci + mc);     // [mc] approximate scores
   int* kc = reinterpret_cast<int*>(ap + mc);         // [mc] gallery rows of the survivors
   const int qrow = qmap ? qmap[crow] : crow;
-  for (int c = lane; c < d; c += 32) qs[c] = static_cast<double>(q[static_cast<size_t>(qrow) * d + c]);
+  // the query row: requested first, consumed after the slot walk below has issued its own loads (one memory round trip for
+  // both instead of one after the other)
+  const bool q_fast = (d & 127) == 0 && d <= 512;
+  float4 qv[4];
+  if (q_fast) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      if (i * 128 < d) qv[i] = *reinterpret_cast<const float4*>(q + static_cast<size_t>(qrow) * d + lane * 4 + i * 128);
+  }
 
   // ---- which (chunk, unit, set) slots cover this q-tile (mirror of SegWalker): lane c owns chunk c, then lane s slot s ----
   const int qi = crow / rows_per_qtile, r = crow % rows_per_qtile;
@@ -1141,6 +1176,18 @@ __global__ void __launch_bounds__(32 * kRescoreWarps)
     const size_t sr = static_cast<size_t>(my_slot) * rows_per_qtile + r;
     cc = cand_cnt[sr];
     thr = cand_thr[sr];
+  }
+  if (q_fast) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      if (i * 128 < d) {
+        double* dst = qs + lane * 4 + i * 128;
+        *reinterpret_cast<double2*>(dst) = make_double2(static_cast<double>(qv[i].x), static_cast<double>(qv[i].y));
+        *reinterpret_cast<double2*>(dst + 2) = make_double2(static_cast<double>(qv[i].z), static_cast<double>(qv[i].w));
+      }
+    }
+  } else {
+    for (int c = lane; c < d; c += 32) qs[c] = static_cast<double>(q[static_cast<size_t>(qrow) * d + c]);
   }
   int off = cc;   // inclusive prefix sum of the slot counts
 #pragma unroll
@@ -1211,6 +1258,15 @@ __global__ void __launch_bounds__(32 * kRescoreWarps)
     m += __popc(mask);
   }
   __syncwarp();
+  // every surviving row's cache lines are requested at once (L2 prefetch): the dot products below then wait for L2, not for
+  // one DRAM round trip per pair of rows
+  {
+    const int lines = (d * 4 + 127) / 128;
+    for (int t = lane; t < m * lines; t += 32) {
+      const float* ptr = g + static_cast<size_t>(kc[t / lines]) * d + (t % lines) * 32;
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr));
+    }
+  }
 
   // ---- exact scores of the survivors (two rows in flight), then selection by (score desc, index asc) ----
   for (int c = 0; c < m; c += 2) {
