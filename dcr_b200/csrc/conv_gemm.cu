@@ -129,13 +129,22 @@ DCR_DEVICE void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;
 //           layers), 1/2/3/4 = TMA-store epilogue with compile-time activation none / ReLU / GELU / QuickGELU (fast mode hot path).
 // Eight epilogue warps: warps w and w+4 share a TMEM lane quadrant and split the tile's columns, so every SM
 // sub-partition has two epilogue warps to switch between (the epilogue is latency bound, not issue bound).
-template <int BN, bool kIm2col, int kEpi>
+//
+// kCG == 2: two CTAs of a cluster (a TPC's SM pair) work one 256 x BN tile with UMMA 256 x BN x 16 (cta_group::2): each CTA
+// loads its own 128 A rows and HALF of the W tile (BN/2 rows), the leader CTA issues the MMAs for both, each CTA's TMEM
+// holds the accumulators of its own 128 rows and each runs its own epilogue.  Per CTA and k-block that is 16 KB + BN*64 B
+// through the L2 -> shared-memory port instead of 16 KB + BN*128 B, and 4 KB + BN*16 B of operand reads per UMMA instead of
+// 4 KB + BN*32 B -- the two resources the 128-wide single-CTA tiles are short of.  Plain (1x1 /
+// Linear) single-term GEMMs with the TMA-store epilogue only; no A-resident mode.
+template <int BN, bool kIm2col, int kEpi, int kCG>
 __global__ void __launch_bounds__(kThreads, 1)
     gemm_bf16_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
+  static_assert(kCG == 1 || (!kIm2col && kEpi != 0), "the CTA-pair form covers plain GEMMs with the TMA-store epilogue");
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   constexpr bool kTma = kEpi != 0;
-  constexpr int kBStage = BN * kBK * 2;
+  constexpr int kBRows = BN / kCG;          // W rows this CTA loads per stage
+  constexpr int kBStage = kBRows * kBK * 2;
   constexpr int kStageBytes = kAStage + kBStage;
   constexpr uint32_t kTmemCols = (2 * BN <= 128) ? 128 : (2 * BN <= 256 ? 256 : 512);
   constexpr int kStagingBytes = (BN / 64) * kBM * 128;   // BN/64 slabs of [128 rows x 64 bf16], 128B swizzle
@@ -144,7 +153,7 @@ __global__ void __launch_bounds__(kThreads, 1)
   const int k_iters = p.n_terms * p.taps * p.cblocks;
   // A-resident mode (wide 1x1 convolutions / Linear layers with small K): [k_iters x 16 KB A rows of the current m-tile]
   // first, then stages that carry only the W tile; the per-channel affine of ALL column blocks is staged once.
-  const bool a_res = p.a_resident != 0;
+  const bool a_res = (kCG == 1) && p.a_resident != 0;
   const int stage_bytes = a_res ? kBStage : kStageBytes;
   const int num_n_tiles = p.num_n_tiles;
   uint8_t* smem_ares = smem;
@@ -165,14 +174,20 @@ __global__ void __launch_bounds__(kThreads, 1)
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // hoist everything the tile loops need out of the constant bank once
   const int M = p.M, N = p.N, num_m_tiles = p.num_m_tiles;
-  const int num_tiles = p.num_m_tiles * p.num_n_tiles;
   const bool has_res = p.res != nullptr;
+  // CTA pair: tiles are 2 m-tiles tall, the pair (cluster) is the scheduling unit and CTA rank r works m-tile 2*pm + r (an
+  // odd last m-tile leaves rank 1 a tile past M: its loads are zero filled, its stores skipped)
+  const uint32_t cta_rank = (kCG == 2) ? cluster_ctarank() : 0;
+  const bool leader = cta_rank == 0;
+  const int pair_m_tiles = (num_m_tiles + kCG - 1) / kCG;
+  const int num_tiles = pair_m_tiles * p.num_n_tiles;
+  const int unit = static_cast<int>(blockIdx.x) / kCG, n_units = static_cast<int>(gridDim.x) / kCG;
   // tile sequence of this CTA: m-fastest round robin (default) or a contiguous range of the n-fastest order (A-resident)
-  const int t_first = a_res ? static_cast<int>(static_cast<long long>(num_tiles) * blockIdx.x / gridDim.x) : static_cast<int>(blockIdx.x);
+  const int t_first = a_res ? static_cast<int>(static_cast<long long>(num_tiles) * blockIdx.x / gridDim.x) : unit;
   const int t_end = a_res ? static_cast<int>(static_cast<long long>(num_tiles) * (blockIdx.x + 1) / gridDim.x) : num_tiles;
-  const int t_step = a_res ? 1 : static_cast<int>(gridDim.x);
-  auto tile_m = [&](int t) { return a_res ? t / num_n_tiles : t % num_m_tiles; };
-  auto tile_n = [&](int t) { return a_res ? t % num_n_tiles : t / num_m_tiles; };
+  const int t_step = a_res ? 1 : n_units;
+  auto tile_m = [&](int t) { return a_res ? t / num_n_tiles : (t % pair_m_tiles) * kCG + static_cast<int>(cta_rank); };
+  auto tile_n = [&](int t) { return a_res ? t % num_n_tiles : t / pair_m_tiles; };
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&maps.out);
@@ -184,12 +199,12 @@ __global__ void __launch_bounds__(kThreads, 1)
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < stages; ++s) {
-      mbar_init(&full[s], 1);
-      mbar_init(&empty[s], 1);
+      mbar_init(&full[s], kCG);        // pair: the leader's barrier takes one arrive per CTA and both CTAs' bytes
+      mbar_init(&empty[s], 1);         // pair: tcgen05.commit multicasts the arrive to both CTAs
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&t_full[b], 1);
-      mbar_init(&t_empty[b], 8);
+      mbar_init(&t_empty[b], 8 * kCG);   // pair: the leader's MMA warp waits for both CTAs' epilogue warps
       mbar_init(&res_full[b], 1);
     }
     mbar_init(a_full, 1);
@@ -197,11 +212,12 @@ __global__ void __launch_bounds__(kThreads, 1)
     fence_mbar_init();
   }
   if (warp == 2) {
-    tmem_alloc<1>(tmem_slot, kTmemCols);
-    tmem_relinquish<1>();
+    tmem_alloc<kCG>(tmem_slot, kTmemCols);
+    tmem_relinquish<kCG>();
   }
   tc_fence_before();
   __syncthreads();
+  if constexpr (kCG == 2) cluster_sync();   // the peer's barriers are initialised before any remote arrive / multicast commit
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -259,7 +275,8 @@ __global__ void __launch_bounds__(kThreads, 1)
               const uint32_t s = st.s, ph = st.ph;
               mbar_wait(&empty[s], ph ^ 1);
               if (elect_one()) {
-                mbar_arrive_expect_tx(&full[s], kStageBytes);
+                if (leader) mbar_arrive_expect_tx(&full[s], kStageBytes * kCG);
+                else mbar_arrive_cluster(&full[s], 0);
                 uint8_t* sa = smem_ab + s * kStageBytes;
                 if constexpr (kIm2col) {
                   if constexpr (kGemmTimingMode == 2)
@@ -268,8 +285,9 @@ __global__ void __launch_bounds__(kThreads, 1)
                     tma_load_im2col_4d<1>(sa, ma, &full[s], cb * kBK, w0, h0, img, static_cast<uint16_t>(sx),
                                           static_cast<uint16_t>(r));
                 } else
-                  tma_load_2d<1>(sa, ma, &full[s], cb * kBK, m0, kEvictNormal);
-                tma_load_2d<1>(sa + kAStage, mw, &full[s], (tap * cblocks + cb) * kBK, n0, kEvictNormal);
+                  tma_load_2d<kCG>(sa, ma, &full[s], cb * kBK, m0, kEvictNormal);
+                tma_load_2d<kCG>(sa + kAStage, mw, &full[s], (tap * cblocks + cb) * kBK, n0 + static_cast<int>(cta_rank) * kBRows,
+                                 kEvictNormal);
               }
               __syncwarp();
             }
@@ -278,8 +296,8 @@ __global__ void __launch_bounds__(kThreads, 1)
       }
     }
   } else if (warp == 1) {
-    {
-      constexpr uint32_t idesc = umma_idesc_bf16(kBM, BN);
+    if (leader) {
+      constexpr uint32_t idesc = umma_idesc_bf16(kBM * kCG, BN);
       uint32_t tc = 0;
       PipeState st(stages);
       // descriptors of stage 0; stage s adds s * kStageBytes to the 16-byte-granular start-address field (no carry out
@@ -322,11 +340,11 @@ __global__ void __launch_bounds__(kThreads, 1)
           const uint64_t db = db0 + static_cast<uint64_t>(s * b_step);
           if (elect_one()) {
 #pragma unroll
-            for (int k = 0; k < kBK / 16; ++k) umma_f16<1>(tmem_d, da + 2 * k, db + 2 * k, idesc, (ki | k) != 0);
-            umma_commit<1>(&empty[s]);
+            for (int k = 0; k < kBK / 16; ++k) umma_f16<kCG>(tmem_d, da + 2 * k, db + 2 * k, idesc, (ki | k) != 0);
+            umma_commit<kCG>(&empty[s]);
             if (ki == k_iters - 1) {
-              umma_commit<1>(&t_full[buf]);
-              if (last_of_m) umma_commit<1>(a_empty);
+              umma_commit<kCG>(&t_full[buf]);
+              if (last_of_m) umma_commit<kCG>(a_empty);
             }
           }
           __syncwarp();
@@ -414,7 +432,10 @@ __global__ void __launch_bounds__(kThreads, 1)
         if (ci == kChunksPerWarp - 1) {
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&t_empty[buf]);
+          if (lane == 0) {
+            if constexpr (kCG == 2) mbar_arrive_cluster(&t_empty[buf], 0);
+            else mbar_arrive(&t_empty[buf]);
+          }
         }
         const int nc = n0 + ch * 32;
         if (nc >= N) continue;
@@ -515,7 +536,7 @@ __global__ void __launch_bounds__(kThreads, 1)
         asm volatile("bar.sync 2, 256;" ::: "memory");
         if (etid == 0) {
           for (int sl = 0; sl < BN / 64; ++sl)
-            if (n0 + sl * 64 < N) tma_store_2d(&maps.out, ostage + sl * kBM * 128, p.out_col_off + n0 + sl * 64, m0);
+            if (n0 + sl * 64 < N && m0 < M) tma_store_2d(&maps.out, ostage + sl * kBM * 128, p.out_col_off + n0 + sl * 64, m0);
           tma_store_commit();
         }
       }
@@ -525,34 +546,40 @@ __global__ void __launch_bounds__(kThreads, 1)
   if (kTma && warp == 2 && lane == 0) tma_store_wait_all();   // etid 0 issued the stores
   tc_fence_before();
   __syncthreads();
-  if (warp == 2) tmem_dealloc<1>(tmem_base, kTmemCols);
+  if constexpr (kCG == 2) cluster_sync();   // the peer's MMAs (issued by the leader) read this CTA's tiles and write its TMEM
+  if (warp == 2) tmem_dealloc<kCG>(tmem_base, kTmemCols);
 }
 
-template <int BN, bool kIm2col, int kEpi>
+// A-resident mode: plain (non-im2col) single-term GEMMs with several column blocks and K <= 256 -- the wide 1x1
+// expansions: the A rows of an m-tile are loaded once instead of once per column block (per-SM-unique data is what
+// the L2 -> shared-memory path is short of; the W tiles are shared by all SMs and cheap)
+// (the resident rows are single buffered: the next m-tile's rows wait for the last MMA on the current ones, a bubble
+// that only pays off when the epilogue is heavy (residual) or the m-tile has >= 4 column blocks; measured on B200,
+// batch 256: 177 -> 157 us for the layer1 expansion with residual, 98 -> 90 us layer2, but 103 -> 130 us for the
+// residual-free 2-block downsample)
+bool wants_a_resident(const GemmParams& p, int BN, bool im2col, size_t max_smem) {
+  const int k_iters_h = p.n_terms * p.taps * p.cblocks;
+  if (!(!im2col && p.tma_epi && p.n_terms == 1 && p.num_n_tiles >= 2 && (p.res != nullptr || p.num_n_tiles >= 4) &&
+        k_iters_h * kAStage <= 64 * 1024 && p.num_n_tiles * BN <= 4096 && !tuning_flag("DCR_GEMM_NO_ARES")))
+    return false;
+  // the resident rows, the all-blocks affine table and the staging tiles must leave at least three W stages; otherwise
+  // the layer runs with the default schedule
+  const size_t staging = static_cast<size_t>(BN / 64) * kBM * 128;
+  const size_t need = 1024 + static_cast<size_t>(2) * p.num_n_tiles * BN * 4 + static_cast<size_t>(k_iters_h) * kAStage + 256 +
+                      static_cast<size_t>(1 + (p.res ? 2 : 0)) * staging + 3 * static_cast<size_t>(BN) * kBK * 2;
+  return need <= max_smem;
+}
+
+template <int BN, bool kIm2col, int kEpi, int kCG>
 int launch(const GemmMaps& maps, GemmParams& p, int num_sms, size_t max_smem, cudaStream_t stream) {
-  constexpr int kStageBytes = kAStage + BN * kBK * 2;
+  constexpr int kStageBytes = kAStage + (BN / kCG) * kBK * 2;
   constexpr size_t kStagingBytes = static_cast<size_t>(BN / 64) * kBM * 128;
   // staging tiles: residual layers get 2 residual + 2 output tiles (prefetch / drain a full tile ahead) when they still
   // leave >= 3 pipeline stages, otherwise one output tile (plus two residual tiles if needed)
   p.n_res_bufs = (p.tma_epi && p.res) ? 2 : 0;
   p.n_out_bufs = p.tma_epi ? 2 : 0;
-  // A-resident mode: plain (non-im2col) single-term GEMMs with several column blocks and K <= 256 -- the wide 1x1
-  // expansions: the A rows of an m-tile are loaded once instead of once per column block (per-SM-unique data is what
-  // the L2 -> shared-memory path is short of; the W tiles are shared by all SMs and cheap)
   const int k_iters_h = p.n_terms * p.taps * p.cblocks;
-  // (the resident rows are single buffered: the next m-tile's rows wait for the last MMA on the current ones, a bubble
-  // that only pays off when the epilogue is heavy (residual) or the m-tile has >= 4 column blocks; measured on B200,
-  // batch 256: 177 -> 157 us for the layer1 expansion with residual, 98 -> 90 us layer2, but 103 -> 130 us for the
-  // residual-free 2-block downsample)
-  p.a_resident = (!kIm2col && kEpi != 0 && p.n_terms == 1 && p.num_n_tiles >= 2 && (p.res != nullptr || p.num_n_tiles >= 4) &&
-                  k_iters_h * kAStage <= 64 * 1024 && p.num_n_tiles * BN <= 4096 && !tuning_flag("DCR_GEMM_NO_ARES")) ? 1 : 0;
-  // the resident rows, the all-blocks affine table and the staging tiles must leave at least three W stages; otherwise
-  // the layer runs with the default schedule
-  if (p.a_resident) {
-    const size_t need = 1024 + static_cast<size_t>(2) * p.num_n_tiles * BN * 4 + static_cast<size_t>(k_iters_h) * kAStage + 256 +
-                        static_cast<size_t>(1 + p.n_res_bufs) * kStagingBytes + 3 * static_cast<size_t>(BN) * kBK * 2;
-    if (need > max_smem) p.a_resident = 0;
-  }
+  p.a_resident = (kCG == 1 && kEpi != 0 && wants_a_resident(p, BN, kIm2col, max_smem)) ? 1 : 0;
   const size_t sb_bytes = p.a_resident ? static_cast<size_t>(2) * p.num_n_tiles * BN * 4 : static_cast<size_t>(4) * BN * 4;
   const size_t ares_bytes = p.a_resident ? static_cast<size_t>(k_iters_h) * kAStage : 0;
   auto fixed_for = [&](int nout, int nres) { return 1024 + sb_bytes + ares_bytes + 256 + static_cast<size_t>(nout + nres) * kStagingBytes; };
@@ -564,7 +591,7 @@ int launch(const GemmMaps& maps, GemmParams& p, int num_sms, size_t max_smem, cu
   stages = std::min(stages, 8);
   p.stages = stages;
   const size_t smem = fixed + static_cast<size_t>(stages) * stage_bytes;
-  auto kern = gemm_bf16_kernel<BN, kIm2col, kEpi>;
+  auto kern = gemm_bf16_kernel<BN, kIm2col, kEpi, kCG>;
   static bool attr_set_dev[64] = {};   // per template instantiation and device (the attribute is per device)
   int cur_dev = 0;
   DCR_CUDA_CHECK(cudaGetDevice(&cur_dev));
@@ -573,9 +600,26 @@ int launch(const GemmMaps& maps, GemmParams& p, int num_sms, size_t max_smem, cu
     DCR_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(max_smem)));
     attr_set = true;
   }
-  const int tiles = p.num_m_tiles * p.num_n_tiles;
-  const int grid = std::min(tiles, num_sms);
-  kern<<<grid, kThreads, smem, stream>>>(maps, p);
+  if constexpr (kCG == 2) {
+    const int pair_tiles = ((p.num_m_tiles + 1) / 2) * p.num_n_tiles;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * std::min(pair_tiles, num_sms / 2));
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    DCR_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, maps, p));
+  } else {
+    const int tiles = p.num_m_tiles * p.num_n_tiles;
+    const int grid = std::min(tiles, num_sms);
+    kern<<<grid, kThreads, smem, stream>>>(maps, p);
+  }
   count_launch();
   DCR_CUDA_CHECK(cudaGetLastError());
   return 0;
@@ -694,13 +738,35 @@ int conv_gemm(const ConvGemmDesc& d, cudaStream_t stream) {
   DCR_REQUIRE(p.res == nullptr || p.ld_res % 8 == 0, "conv_gemm: residual leading dim must be a multiple of 8");
   DCR_REQUIRE(p.out_f32 == nullptr || p.ld_out_f32 % 4 == 0, "conv_gemm: fp32 output leading dim must be a multiple of 4");
 
+  // ---- CTA-pair form (cta_group::2, 256-row tiles, half a W tile per CTA): plain single-term GEMMs with the TMA-store
+  // epilogue whose A rows are not kept resident and that have enough m-tiles to fill the pairs
+  const int want_cg2 = tuning_int("DCR_GEMM_CG2", -1);   // 0: never, 1: wherever the kernel form exists, default: policy
+  bool use_cg2 = !im2col && p.tma_epi && p.n_terms == 1 && (BN == 128 || BN == 256) && kGemmTimingMode == 0 && want_cg2 != 0;
+  if (use_cg2 && want_cg2 < 0)
+    use_cg2 = !wants_a_resident(p, BN, im2col, di->max_smem_optin) && ktot >= 256 && p.num_m_tiles >= di->num_sms;
+  if (use_cg2) {
+    for (int pl = 0; pl < 3; ++pl) {
+      const int pw = std::min(pl, w_planes - 1);
+      if (int rc = make_tmap_2d_bf16(&maps.w[pl], d.weight + pw * d.w_plane_stride, d.N, ktot, ktot, BN / 2, kBK)) return rc;
+    }
+  }
+  const int epi = p.tma_epi ? 1 + p.act : 0;   // compile-time activation on the TMA-store path
+  if (use_cg2) {
+#define DCR_LAUNCH_PAIR(BNv)                                                                                     \
+  (epi == 1 ? launch<BNv, false, 1, 2>(maps, p, di->num_sms, di->max_smem_optin, stream)                         \
+            : (epi == 2 ? launch<BNv, false, 2, 2>(maps, p, di->num_sms, di->max_smem_optin, stream)             \
+                        : (epi == 3 ? launch<BNv, false, 3, 2>(maps, p, di->num_sms, di->max_smem_optin, stream) \
+                                    : launch<BNv, false, 4, 2>(maps, p, di->num_sms, di->max_smem_optin, stream))))
+    return BN == 128 ? DCR_LAUNCH_PAIR(128) : DCR_LAUNCH_PAIR(256);
+#undef DCR_LAUNCH_PAIR
+  }
+
 #define DCR_LAUNCH_E(BNv, E)                                                                      \
-  (im2col ? launch<BNv, true, E>(maps, p, di->num_sms, di->max_smem_optin, stream)              \
-          : launch<BNv, false, E>(maps, p, di->num_sms, di->max_smem_optin, stream))
+  (im2col ? launch<BNv, true, E, 1>(maps, p, di->num_sms, di->max_smem_optin, stream)              \
+          : launch<BNv, false, E, 1>(maps, p, di->num_sms, di->max_smem_optin, stream))
 #define DCR_LAUNCH(BNv)                                                                          \
   (epi == 0 ? DCR_LAUNCH_E(BNv, 0)                                                                \
             : (epi == 1 ? DCR_LAUNCH_E(BNv, 1) : (epi == 2 ? DCR_LAUNCH_E(BNv, 2) : (epi == 3 ? DCR_LAUNCH_E(BNv, 3) : DCR_LAUNCH_E(BNv, 4)))))
-  const int epi = p.tma_epi ? 1 + p.act : 0;   // compile-time activation on the TMA-store path
   switch (BN) {
     case 64: return DCR_LAUNCH(64);
     case 128: return DCR_LAUNCH(128);
