@@ -72,6 +72,9 @@ struct GemmParams {
   int tma_epi;                // 1: stage the bf16 output tile in shared memory and write it with TMA stores
   int n_out_bufs;             // 1 or 2 output staging tiles (2: the TMA store of tile i drains during tile i+1)
   int n_res_bufs;             // 0 or 2 residual staging tiles (the residual of tile i+1 is prefetched during tile i)
+  int n_fastest;              // 1: consecutive tiles are the column blocks of one m-tile (round robin over the CTAs: the CTAs that
+                              //    share an m-tile's A rows read them at the same time, one HBM read + L2 hits).  Default order is
+                              //    m-fastest (a CTA keeps its column block, W tile and affine for many tiles): right while A fits L2
   int a_resident;             // 1: the A rows of an m-tile (all of K) stay in shared memory while the CTA walks that m-tile's
                               //    column blocks (tiles n-fastest, contiguous tile range per CTA); stages carry only W tiles
 };
@@ -186,8 +189,11 @@ __global__ void __launch_bounds__(kThreads, 1)
   const int t_first = a_res ? static_cast<int>(static_cast<long long>(num_tiles) * blockIdx.x / gridDim.x) : unit;
   const int t_end = a_res ? static_cast<int>(static_cast<long long>(num_tiles) * (blockIdx.x + 1) / gridDim.x) : num_tiles;
   const int t_step = a_res ? 1 : n_units;
-  auto tile_m = [&](int t) { return a_res ? t / num_n_tiles : (t % pair_m_tiles) * kCG + static_cast<int>(cta_rank); };
-  auto tile_n = [&](int t) { return a_res ? t % num_n_tiles : t / pair_m_tiles; };
+  const bool n_fast = p.n_fastest != 0;
+  auto tile_m = [&](int t) {
+    return a_res ? t / num_n_tiles : ((n_fast ? t / num_n_tiles : t % pair_m_tiles) * kCG + static_cast<int>(cta_rank));
+  };
+  auto tile_n = [&](int t) { return (a_res || n_fast) ? t % num_n_tiles : t / pair_m_tiles; };
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&maps.out);
@@ -715,6 +721,10 @@ int conv_gemm(const ConvGemmDesc& d, cudaStream_t stream) {
   p.out_f32 = d.out_f32;
   p.ld_out_f32 = d.ld_out_f32;
   p.act = d.act;
+  // tile order: with several column blocks and an A matrix larger than what L2 keeps between the passes, m-fastest order
+  // streams A from HBM once per column block (ViT-S fc2: 155 MB x 3 = 83 us of HBM time for a 99 us layer)
+  const double a_bytes = 2.0 * a_planes * (im2col ? static_cast<double>(d.B) * d.H * d.W * d.C : static_cast<double>(M) * d.C);
+  p.n_fastest = (p.num_n_tiles >= 2 && a_bytes > 48e6 && !tuning_flag("DCR_GEMM_M_FASTEST")) ? 1 : 0;
   if (kGemmTimingMode == 2 && im2col && !windowed) {
     if (int rc = make_tmap_2d_bf16(&maps.a_flat, d.in, static_cast<uint64_t>(d.B) * d.H * d.W, d.C, d.C, kBM, kBK)) return rc;
   }
@@ -742,8 +752,14 @@ int conv_gemm(const ConvGemmDesc& d, cudaStream_t stream) {
   // epilogue whose A rows are not kept resident and that have enough m-tiles to fill the pairs
   const int want_cg2 = tuning_int("DCR_GEMM_CG2", -1);   // 0: never, 1: wherever the kernel form exists, default: policy
   bool use_cg2 = !im2col && p.tma_epi && p.n_terms == 1 && (BN == 128 || BN == 256) && kGemmTimingMode == 0 && want_cg2 != 0;
-  if (use_cg2 && want_cg2 < 0)
-    use_cg2 = !wants_a_resident(p, BN, im2col, di->max_smem_optin) && ktot >= 256 && p.num_m_tiles >= di->num_sms;
+  if (use_cg2 && want_cg2 < 0) {
+    // measured per layer at batch 256 (tools/pair_bench.py, B200): 256-wide tiles gain 5-11 % from K = 384 up (ResNet layer3/4
+    // reductions 256<-1024, 512<-1024; ViT qkv 1152<-384, ViT-B qkv / fc1); 128-wide residual tiles gain only with many column
+    // blocks and K >= 512 (layer4 expansion 2048<-512: 9 %; ViT fc2 / proj with 3 column blocks: none); short K loses
+    const long long pair_tiles = static_cast<long long>((p.num_m_tiles + 1) / 2) * p.num_n_tiles;
+    const bool shape_ok = (BN == 256) ? ktot >= 384 : (ktot >= 512 && p.num_n_tiles >= 8);
+    use_cg2 = !wants_a_resident(p, BN, im2col, di->max_smem_optin) && shape_ok && pair_tiles >= di->num_sms;
+  }
   if (use_cg2) {
     for (int pl = 0; pl < 3; ++pl) {
       const int pw = std::min(pl, w_planes - 1);
