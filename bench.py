@@ -533,6 +533,7 @@ def run_retrieval_bench(args, rank, local_rank, world):
     flops_net = net.flops_per_image
     if args.parity_steps > 0:
         del net
+        step = None          # the closure held the fast-mode network (and its fork's activations) alive
         for other_name in [m for m in args.other_modes.split(",") if m and m != args.precision]:
             keep.clear()
             torch.cuda.empty_cache()

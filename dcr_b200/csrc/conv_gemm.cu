@@ -72,6 +72,7 @@ struct GemmParams {
   int tma_epi;                // 1: stage the bf16 output tile in shared memory and write it with TMA stores
   int n_out_bufs;             // 1 or 2 output staging tiles (2: the TMA store of tile i drains during tile i+1)
   int n_res_bufs;             // 0 or 2 residual staging tiles (the residual of tile i+1 is prefetched during tile i)
+  int fast_gelu;              // 1: single-plane bf16 mode: act 2 is the tanh-form GELU (gelu_tanh_fast); 0: erf form
   int n_fastest;              // 1: consecutive tiles are the column blocks of one m-tile (round robin over the CTAs: the CTAs that
                               //    share an m-tile's A rows read them at the same time, one HBM read + L2 hits).  Default order is
                               //    m-fastest (a CTA keeps its column block, W tile and affine for many tiles): right while A fits L2
@@ -94,6 +95,21 @@ DCR_DEVICE float gelu_erf_fast(float y) {
   poly = fmaf(poly, t, 0.254829592f);
   const float erf_abs = fmaf(-poly * t, e, 1.f);               // erf(|y| / sqrt 2)
   return 0.5f * y + 0.5f * fabsf(y) * erf_abs;                 // 0.5 y (1 + erf(y / sqrt 2)),  y erf(..) = |y| erf(|..|)
+}
+
+// GELU of the single-plane bf16 ("fast") mode: the tanh form with the hardware tanh -- 0.5 y (1 + tanh(0.79788 (y + 0.044715 y^3))),
+// five FMA-pipe instructions and one MUFU per element.  It differs from the erf form by <= 4.7e-4 absolute (the form itself) plus
+// <= 5e-4 |y| / 2 (tanh.approx.f32), below the bf16 rounding of the stored activation (2^-9 relative) for every |y| >= 0.1 and
+// within two bf16 ulps below that.  The erf polynomial above costs 16 instructions and TWO MUFU ops per element: over a 128 x 256
+// tile that is 4096 MUFU cycles against 3072 MMA cycles, which made fc1 + GELU epilogue bound (95 us at 627 TFLOP/s on ViT-S/16).
+// The split-bf16 (fp32-level) modes and the float64 mode keep the erf forms.
+DCR_DEVICE float gelu_tanh_fast(float y) {
+  const float u = y * y;
+  const float inner = y * fmaf(0.0356774081f, u, 0.7978845608f);
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(inner));
+  const float h = 0.5f * y;
+  return fmaf(h, t, h);
 }
 
 DCR_DEVICE float apply_act(float y, int act) {
@@ -473,7 +489,7 @@ __global__ void __launch_bounds__(kThreads, 1)
             }
           }
 #pragma unroll
-          for (int c = 0; c < 32; ++c) y[c] = (kEpi == 3) ? gelu_erf_fast(y[c]) : apply_act(y[c], kEpi - 1);
+          for (int c = 0; c < 32; ++c) y[c] = (kEpi == 3) ? gelu_tanh_fast(y[c]) : apply_act(y[c], kEpi - 1);
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             uint4 v;
@@ -504,7 +520,7 @@ __global__ void __launch_bounds__(kThreads, 1)
             }
           }
 #pragma unroll
-          for (int c = 0; c < 32; ++c) y[c] = apply_act(y[c], act);
+          for (int c = 0; c < 32; ++c) y[c] = (act == 2 && p.fast_gelu) ? gelu_tanh_fast(y[c]) : apply_act(y[c], act);
           if (p.out_f32) {
             float* op = p.out_f32 + static_cast<size_t>(m) * p.ld_out_f32 + nc;
 #pragma unroll
@@ -721,6 +737,7 @@ int conv_gemm(const ConvGemmDesc& d, cudaStream_t stream) {
   p.out_f32 = d.out_f32;
   p.ld_out_f32 = d.ld_out_f32;
   p.act = d.act;
+  p.fast_gelu = (d.n_terms == 1 && p.out_planes <= 1 && !tuning_flag("DCR_GELU_ERF")) ? 1 : 0;
   // tile order: with several column blocks and an A matrix larger than what L2 keeps between the passes, m-fastest order
   // streams A from HBM once per column block (ViT-S fc2: 155 MB x 3 = 83 us of HBM time for a 99 us layer)
   const double a_bytes = 2.0 * a_planes * (im2col ? static_cast<double>(d.B) * d.H * d.W * d.C : static_cast<double>(M) * d.C);
@@ -729,6 +746,7 @@ int conv_gemm(const ConvGemmDesc& d, cudaStream_t stream) {
     if (int rc = make_tmap_2d_bf16(&maps.a_flat, d.in, static_cast<uint64_t>(d.B) * d.H * d.W, d.C, d.C, kBM, kBK)) return rc;
   }
   p.tma_epi = (p.out != nullptr && p.out_planes == 1 && p.out_f32 == nullptr && (p.res == nullptr || p.res_planes == 1) &&
+               (d.act != 2 || p.fast_gelu) &&   // the TMA-store epilogue's compile-time GELU is the tanh form
                !tuning_flag("DCR_GEMM_DIRECT_EPILOGUE"))
                   ? 1
                   : 0;

@@ -70,6 +70,10 @@ def test_conv_matches_torch(shape, planes):
     # three planes (6 cross terms): fp32-level agreement, limited by the tensor core's fp32 accumulator rounding
     mx = max(1.0, ref.abs().max().item())
     tol = (3e-4 if planes == 1 else 5e-5) * mx   # the tensor core's fp32 accumulator truncates: ~1e-5 relative at K~2000
+    if planes == 1 and act == 2:
+        # single-plane (bf16) mode evaluates GELU in its tanh form with tanh.approx.f32: <= 4.7e-4 from the erf form plus
+        # 2^-11 relative on 0.5 y (conv_gemm.cu gelu_tanh_fast); the split-bf16 modes keep the erf form
+        tol += 1.2e-3 * mx
     err32 = (out32 - ref).abs().max().item()
     assert err32 < tol, f"fp32 out err {err32}"
     got = ops.merge_planes(out)
