@@ -5,7 +5,7 @@ OUT=${1:-gpurun_out}
 mkdir -p "$OUT"
 CS=/usr/local/cuda/bin/compute-sanitizer
 for TOOL in memcheck synccheck racecheck; do
-  for CASE in sim sscd vit fid; do
+  for CASE in ${SANITIZE_CASES:-sim sscd vit fid pair}; do
     LOG="$OUT/sanitizer_${TOOL}_${CASE}.txt"
     timeout ${SANITIZE_TIMEOUT:-300} $CS --tool $TOOL --print-limit 20 --launch-timeout 120 \
         python tools/sanitize_case.py $CASE > "$LOG" 2>&1

@@ -44,4 +44,28 @@ if which in ("all", "fid"):
     st.update(net(img))
     mu, sigma = st.finalize()
     print("inception + fid stats ok", float(mu.sum()))
+if which in ("all", "pair"):
+    # CTA-pair form of the GEMM kernel (cta_group::2), forced on small shapes, against the single-CTA kernel; then two forward
+    # passes in flight (network + fork on two streams) through extract_features
+    from dcr_b200 import ops, retrieval
+    os.environ["DCR_B200_TUNING"] = "1"
+    gen = torch.Generator(device="cuda").manual_seed(5)
+    for (m, k, n, with_res, act) in [(4 * 196, 1024, 256, False, 1), (98, 512, 2048, True, 1), (600, 384, 1152, False, 2)]:
+        x = ops.split_planes(torch.randn(m, 1, 1, k, device="cuda", generator=gen), 1)
+        w = ops.prepare_conv_weight(torch.randn(n, k, 1, 1, device="cuda", generator=gen) / k ** 0.5, 1)
+        res = ops.split_planes(torch.randn(m, 1, 1, n, device="cuda", generator=gen), 1) if with_res else None
+        outs = []
+        for mode in ("0", "1"):
+            os.environ["DCR_GEMM_CG2"] = mode
+            o, _ = ops.conv2d(x, w, n, 1, 1, 1, 0, 0, residual=res, act=act)
+            torch.cuda.synchronize()
+            outs.append(o)
+        print("pair gemm", m, k, n, "identical:", torch.equal(outs[0], outs[1]))
+    del os.environ["DCR_GEMM_CG2"]
+    net = nets.build_sscd_resnet50(om.make_sscd_state_dict(0), max_batch=2, precision="fast")
+    img = synthetic.images(5, seed=4)
+    a = retrieval.extract_features(net, img.cuda(), 2, two_in_flight=False)
+    b = retrieval.extract_features(net, img.pin_memory(), 2, two_in_flight=True)
+    torch.cuda.synchronize()
+    print("two in flight identical:", torch.equal(a, b))
 print("sanitize_case done")
