@@ -690,6 +690,10 @@ int conv_gemm(const ConvGemmDesc& d, cudaStream_t stream) {
     while (BN > 64 && ktot >= 1024 && m_tiles * ((d.N + BN - 1) / BN) * 4 <= di->num_sms) BN /= 2;
   }
   if (d.force_bn) BN = d.force_bn;
+  {
+    const int bn_im2col = tuning_int("DCR_GEMM_BN_IM2COL", 0);   // tuning experiments: tile width of the k x k convolutions
+    if (im2col && (bn_im2col == 64 || bn_im2col == 128 || bn_im2col == 256) && d.N >= bn_im2col) BN = bn_im2col;
+  }
   for (int pl = 0; pl < 3; ++pl) {
     const int pa = std::min(pl, a_planes - 1), pw = std::min(pl, w_planes - 1);
     const __nv_bfloat16* abase = d.in + pa * d.in_plane_stride;

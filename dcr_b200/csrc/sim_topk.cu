@@ -166,33 +166,56 @@ __global__ void __launch_bounds__(256) to_bf16_rows_kernel(const float* __restri
   }
 }
 
-// column sums of x[n, d] accumulated in double (one atomicAdd per column per block); mean = sum / n afterwards
-// (rows r*row_stride, r < n: any fixed vector works as the centre, so a strided sample of the gallery is enough)
-__global__ void col_sum_kernel(const float* __restrict__ x, int n, int row_stride, int d, double* __restrict__ sums,
-                               double* __restrict__ sq_sums) {
+// column sums of x[n, d] accumulated in double; mean = sum / n afterwards (rows r*row_stride, r < n: any fixed vector works
+// as the centre, so a strided sample of the gallery is enough).  A thread owns one 16-byte column group and a slice of the
+// block's rows (independent loads, four in flight), the slices meet in shared memory and the block does ONE atomicAdd per
+// column: the first version had 592 blocks each add all d columns -- 300k same-address double atomics, 22 us for a 16 MB sample.
+constexpr int kColSumThreads = 512;
+__global__ void __launch_bounds__(kColSumThreads)
+    col_sum_kernel(const float* __restrict__ x, int n, int row_stride, int d, double* __restrict__ sums,
+                   double* __restrict__ sq_sums) {
+  __shared__ double red[kColSumThreads][8];
+  const int groups = d >> 2;                                   // d % 4 == 0 (checked by the caller)
+  const int G = min(groups, kColSumThreads), S = kColSumThreads / G;
+  const int tg = threadIdx.x % G, sl = threadIdx.x / G;         // threads with sl >= S idle (G does not divide the block)
   const int rows_per_block = (n + gridDim.x - 1) / gridDim.x;
   const int r0 = blockIdx.x * rows_per_block, r1 = min(n, r0 + rows_per_block);
-  for (int c = threadIdx.x; c < d; c += blockDim.x) {
-    float acc = 0.f, acc2 = 0.f;
-    double dacc = 0.0, dacc2 = 0.0;
-    int cnt = 0;
-    for (int r = r0; r < r1; ++r) {
-      const float v = x[static_cast<size_t>(r) * row_stride * d + c];
-      acc += v;
-      acc2 += v * v;
-      if (++cnt == 256) {   // flush the fp32 partials into the double accumulators every 256 rows
-        dacc += acc;
-        dacc2 += acc2;
-        acc = acc2 = 0.f;
-        cnt = 0;
+  for (int cg = tg; cg < groups; cg += G) {
+    double da[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) da[e] = 0.0;
+    if (sl < S) {
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f), acc2 = make_float4(0.f, 0.f, 0.f, 0.f);
+      int cnt = 0;
+#pragma unroll 4
+      for (int r = r0 + sl; r < r1; r += S) {
+        const float4 v = *reinterpret_cast<const float4*>(x + static_cast<size_t>(r) * row_stride * d + cg * 4);
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        acc2.x += v.x * v.x; acc2.y += v.y * v.y; acc2.z += v.z * v.z; acc2.w += v.w * v.w;
+        if (++cnt == 256) {   // flush the fp32 partials into the double accumulators every 256 rows
+          da[0] += acc.x; da[1] += acc.y; da[2] += acc.z; da[3] += acc.w;
+          da[4] += acc2.x; da[5] += acc2.y; da[6] += acc2.z; da[7] += acc2.w;
+          acc = make_float4(0.f, 0.f, 0.f, 0.f);
+          acc2 = make_float4(0.f, 0.f, 0.f, 0.f);
+          cnt = 0;
+        }
+      }
+      da[0] += acc.x; da[1] += acc.y; da[2] += acc.z; da[3] += acc.w;
+      da[4] += acc2.x; da[5] += acc2.y; da[6] += acc2.z; da[7] += acc2.w;
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) red[threadIdx.x][e] = da[e];
+    __syncthreads();
+    if (sl == 0 && r1 > r0) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        double t = 0.0;
+        for (int s2 = 0; s2 < S; ++s2) t += red[s2 * G + tg][e];   // fixed order within the block
+        if (e < 4) atomicAdd(sums + cg * 4 + e, t);
+        else if (sq_sums) atomicAdd(sq_sums + cg * 4 + (e - 4), t);
       }
     }
-    dacc += acc;
-    dacc2 += acc2;
-    if (r1 > r0) {
-      atomicAdd(sums + c, dacc);
-      if (sq_sums) atomicAdd(sq_sums + c, dacc2);
-    }
+    __syncthreads();
   }
 }
 __global__ void col_mean_finish_kernel(const double* __restrict__ sums, int n, int d, float* __restrict__ mu) {
@@ -898,7 +921,7 @@ __global__ void __launch_bounds__(128)
   float* ap = reinterpret_cast<float*>(ci + max_cand);                  // [max_cand] approximate scores
   int* kc = reinterpret_cast<int*>(ap + max_cand);                      // [max_cand] gallery rows of the survivors
   __shared__ int s_n, s_overflow, s_kept, s_nslots, s_off[kMaxSlotsPerQuery], s_cnt[kMaxSlotsPerQuery], s_slot[kMaxSlotsPerQuery];
-  __shared__ float s_thr, s_eps, s_qx, s_gn, s_ak;
+  __shared__ float s_thr, s_eps, s_qx, s_gn, s_ak, s_nun, s_mun;
   __shared__ double s_qmu, s_kth;
   __shared__ BlockBest s_bb;
 
@@ -956,15 +979,28 @@ __global__ void __launch_bounds__(128)
       for (int c = lane; c < d; c += 32) acc += nu[c] * nu[c];
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(kFull, acc, off);
-    if (lane == 0) s_eps += 3e-7f * (s_qx + sqrtf(acc) * 1.001f) * s_gn;
+    if (lane == 0) {
+      s_nun = sqrtf(acc) * 1.001f;
+      s_eps += 3e-7f * (s_qx + s_nun) * s_gn;
+    }
   }
   if (warp == 0) {   // q . mu in fp64: the constant the centred approximate scores are offset by
     double acc = 0.0;
+    float mu2 = 0.f;
     if (mu)
-      for (int c = lane; c < d; c += 32) acc = fma(qs[c], static_cast<double>(mu[c]), acc);
+      for (int c = lane; c < d; c += 32) {
+        acc = fma(qs[c], static_cast<double>(mu[c]), acc);
+        mu2 = fmaf(mu[c], mu[c], mu2);
+      }
 #pragma unroll
-    for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(kFull, acc, off);
-    if (lane == 0) s_qmu = acc;
+    for (int off = 16; off > 0; off >>= 1) {
+      acc += __shfl_xor_sync(kFull, acc, off);
+      mu2 += __shfl_xor_sync(kFull, mu2, off);
+    }
+    if (lane == 0) {
+      s_qmu = acc;
+      s_mun = sqrtf(mu2) * 1.001f;
+    }
   }
   const int nslots = s_nslots;
   for (int t = threadIdx.x; t < nslots * kKPMax; t += blockDim.x) {
@@ -1031,8 +1067,11 @@ __global__ void __launch_bounds__(128)
     // certificate: every gallery row g that is not a candidate has approximate centred score <= s_thr, hence exact
     // score q.g <= s_thr + eps + q.mu
     const bool closed = s_thr > -INFINITY;   // some segment dropped rows
+    // fp64 rounding of kth and q.mu themselves (each a d-term dot of vectors no longer than (|q'| + |nu|), (|g'| + |mu|)):
+    // irrelevant next to eps except when the centred gallery is (nearly) zero -- all rows identical -- and eps with it
+    const double slack = 4.6e-16 * (d + 8) * static_cast<double>(s_qx + s_nun) * static_cast<double>(s_gn + s_mun);
     const bool ok = (n >= k) && (m >= k) && !s_overflow &&
-                    (!closed || kth > static_cast<double>(s_thr) + static_cast<double>(s_eps) + s_qmu);
+                    (!closed || kth > static_cast<double>(s_thr) + static_cast<double>(s_eps) + s_qmu + slack);
     if (!ok) {
       const int pos = atomicAdd(n_flagged, 1);
       flagged[pos] = qrow;
@@ -1218,20 +1257,30 @@ __global__ void __launch_bounds__(32 * kRescoreWarps)
   const float g_norm = __uint_as_float(g_max[0]), g_res = __uint_as_float(g_max[1]);
   const float qh = q_norm_hat[qrow], qr = q_norm_res[qrow], qx = q_norm_x[qrow];
   float eps = 1.001f * (qh * g_res + qr * g_norm) + d_pad * 2.4e-7f * qh * (g_norm + g_res) + 1e-30f;
+  float nun = 0.f, mun = 0.f;   // |nu|, |mu| (upper bounds)
   {
     float acc = 0.f;
     if (nu && nu_flag && *nu_flag)
       for (int c = lane; c < d; c += 32) acc += nu[c] * nu[c];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(kFull, acc, o);
-    eps += 3e-7f * (qx + sqrtf(acc) * 1.001f) * g_norm;
+    nun = sqrtf(acc) * 1.001f;
+    eps += 3e-7f * (qx + nun) * g_norm;
   }
   __syncwarp();
   double qmu = 0.0;   // q . mu in fp64: the constant the centred approximate scores are offset by
   if (mu) {
-    for (int c = lane; c < d; c += 32) qmu = fma(qs[c], static_cast<double>(mu[c]), qmu);
+    float mu2 = 0.f;
+    for (int c = lane; c < d; c += 32) {
+      qmu = fma(qs[c], static_cast<double>(mu[c]), qmu);
+      mu2 = fmaf(mu[c], mu[c], mu2);
+    }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) qmu += __shfl_xor_sync(kFull, qmu, o);
+    for (int o = 16; o > 0; o >>= 1) {
+      qmu += __shfl_xor_sync(kFull, qmu, o);
+      mu2 += __shfl_xor_sync(kFull, mu2, o);
+    }
+    mun = sqrtf(mu2) * 1.001f;
   }
 
   // ---- prune by approximate score: A_k by rank counting ----
@@ -1302,8 +1351,10 @@ __global__ void __launch_bounds__(32 * kRescoreWarps)
     // certificate: every gallery row that is not a candidate has approximate centred score <= thr, hence exact score
     // q.g <= thr + eps + q.mu
     const bool closed = thr > -INFINITY;
+    // fp64 rounding of kth and q.mu themselves: see the block form
+    const double slack = 4.6e-16 * (d + 8) * static_cast<double>(qx + nun) * static_cast<double>(g_norm + mun);
     const bool ok = (n >= k) && (m >= k) && !overflow &&
-                    (!closed || kth > static_cast<double>(thr) + static_cast<double>(eps) + qmu);
+                    (!closed || kth > static_cast<double>(thr) + static_cast<double>(eps) + qmu + slack);
     if (!ok) {
       const int pos = atomicAdd(n_flagged, 1);
       flagged[pos] = qrow;
@@ -1781,8 +1832,8 @@ int sim_topk(const float* q, int nq, const float* g, int ng, int d, int k, long 
     DCR_CUDA_CHECK(cudaMemsetAsync(colsum, 0, static_cast<size_t>(d) * 16, stream));
     const int row_stride = std::max(1, n / 8192);
     const int n_sample = (n + row_stride - 1) / row_stride;
-    col_sum_kernel<<<std::min(n_sample, di->num_sms * 4), 256, 0, stream>>>(x, n_sample, row_stride, d, colsum,
-                                                                            decide ? colsum + d : nullptr);
+    col_sum_kernel<<<std::max(1, std::min((n_sample + 63) / 64, di->num_sms)), kColSumThreads, 0, stream>>>(
+        x, n_sample, row_stride, d, colsum, decide ? colsum + d : nullptr);
     count_launch();
     col_mean_finish_kernel<<<(d + 255) / 256, 256, 0, stream>>>(colsum, n_sample, d, out);
     count_launch();
