@@ -42,6 +42,11 @@ constexpr int kAStage = kBM * kBK * 2;   // 16 KB
 #define DCR_GEMM_TIMING_MODE 0
 #endif
 constexpr int kGemmTimingMode = DCR_GEMM_TIMING_MODE;
+// direct epilogue: per epilogue warp a [32 rows][64 B + 16 B pad] buffer through which the bf16 planes are transposed, so that
+// one warp instruction touches 8 rows x 64 contiguous bytes of global memory instead of 32 rows x 16 bytes
+constexpr int kXposePitch = 80;
+constexpr int kXposeWarpBytes = 32 * kXposePitch;
+constexpr int kXposeBytes = 8 * kXposeWarpBytes;
 
 struct GemmMaps {
   CUtensorMap a[3];
@@ -178,7 +183,8 @@ __global__ void __launch_bounds__(kThreads, 1)
   uint8_t* smem_ares = smem;
   uint8_t* smem_ab = smem + (a_res ? k_iters * kAStage : 0);
   uint8_t* out_stage = smem_ab + stages * stage_bytes;                      // n_out_bufs tiles, 1024-aligned
-  uint8_t* res_stage = out_stage + p.n_out_bufs * kStagingBytes;            // n_res_bufs tiles
+  // direct epilogue (kEpi == 0): no staging tiles; one 32-row x 64-byte transpose buffer per epilogue warp instead
+  uint8_t* res_stage = out_stage + (kTma ? p.n_out_bufs * kStagingBytes : kXposeBytes);   // n_res_bufs tiles
   float* sb = reinterpret_cast<float*>(res_stage + p.n_res_bufs * kStagingBytes);   // [2 bufs][2 (scale,bias)][BN] | a_res: [2][n_tiles*BN]
   uint64_t* bars = reinterpret_cast<uint64_t*>(sb + (a_res ? 2 * num_n_tiles * BN : 4 * BN));
   uint64_t* full = bars;          // [stages] (<= 12)
@@ -500,28 +506,60 @@ __global__ void __launch_bounds__(kThreads, 1)
             st_shared_v4(srow + ((((ch & 1) * 4 + j) ^ sw) << 4), v);
           }
         } else {
-          if (!row_ok) continue;
+          // Direct epilogue (split-bf16 planes, fp32 outputs, final layers).  Thread = accumulator row, but a row's 32 columns
+          // are only 64 bytes per plane: written straight from the registers, one warp instruction touched 32 rows x 16 bytes
+          // (32 half-used sectors, 32 LSU wavefronts) and the 1x1 expansions of the fp32-level modes ran at 0.5 TB/s (layer1:
+          // 870 us against 97 us with the TMA-store epilogue in one-plane mode).  Every plane now goes through the warp's
+          // transpose buffer: rows -> shared memory, then 8 rows x 64 contiguous bytes per instruction to / from global memory.
           const int nvalid = min(32, N - nc);   // multiple of 8 (N % 8 == 0 enforced on the host)
+          const uint32_t xw = smem_u32(out_stage) + ewarp * kXposeWarpBytes;
+          const uint32_t x_own = xw + lane * kXposePitch;           // this thread's row
+          const int m_w0 = m0 + static_cast<int>(quad) * 32;        // first row of this warp
           if (has_res) {
             for (int pl = 0; pl < p.res_planes; ++pl) {
-              const __nv_bfloat16* rp = p.res + pl * p.res_plane_stride + static_cast<size_t>(m) * p.ld_res + nc;
+              const __nv_bfloat16* rbase = p.res + pl * p.res_plane_stride + nc;
+              __syncwarp();
 #pragma unroll
-              for (int c = 0; c < 32; c += 8) {
-                if (c < nvalid) {
-                  const uint4 rv = *reinterpret_cast<const uint4*>(rp + c);
+              for (int t = 0; t < 4; ++t) {
+                const int piece = t * 32 + static_cast<int>(lane), r = piece >> 2, part = piece & 3;
+                if (m_w0 + r < M && part * 8 < nvalid)
+                  st_shared_v4(xw + r * kXposePitch + part * 16,
+                               *reinterpret_cast<const uint4*>(rbase + static_cast<size_t>(m_w0 + r) * p.ld_res + part * 8));
+              }
+              __syncwarp();
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                if (j * 8 < nvalid && row_ok) {
+                  const uint4 rv = ld_shared_v4(x_own + j * 16);
                   const uint32_t w[4] = {rv.x, rv.y, rv.z, rv.w};
 #pragma unroll
-                  for (int j = 0; j < 4; ++j) {
-                    y[c + 2 * j] += __uint_as_float(w[j] << 16);
-                    y[c + 2 * j + 1] += __uint_as_float(w[j] & 0xffff0000u);
+                  for (int e = 0; e < 4; ++e) {
+                    y[j * 8 + 2 * e] += __uint_as_float(w[e] << 16);
+                    y[j * 8 + 2 * e + 1] += __uint_as_float(w[e] & 0xffff0000u);
                   }
                 }
               }
             }
           }
+          // the activation is a run-time value here: ONE warp-uniform switch per chunk (inside the element loop the compiler
+          // kept a compare-and-branch chain per element: 660 instructions per 32-column chunk, a quarter of the warp samples on
+          // instruction fetch)
+          if (act == 1) {
 #pragma unroll
-          for (int c = 0; c < 32; ++c) y[c] = (act == 2 && p.fast_gelu) ? gelu_tanh_fast(y[c]) : apply_act(y[c], act);
-          if (p.out_f32) {
+            for (int c = 0; c < 32; ++c) y[c] = fmaxf(y[c], 0.f);
+          } else if (act == 2) {
+            if (p.fast_gelu) {
+#pragma unroll
+              for (int c = 0; c < 32; ++c) y[c] = gelu_tanh_fast(y[c]);
+            } else {
+#pragma unroll
+              for (int c = 0; c < 32; ++c) y[c] = gelu_erf_fast(y[c]);
+            }
+          } else if (act == 3) {
+#pragma unroll
+            for (int c = 0; c < 32; ++c) y[c] = apply_act(y[c], 3);
+          }
+          if (p.out_f32 && row_ok) {
             float* op = p.out_f32 + static_cast<size_t>(m) * p.ld_out_f32 + nc;
 #pragma unroll
             for (int c = 0; c < 32; c += 4)
@@ -529,17 +567,24 @@ __global__ void __launch_bounds__(kThreads, 1)
           }
           if (p.out) {
             for (int pl = 0; pl < p.out_planes; ++pl) {
-              __nv_bfloat16* op = p.out + pl * p.out_plane_stride + static_cast<size_t>(m) * p.ld_out + p.out_col_off + nc;
+              __nv_bfloat16* obase = p.out + pl * p.out_plane_stride + p.out_col_off + nc;
+              __syncwarp();
 #pragma unroll
-              for (int c = 0; c < 32; c += 8) {
-                if (c < nvalid) {
-                  uint4 v;
-                  v.x = pack_bf16(y[c + 0], y[c + 1]);
-                  v.y = pack_bf16(y[c + 2], y[c + 3]);
-                  v.z = pack_bf16(y[c + 4], y[c + 5]);
-                  v.w = pack_bf16(y[c + 6], y[c + 7]);
-                  *reinterpret_cast<uint4*>(op + c) = v;
-                }
+              for (int j = 0; j < 4; ++j) {
+                uint4 v;
+                v.x = pack_bf16(y[j * 8 + 0], y[j * 8 + 1]);
+                v.y = pack_bf16(y[j * 8 + 2], y[j * 8 + 3]);
+                v.z = pack_bf16(y[j * 8 + 4], y[j * 8 + 5]);
+                v.w = pack_bf16(y[j * 8 + 6], y[j * 8 + 7]);
+                st_shared_v4(x_own + j * 16, v);
+              }
+              __syncwarp();
+#pragma unroll
+              for (int t = 0; t < 4; ++t) {
+                const int piece = t * 32 + static_cast<int>(lane), r = piece >> 2, part = piece & 3;
+                if (m_w0 + r < M && part * 8 < nvalid)
+                  *reinterpret_cast<uint4*>(obase + static_cast<size_t>(m_w0 + r) * p.ld_out + part * 8) =
+                      ld_shared_v4(xw + r * kXposePitch + part * 16);
               }
               if (pl + 1 < p.out_planes) {
                 // next plane holds the rounding residual of this one
@@ -604,7 +649,9 @@ int launch(const GemmMaps& maps, GemmParams& p, int num_sms, size_t max_smem, cu
   p.a_resident = (kCG == 1 && kEpi != 0 && wants_a_resident(p, BN, kIm2col, max_smem)) ? 1 : 0;
   const size_t sb_bytes = p.a_resident ? static_cast<size_t>(2) * p.num_n_tiles * BN * 4 : static_cast<size_t>(4) * BN * 4;
   const size_t ares_bytes = p.a_resident ? static_cast<size_t>(k_iters_h) * kAStage : 0;
-  auto fixed_for = [&](int nout, int nres) { return 1024 + sb_bytes + ares_bytes + 256 + static_cast<size_t>(nout + nres) * kStagingBytes; };
+  auto fixed_for = [&](int nout, int nres) {
+    return 1024 + sb_bytes + ares_bytes + 256 + static_cast<size_t>(nout + nres) * kStagingBytes + (p.tma_epi ? 0 : kXposeBytes);
+  };
   const size_t stage_bytes = p.a_resident ? static_cast<size_t>(BN) * kBK * 2 : static_cast<size_t>(kStageBytes);
   if (p.tma_epi && (fixed_for(p.n_out_bufs, p.n_res_bufs) + 3 * stage_bytes > max_smem)) p.n_out_bufs = 1;
   const size_t fixed = fixed_for(p.n_out_bufs, p.n_res_bufs);

@@ -1,4 +1,5 @@
-"""A/B of one convolution shape under a tuning environment variable: python tools/conv_ab.py VAR v0 v1 B H W C N k stride pad"""
+"""A/B of one convolution shape under a tuning environment variable: python tools/conv_ab.py VAR v0 v1 B H W C N k stride pad
+(a value of "-" leaves the variable unset)"""
 import os
 import sys
 
@@ -16,7 +17,10 @@ x = ops.split_planes(torch.randn(b, h, w_, c, device="cuda", generator=gen), 1)
 w = ops.prepare_conv_weight(torch.randn(n, c, k, k, device="cuda", generator=gen) / (c * k * k) ** 0.5, 1)
 t, outs = {}, {}
 for mode in (v0, v1, v0, v1):
-    os.environ[var] = mode
+    if mode == "-":
+        os.environ.pop(var, None)      # flags are tested for presence
+    else:
+        os.environ[var] = mode
     for _ in range(3):
         o, _ = ops.conv2d(x, w, n, k, k, stride, pad, pad, act=1)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

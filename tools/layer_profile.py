@@ -27,7 +27,8 @@ if sys.argv[1] == "run":
     from oracle import models as om
     kind, batch = sys.argv[2], int(sys.argv[3])
     if kind == "sscd":
-        net = nets.build_sscd_resnet50(om.make_sscd_state_dict(0), max_batch=batch, stem=(sys.argv[4] if len(sys.argv) > 4 else None))
+        net = nets.build_sscd_resnet50(om.make_sscd_state_dict(0), max_batch=batch, stem=(sys.argv[4] if len(sys.argv) > 4 else None),
+                                       precision=os.environ.get("DCR_LP_PRECISION", "fast"))
         img = synthetic.images(32, seed=0)
     elif kind == "vit":
         net = nets.build_dino_vit(om.make_vit_state_dict(0), max_batch=batch)
