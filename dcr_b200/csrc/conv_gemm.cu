@@ -792,7 +792,8 @@ int conv_gemm(const ConvGemmDesc& d, cudaStream_t stream) {
   // tile order: with several column blocks and an A matrix larger than what L2 keeps between the passes, m-fastest order
   // streams A from HBM once per column block (ViT-S fc2: 155 MB x 3 = 83 us of HBM time for a 99 us layer)
   const double a_bytes = 2.0 * a_planes * (im2col ? static_cast<double>(d.B) * d.H * d.W * d.C : static_cast<double>(M) * d.C);
-  p.n_fastest = (p.num_n_tiles >= 2 && a_bytes > 48e6 && !tuning_flag("DCR_GEMM_M_FASTEST")) ? 1 : 0;
+  const int order = tuning_int("DCR_GEMM_TILE_ORDER", -1);   // tuning / tests: 0 = m-fastest, 1 = n-fastest, default by size
+  p.n_fastest = (order >= 0) ? (order == 1 && p.num_n_tiles >= 2) : (p.num_n_tiles >= 2 && a_bytes > 48e6);
   if (kGemmTimingMode == 2 && im2col && !windowed) {
     if (int rc = make_tmap_2d_bf16(&maps.a_flat, d.in, static_cast<uint64_t>(d.B) * d.H * d.W, d.C, d.C, kBM, kBK)) return rc;
   }

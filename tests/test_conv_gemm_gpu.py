@@ -171,3 +171,38 @@ def test_cta_pair_gemm_matches_single_cta(shape, monkeypatch):
                ops.merge_planes(rp) if with_res else None, act, 1, (0, 0))
     mx = max(1.0, ref.abs().max().item())
     assert (ops.merge_planes(two) - ref).abs().max().item() < (2 ** -8 + 3e-4) * mx
+
+
+@pytest.mark.parametrize("shape", [
+    ((600, 1, 1), 1536, 384, 1, 1, 0, True, 0),     # plain GEMM, three column blocks, residual
+    ((3, 28, 28), 128, 512, 3, 2, 1, False, 1),    # strided 3x3 through TMA im2col, four column blocks
+    ((4, 14, 14), 1024, 512, 1, 1, 0, False, 1),   # two 256-wide column blocks (CTA-pair form when forced)
+])
+@pytest.mark.parametrize("pair", ["0", "1"])
+def test_tile_order_does_not_change_results(shape, pair, monkeypatch):
+    """n-fastest tile order (chosen when A is larger than L2: consecutive tiles share an m-tile's rows) against the default
+    m-fastest order, in the single-CTA and the CTA-pair kernel: every tile computes the same thing, only who computes it
+    and when changes."""
+    (b, h, w_), c, n, k, stride, pad, with_res, act = shape
+    gen = torch.Generator(device="cuda").manual_seed(c + n + k)
+    x = torch.randn(b, h, w_, c, device="cuda", generator=gen)
+    w = torch.randn(n, c, k, k, device="cuda", generator=gen) / (c * k * k) ** 0.5
+    ho = (h + 2 * pad - k) // stride + 1
+    wo = (w_ + 2 * pad - k) // stride + 1
+    res = torch.randn(b, ho, wo, n, device="cuda", generator=gen) if with_res else None
+    xp, wp = ops.split_planes(x, 1), ops.prepare_conv_weight(w, 1)
+    rp = ops.split_planes(res, 1) if with_res else None
+    monkeypatch.setenv("DCR_B200_TUNING", "1")
+    monkeypatch.setenv("DCR_GEMM_CG2", pair)
+    outs = []
+    for order in ("0", "1"):
+        monkeypatch.setenv("DCR_GEMM_TILE_ORDER", order)
+        o, _ = ops.conv2d(xp, wp, n, k, k, stride, pad, pad, residual=rp, act=act)
+        torch.cuda.synchronize()
+        outs.append(o)
+    assert torch.equal(outs[0], outs[1])
+    ref = _ref(ops.merge_planes(xp), ops.merge_planes(wp).reshape(n, k, k, -1)[..., :c].permute(0, 3, 1, 2),
+               torch.ones(n, device="cuda"), torch.zeros(n, device="cuda"), ops.merge_planes(rp) if with_res else None, act,
+               stride, (pad, pad))
+    mx = max(1.0, ref.abs().max().item())
+    assert (ops.merge_planes(outs[1]) - ref).abs().max().item() < (2 ** -8 + 3e-4) * mx
