@@ -125,7 +125,9 @@ int dcr_split_rescore(const float* q, const float* g, int nq, int d, int n_chunk
  *            (dcr_b200.ops.prepare_conv_weight); N % 8 == 0.
  *   terms    1 = bf16 x bf16 (fast); 3 or 6 = split-bf16 cross terms hi*hi, hi*mid, mid*hi[, mid*mid, hi*lo, lo*hi]
  *            which need x_planes/w_planes >= 2 (3 terms) or 3 (6 terms) and reproduce fp32 accuracy.
- *   scale/bias  fp32 [N] or NULL; residual: bf16 planes [res_planes][M][N] or NULL; act: 0 none, 1 ReLU, 2 GELU(erf)
+ *   scale/bias  fp32 [N] or NULL; residual: bf16 planes [res_planes][M][N] or NULL; act: 0 none, 1 ReLU, 2 GELU, 3 QuickGELU
+ *            (GELU: the erf form, |error| <= 2e-7, with split planes; with ONE plane -- bf16 activations -- its tanh form through
+ *            tanh.approx, within 1.5e-3 absolute of the erf form, i.e. below the bf16 rounding of the stored value)
  *   out      bf16 planes [out_planes][M][ld_out] written at column offset out_col_off (concat by offset), or NULL;
  *   out_f32  fp32 [M][N] or NULL.   M = B * Hout * Wout.
  * Replaces the cuDNN / cuBLAS calls behind `model(samples)`        utils_ret.py:751 (nn.Conv2d+BatchNorm2d+ReLU of the
@@ -173,7 +175,7 @@ int dcr_conv2d_bf16(const void* x, int x_planes, int64_t x_plane_stride, int B, 
  *  13 STEM_CONV  i: planes_t, out_t, OH, OW, w_param ([64][256] bf16, k = ((a*2+e)*4+b)*8 + i*3+c), scale_param|-1, bias_param|-1 [, pool]
  *                7x7/2/pad-3 convolution + BN + ReLU -> NHWC [OH*OW, 64]; pool = 1: the following 3x3/2/pad-1 max pool is
  *                taken in the epilogue and out_t is [((OH-1)/2+1) * ((OW-1)/2+1), 64]
- * CONV act: 0 none, 1 ReLU, 2 GELU (erf), 3 QuickGELU x*sigmoid(1.702x). */
+ * CONV act: 0 none, 1 ReLU, 2 GELU (erf form; tanh form in one-plane mode, see dcr_conv2d_bf16), 3 QuickGELU x*sigmoid(1.702x). */
 typedef struct dcr_net dcr_net;
 int dcr_net_create(int max_batch, int planes, dcr_net** out);
 /* on != 0: every CONV op accumulates its products in float64 on the CUDA cores (correctly rounded fp32 layer outputs,
